@@ -1,0 +1,41 @@
+// Host-side helpers shared by the translation units of libgap_b200: error reporting, the
+// driver-entry-point lookup for cuTensorMapEncodeTiled (so the library links against cudart only),
+// and device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gap_b200.h"
+
+namespace gap {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+int debug_get(const char* key, int dflt);
+
+// Encode a tiled TMA descriptor for a bf16 tensor.  dims/strides are innermost-first; strides[i]
+// is the byte stride of dimension i+1 (dimension 0 is contiguous).  Returns 0 or a gap_status.
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                     bool swizzle128);
+
+#define GAP_CHECK_ARG(cond, ...)      \
+  do {                                \
+    if (!(cond)) {                    \
+      gap::set_error(__VA_ARGS__);    \
+      return GAP_ERR_BAD_ARG;         \
+    }                                 \
+  } while (0)
+
+#define GAP_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      gap::set_error("%s failed: %s", #call, cudaGetErrorString(e__));             \
+      return static_cast<int>(e__);                                                \
+    }                                                                              \
+  } while (0)
+
+}  // namespace gap

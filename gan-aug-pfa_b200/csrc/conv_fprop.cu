@@ -1,0 +1,506 @@
+// Implicit-GEMM convolution engine ("fprop-like" contraction) for sm_100a.
+//
+//   D[pixel, co] = sum_k A[pixel, k] * B[co, k]
+//
+// A is never materialised: a tile of 128 output-grid points (BW x BH x BNI, all powers of two) is
+// fetched per filter tap and per 64-channel chunk straight from the NHWC bf16 activation tensor
+// by ONE 4-D tiled TMA box (traversal stride = conv stride, out-of-bounds = zero padding) into a
+// 128-byte-swizzled K-major shared-memory tile that tcgen05.mma consumes through a shared-memory
+// matrix descriptor.  B (packed weights, K-major) comes through a second TMA box.  Accumulators
+// live in TMEM (two 256-column buffers, so the epilogue of tile i overlaps the main loop of tile
+// i+1).  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 =
+// epilogue (tcgen05.ld -> bias -> BatchNorm partial statistics -> activation(s) -> bf16 stores).
+//
+// The same kernel serves Conv2d forward, Conv2d dgrad (stride 1: flipped taps; stride 2: four
+// output-parity phases of 2x2 taps), ConvTranspose2d forward (the same four phases) and
+// ConvTranspose2d dgrad (a strided gather) — see gap_b200.h.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace gap {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kFpropThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
+constexpr int kTmemCols = 512;
+constexpr int kStatsBytes = 4 * 256 * 2 * 8;  // per-epilogue-warp fp64 partial sums
+constexpr int kBarrierBytes = 256;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct alignas(64) FpropParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  int src_chunks[2];
+  int n_img, gh, gw;
+  int n_phase, taps_h, taps_w, in_stride;
+  int in_off_h[2], in_off_w[2];
+  int out_stride;
+  int log_bw, log_bh;
+  int tiles_w, tiles_h, tiles_n;
+  int n_tiles, block_n;
+  int n_out, OH, OW;
+  __nv_bfloat16* out;
+  long long out_ld;
+  int act;
+  __nv_bfloat16* out2;
+  long long out2_ld;
+  int act2;
+  const float* bias;
+  double* stats;
+  int num_stages;
+  uint32_t idesc;
+  int total_tiles;
+  int k_iters;
+  int vec_ok;  // outputs are 16-byte aligned per pixel: use vector stores
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case GAP_ACT_LRELU:
+      return v > 0.f ? v : 0.2f * v;
+    case GAP_ACT_RELU:
+      return fmaxf(v, 0.f);
+    case GAP_ACT_TANH:
+      return tanhf(v);
+    case GAP_ACT_SIGMOID:
+      return 1.f / (1.f + __expf(-v));
+    default:
+      return v;
+  }
+}
+
+struct TileCoord {
+  int n_tile, tw, th, tn, ph, pw, phase;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const FpropParams& p, int t) {
+  TileCoord c;
+  c.n_tile = t % p.n_tiles;
+  t /= p.n_tiles;
+  c.tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  c.th = t % p.tiles_h;
+  t /= p.tiles_h;
+  c.tn = t % p.tiles_n;
+  c.phase = t / p.tiles_n;
+  c.ph = c.phase >> 1;
+  c.pw = c.phase & 1;
+  return c;
+}
+
+// Sum the 16 per-row values of v across the 32 lanes of the warp.  On return lane l holds in its
+// return value the full column sum of column ((l>>1) & 15) ... precisely: column index
+// 8*b4 + 4*b3 + 2*b2 + b1 where b_i are bits of the lane id (lanes differing in bit 0 agree).
+__device__ __forceinline__ float transpose_reduce16(const float (&v)[16], uint32_t lane) {
+  float w8[8];
+  const bool b4 = lane & 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float mine = b4 ? v[8 + j] : v[j];
+    float other = b4 ? v[j] : v[8 + j];
+    w8[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+  }
+  float w4[4];
+  const bool b3 = lane & 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mine = b3 ? w8[4 + j] : w8[j];
+    float other = b3 ? w8[j] : w8[4 + j];
+    w4[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+  }
+  float w2[2];
+  const bool b2 = lane & 4;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float mine = b2 ? w4[2 + j] : w4[j];
+    float other = b2 ? w4[j] : w4[2 + j];
+    w2[j] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+  }
+  const bool b1 = lane & 2;
+  float mine = b1 ? w2[1] : w2[0];
+  float other = b1 ? w2[0] : w2[1];
+  float w1 = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  return w1;
+}
+
+__global__ void __launch_bounds__(kFpropThreads, 1)
+conv_fprop_kernel(const __grid_constant__ FpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int stage_bytes = kATileBytes + p.block_n * 128;
+  const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
+  // barrier slots (8 bytes each): full[0..7], empty[8..15], tfull[16..17], tempty[18..19]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  uint8_t* bar_gen = smem_gen + p.num_stages * stage_bytes;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 20);
+  double* stats_sm = reinterpret_cast<double*>(bar_gen + kBarrierBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    if (p.src_chunks[1] > 0) tma_prefetch_desc(&p.tmA[1]);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int BW = 1 << p.log_bw, BH = 1 << p.log_bh;
+  const int BNI = kBlockM >> (p.log_bw + p.log_bh);
+  const int n_taps = p.taps_h * p.taps_w;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int x_base = tc.tw * BW * p.in_stride + p.in_off_w[tc.pw];
+        const int y_base = tc.th * BH * p.in_stride + p.in_off_h[tc.ph];
+        const int n_base = tc.tn * BNI;
+        int kcol = 0;
+        for (int tap = 0; tap < n_taps; ++tap) {
+          const int t_h = tap / p.taps_w, t_w = tap - t_h * p.taps_w;
+          for (int s = 0; s < 2; ++s) {
+            for (int c = 0; c < p.src_chunks[s]; ++c) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x_base + t_w,
+                          y_base + t_h, n_base);
+              tma_load_3d(a_dst + kATileBytes, &p.tmB, full_bar(stage), kcol,
+                          tc.n_tile * p.block_n, tc.phase);
+              kcol += kBlockK;
+              if (++stage == p.num_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int k_iter = 0; k_iter < p.k_iters; ++k_iter) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (k_iter | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int e_tid = threadIdx.x - 64;  // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_ntile = -1;
+    double* my_stats = stats_sm + q * 512;  // [256 sum][256 sumsq]
+    const bool do_stats = p.stats != nullptr;
+    const int stat_col = ((lane >> 1) & 15);
+
+    auto flush_stats = [&](int n_tile) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = e_tid; c < 2 * p.block_n; c += 128) {
+        const int which = c / p.block_n, col = c - which * p.block_n;
+        const int gcol = n_tile * p.block_n + col;
+        const int idx = which * 256 + col;
+        double tot = stats_sm[idx] + stats_sm[512 + idx] + stats_sm[1024 + idx] + stats_sm[1536 + idx];
+        if (gcol < p.n_out) atomicAdd(p.stats + which * p.n_out + gcol, tot);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      if (do_stats && tc.n_tile != cur_ntile) {
+        if (cur_ntile >= 0) flush_stats(cur_ntile);
+        for (int c = lane; c < 512; c += 32) my_stats[c] = 0.0;
+        __syncwarp();
+        cur_ntile = tc.n_tile;
+      }
+      const int wi = row & (BW - 1);
+      const int hi = (row >> p.log_bw) & (BH - 1);
+      const int ni = row >> (p.log_bw + p.log_bh);
+      const int gx = tc.tw * BW + wi, gy = tc.th * BH + hi, n = tc.tn * BNI + ni;
+      const bool valid = (gx < p.gw) && (gy < p.gh) && (n < p.n_img);
+      const long long pix =
+          (static_cast<long long>(n) * p.OH + (gy * p.out_stride + tc.ph)) * p.OW +
+          (gx * p.out_stride + tc.pw);
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      const int n_chunks = p.block_n >> 4;
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t raw[16];
+        tmem_ld16(t_row + c * 16, raw);
+        tmem_ld_wait();
+        const int col0 = tc.n_tile * p.block_n + c * 16;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f[j] = __uint_as_float(raw[j]);
+          if (p.bias != nullptr && col0 + j < p.n_out) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (do_stats) {
+          float m[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = valid ? f[j] : 0.f;
+          const float s = transpose_reduce16(m, lane);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = m[j] * m[j];
+          const float s2 = transpose_reduce16(m, lane);
+          if ((lane & 1) == 0) {
+            my_stats[c * 16 + stat_col] += static_cast<double>(s);
+            my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
+          }
+        }
+        if (valid && col0 < p.n_out) {
+          if (p.vec_ok && col0 + 16 <= p.n_out) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pk[j] = pack_bf16x2(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
+            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + col0);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (p.out2 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                pk[j] = pack_bf16x2(apply_act(f[2 * j], p.act2), apply_act(f[2 * j + 1], p.act2));
+              uint4* dst2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_ld + col0);
+              dst2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (col0 + j < p.n_out) {
+                p.out[pix * p.out_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act));
+                if (p.out2 != nullptr)
+                  p.out2[pix * p.out2_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act2));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (do_stats && cur_ntile >= 0) flush_stats(cur_ntile);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+static int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+}  // namespace gap
+
+using namespace gap;
+
+extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  GAP_CHECK_ARG(a != nullptr, "gap_conv_gemm: null args");
+  GAP_CHECK_ARG(a->src[0] && a->wpk && a->out, "gap_conv_gemm: null src/wpk/out pointer");
+  GAP_CHECK_ARG(a->src_c[0] > 0 && a->src_c[0] % 64 == 0 && a->src_c[1] >= 0 &&
+                    a->src_c[1] % 64 == 0,
+                "gap_conv_gemm: source channels (%d, %d) must be multiples of 64", a->src_c[0],
+                a->src_c[1]);
+  GAP_CHECK_ARG(a->src_c[1] == 0 || a->src[1] != nullptr, "gap_conv_gemm: src[1] is null");
+  GAP_CHECK_ARG(a->n > 0 && a->ih > 0 && a->iw > 0 && a->gh > 0 && a->gw > 0,
+                "gap_conv_gemm: empty shape n=%d ih=%d iw=%d gh=%d gw=%d", a->n, a->ih, a->iw,
+                a->gh, a->gw);
+  GAP_CHECK_ARG(a->n_phase == 1 || a->n_phase == 4, "gap_conv_gemm: n_phase must be 1 or 4");
+  GAP_CHECK_ARG(a->taps_h >= 1 && a->taps_w >= 1 && a->taps_h <= 7 && a->taps_w <= 7,
+                "gap_conv_gemm: taps out of range");
+  GAP_CHECK_ARG(a->in_stride >= 1 && a->in_stride <= 2 && a->out_stride >= 1,
+                "gap_conv_gemm: strides out of range");
+  GAP_CHECK_ARG(a->n_out >= 1 && a->w_rows >= a->n_out, "gap_conv_gemm: n_out/w_rows invalid");
+  GAP_CHECK_ARG(a->act >= 0 && a->act <= 4 && a->act2 >= 0 && a->act2 <= 4,
+                "gap_conv_gemm: unknown activation");
+  for (int s = 0; s < 2; ++s) {
+    if (a->src_c[s] == 0) continue;
+    if (a->src_ld[s] < a->src_c[s] || a->src_ld[s] % 8 != 0) {
+      set_error("gap_conv_gemm: src_ld[%d]=%lld must be >= channels and a multiple of 8", s,
+                (long long)a->src_ld[s]);
+      return GAP_ERR_ALIGNMENT;
+    }
+  }
+  const bool vec_ok =
+      a->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
+      (!a->out2 || (a->out2_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0));
+
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  // ---- M tile shape
+  const int log_bw = std::min(7, ilog2_ceil(a->gw));
+  const int log_bh = std::min(7 - log_bw, ilog2_ceil(a->gh));
+  const int BW = 1 << log_bw, BH = 1 << log_bh, BNI = kBlockM / (BW * BH);
+  p.log_bw = log_bw;
+  p.log_bh = log_bh;
+  p.tiles_w = (a->gw + BW - 1) / BW;
+  p.tiles_h = (a->gh + BH - 1) / BH;
+  p.tiles_n = (a->n + BNI - 1) / BNI;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n * a->n_phase;
+  // ---- N tile
+  const int n_pad = (a->n_out + 15) / 16 * 16;
+  int n_tiles = (n_pad + 255) / 256;
+  int block_n = ((n_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  const int sms = sm_count();
+  const int force_bn = debug_get("fprop_block_n", 0);
+  if (force_bn > 0) {
+    block_n = force_bn;
+    n_tiles = (n_pad + block_n - 1) / block_n;
+  } else {
+    while (m_tiles * n_tiles < sms && block_n >= 64 && block_n % 32 == 0) {
+      block_n /= 2;
+      n_tiles = (n_pad + block_n - 1) / block_n;
+    }
+  }
+  p.block_n = block_n;
+  p.n_tiles = n_tiles;
+  p.total_tiles = m_tiles * n_tiles;
+  const int ctot = a->src_c[0] + a->src_c[1];
+  p.src_chunks[0] = a->src_c[0] / 64;
+  p.src_chunks[1] = a->src_c[1] / 64;
+  p.k_iters = a->taps_h * a->taps_w * (ctot / 64);
+  p.n_img = a->n;
+  p.gh = a->gh;
+  p.gw = a->gw;
+  p.n_phase = a->n_phase;
+  p.taps_h = a->taps_h;
+  p.taps_w = a->taps_w;
+  p.in_stride = a->in_stride;
+  for (int i = 0; i < 2; ++i) {
+    p.in_off_h[i] = a->in_off_h[i];
+    p.in_off_w[i] = a->in_off_w[i];
+  }
+  p.out_stride = a->out_stride;
+  p.n_out = a->n_out;
+  p.OH = a->oh;
+  p.OW = a->ow;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.out_ld = a->out_ld;
+  p.act = a->act;
+  p.out2 = static_cast<__nv_bfloat16*>(a->out2);
+  p.out2_ld = a->out2_ld;
+  p.act2 = a->act2;
+  p.bias = a->bias;
+  p.stats = a->stats;
+  p.idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
+  p.vec_ok = vec_ok ? 1 : 0;
+
+  const int stage_bytes = kATileBytes + block_n * 128;
+  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes) / stage_bytes;
+  stages = std::min(stages, kMaxStages);
+  stages = std::min(stages, std::max(2, p.k_iters));
+  const int force_st = debug_get("fprop_stages", 0);
+  if (force_st > 0) stages = std::min(force_st, stages);
+  p.num_stages = stages;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes;
+
+  // ---- tensor maps
+  const uint32_t bx_w = static_cast<uint32_t>(BW * a->in_stride);
+  const uint32_t bx_h = static_cast<uint32_t>(BH * a->in_stride);
+  if (bx_w > 256 || bx_h > 256) {
+    set_error("gap_conv_gemm: TMA box %ux%u exceeds 256", bx_w, bx_h);
+    return GAP_ERR_UNSUPPORTED;
+  }
+  for (int s = 0; s < 2; ++s) {
+    if (a->src_c[s] == 0) continue;
+    const uint64_t ld_b = static_cast<uint64_t>(a->src_ld[s]) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(a->src_c[s]), static_cast<uint64_t>(a->iw),
+                        static_cast<uint64_t>(a->ih), static_cast<uint64_t>(a->n)};
+    uint64_t strides[3] = {ld_b, ld_b * a->iw, ld_b * a->iw * a->ih};
+    uint32_t box[4] = {64, bx_w, bx_h, static_cast<uint32_t>(BNI)};
+    uint32_t es[4] = {1, static_cast<uint32_t>(a->in_stride), static_cast<uint32_t>(a->in_stride), 1};
+    int rc = encode_tmap_bf16(&p.tmA[s], a->src[s], 4, dims, strides, box, es, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t ktot = static_cast<uint64_t>(a->taps_h) * a->taps_w * ctot;
+    uint64_t dims[3] = {ktot, static_cast<uint64_t>(a->w_rows), static_cast<uint64_t>(a->n_phase)};
+    uint64_t strides[2] = {ktot * 2, ktot * 2 * a->w_rows};
+    uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+    int rc = encode_tmap_bf16(&p.tmB, a->wpk, 3, dims, strides, box, nullptr, true);
+    if (rc) return rc;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemBudget));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_tiles, sms);
+  conv_fprop_kernel<<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
