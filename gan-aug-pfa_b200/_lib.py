@@ -43,6 +43,19 @@ class ConvGemmArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    """Mirror of ``gap_wgrad_args``."""
+
+    _fields_ = [
+        ("mop", C.c_void_p), ("m_c", C.c_int), ("m_ld", C.c_int64),
+        ("nop", C.c_void_p), ("n_c", C.c_int), ("n_ld", C.c_int64),
+        ("n", C.c_int), ("gh", C.c_int), ("gw", C.c_int), ("nh", C.c_int), ("nw", C.c_int),
+        ("taps_h", C.c_int), ("taps_w", C.c_int), ("stride", C.c_int),
+        ("off_h", C.c_int), ("off_w", C.c_int),
+        ("out", C.c_void_p), ("ld_m", C.c_int64), ("ld_tap", C.c_int64),
+    ]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/gap_b200.h declares is listed here, and
@@ -53,6 +66,7 @@ _SIGNATURES = {
     "gap_sm_count": (C.c_int, []),
     "gap_debug_set": (C.c_int, [C.c_char_p, C.c_int]),
     "gap_conv_gemm": (C.c_int, [C.POINTER(ConvGemmArgs), C.c_void_p]),
+    "gap_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
 }
 
 

@@ -130,3 +130,24 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
     else:
         a.stats = None
     _lib.check(_lib.lib().gap_conv_gemm(C.byref(a), _stream()), "gap_conv_gemm")
+
+
+def conv_wgrad(mop: torch.Tensor, nop: torch.Tensor, out: torch.Tensor, taps: tuple[int, int], stride: int,
+               off: tuple[int, int], ld_m: int, ld_tap: int) -> None:
+    """out[m*ld_m + tap*ld_tap + c] += sum_pix mop[pix, m] * nop[gather(pix, tap), c]   (fp32 out)."""
+    a = _lib.WgradArgs()
+    n, gh, gw, mc, mld = _nhwc_view(mop)
+    n2, nh, nw, nc, nld = _nhwc_view(nop)
+    if n != n2:
+        raise ValueError("mop / nop batch mismatch")
+    if out.dtype != torch.float32 or not out.is_cuda:
+        raise ValueError("wgrad output must be a CUDA fp32 tensor")
+    a.mop, a.m_c, a.m_ld = mop.data_ptr(), mc, mld
+    a.nop, a.n_c, a.n_ld = nop.data_ptr(), nc, nld
+    a.n, a.gh, a.gw, a.nh, a.nw = n, gh, gw, nh, nw
+    a.taps_h, a.taps_w = taps
+    a.stride = stride
+    a.off_h, a.off_w = off
+    a.out = out.data_ptr()
+    a.ld_m, a.ld_tap = ld_m, ld_tap
+    _lib.check(_lib.lib().gap_conv_wgrad(C.byref(a), _stream()), "gap_conv_wgrad")

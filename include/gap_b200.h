@@ -98,6 +98,33 @@ typedef struct gap_conv_gemm_args {
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Weight-gradient contraction (tcgen05, MN-major operands, split-K with fp32 red.add):
+ *
+ *   out[m*ld_m + tap*ld_tap + c] += sum over images and grid points (gy, gx) of
+ *        mop[img, gy, gx, m] * nop[img, gy*stride + off_h + th, gx*stride + off_w + tw, c]
+ *
+ * Conv2d wgrad (autograd of models.py:177,223,230,238,243,9,12,...): mop = dY, nop = X,
+ * out = dW viewed as [Cout][kh*kw][Cin].  ConvTranspose2d wgrad (models.py:184,189,194):
+ * mop = X, nop = dY, out = dW viewed as [Cin][kh*kw][Cout].  The caller zeroes `out` (that is
+ * optimizer.zero_grad(), train_gan.py:55,64); concatenated inputs are handled by one call per
+ * source with `out` offset to the source's channel range.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gap_wgrad_args {
+  const void* mop; /* NHWC bf16 [n, gh, gw, m_c] */
+  int m_c;
+  int64_t m_ld;
+  const void* nop; /* NHWC bf16 [n, nh, nw, n_c] */
+  int n_c;
+  int64_t n_ld;
+  int n, gh, gw, nh, nw;
+  int taps_h, taps_w, stride, off_h, off_w;
+  float* out;
+  int64_t ld_m, ld_tap;
+} gap_wgrad_args;
+
+int gap_conv_wgrad(const gap_wgrad_args* args, void* stream);
+
 /* Debug knobs for bring-up (descriptor conventions); not part of the stable surface. */
 int gap_debug_set(const char* key, int value);
 
