@@ -40,6 +40,7 @@ class ConvGemmArgs(C.Structure):
         ("act2", C.c_int),
         ("bias", C.c_void_p),
         ("stats", C.c_void_p),
+        ("out_f32", C.c_int),
     ]
 
 
@@ -47,7 +48,7 @@ class WgradArgs(C.Structure):
     """Mirror of ``gap_wgrad_args``."""
 
     _fields_ = [
-        ("mop", C.c_void_p), ("m_c", C.c_int), ("m_ld", C.c_int64),
+        ("mop", C.c_void_p), ("m_c", C.c_int), ("m_rows", C.c_int), ("m_ld", C.c_int64),
         ("nop", C.c_void_p), ("n_c", C.c_int), ("n_ld", C.c_int64),
         ("n", C.c_int), ("gh", C.c_int), ("gw", C.c_int), ("nh", C.c_int), ("nw", C.c_int),
         ("taps_h", C.c_int), ("taps_w", C.c_int), ("stride", C.c_int),
@@ -57,6 +58,7 @@ class WgradArgs(C.Structure):
 
 
 _lib = None
+_P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol include/gap_b200.h declares is listed here, and
 # tests/test_abi.py checks the two stay in sync.
@@ -67,6 +69,21 @@ _SIGNATURES = {
     "gap_debug_set": (C.c_int, [C.c_char_p, C.c_int]),
     "gap_conv_gemm": (C.c_int, [C.POINTER(ConvGemmArgs), C.c_void_p]),
     "gap_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "gap_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _P]),
+    "gap_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _L, _P]),
+    "gap_im2col_k4s2p1": (C.c_int, [_P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _P]),
+    "gap_col2im_k4s2p1": (C.c_int, [_P, _L, _I, _I, _I, _P, _I, _P, _L, _P, _L, _I, _I, _I, _P]),
+    "gap_gen_out_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _L, _L, _I, _P, _P]),
+    "gap_bce_logits_const": (C.c_int, [_P, _L, _F, _F, _P, _L, _P, _P]),
+    "gap_bn_finalize": (C.c_int, [_P, _I, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gap_bn_eval_scale_shift": (C.c_int, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
+    "gap_bn_act": (C.c_int, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P]),
+    "gap_bn_bwd_reduce": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "gap_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _P, _P, _P, _L, _I, _P, _D, _P, _L, _P]),
+    "gap_bn_param_grads": (C.c_int, [_P, _I, _P, _P, _P]),
+    "gap_colsum_bf16": (C.c_int, [_P, _L, _L, _I, _P, _P]),
+    "gap_adam_flat": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _F, _P]),
+    "gap_pack_weights": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P]),
 }
 
 

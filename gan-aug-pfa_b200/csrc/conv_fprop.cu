@@ -55,6 +55,7 @@ struct alignas(64) FpropParams {
   int total_tiles;
   int k_iters;
   int vec_ok;  // outputs are 16-byte aligned per pixel: use vector stores
+  int out_f32;  // `out` is fp32 (scalar stores; used for the 1-channel logits)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -309,7 +310,12 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
           }
         }
-        if (valid && col0 < p.n_out) {
+        if (valid && col0 < p.n_out && p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < p.n_out) o[j] = apply_act(f[j], p.act);
+        } else if (valid && col0 < p.n_out) {
           if (p.vec_ok && col0 + 16 <= p.n_out) {
             uint32_t pk[8];
 #pragma unroll
@@ -456,6 +462,8 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.stats = a->stats;
   p.idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
   p.vec_ok = vec_ok ? 1 : 0;
+  p.out_f32 = a->out_f32;
+  GAP_CHECK_ARG(!(a->out_f32 && a->out2), "gap_conv_gemm: out2 is not supported with fp32 output");
 
   const int stage_bytes = kATileBytes + block_n * 128;
   int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes) / stage_bytes;

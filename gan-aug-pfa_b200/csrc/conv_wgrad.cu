@@ -27,7 +27,7 @@ constexpr int kWgSmemBudget = 227 * 1024;
 struct alignas(64) WgradParams {
   CUtensorMap tmM;
   CUtensorMap tmN;
-  int m_c, n_c;
+  int m_c, n_c, m_rows;
   int n_img, gh, gw;
   int taps_w, n_taps, stride, off_h, off_w;
   int log_bw, log_bh;
@@ -170,7 +170,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
           tmem_ld16(t_row + t_i * p.block_n + c * 16, raw);
           tmem_ld_wait();
           const int col0 = n_tile * p.block_n + c * 16;
-          if (m < p.m_c) {
+          if (m < p.m_rows) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (col0 + j < p.n_c) atomicAdd(dst_row + col0 + j, __uint_as_float(raw[j]));
@@ -224,6 +224,7 @@ extern "C" int gap_conv_wgrad(const gap_wgrad_args* a, void* stream_v) {
   p.tiles_n = (a->n + BNI - 1) / BNI;
   p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   p.m_c = a->m_c;
+  p.m_rows = a->m_rows > 0 ? std::min(a->m_rows, a->m_c) : a->m_c;
   p.n_c = a->n_c;
   p.n_img = a->n;
   p.gh = a->gh;

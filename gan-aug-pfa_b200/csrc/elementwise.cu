@@ -1,0 +1,760 @@
+// HBM-bound companions of the GEMM kernels: layout conversion, first/last-layer im2col / col2im,
+// BatchNorm (finalize, apply + activation, backward reduce / apply), losses, Adam, weight packing.
+// All are plain coalesced / vectorised SIMT kernels with warp-shuffle reductions; none stages a
+// tensor through an extra HBM round trip beyond the one pass its definition needs.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace gap {
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  switch (act) {
+    case GAP_ACT_LRELU:
+      return v > 0.f ? v : 0.2f * v;
+    case GAP_ACT_RELU:
+      return fmaxf(v, 0.f);
+    case GAP_ACT_TANH:
+      return tanhf(v);
+    case GAP_ACT_SIGMOID:
+      return 1.f / (1.f + __expf(-v));
+    default:
+      return v;
+  }
+}
+
+static inline int grid_for(long long work, int block, int max_blocks = 148 * 16) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion (model boundary only: 1..8 channels)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                             int n, int c, long long hw, long long ld) {
+  const long long total = static_cast<long long>(n) * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, pix = i - img * hw;
+    for (int ch = 0; ch < c; ++ch)
+      out[i * ld + ch] = __float2bfloat16(x[(img * c + ch) * hw + pix]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restrict__ out, int n, int c,
+                                        long long hw, long long ld) {
+  const long long total = static_cast<long long>(n) * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, pix = i - img * hw;
+    for (int ch = 0; ch < c; ++ch) out[(img * c + ch) * hw + pix] = static_cast<float>(x[i * ld + ch]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for Conv2d(k4,s2,p1) over tiny-channel NHWC inputs (first layers, Cin = 3 or 6):
+//   col[(n,oh,ow)][(kh*4+kw)*ctot + c] = cat(src0, src1)[n, 2oh-1+kh, 2ow-1+kw, c], zero padded
+// One thread builds one full row (krow elements) in registers and writes it as 16-byte vectors.
+// ------------------------------------------------------------------------------------------------
+template <int CTOT, int KROW>
+__global__ void im2col_k4s2p1_kernel(const __nv_bfloat16* __restrict__ s0, int c0, long long ld0,
+                                     const __nv_bfloat16* __restrict__ s1, int c1, long long ld1,
+                                     __nv_bfloat16* __restrict__ col, int n, int h, int w) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = static_cast<long long>(n) * ho * wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ow = static_cast<int>(i % wo);
+    const int oh = static_cast<int>((i / wo) % ho);
+    const long long img = i / (static_cast<long long>(wo) * ho);
+    __align__(16) __nv_bfloat16 row[KROW];
+#pragma unroll
+    for (int k = 0; k < KROW; ++k) row[k] = __float2bfloat16(0.f);
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const int y = 2 * oh - 1 + kh;
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) {
+        const int x = 2 * ow - 1 + kw;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+          const long long pix = (img * h + y) * w + x;
+#pragma unroll
+          for (int c = 0; c < CTOT; ++c) {
+            const __nv_bfloat16 v = (c < c0) ? s0[pix * ld0 + c] : s1[pix * ld1 + (c - c0)];
+            row[(kh * 4 + kw) * CTOT + c] = v;
+          }
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(col + i * KROW);
+    const uint4* srcv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int k = 0; k < KROW / 8; ++k) dst[k] = srcv[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// col2im for the k4,s2,p1 transposed geometry:
+//   out[n,y,x,c] = act( bias[c] + sum over (kh,kw) with (y+1-kh), (x+1-kw) even and in range of
+//                  col[(n,(y+1-kh)/2,(x+1-kw)/2)][(kh*4+kw)*ctot + c0 + c] )
+// Used for the generator's last ConvTranspose2d (+bias, Tanh; models.py:184,186) and for the
+// input gradient of the discriminator's first conv (channel slice of the col gradient).
+// ------------------------------------------------------------------------------------------------
+__global__ void col2im_k4s2p1_kernel(const __nv_bfloat16* __restrict__ col, long long ldc, int ctot, int c0,
+                                     int cn, const float* __restrict__ bias, int act,
+                                     __nv_bfloat16* __restrict__ out_bf, long long ld_bf,
+                                     float* __restrict__ out_f32, long long ld_f32, int n, int hi, int wi) {
+  const int ho = hi * 2, wo = wi * 2;
+  const long long total = static_cast<long long>(n) * ho * wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % wo);
+    const int y = static_cast<int>((i / wo) % ho);
+    const long long img = i / (static_cast<long long>(wo) * ho);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int kh = ((y + 1) & 1) + 2 * a;
+      const int iy = (y + 1 - kh) >> 1;
+      if (iy < 0 || iy >= hi) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int kw = ((x + 1) & 1) + 2 * b;
+        const int ix = (x + 1 - kw) >> 1;
+        if (ix < 0 || ix >= wi) continue;
+        const __nv_bfloat16* src = col + ((img * hi + iy) * wi + ix) * ldc + (kh * 4 + kw) * ctot + c0;
+        for (int c = 0; c < cn; ++c) acc[c] += __bfloat162float(src[c]);
+      }
+    }
+    for (int c = 0; c < cn; ++c) {
+      float v = acc[c] + (bias ? bias[c] : 0.f);
+      v = act_fwd(v, act);
+      if (out_bf) out_bf[i * ld_bf + c] = __float2bfloat16(v);
+      if (out_f32) out_f32[i * ld_f32 + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generator output backward + L1 loss (train_gan.py:68-70 through Tanh, models.py:186):
+//   l1 += sum |fake - real|;  g = dfake_d + l1_scale * sign(fake - real);  dpre = g * (1 - fake^2)
+// fake: fp32 NHWC (ld_f), real: fp32 NCHW (the caller's tensor), dfake_d: fp32 NHWC (ld_d, may be
+// NULL), dpre: bf16 NHWC (ld_p).  loss_acc[0] accumulates the raw L1 sum in fp64.
+// ------------------------------------------------------------------------------------------------
+__global__ void gen_out_bwd_kernel(const float* __restrict__ fake, long long ld_f,
+                                   const float* __restrict__ real, long long hw,
+                                   const float* __restrict__ dfake_d, long long ld_d, float l1_scale,
+                                   __nv_bfloat16* __restrict__ dpre, long long ld_p, long long pixels, int c,
+                                   double* __restrict__ loss_acc) {
+  float part = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, pix = i - img * hw;
+    for (int ch = 0; ch < c; ++ch) {
+      const float f = fake[i * ld_f + ch];
+      const float r = real[(img * c + ch) * hw + pix];
+      const float d = f - r;
+      part += fabsf(d);
+      float g = l1_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      if (dfake_d) g += dfake_d[i * ld_d + ch];
+      dpre[i * ld_p + ch] = __float2bfloat16(g * (1.f - f * f));
+    }
+  }
+  part = warp_sum(part);
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = part;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(loss_acc, static_cast<double>(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BCE-with-logits against a constant target (train_gan.py:42,58,60,67):
+//   loss_acc += sum max(x,0) - x*t + log1p(exp(-|x|));  dlogit = grad_scale * (sigmoid(x) - t)
+// ------------------------------------------------------------------------------------------------
+__global__ void bce_logits_const_kernel(const float* __restrict__ x, long long count, float t,
+                                        float grad_scale, __nv_bfloat16* __restrict__ dx, long long ld_dx,
+                                        double* __restrict__ loss_acc) {
+  float part = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    part += fmaxf(v, 0.f) - v * t + log1pf(__expf(-fabsf(v)));
+    if (dx) {
+      const float s = 1.f / (1.f + __expf(-v));
+      dx[i * ld_dx] = __float2bfloat16(grad_scale * (s - t));
+    }
+  }
+  part = warp_sum(part);
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = part;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(loss_acc, static_cast<double>(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm2d training-mode bookkeeping (models.py:179,181,231,239): from the fp64 sums the conv
+// epilogue accumulated, produce the fused scale/shift, the saved mean / inv-std for backward, and
+// update running_mean / running_var (momentum 0.1, unbiased variance) and num_batches_tracked.
+// `repeat` applies the running update that many times (an elided identical forward pass, e.g. the
+// reference's second generator forward, train_gan.py:56 vs 65).  The sums are re-zeroed.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(double* __restrict__ stats, int c, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, int repeat, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ nbt,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    const double mean = stats[i] / count;
+    double var = stats[c + i] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+    const float sc = g * invstd;
+    scale[i] = sc;
+    shift[i] = b - static_cast<float>(mean) * sc;
+    if (save_mean) save_mean[i] = static_cast<float>(mean);
+    if (save_invstd) save_invstd[i] = invstd;
+    if (running_mean) {
+      const float unbiased = static_cast<float>(count > 1.0 ? var * count / (count - 1.0) : var);
+      float rm = running_mean[i], rv = running_var[i];
+      for (int r = 0; r < repeat; ++r) {
+        rm = (1.f - momentum) * rm + momentum * static_cast<float>(mean);
+        rv = (1.f - momentum) * rv + momentum * unbiased;
+      }
+      running_mean[i] = rm;
+      running_var[i] = rv;
+    }
+    stats[i] = 0.0;
+    stats[c + i] = 0.0;
+  }
+  if (i == 0 && nbt) *nbt += repeat;
+}
+
+// eval-mode scale/shift from the running statistics
+__global__ void bn_eval_scale_shift_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                           float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    const float sc = gamma[i] * rsqrtf(rv[i] + eps);
+    scale[i] = sc;
+    shift[i] = beta[i] - rm[i] * sc;
+  }
+}
+
+// out1 = act1(y*scale + shift), out2 = act2(same) (optional) — 8 channels (16 bytes) per thread.
+__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, long long ld_y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, long long pixels, int c,
+                              __nv_bfloat16* __restrict__ o1, long long ld1, int act1,
+                              __nv_bfloat16* __restrict__ o2, long long ld2, int act2) {
+  const int cv = c >> 3;
+  const long long total = pixels * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c8 = static_cast<int>(i - pix * cv) << 3;
+    const uint4 raw = *reinterpret_cast<const uint4*>(y + pix * ld_y + c8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = bf16_lo(w[j]);
+      v[2 * j + 1] = bf16_hi(w[j]);
+    }
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c8), s1 = *reinterpret_cast<const float4*>(scale + c8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + c8), h1 = *reinterpret_cast<const float4*>(shift + c8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act1), act_fwd(v[2 * j + 1], act1));
+    *reinterpret_cast<uint4*>(o1 + pix * ld1 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (o2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act2), act_fwd(v[2 * j + 1], act2));
+      *reinterpret_cast<uint4*>(o2 + pix * ld2 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + activation backward.
+//   yhat = y*scale + shift;  xhat = (y - mean) * invstd
+//   dyhat = yhat > 0 ? (g1 + g2) : slope * g1           (g2 optional: the ReLU'd skip consumer)
+//   pass 1: sums[c] += dyhat, sums[C+c] += dyhat * xhat                         (fp64 atomics)
+//   pass 2: dy = scale * (dyhat - sums[c]/cnt - xhat * sums[C+c]/cnt)           (bf16)
+// identity mode (scale == NULL): yhat = y, dy = dyhat (activation-only layers).
+// Thread layout: threadIdx.x walks 8-channel groups, threadIdx.y walks pixels.
+// ------------------------------------------------------------------------------------------------
+struct BnBwdArgs {
+  const __nv_bfloat16* y;
+  long long ld_y;
+  const __nv_bfloat16* g1;
+  long long ld_g1;
+  const __nv_bfloat16* g2;
+  long long ld_g2;
+  float slope;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  long long pixels;
+  int c;
+  double* sums;
+  double inv_count;
+  __nv_bfloat16* dy;
+  long long ld_dy;
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = bf16_lo(w[j]);
+    v[2 * j + 1] = bf16_hi(w[j]);
+  }
+}
+__device__ __forceinline__ void loadf8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <bool APPLY>
+__global__ void bn_bwd_kernel(const BnBwdArgs a) {
+  const int cv = a.c >> 3;
+  const bool ident = a.scale == nullptr;
+  extern __shared__ float sm_red[];  // [blockDim.y][cv*8][2] for the reduce pass
+  for (int cg = threadIdx.x; cg < cv; cg += blockDim.x) {
+    const int c8 = cg << 3;
+    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+    if (!ident) {
+      loadf8(a.scale + c8, sc);
+      loadf8(a.shift + c8, sh);
+      loadf8(a.mean + c8, mu);
+      loadf8(a.invstd + c8, is);
+    }
+    if (APPLY && !ident) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        m1[j] = static_cast<float>(a.sums[c8 + j] * a.inv_count);
+        m2[j] = static_cast<float>(a.sums[a.c + c8 + j] * a.inv_count);
+      }
+    }
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long pix = blockIdx.x * (long long)blockDim.y + threadIdx.y; pix < a.pixels;
+         pix += (long long)gridDim.x * blockDim.y) {
+      float y[8], g1[8], g2[8];
+      load8(a.y + pix * a.ld_y + c8, y);
+      load8(a.g1 + pix * a.ld_g1 + c8, g1);
+      if (a.g2) load8(a.g2 + pix * a.ld_g2 + c8, g2);
+      float d[8], xh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yh = ident ? y[j] : fmaf(y[j], sc[j], sh[j]);
+        const float gp = a.g2 ? g1[j] + g2[j] : g1[j];
+        d[j] = yh > 0.f ? gp : a.slope * g1[j];
+        xh[j] = ident ? 0.f : (y[j] - mu[j]) * is[j];
+      }
+      if (APPLY) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o0 = d[2 * j], o1 = d[2 * j + 1];
+          if (!ident) {
+            o0 = sc[2 * j] * (o0 - m1[2 * j] - xh[2 * j] * m2[2 * j]);
+            o1 = sc[2 * j + 1] * (o1 - m1[2 * j + 1] - xh[2 * j + 1] * m2[2 * j + 1]);
+          }
+          pk[j] = pack_bf16x2(o0, o1);
+        }
+        *reinterpret_cast<uint4*>(a.dy + pix * a.ld_dy + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += d[j];
+          s2[j] += d[j] * xh[j];
+        }
+      }
+    }
+    if (!APPLY) {
+      float* slot = sm_red + (static_cast<size_t>(threadIdx.y) * cv * 8 + c8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        slot[2 * j] = s1[j];
+        slot[2 * j + 1] = s2[j];
+      }
+    }
+  }
+  if (!APPLY) {
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthr = blockDim.x * blockDim.y;
+    for (int i = tid; i < a.c * 2; i += nthr) {
+      const int ch = i >> 1, which = i & 1;
+      double tot = 0.0;
+      for (int r = 0; r < blockDim.y; ++r) tot += sm_red[(static_cast<size_t>(r) * cv * 8 + ch) * 2 + which];
+      atomicAdd(a.sums + which * a.c + ch, tot);
+    }
+  }
+}
+
+// dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), then re-zero the sums.
+__global__ void bn_param_grads_kernel(double* __restrict__ sums, int c, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    if (dbeta) dbeta[i] += static_cast<float>(sums[i]);
+    if (dgamma) dgamma[i] += static_cast<float>(sums[c + i]);
+    sums[i] = 0.0;
+    sums[c + i] = 0.0;
+  }
+}
+
+// per-channel column sums of a bf16 [pixels][c] tensor into fp32 (bias gradients)
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long pixels, int c,
+                              float* __restrict__ out) {
+  // blockDim.x threads over channels (c <= 1024 handled by loop), blockIdx over pixel slabs
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (long long pix = blockIdx.x; pix < pixels; pix += gridDim.x) s += __bfloat162float(x[pix * ld + ch]);
+    atomicAdd(out + ch, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam / AdamW on a flat fp32 buffer (torch.optim semantics; train_gan.py:140-141, train.py:295)
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                            float wd, int decoupled, float bc1, float bc2_sqrt, float grad_scale) {
+  const long long n4 = n >> 2;
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x;
+    const float* ga = &gg.x;
+    float* ma = &mm.x;
+    float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = ga[j] * grad_scale;
+      if (decoupled) pa[j] *= (1.f - lr * wd);
+      else if (wd != 0.f) gr += wd * pa[j];
+      ma[j] = b1 * ma[j] + (1.f - b1) * gr;
+      va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(va[j]) / bc2_sqrt + eps;
+      pa[j] -= step_size * (ma[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  const long long tail0 = n4 << 2;
+  for (long long i = tail0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gr = g[i] * grad_scale;
+    float pv = p[i];
+    if (decoupled) pv *= (1.f - lr * wd);
+    else if (wd != 0.f) gr += wd * pv;
+    const float mv = b1 * m[i] + (1.f - b1) * gr;
+    const float vv2 = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mv;
+    v[i] = vv2;
+    p[i] = pv - step_size * (mv / (sqrtf(vv2) / bc2_sqrt + eps));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 master weights (any strides) -> bf16 K-major GEMM operand
+//   out[p][r][t*c_pad + c] = w[r*s_r + c*s_c + kh*s_kh + kw*s_kw]   (zero where c >= C, r >= R,
+//   or beyond taps*c_pad), (kh,kw) from (phase p, tap t) by `mode`:
+//   0 direct (kh=th,kw=tw)   1 flipped (kh=KH-1-th)   2 k4s2p1 phases (kh=3-ph-2th, kw=3-pw-2tw)
+// mode 3 ("col-T"): rows are (tap, c) pairs: out[0][t*C + c][k] = w[k*s_r + c*s_c + kh*s_kh + kw*s_kw]
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* w;
+  __nv_bfloat16* out;
+  int mode, n_phase, rows, rows_pad, taps_h, taps_w, c, c_pad, krow;
+  long long s_r, s_c, s_kh, s_kw;
+  int kdim;  // mode 3: valid K (source "row" count)
+};
+
+__global__ void pack_weights_kernel(const PackArgs a) {
+  const long long total = static_cast<long long>(a.n_phase) * a.rows_pad * a.krow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = static_cast<int>(i % a.krow);
+    const int r = static_cast<int>((i / a.krow) % a.rows_pad);
+    const int p = static_cast<int>(i / (static_cast<long long>(a.krow) * a.rows_pad));
+    float v = 0.f;
+    if (a.mode == 3) {
+      const int t = r / a.c, c = r - t * a.c;
+      if (r < a.rows && k < a.kdim) {
+        const int kh = t / a.taps_w, kw = t - kh * a.taps_w;
+        v = a.w[k * a.s_r + c * a.s_c + kh * a.s_kh + kw * a.s_kw];
+      }
+    } else {
+      const int t = k / a.c_pad, c = k - t * a.c_pad;
+      if (r < a.rows && t < a.taps_h * a.taps_w && c < a.c) {
+        const int th = t / a.taps_w, tw = t - th * a.taps_w;
+        int kh = th, kw = tw;
+        if (a.mode == 1) {
+          kh = a.taps_h - 1 - th;
+          kw = a.taps_w - 1 - tw;
+        } else if (a.mode == 2) {
+          kh = 3 - (p >> 1) - 2 * th;
+          kw = 3 - (p & 1) - 2 * tw;
+        }
+        v = a.w[r * a.s_r + c * a.s_c + kh * a.s_kh + kw * a.s_kw];
+      }
+    }
+    a.out[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace gap
+
+using namespace gap;
+
+#define GAP_LAUNCH_CHECK()                 \
+  do {                                     \
+    GAP_CUDA(cudaGetLastError());          \
+  } while (0)
+
+extern "C" {
+
+int gap_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, int h, int w, int64_t out_ld,
+                              void* stream) {
+  GAP_CHECK_ARG(x && out && n > 0 && c > 0 && c <= out_ld, "gap_nchw_f32_to_nhwc_bf16: bad arguments");
+  const long long hw = static_cast<long long>(h) * w;
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(out), n, c, hw, out_ld);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* out, int n, int c, int h, int w, int64_t x_ld,
+                         void* stream) {
+  GAP_CHECK_ARG(x && out && n > 0 && c > 0 && c <= x_ld, "gap_nhwc_to_nchw_f32: bad arguments");
+  const long long hw = static_cast<long long>(h) * w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_f32)
+    nhwc_to_nchw_f32_kernel<float><<<grid_for(n * hw, 256), 256, 0, st>>>(static_cast<const float*>(x), out, n, c, hw, x_ld);
+  else
+    nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid_for(n * hw, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), out, n, c, hw, x_ld);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_im2col_k4s2p1(const void* s0, int c0, int64_t ld0, const void* s1, int c1, int64_t ld1, void* col,
+                      int krow, int n, int h, int w, void* stream) {
+  GAP_CHECK_ARG(s0 && col && n > 0 && h % 2 == 0 && w % 2 == 0, "gap_im2col_k4s2p1: bad arguments");
+  GAP_CHECK_ARG(c1 == 0 || s1, "gap_im2col_k4s2p1: src1 is null");
+  const int ctot = c0 + c1;
+  const long long rows = static_cast<long long>(n) * (h / 2) * (w / 2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(s0);
+  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(s1);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(col);
+  if (ctot == 3 && krow == 64)
+    im2col_k4s2p1_kernel<3, 64><<<grid_for(rows, 128), 128, 0, st>>>(a, c0, ld0, b, c1, ld1, o, n, h, w);
+  else if (ctot == 6 && krow == 128)
+    im2col_k4s2p1_kernel<6, 128><<<grid_for(rows, 128), 128, 0, st>>>(a, c0, ld0, b, c1, ld1, o, n, h, w);
+  else {
+    set_error("gap_im2col_k4s2p1: unsupported (channels %d, row %d); supported: (3,64), (6,128)", ctot, krow);
+    return GAP_ERR_UNSUPPORTED;
+  }
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_col2im_k4s2p1(const void* col, int64_t ldc, int ctot, int c0, int cn, const float* bias, int act,
+                      void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, int n, int hi, int wi,
+                      void* stream) {
+  GAP_CHECK_ARG(col && (out_bf16 || out_f32) && cn >= 1 && cn <= 4 && c0 + cn <= ctot && n > 0,
+                "gap_col2im_k4s2p1: bad arguments");
+  const long long total = static_cast<long long>(n) * hi * wi * 4;
+  col2im_k4s2p1_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(col), ldc, ctot, c0, cn, bias, act, static_cast<__nv_bfloat16*>(out_bf16),
+      ld_bf16, out_f32, ld_f32, n, hi, wi);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_gen_out_bwd(const float* fake, int64_t ld_f, const float* real_nchw, int64_t hw, const float* dfake_d,
+                    int64_t ld_d, float l1_scale, void* dpre, int64_t ld_p, int64_t pixels, int c,
+                    double* loss_acc, void* stream) {
+  GAP_CHECK_ARG(fake && real_nchw && dpre && loss_acc && pixels > 0 && c > 0 && hw > 0 && pixels % hw == 0,
+                "gap_gen_out_bwd: bad arguments");
+  gen_out_bwd_kernel<<<grid_for(pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fake, ld_f, real_nchw, hw, dfake_d, ld_d, l1_scale, static_cast<__nv_bfloat16*>(dpre), ld_p, pixels, c,
+      loss_acc);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_bce_logits_const(const float* logits, int64_t count, float target, float grad_scale, void* dlogits,
+                         int64_t ld_d, double* loss_acc, void* stream) {
+  GAP_CHECK_ARG(logits && loss_acc && count > 0, "gap_bce_logits_const: bad arguments");
+  bce_logits_const_kernel<<<grid_for(count, 256, 148), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, count, target, grad_scale, static_cast<__nv_bfloat16*>(dlogits), ld_d, loss_acc);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_bn_finalize(double* stats, int c, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, int repeat, float* running_mean, float* running_var, int64_t* nbt,
+                    float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  GAP_CHECK_ARG(stats && scale && shift && c > 0 && count > 0, "gap_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, c, count, gamma, beta, eps, momentum, repeat, running_mean, running_var,
+      reinterpret_cast<long long*>(nbt), scale, shift, save_mean, save_invstd);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_bn_eval_scale_shift(int c, const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  GAP_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && c > 0,
+                "gap_bn_eval_scale_shift: bad arguments");
+  bn_eval_scale_shift_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      c, gamma, beta, running_mean, running_var, eps, scale, shift);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_bn_act(const void* y, int64_t ld_y, const float* scale, const float* shift, int64_t pixels, int c,
+               void* out1, int64_t ld1, int act1, void* out2, int64_t ld2, int act2, void* stream) {
+  GAP_CHECK_ARG(y && scale && shift && out1 && pixels > 0 && c > 0 && c % 8 == 0, "gap_bn_act: bad arguments");
+  if (ld_y % 8 || ld1 % 8 || (out2 && ld2 % 8)) {
+    set_error("gap_bn_act: pixel strides must be multiples of 8");
+    return GAP_ERR_ALIGNMENT;
+  }
+  bn_act_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, pixels, c, static_cast<__nv_bfloat16*>(out1), ld1,
+      act1, static_cast<__nv_bfloat16*>(out2), ld2, act2);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
+  const int cv = a.c / 8;
+  int bx = cv < 128 ? cv : 128;
+  int by = 256 / bx;
+  if (by < 1) by = 1;
+  dim3 block(bx, by);
+  const long long slabs = (a.pixels + by - 1) / by;
+  const int grid = static_cast<int>(slabs < 148 * 8 ? (slabs < 1 ? 1 : slabs) : 148 * 8);
+  if (apply) {
+    bn_bwd_kernel<true><<<grid, block, 0, st>>>(a);
+  } else {
+    const size_t smem = static_cast<size_t>(by) * a.c * 2 * sizeof(float);
+    if (smem > 48 * 1024) {
+      static bool set = false;
+      if (!set) {
+        GAP_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        set = true;
+      }
+    }
+    bn_bwd_kernel<false><<<grid, block, smem, st>>>(a);
+  }
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_bn_bwd_reduce(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1, const void* g2, int64_t ld_g2,
+                      float slope, const float* scale, const float* shift, const float* mean,
+                      const float* invstd, int64_t pixels, int c, double* sums, void* stream) {
+  GAP_CHECK_ARG(y && g1 && scale && shift && mean && invstd && sums && pixels > 0 && c > 0 && c % 8 == 0,
+                "gap_bn_bwd_reduce: bad arguments");
+  BnBwdArgs a{static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(g1), ld_g1,
+              static_cast<const __nv_bfloat16*>(g2), ld_g2, slope, scale, shift, mean, invstd, pixels, c, sums,
+              0.0, nullptr, 0};
+  return bn_bwd_launch(false, a, static_cast<cudaStream_t>(stream));
+}
+
+int gap_bn_bwd_apply(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1, const void* g2, int64_t ld_g2,
+                     float slope, const float* scale, const float* shift, const float* mean, const float* invstd,
+                     int64_t pixels, int c, const double* sums, double count, void* dy, int64_t ld_dy,
+                     void* stream) {
+  GAP_CHECK_ARG(y && g1 && dy && pixels > 0 && c > 0 && c % 8 == 0, "gap_bn_bwd_apply: bad arguments");
+  GAP_CHECK_ARG(scale == nullptr || (shift && mean && invstd && sums && count > 0),
+                "gap_bn_bwd_apply: BatchNorm mode needs shift/mean/invstd/sums/count");
+  BnBwdArgs a{static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(g1), ld_g1,
+              static_cast<const __nv_bfloat16*>(g2), ld_g2, slope, scale, shift, mean, invstd, pixels, c,
+              const_cast<double*>(sums), count > 0 ? 1.0 / count : 0.0, static_cast<__nv_bfloat16*>(dy), ld_dy};
+  return bn_bwd_launch(true, a, static_cast<cudaStream_t>(stream));
+}
+
+int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* stream) {
+  GAP_CHECK_ARG(sums && c > 0, "gap_bn_param_grads: bad arguments");
+  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, c, dgamma, dbeta);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_colsum_bf16(const void* x, int64_t ld, int64_t pixels, int c, float* out, void* stream) {
+  GAP_CHECK_ARG(x && out && pixels > 0 && c > 0, "gap_colsum_bf16: bad arguments");
+  const int block = c < 256 ? ((c + 31) / 32) * 32 : 256;
+  const int grid = static_cast<int>(pixels < 148 * 4 ? pixels : 148 * 4);
+  colsum_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld,
+                                                                      pixels, c, out);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, int step, float grad_scale, void* stream) {
+  GAP_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "gap_adam_flat: bad arguments");
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15) {
+    set_error("gap_adam_flat: buffers must be 16-byte aligned");
+    return GAP_ERR_ALIGNMENT;
+  }
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, static_cast<float>(bc1),
+      static_cast<float>(sqrt(bc2)), grad_scale);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows, int rows_pad, int taps_h,
+                     int taps_w, int c, int c_pad, int krow, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
+                     int kdim, void* stream) {
+  GAP_CHECK_ARG(w && out && mode >= 0 && mode <= 3 && n_phase >= 1 && rows >= 1 && rows_pad >= rows && krow >= 1,
+                "gap_pack_weights: bad arguments");
+  GAP_CHECK_ARG(mode == 3 || (c_pad >= c && krow >= taps_h * taps_w * c_pad), "gap_pack_weights: krow too small");
+  PackArgs a{w, static_cast<__nv_bfloat16*>(out), mode, n_phase, rows, rows_pad, taps_h, taps_w, c, c_pad, krow,
+             s_r, s_c, s_kh, s_kw, kdim};
+  const long long total = static_cast<long long>(n_phase) * rows_pad * krow;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

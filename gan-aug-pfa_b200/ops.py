@@ -20,9 +20,9 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _nhwc_view(t: torch.Tensor) -> tuple[int, int, int, int, int]:
+def _nhwc_view(t: torch.Tensor, dtype=torch.bfloat16) -> tuple[int, int, int, int, int]:
     """Return (n, h, w, c, pixel_stride) of an NHWC bf16 tensor that may be a channel slice."""
-    if t.dtype != torch.bfloat16 or t.dim() != 4 or not t.is_cuda:
+    if t.dtype != dtype or t.dim() != 4 or not t.is_cuda:
         raise ValueError(f"expected a CUDA NHWC bf16 tensor, got {t.dtype} {tuple(t.shape)} {t.device}")
     n, h, w, c = t.shape
     sn, sh, sw, sc = t.stride()
@@ -100,7 +100,8 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
     a.wpk = wpk.data_ptr()
     a.w_rows = wpk.shape[1]
     a.n_out = n_out
-    on, oh, ow, oc, old = _nhwc_view(out)
+    on, oh, ow, oc, old = _nhwc_view(out, out.dtype if out.dtype == torch.float32 else torch.bfloat16)
+    a.out_f32 = 1 if out.dtype == torch.float32 else 0
     if on != n or oc < n_out:
         raise ValueError("output tensor does not match")
     a.oh, a.ow = oh, ow
@@ -133,7 +134,7 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
 
 
 def conv_wgrad(mop: torch.Tensor, nop: torch.Tensor, out: torch.Tensor, taps: tuple[int, int], stride: int,
-               off: tuple[int, int], ld_m: int, ld_tap: int) -> None:
+               off: tuple[int, int], ld_m: int, ld_tap: int, m_rows: int = 0) -> None:
     """out[m*ld_m + tap*ld_tap + c] += sum_pix mop[pix, m] * nop[gather(pix, tap), c]   (fp32 out)."""
     a = _lib.WgradArgs()
     n, gh, gw, mc, mld = _nhwc_view(mop)
@@ -143,6 +144,7 @@ def conv_wgrad(mop: torch.Tensor, nop: torch.Tensor, out: torch.Tensor, taps: tu
     if out.dtype != torch.float32 or not out.is_cuda:
         raise ValueError("wgrad output must be a CUDA fp32 tensor")
     a.mop, a.m_c, a.m_ld = mop.data_ptr(), mc, mld
+    a.m_rows = m_rows
     a.nop, a.n_c, a.n_ld = nop.data_ptr(), nc, nld
     a.n, a.gh, a.gw, a.nh, a.nw = n, gh, gw, nh, nw
     a.taps_h, a.taps_w = taps
@@ -151,3 +153,127 @@ def conv_wgrad(mop: torch.Tensor, nop: torch.Tensor, out: torch.Tensor, taps: tu
     a.out = out.data_ptr()
     a.ld_m, a.ld_tap = ld_m, ld_tap
     _lib.check(_lib.lib().gap_conv_wgrad(C.byref(a), _stream()), "gap_conv_wgrad")
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers over the elementwise / reduction entry points
+# ------------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _rows_ld(t: torch.Tensor) -> tuple[int, int, int]:
+    """(pixels, channels, pixel stride) of a channel-contiguous [..., C] tensor dense in the rest."""
+    c = t.shape[-1]
+    ld = t.stride(-2) if t.dim() >= 2 else c
+    return t.numel() // c, c, ld
+
+
+def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
+    n, c, h, w = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("expected a contiguous fp32 NCHW tensor")
+    _lib.check(_lib.lib().gap_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), n, c, h, w, out.stride(2), _stream()),
+               "gap_nchw_f32_to_nhwc_bf16")
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor, c: int) -> None:
+    n, h, w, _ = x.shape
+    _lib.check(_lib.lib().gap_nhwc_to_nchw_f32(_ptr(x), 1 if x.dtype == torch.float32 else 0, _ptr(out), n, c, h, w,
+                                               x.stride(2), _stream()), "gap_nhwc_to_nchw_f32")
+
+
+def im2col_k4s2p1(s0: torch.Tensor, c0: int, s1: Optional[torch.Tensor], c1: int, col: torch.Tensor) -> None:
+    n, h, w, _ = s0.shape
+    _lib.check(_lib.lib().gap_im2col_k4s2p1(_ptr(s0), c0, s0.stride(2), _ptr(s1), c1,
+                                            0 if s1 is None else s1.stride(2), _ptr(col), col.shape[-1], n, h, w,
+                                            _stream()), "gap_im2col_k4s2p1")
+
+
+def col2im_k4s2p1(col: torch.Tensor, ctot: int, c0: int, cn: int, bias: Optional[torch.Tensor], act: int,
+                  out_bf16: Optional[torch.Tensor], out_f32: Optional[torch.Tensor]) -> None:
+    n, hi, wi, ldc = col.shape
+    _lib.check(_lib.lib().gap_col2im_k4s2p1(
+        _ptr(col), ldc, ctot, c0, cn, _ptr(bias), act, _ptr(out_bf16),
+        0 if out_bf16 is None else out_bf16.stride(2), _ptr(out_f32), 0 if out_f32 is None else out_f32.stride(2),
+        n, hi, wi, _stream()), "gap_col2im_k4s2p1")
+
+
+def gen_out_bwd(fake_f32: torch.Tensor, real_nchw: torch.Tensor, dfake_d: Optional[torch.Tensor], l1_scale: float,
+                dpre: torch.Tensor, loss_acc: torch.Tensor) -> None:
+    n, h, w, _ = fake_f32.shape
+    c = real_nchw.shape[1]
+    _lib.check(_lib.lib().gap_gen_out_bwd(_ptr(fake_f32), fake_f32.stride(2), _ptr(real_nchw), h * w, _ptr(dfake_d),
+                                          0 if dfake_d is None else dfake_d.stride(2), l1_scale, _ptr(dpre),
+                                          dpre.stride(2), n * h * w, c, _ptr(loss_acc), _stream()), "gap_gen_out_bwd")
+
+
+def bce_logits_const(logits: torch.Tensor, target: float, grad_scale: float, dlogits: Optional[torch.Tensor],
+                     loss_acc: torch.Tensor) -> None:
+    _lib.check(_lib.lib().gap_bce_logits_const(_ptr(logits), logits.numel(), target, grad_scale, _ptr(dlogits),
+                                               0 if dlogits is None else dlogits.stride(2), _ptr(loss_acc), _stream()),
+               "gap_bce_logits_const")
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, nbt, scale, shift,
+                save_mean, save_invstd) -> None:
+    c = scale.numel()
+    _lib.check(_lib.lib().gap_bn_finalize(_ptr(stats), c, float(count), _ptr(gamma), _ptr(beta), eps, momentum, repeat,
+                                          _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(scale), _ptr(shift),
+                                          _ptr(save_mean), _ptr(save_invstd), _stream()), "gap_bn_finalize")
+
+
+def bn_eval_scale_shift(gamma, beta, running_mean, running_var, eps, scale, shift) -> None:
+    _lib.check(_lib.lib().gap_bn_eval_scale_shift(scale.numel(), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                                  _ptr(running_var), eps, _ptr(scale), _ptr(shift), _stream()),
+               "gap_bn_eval_scale_shift")
+
+
+def bn_act(y: torch.Tensor, scale, shift, out1: torch.Tensor, act1: int, out2: Optional[torch.Tensor] = None,
+           act2: int = ACT_NONE) -> None:
+    pixels, c, ld = _rows_ld(y)
+    _lib.check(_lib.lib().gap_bn_act(_ptr(y), ld, _ptr(scale), _ptr(shift), pixels, c, _ptr(out1), out1.stride(-2),
+                                     act1, _ptr(out2), 0 if out2 is None else out2.stride(-2), act2, _stream()),
+               "gap_bn_act")
+
+
+def bn_bwd_reduce(y, g1, g2, slope, scale, shift, mean, invstd, sums) -> None:
+    pixels, c, ld = _rows_ld(y)
+    _lib.check(_lib.lib().gap_bn_bwd_reduce(_ptr(y), ld, _ptr(g1), g1.stride(-2), _ptr(g2),
+                                            0 if g2 is None else g2.stride(-2), slope, _ptr(scale), _ptr(shift),
+                                            _ptr(mean), _ptr(invstd), pixels, c, _ptr(sums), _stream()),
+               "gap_bn_bwd_reduce")
+
+
+def bn_bwd_apply(y, g1, g2, slope, scale, shift, mean, invstd, sums, count, dy) -> None:
+    pixels, c, ld = _rows_ld(y)
+    _lib.check(_lib.lib().gap_bn_bwd_apply(_ptr(y), ld, _ptr(g1), g1.stride(-2), _ptr(g2),
+                                           0 if g2 is None else g2.stride(-2), slope, _ptr(scale), _ptr(shift),
+                                           _ptr(mean), _ptr(invstd), pixels, c, _ptr(sums), float(count), _ptr(dy),
+                                           dy.stride(-2), _stream()), "gap_bn_bwd_apply")
+
+
+def bn_param_grads(sums, dgamma, dbeta) -> None:
+    _lib.check(_lib.lib().gap_bn_param_grads(_ptr(sums), sums.numel() // 2, _ptr(dgamma), _ptr(dbeta), _stream()),
+               "gap_bn_param_grads")
+
+
+def colsum_bf16(x: torch.Tensor, c: int, out: torch.Tensor) -> None:
+    pixels = x.numel() // x.shape[-1]
+    _lib.check(_lib.lib().gap_colsum_bf16(_ptr(x), x.stride(-2), pixels, c, _ptr(out), _stream()), "gap_colsum_bf16")
+
+
+def adam_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step, grad_scale=1.0) -> None:
+    _lib.check(_lib.lib().gap_adam_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps,
+                                        weight_decay, 1 if decoupled else 0, step, grad_scale, _stream()),
+               "gap_adam_flat")
+
+
+def pack_weights(w: torch.Tensor, w_off: int, out: torch.Tensor, mode: int, n_phase: int, rows: int, rows_pad: int,
+                 taps: tuple[int, int], c: int, c_pad: int, krow: int, strides: tuple[int, int, int, int],
+                 kdim: int = 0) -> None:
+    """``w`` is a flat fp32 buffer, ``w_off`` the element offset of this layer's weights in it."""
+    src = C.c_void_p(w.data_ptr() + 4 * w_off)
+    _lib.check(_lib.lib().gap_pack_weights(src, _ptr(out), mode, n_phase, rows, rows_pad, taps[0], taps[1], c, c_pad,
+                                           krow, strides[0], strides[1], strides[2], strides[3], kdim, _stream()),
+               "gap_pack_weights")

@@ -1,0 +1,679 @@
+"""Native Pix2Pix engine: the U-Net generator, the PatchGAN discriminator and one GAN training
+iteration, sequenced entirely as C-ABI kernel launches (libgap_b200.so).
+
+What it mirrors in the reference:
+  * UNetGenerator / UnetSkipConnectionBlock  (models.py:149-208)
+  * NLayerDiscriminator                      (models.py:212-247)
+  * train_gan_one_epoch's loop body          (train_gan.py:52-74), Adam(lr, betas=(0.5, 0.999))
+  * generator inference under eval()/no_grad (generate_synthetic_data.py:55-68)
+
+Data layout in HBM: activations NHWC bf16; U-Net skips live in per-level concat buffers
+R_j = [ReLU(down_j) | ReLU(up_{j+1})] so torch.cat (models.py:208) never copies; master weights,
+gradients and Adam moments are fp32 in flat buffers whose per-layer segments use the GEMM-native
+order ([Cout][kh][kw][Cin] for Conv2d, [Cin][kh][kw][Cout] for ConvTranspose2d) and are exposed to
+state_dict() as strided views with the reference's shapes.
+
+Legal savings vs the reference's execution: the second, numerically identical
+generator forward (train_gan.py:65) is not recomputed (BatchNorm buffers receive both updates), and
+the discriminator weight gradients of the G step (cleared by opt_d.zero_grad(), train_gan.py:55)
+are not computed.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+LAMBDA_L1 = 100.0  # train_gan.py:33
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient / Adam-moment buffers with named, 16-byte-aligned segments."""
+
+    def __init__(self) -> None:
+        self.segs: Dict[str, Tuple[int, int]] = {}
+        self.total = 0
+        self.p = self.g = self.m = self.v = None
+        self.step = 0
+
+    def add(self, name: str, numel: int) -> int:
+        off = self.total
+        self.segs[name] = (off, numel)
+        self.total += _pad4(numel)
+        return off
+
+    def allocate(self, device: torch.device) -> None:
+        self.p = torch.zeros(self.total, device=device, dtype=torch.float32)
+        self.g = torch.zeros_like(self.p)
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+
+    def seg(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, n = self.segs[name]
+        return buf[off:off + n]
+
+    def off(self, name: str) -> int:
+        return self.segs[name][0]
+
+
+@dataclass
+class _BN:
+    """BatchNorm2d state for one layer: affine params live in the ParamStore, buffers here."""
+    name: str
+    c: int
+    running_mean: torch.Tensor = None
+    running_var: torch.Tensor = None
+    nbt: torch.Tensor = None
+    stats: torch.Tensor = None      # fp64 [2C] forward sums (conv epilogue)
+    sums: torch.Tensor = None       # fp64 [2C] backward sums
+    scale: torch.Tensor = None
+    shift: torch.Tensor = None
+    mean: torch.Tensor = None
+    invstd: torch.Tensor = None
+
+    def allocate(self, dev: torch.device) -> None:
+        self.running_mean = torch.zeros(self.c, device=dev)
+        self.running_var = torch.ones(self.c, device=dev)
+        self.nbt = torch.zeros((), device=dev, dtype=torch.int64)
+        self.stats = torch.zeros(2 * self.c, device=dev, dtype=torch.float64)
+        self.sums = torch.zeros(2 * self.c, device=dev, dtype=torch.float64)
+        self.scale = torch.empty(self.c, device=dev)
+        self.shift = torch.empty(self.c, device=dev)
+        self.mean = torch.empty(self.c, device=dev)
+        self.invstd = torch.empty(self.c, device=dev)
+
+
+class _Net:
+    """Shared plumbing: parameter store, BatchNorm bookkeeping, state_dict import/export."""
+
+    def __init__(self, device: torch.device) -> None:
+        self.dev = device
+        self.store = ParamStore()
+        self.bns: Dict[str, _BN] = {}
+        # state_dict key -> (segment name, shape, strides) for weights / biases / BN affine
+        self.views: Dict[str, Tuple[str, Tuple[int, ...], Tuple[int, ...]]] = {}
+        self.key_order: List[str] = []
+        self.training = True
+
+    # -- registration helpers -------------------------------------------------------------------
+    def _reg(self, key: str, numel: int, shape, strides) -> None:
+        self.store.add(key, numel)
+        self.views[key] = (key, tuple(shape), tuple(strides))
+
+    def _reg_conv(self, key: str, cout: int, cin: int) -> None:
+        """Conv2d weight (Cout,Cin,4,4) stored [Cout][kh][kw][Cin]."""
+        self._reg(key, cout * 16 * cin, (cout, cin, 4, 4), (16 * cin, 1, 4 * cin, cin))
+
+    def _reg_convT(self, key: str, cin: int, cout: int) -> None:
+        """ConvTranspose2d weight (Cin,Cout,4,4) stored [Cin][kh][kw][Cout]."""
+        self._reg(key, cin * 16 * cout, (cin, cout, 4, 4), (16 * cout, 1, 4 * cout, cout))
+
+    def _reg_small(self, key: str, rows: int, c: int, krow: int) -> None:
+        """(rows, c, 4, 4) weight of a tiny-channel layer stored [rows][(kh*4+kw)*c + ch] padded to krow."""
+        self._reg(key, rows * krow, (rows, c, 4, 4), (krow, 1, 4 * c, c))
+
+    def _reg_vec(self, key: str, n: int) -> None:
+        self._reg(key, n, (n,), (1,))
+
+    def _reg_bn(self, prefix: str, c: int) -> _BN:
+        self._reg_vec(prefix + ".weight", c)
+        self._reg_vec(prefix + ".bias", c)
+        bn = _BN(prefix, c)
+        self.bns[prefix] = bn
+        return bn
+
+    # -- parameter views ------------------------------------------------------------------------
+    def view(self, buf: torch.Tensor, key: str) -> torch.Tensor:
+        seg, shape, strides = self.views[key]
+        return torch.as_strided(buf, shape, strides, self.store.off(seg))
+
+    def param(self, key: str) -> torch.Tensor:
+        return self.view(self.store.p, key)
+
+    def grad(self, key: str) -> torch.Tensor:
+        return self.view(self.store.g, key)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-format state_dict (keys / shapes / dtypes of models.py)."""
+        out: Dict[str, torch.Tensor] = {}
+        for key in self.key_order:
+            if key in self.views:
+                out[key] = self.param(key)
+            else:
+                prefix, leaf = key.rsplit(".", 1)
+                bn = self.bns[prefix]
+                out[key] = {"running_mean": bn.running_mean, "running_var": bn.running_var,
+                            "num_batches_tracked": bn.nbt}[leaf]
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        mine = self.state_dict()
+        missing = [k for k in mine if k not in sd]
+        extra = [k for k in sd if k not in mine]
+        if missing or extra:
+            raise KeyError(f"state_dict mismatch: missing {missing[:4]} unexpected {extra[:4]}")
+        with torch.no_grad():
+            for k, dst in mine.items():
+                src = sd[k]
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError(f"{k}: shape {tuple(src.shape)} != {tuple(dst.shape)}")
+                dst.copy_(src.to(self.dev))
+        self.repack()
+
+    def init_from_torch_default(self) -> None:
+        """Default torch init (kaiming-uniform(a=sqrt(5)) weights, uniform bias, BN gamma=1 beta=0),
+        drawn from the global RNG in the reference's module-construction order."""
+        raise NotImplementedError
+
+    def repack(self) -> None:
+        raise NotImplementedError
+
+    def zero_grad(self) -> None:
+        self.store.g.zero_()
+
+    def adam_step(self, lr: float, betas=(0.5, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                  decoupled: bool = False, grad_scale: float = 1.0) -> None:
+        s = self.store
+        s.step += 1
+        ops.adam_flat(s.p, s.g, s.m, s.v, lr, betas[0], betas[1], eps, weight_decay, decoupled, s.step, grad_scale)
+        self.repack()
+
+    # -- BatchNorm helpers -----------------------------------------------------------------------
+    def _bn_forward(self, bn: _BN, y: torch.Tensor, out1, act1, out2=None, act2=ACT_NONE, repeat: int = 1) -> None:
+        gamma = self.param(bn.name + ".weight")
+        beta = self.param(bn.name + ".bias")
+        if self.training:
+            count = y.numel() // y.shape[-1]
+            ops.bn_finalize(bn.stats, count, gamma, beta, BN_EPS, BN_MOMENTUM, repeat, bn.running_mean,
+                            bn.running_var, bn.nbt, bn.scale, bn.shift, bn.mean, bn.invstd)
+        else:
+            ops.bn_eval_scale_shift(gamma, beta, bn.running_mean, bn.running_var, BN_EPS, bn.scale, bn.shift)
+        ops.bn_act(y, bn.scale, bn.shift, out1, act1, out2, act2)
+
+    def _bn_backward(self, bn: _BN, y, g1, g2, slope: float, dy, param_grads: bool = True) -> None:
+        count = y.numel() // y.shape[-1]
+        ops.bn_bwd_reduce(y, g1, g2, slope, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums)
+        ops.bn_bwd_apply(y, g1, g2, slope, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums, count, dy)
+        if param_grads:
+            ops.bn_param_grads(bn.sums, self.grad(bn.name + ".weight"), self.grad(bn.name + ".bias"))
+        else:
+            ops.bn_param_grads(bn.sums, None, None)
+
+
+def _kaiming_uniform_(t: torch.Tensor, fan_in: int) -> None:
+    """nn.Conv2d / nn.ConvTranspose2d.reset_parameters: kaiming_uniform_(a=sqrt(5)); torch derives the
+    fan-in from weight.size(1) * kh * kw for both layouts, which equals `fan_in` at every call site."""
+    assert fan_in == t.size(1) * t.size(2) * t.size(3)
+    torch.nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+
+
+def _bias_uniform_(b: torch.Tensor, fan_in: int) -> None:
+    bound = 1 / math.sqrt(fan_in)
+    torch.nn.init.uniform_(b, -bound, bound)
+
+
+# ================================================================================================
+# Generator
+# ================================================================================================
+class GeneratorEngine(_Net):
+    """UNetGenerator(input_nc=3, output_nc=3, num_downs, ngf, BatchNorm2d, use_dropout=False)."""
+
+    def __init__(self, device, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64) -> None:
+        super().__init__(device)
+        if input_nc != 3 or output_nc != 3:
+            raise NotImplementedError("the native generator supports input_nc = output_nc = 3")
+        if ngf % 64 != 0 or num_downs < 5:
+            raise NotImplementedError("ngf must be a multiple of 64 and num_downs >= 5")
+        self.L = L = num_downs
+        self.C = [ngf * min(2 ** j, 8) for j in range(L)]
+        C = self.C
+        # state_dict prefixes of the nested Sequentials (models.py:183-200)
+        pref = ["model.model"]
+        for j in range(1, L):
+            pref.append(pref[-1] + (".1.model" if j == 1 else ".3.model"))
+        self.k_down = [pref[0] + ".0"] + [pref[j] + ".1" for j in range(1, L)]
+        self.k_dbn = [None] + [pref[j] + ".2" for j in range(1, L - 1)] + [None]
+        self.k_up = [pref[0] + ".3"] + [pref[j] + ".5" for j in range(1, L - 1)] + [pref[L - 1] + ".3"]
+        self.k_ubn = [None] + [pref[j] + ".6" for j in range(1, L - 1)] + [pref[L - 1] + ".4"]
+        # flat-buffer order = order in which gradients complete in backward (DP buckets)
+        self._reg_small(self.k_up[0] + ".weight", 2 * C[0], 3, 64)
+        self._reg_vec(self.k_up[0] + ".bias", 3)
+        self.ubn: List[Optional[_BN]] = [None] * L
+        self.dbn: List[Optional[_BN]] = [None] * L
+        for j in range(1, L):
+            cin = C[j] if j == L - 1 else 2 * C[j]
+            self._reg_convT(self.k_up[j] + ".weight", cin, C[j - 1])
+            self.ubn[j] = self._reg_bn(self.k_ubn[j], C[j - 1])
+        for j in range(L - 1, 0, -1):
+            self._reg_conv(self.k_down[j] + ".weight", C[j], C[j - 1])
+            if self.k_dbn[j] is not None:
+                self.dbn[j] = self._reg_bn(self.k_dbn[j], C[j])
+        self._reg_small(self.k_down[0] + ".weight", C[0], 3, 64)
+        self.store.allocate(device)
+        for bn in self.bns.values():
+            bn.allocate(device)
+        self.key_order = self._reference_key_order(pref)
+        # packed bf16 GEMM operands
+        bf = dict(device=device, dtype=torch.bfloat16)
+        self.w_d_fwd = [torch.empty(1, C[0], 64, **bf)] + [torch.empty(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
+        self.w_d_dg = [None] + [torch.empty(4, C[j - 1], 4 * C[j], **bf) for j in range(1, L)]
+        self.w_u_fwd = [torch.empty(1, 64, 2 * C[0], **bf)]
+        self.w_u_dg = [torch.empty(1, 2 * C[0], 64, **bf)]
+        for j in range(1, L):
+            cin = C[j] if j == L - 1 else 2 * C[j]
+            self.w_u_fwd.append(torch.empty(4, C[j - 1], 4 * cin, **bf))
+            self.w_u_dg.append(torch.empty(1, cin, 16 * C[j - 1], **bf))
+        self._n = None
+        self.init_from_torch_default()
+
+    def _reference_key_order(self, pref: List[str]) -> List[str]:
+        """Key order of the reference module's state_dict(): depth-first through the Sequentials."""
+        L = self.L
+        bn_leaves = ["weight", "bias", "running_mean", "running_var", "num_batches_tracked"]
+
+        def block(j: int) -> List[str]:
+            keys = []
+            if j == 0:
+                keys.append(self.k_down[0] + ".weight")
+                keys += block(1)
+                keys += [self.k_up[0] + ".weight", self.k_up[0] + ".bias"]
+                return keys
+            keys.append(self.k_down[j] + ".weight")
+            if j < L - 1:
+                keys += [self.k_dbn[j] + "." + l for l in bn_leaves]
+                keys += block(j + 1)
+            keys.append(self.k_up[j] + ".weight")
+            keys += [self.k_ubn[j] + "." + l for l in bn_leaves]
+            return keys
+
+        return block(0)
+
+    def init_from_torch_default(self) -> None:
+        """Consume the global RNG exactly like UNetGenerator.__init__ (models.py:155-161): blocks are
+        constructed innermost first; inside a block downconv, (norms have no RNG), upconv."""
+        L, C = self.L, self.C
+        with torch.no_grad():
+            for bn in self.bns.values():
+                self.param(bn.name + ".weight").fill_(1.0)
+                self.param(bn.name + ".bias").zero_()
+            for j in range(L - 1, -1, -1):
+                cin_d = 3 if j == 0 else C[j - 1]
+                w = torch.empty(C[j], cin_d, 4, 4)
+                _kaiming_uniform_(w, cin_d * 16)
+                self.param(self.k_down[j] + ".weight").copy_(w.to(self.dev))
+                cin_u = C[j] if j == L - 1 else 2 * C[j]
+                cout_u = 3 if j == 0 else C[j - 1]
+                w = torch.empty(cin_u, cout_u, 4, 4)
+                _kaiming_uniform_(w, cout_u * 16)  # ConvTranspose2d fan_in = weight.size(1)*k*k
+                self.param(self.k_up[j] + ".weight").copy_(w.to(self.dev))
+                if j == 0:
+                    b = torch.empty(3)
+                    _bias_uniform_(b, cout_u * 16)
+                    self.param(self.k_up[0] + ".bias").copy_(b.to(self.dev))
+        self.repack()
+
+    def repack(self) -> None:
+        L, C, p = self.L, self.C, self.store.p
+        off = self.store.off
+        ops.pack_weights(p, off(self.k_down[0] + ".weight"), self.w_d_fwd[0], 0, 1, C[0], C[0], (1, 1), 64, 64, 64,
+                         (64, 1, 0, 0))
+        for j in range(1, L):
+            ci, co = C[j - 1], C[j]
+            o = off(self.k_down[j] + ".weight")
+            ops.pack_weights(p, o, self.w_d_fwd[j], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
+            ops.pack_weights(p, o, self.w_d_dg[j], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
+        k0 = off(self.k_up[0] + ".weight")
+        c2 = 2 * C[0]
+        ops.pack_weights(p, k0, self.w_u_fwd[0], 0, 1, 64, 64, (1, 1), c2, c2, c2, (1, 64, 0, 0))
+        ops.pack_weights(p, k0, self.w_u_dg[0], 0, 1, c2, c2, (1, 1), 64, 64, 64, (64, 1, 0, 0))
+        for j in range(1, L):
+            ci = C[j] if j == L - 1 else 2 * C[j]
+            co = C[j - 1]
+            o = off(self.k_up[j] + ".weight")
+            ops.pack_weights(p, o, self.w_u_fwd[j], 2, 4, co, co, (2, 2), ci, ci, 4 * ci, (1, 16 * co, 4 * co, co))
+            ops.pack_weights(p, o, self.w_u_dg[j], 0, 1, ci, ci, (4, 4), co, co, 16 * co, (16 * co, 1, 4 * co, co))
+
+    # -- activation buffers ---------------------------------------------------------------------
+    def _alloc(self, n: int, h: int, w: int) -> None:
+        if self._n == (n, h, w):
+            return
+        L, C = self.L, self.C
+        if h % (1 << L) or w % (1 << L):
+            raise ValueError(f"input {h}x{w} must be divisible by 2^{L}")
+        bf = dict(device=self.dev, dtype=torch.bfloat16)
+        S = [(h >> (j + 1), w >> (j + 1)) for j in range(L)]
+        self.S = S
+        self.x_nhwc = torch.zeros(n, h, w, 4, **bf)
+        self.col0 = torch.empty(n, S[0][0], S[0][1], 64, **bf)
+        self.A = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
+        self.R = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
+        self.Rin = torch.empty(n, S[L - 1][0], S[L - 1][1], C[L - 1], **bf)
+        self.yd = [None] + [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(1, L - 1)] + [None]
+        self.yu = [None] + [torch.empty(n, S[j - 1][0], S[j - 1][1], C[j - 1], **bf) for j in range(1, L)]
+        self.ycol = torch.empty(n, S[0][0], S[0][1], 64, **bf)
+        self.fake_bf = torch.zeros(n, h, w, 4, **bf)
+        self.fake_f32 = torch.zeros(n, h, w, 4, device=self.dev)
+        # backward scratch
+        self.dpre = torch.zeros(n, h, w, 4, **bf)
+        self.dycol = torch.empty(n, S[0][0], S[0][1], 64, **bf)
+        self.gR = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
+        self.gRin = torch.empty_like(self.Rin)
+        self.gA = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
+        self.dyu = [None] + [torch.empty_like(self.yu[j]) for j in range(1, L)]
+        self.dyd = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L)]
+        self._n = (n, h, w)
+
+    # -- forward --------------------------------------------------------------------------------
+    def forward(self, x_nchw: torch.Tensor, bn_repeat: int = 1) -> torch.Tensor:
+        """x: fp32 NCHW on the device.  Returns fake as fp32 NHWC [n,h,w,4] (channel 3 is padding);
+        the bf16 copy is self.fake_bf.  bn_repeat=2 folds the reference's second identical forward."""
+        n, _, h, w = x_nchw.shape
+        self._alloc(n, h, w)
+        L, C, S = self.L, self.C, self.S
+        g_s2 = ops.geom_conv_fwd(4, 2, 1)
+        g_1x1 = ops.geom_conv_fwd(1, 1, 0)
+        g_ph = ops.geom_phase_k4s2p1()
+        ops.nchw_to_nhwc_bf16(x_nchw, self.x_nhwc)
+        ops.im2col_k4s2p1(self.x_nhwc, 3, None, 0, self.col0)
+        ops.conv_gemm([self.col0], self.w_d_fwd[0], g_1x1, self.A[0], C[0], S[0], act=ACT_LRELU,
+                      out2=self.R[0][..., :C[0]], act2=ACT_RELU)
+        for j in range(1, L - 1):
+            bn = self.dbn[j]
+            ops.conv_gemm([self.A[j - 1]], self.w_d_fwd[j], g_s2, self.yd[j], C[j], S[j],
+                          stats=bn.stats if self.training else None)
+            self._bn_forward(bn, self.yd[j], self.A[j], ACT_LRELU, self.R[j][..., :C[j]], ACT_RELU, bn_repeat)
+        ops.conv_gemm([self.A[L - 2]], self.w_d_fwd[L - 1], g_s2, self.Rin, C[L - 1], S[L - 1], act=ACT_RELU)
+        for j in range(L - 1, 0, -1):
+            src = self.Rin if j == L - 1 else self.R[j]
+            bn = self.ubn[j]
+            ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats if self.training else None)
+            self._bn_forward(bn, self.yu[j], self.R[j - 1][..., C[j - 1]:], ACT_RELU, repeat=bn_repeat)
+        ops.conv_gemm([self.R[0]], self.w_u_fwd[0], g_1x1, self.ycol, 64, S[0])
+        ops.col2im_k4s2p1(self.ycol, 3, 0, 3, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32)
+        return self.fake_f32
+
+    def output_nchw(self) -> torch.Tensor:
+        n, h, w = self._n
+        out = torch.empty(n, 3, h, w, device=self.dev)
+        ops.nhwc_to_nchw_f32(self.fake_f32, out, 3)
+        return out
+
+    # -- backward -------------------------------------------------------------------------------
+    def backward(self) -> None:
+        """Consumes self.dpre (gradient w.r.t. the pre-Tanh output, bf16 NHWC) and accumulates every
+        parameter gradient into the flat gradient buffer."""
+        L, C, S = self.L, self.C, self.S
+        g_s2 = ops.geom_conv_fwd(4, 2, 1)
+        g_1x1 = ops.geom_conv_fwd(1, 1, 0)
+        g_ph = ops.geom_phase_k4s2p1()
+        # outermost up-conv (GEMM + col2im form)
+        ops.im2col_k4s2p1(self.dpre, 3, None, 0, self.dycol)
+        ops.conv_wgrad(self.R[0], self.dycol, self.store.seg(self.store.g, self.k_up[0] + ".weight"), (1, 1), 1,
+                       (0, 0), 64, 0)
+        ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
+        ops.conv_gemm([self.dycol], self.w_u_dg[0], g_1x1, self.gR[0], 2 * C[0], S[0])
+        # up path, outer -> inner
+        for j in range(1, L):
+            bn = self.ubn[j]
+            co = C[j - 1]
+            self._bn_backward(bn, self.yu[j], self.gR[j - 1][..., co:], None, 0.0, self.dyu[j])
+            src = self.Rin if j == L - 1 else self.R[j]
+            ci = src.shape[-1]
+            ops.conv_wgrad(src, self.dyu[j], self.store.seg(self.store.g, self.k_up[j] + ".weight"), (4, 4), 2,
+                           (-1, -1), 16 * co, co)
+            dst = self.gRin if j == L - 1 else self.gR[j]
+            ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, dst, ci, S[j])
+        # innermost down conv: ReLU backward, wgrad, dgrad
+        ops.bn_bwd_apply(self.Rin, self.gRin, None, 0.0, None, None, None, None, None, 0, self.dyd[L - 1])
+        for j in range(L - 1, 0, -1):
+            ops.conv_wgrad(self.dyd[j], self.A[j - 1], self.store.seg(self.store.g, self.k_down[j] + ".weight"),
+                           (4, 4), 2, (-1, -1), 16 * C[j - 1], C[j - 1])
+            ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.gA[j - 1], C[j - 1], S[j])
+            jj = j - 1
+            if jj >= 1:
+                self._bn_backward(self.dbn[jj], self.yd[jj], self.gA[jj], self.gR[jj][..., :C[jj]], 0.2, self.dyd[jj])
+            else:
+                ops.bn_bwd_apply(self.A[0], self.gA[0], self.gR[0][..., :C[0]], 0.2, None, None, None, None, None, 0,
+                                 self.dyd[0])
+        ops.conv_wgrad(self.dyd[0], self.col0, self.store.seg(self.store.g, self.k_down[0] + ".weight"), (1, 1), 1,
+                       (0, 0), 64, 0)
+
+
+# ================================================================================================
+# Discriminator
+# ================================================================================================
+class DiscriminatorEngine(_Net):
+    """NLayerDiscriminator(input_nc=6, ndf, n_layers, BatchNorm2d)."""
+
+    def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3) -> None:
+        super().__init__(device)
+        if input_nc != 6:
+            raise NotImplementedError("the native discriminator supports input_nc = 6 (cat of two RGB images)")
+        if ndf % 64 != 0 or n_layers < 1:
+            raise NotImplementedError("ndf must be a multiple of 64")
+        self.nl = n_layers
+        self.C = [ndf * min(2 ** k, 8) for k in range(n_layers + 1)]   # conv0..conv_nl output channels
+        C = self.C
+        idx = [0] + [2 + 3 * (k - 1) for k in range(1, n_layers + 2)]    # Sequential indices of the convs
+        self.k_conv = [f"model.{i}" for i in idx]
+        self.k_bn = [None] + [f"model.{i + 1}" for i in idx[1:-1]] + [None]
+        self.n_conv = n_layers + 2
+        self._reg_small(self.k_conv[0] + ".weight", C[0], 6, 128)
+        self._reg_vec(self.k_conv[0] + ".bias", C[0])
+        self.bn: List[Optional[_BN]] = [None] * self.n_conv
+        for k in range(1, n_layers + 1):
+            self._reg_conv(self.k_conv[k] + ".weight", C[k], C[k - 1])
+            self.bn[k] = self._reg_bn(self.k_bn[k], C[k])
+        self._reg_conv(self.k_conv[-1] + ".weight", 1, C[-1])
+        self._reg_vec(self.k_conv[-1] + ".bias", 1)
+        self.store.allocate(device)
+        for bn in self.bns.values():
+            bn.allocate(device)
+        self.key_order = []
+        bn_leaves = ["weight", "bias", "running_mean", "running_var", "num_batches_tracked"]
+        for k in range(self.n_conv):
+            self.key_order.append(self.k_conv[k] + ".weight")
+            if k == 0 or k == self.n_conv - 1:
+                self.key_order.append(self.k_conv[k] + ".bias")
+            else:
+                self.key_order += [self.k_bn[k] + "." + l for l in bn_leaves]
+        bf = dict(device=device, dtype=torch.bfloat16)
+        self.w_fwd = [torch.empty(1, C[0], 128, **bf)] + [torch.empty(1, C[k], 16 * C[k - 1], **bf) for k in range(1, n_layers + 1)]
+        self.w_fwd.append(torch.empty(1, 1, 16 * C[-1], **bf))
+        self.w_dg = [torch.empty(1, 128, C[0], **bf)]
+        for k in range(1, n_layers + 1):
+            if k < n_layers:
+                self.w_dg.append(torch.empty(4, C[k - 1], 4 * C[k], **bf))     # stride 2: four phases
+            else:
+                self.w_dg.append(torch.empty(1, C[k - 1], 16 * C[k], **bf))    # stride 1: flipped taps
+        self.w_dg.append(torch.empty(1, C[-1], 16 * 64, **bf))                 # Cout = 1 padded to 64 channels
+        self._n = None
+        self.init_from_torch_default()
+
+    def stride(self, k: int) -> int:
+        return 2 if k < self.nl else 1
+
+    def init_from_torch_default(self) -> None:
+        """RNG order of NLayerDiscriminator.__init__ (models.py:223-243): convs in sequence order, each
+        weight then bias."""
+        C = self.C
+        with torch.no_grad():
+            for bn in self.bns.values():
+                self.param(bn.name + ".weight").fill_(1.0)
+                self.param(bn.name + ".bias").zero_()
+            for k in range(self.n_conv):
+                cin = 6 if k == 0 else C[k - 1]
+                cout = 1 if k == self.n_conv - 1 else C[k]
+                w = torch.empty(cout, cin, 4, 4)
+                _kaiming_uniform_(w, cin * 16)
+                self.param(self.k_conv[k] + ".weight").copy_(w.to(self.dev))
+                if k == 0 or k == self.n_conv - 1:
+                    b = torch.empty(cout)
+                    _bias_uniform_(b, cin * 16)
+                    self.param(self.k_conv[k] + ".bias").copy_(b.to(self.dev))
+        self.repack()
+
+    def repack(self) -> None:
+        C, p, off = self.C, self.store.p, self.store.off
+        o = off(self.k_conv[0] + ".weight")
+        ops.pack_weights(p, o, self.w_fwd[0], 0, 1, C[0], C[0], (1, 1), 128, 128, 128, (128, 1, 0, 0))
+        ops.pack_weights(p, o, self.w_dg[0], 0, 1, 128, 128, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0))
+        for k in range(1, self.n_conv):
+            ci = C[k - 1]
+            co = 1 if k == self.n_conv - 1 else C[k]
+            o = off(self.k_conv[k] + ".weight")
+            ops.pack_weights(p, o, self.w_fwd[k], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
+            if self.stride(k) == 2:
+                ops.pack_weights(p, o, self.w_dg[k], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
+            else:
+                cp = max(co, 64)
+                ops.pack_weights(p, o, self.w_dg[k], 1, 1, ci, ci, (4, 4), co, cp, 16 * cp, (1, 16 * ci, 4 * ci, ci))
+
+    def _alloc(self, n: int, h: int, w: int) -> None:
+        if self._n == (n, h, w):
+            return
+        C = self.C
+        bf = dict(device=self.dev, dtype=torch.bfloat16)
+        hs, ws = [h // 2], [w // 2]
+        for k in range(1, self.n_conv):
+            if self.stride(k) == 2:
+                hs.append(hs[-1] // 2)
+                ws.append(ws[-1] // 2)
+            else:
+                hs.append(hs[-1] - 1)
+                ws.append(ws[-1] - 1)
+        self.hs, self.ws = hs, ws
+        self.col = torch.empty(n, hs[0], ws[0], 128, **bf)
+        self.H = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
+        self.y = [None] + [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(1, self.n_conv - 1)]
+        self.logits = torch.empty(n, hs[-1], ws[-1], 1, device=self.dev)
+        self.dlogits = torch.zeros(n, hs[-1], ws[-1], 64, **bf)
+        self.gH = [torch.empty_like(t) for t in self.H]
+        self.dy = [torch.empty_like(t) for t in self.H]
+        self.dcol = torch.empty(n, hs[0], ws[0], 128, **bf)
+        self.dfake = torch.zeros(n, h, w, 4, device=self.dev)
+        self._n = (n, h, w)
+
+    def forward(self, xa: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
+        """xa, xb: NHWC bf16 [n,h,w,>=3] (the two halves of torch.cat((A, B), 1), train_gan.py:57,59,66).
+        Returns fp32 logits [n,h',w',1]."""
+        n, h, w, _ = xa.shape
+        self._alloc(n, h, w)
+        C = self.C
+        ops.im2col_k4s2p1(xa, 3, xb, 3, self.col)
+        ops.conv_gemm([self.col], self.w_fwd[0], ops.geom_conv_fwd(1, 1, 0), self.H[0], C[0], (self.hs[0], self.ws[0]),
+                      act=ACT_LRELU, bias=self.param(self.k_conv[0] + ".bias"))
+        for k in range(1, self.n_conv - 1):
+            bn = self.bn[k]
+            ops.conv_gemm([self.H[k - 1]], self.w_fwd[k], ops.geom_conv_fwd(4, self.stride(k), 1), self.y[k], C[k],
+                          (self.hs[k], self.ws[k]), stats=bn.stats if self.training else None)
+            self._bn_forward(bn, self.y[k], self.H[k], ACT_LRELU)
+        k = self.n_conv - 1
+        ops.conv_gemm([self.H[k - 1]], self.w_fwd[k], ops.geom_conv_fwd(4, 1, 1), self.logits, 1,
+                      (self.hs[k], self.ws[k]), bias=self.param(self.k_conv[k] + ".bias"))
+        return self.logits
+
+    def backward(self, wgrad: bool, input_grad: bool) -> Optional[torch.Tensor]:
+        """Consumes self.dlogits (bf16, channel 0 of a 64-channel-padded map).  wgrad=False skips
+        every parameter gradient (the G step); input_grad=True returns d(loss)/d(xb) as fp32 NHWC."""
+        C = self.C
+        last = self.n_conv - 1
+        g = self.store.g
+        if wgrad:
+            ops.conv_wgrad(self.dlogits, self.H[last - 1], self.store.seg(g, self.k_conv[last] + ".weight"), (4, 4), 1,
+                           (-1, -1), 16 * C[last - 1], C[last - 1], m_rows=1)
+            ops.colsum_bf16(self.dlogits, 1, self.grad(self.k_conv[last] + ".bias"))
+        ops.conv_gemm([self.dlogits], self.w_dg[last], ops.geom_conv_dgrad_s1(4, 1), self.gH[last - 1], C[last - 1],
+                      (self.hs[last - 1], self.ws[last - 1]))
+        for k in range(last - 1, 0, -1):
+            self._bn_backward(self.bn[k], self.y[k], self.gH[k], None, 0.2, self.dy[k], param_grads=wgrad)
+            s = self.stride(k)
+            if wgrad:
+                ops.conv_wgrad(self.dy[k], self.H[k - 1], self.store.seg(g, self.k_conv[k] + ".weight"), (4, 4), s,
+                               (-1, -1), 16 * C[k - 1], C[k - 1])
+            geom = ops.geom_phase_k4s2p1() if s == 2 else ops.geom_conv_dgrad_s1(4, 1)
+            grid = (self.hs[k], self.ws[k]) if s == 2 else (self.hs[k - 1], self.ws[k - 1])
+            ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.gH[k - 1], C[k - 1], grid)
+        ops.bn_bwd_apply(self.H[0], self.gH[0], None, 0.2, None, None, None, None, None, 0, self.dy[0])
+        if wgrad:
+            ops.conv_wgrad(self.dy[0], self.col, self.store.seg(g, self.k_conv[0] + ".weight"), (1, 1), 1, (0, 0),
+                           128, 0)
+            ops.colsum_bf16(self.dy[0], C[0], self.grad(self.k_conv[0] + ".bias"))
+        if input_grad:
+            ops.conv_gemm([self.dy[0]], self.w_dg[0], ops.geom_conv_fwd(1, 1, 0), self.dcol, 128,
+                          (self.hs[0], self.ws[0]))
+            ops.col2im_k4s2p1(self.dcol, 6, 3, 3, None, ACT_NONE, None, self.dfake)
+            return self.dfake
+        return None
+
+
+# ================================================================================================
+# One GAN training iteration
+# ================================================================================================
+class Pix2PixTrainer:
+    """train_gan_one_epoch's loop body (train_gan.py:52-74) on one GPU; `world` > 1 adds the
+    data-parallel gradient all-reduce (see parallel.py)."""
+
+    def __init__(self, device, lr_g: float = 1e-4, lr_d: float = 1e-4, beta1: float = 0.5, num_downs: int = 7,
+                 ngf: int = 64, ndf: int = 64, n_layers: int = 3, allreduce=None, world: int = 1) -> None:
+        self.dev = torch.device(device)
+        # construction order G then D fixes the seeded weights (train_gan.py:138-139)
+        self.G = GeneratorEngine(self.dev, 3, 3, num_downs, ngf)
+        self.D = DiscriminatorEngine(self.dev, 6, ndf, n_layers)
+        self.lr_g, self.lr_d, self.betas = lr_g, lr_d, (beta1, 0.999)
+        self.loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float64)  # d_real, d_fake, g_gan, l1
+        self.allreduce = allreduce
+        self.world = world
+        self.a_nhwc = None
+
+    def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
+        """real_A / real_B: fp32 NCHW on the device.  Returns a device tensor [loss_d, loss_g] (fp64);
+        no host synchronisation happens here."""
+        G, D = self.G, self.D
+        n, _, h, w = real_A.shape
+        if self.a_nhwc is None or self.a_nhwc.shape[:3] != (n, h, w):
+            self.a_nhwc = torch.zeros(n, h, w, 4, device=self.dev, dtype=torch.bfloat16)
+            self.b_nhwc = torch.zeros_like(self.a_nhwc)
+        G.training = D.training = True
+        self.loss_acc.zero_()
+        ops.nchw_to_nhwc_bf16(real_B, self.b_nhwc)
+        # ---- D step (train_gan.py:55-63)
+        D.zero_grad()
+        G.forward(real_A, bn_repeat=2)                     # :56 and :65 (identical forward, done once)
+        a_nhwc = G.x_nhwc
+        logits = D.forward(a_nhwc, self.b_nhwc)            # :57
+        cnt = logits.numel()
+        ops.bce_logits_const(logits, 1.0, 0.5 / cnt, D.dlogits, self.loss_acc[0:1])   # :58,61
+        D.backward(wgrad=True, input_grad=False)
+        logits = D.forward(a_nhwc, G.fake_bf)              # :59
+        ops.bce_logits_const(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2])   # :60,61
+        D.backward(wgrad=True, input_grad=False)           # :62
+        if self.allreduce is not None:
+            self.allreduce(D.store.g)
+        D.adam_step(self.lr_d, self.betas, grad_scale=1.0 / self.world)   # :63
+        # ---- G step (train_gan.py:64-71)
+        G.zero_grad()
+        logits = D.forward(a_nhwc, G.fake_bf)              # :66 (updated D)
+        ops.bce_logits_const(logits, 1.0, 1.0 / cnt, D.dlogits, self.loss_acc[2:3])   # :67
+        dfake = D.backward(wgrad=False, input_grad=True)
+        numel = n * 3 * h * w
+        ops.gen_out_bwd(G.fake_f32, real_B, dfake, LAMBDA_L1 / numel, G.dpre, self.loss_acc[3:4])  # :68-70
+        G.backward()
+        if self.allreduce is not None:
+            self.allreduce(G.store.g)
+        G.adam_step(self.lr_g, self.betas, grad_scale=1.0 / self.world)   # :71
+        la = self.loss_acc
+        loss_d = 0.5 * (la[0] + la[1]) / cnt
+        loss_g = la[2] / cnt + LAMBDA_L1 * la[3] / numel
+        return torch.stack([loss_d, loss_g])

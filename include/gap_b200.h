@@ -94,6 +94,7 @@ typedef struct gap_conv_gemm_args {
   int act2;
   const float* bias; /* may be NULL */
   double* stats;     /* may be NULL; [2*n_out] */
+  int out_f32;       /* 1: `out` is fp32 instead of bf16 (out2 must be NULL) */
 } gap_conv_gemm_args;
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);
@@ -113,6 +114,7 @@ int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);
 typedef struct gap_wgrad_args {
   const void* mop; /* NHWC bf16 [n, gh, gw, m_c] */
   int m_c;
+  int m_rows; /* rows of `out` that exist (<= m_c); rows beyond are not written */
   int64_t m_ld;
   const void* nop; /* NHWC bf16 [n, nh, nw, n_c] */
   int n_c;
@@ -124,6 +126,74 @@ typedef struct gap_wgrad_args {
 } gap_wgrad_args;
 
 int gap_conv_wgrad(const gap_wgrad_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model-boundary layout conversion (replaces the implicit NCHW fp32 contract of models.py:163,246)
+ * ---------------------------------------------------------------------------------------------- */
+int gap_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, int h, int w, int64_t out_ld,
+                              void* stream);
+int gap_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* out, int n, int c, int h, int w, int64_t x_ld,
+                         void* stream);
+
+/* First-layer im2col for Conv2d(k4,s2,p1) with 3 or 6 input channels (models.py:177 outermost,
+ * models.py:223; the 6-channel input is torch.cat((real_A, B), 1), train_gan.py:57,59,66):
+ * col[(n,oh,ow)][(kh*4+kw)*(c0+c1) + c], zero padded to `krow` (64 for 3 channels, 128 for 6). */
+int gap_im2col_k4s2p1(const void* src0, int c0, int64_t ld0, const void* src1, int c1, int64_t ld1, void* col,
+                      int krow, int n, int h, int w, void* stream);
+
+/* col2im of the k4,s2,p1 transposed geometry (+bias, activation): the generator's last
+ * ConvTranspose2d + Tanh (models.py:184,186) after its GEMM, and the input gradient of the
+ * discriminator's first conv (channel slice [c0, c0+cn) of the col gradient). */
+int gap_col2im_k4s2p1(const void* col, int64_t ldc, int ctot, int c0, int cn, const float* bias, int act,
+                      void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, int n, int hi, int wi,
+                      void* stream);
+
+/* L1Loss(fake, real) * lambda (train_gan.py:43,68) fused with the Tanh backward:
+ * loss_acc += sum|fake-real|; dpre = (dfake_d + l1_scale*sign(fake-real)) * (1 - fake^2). */
+int gap_gen_out_bwd(const float* fake, int64_t ld_f, const float* real_nchw, int64_t hw, const float* dfake_d,
+                    int64_t ld_d, float l1_scale, void* dpre, int64_t ld_p, int64_t pixels, int c,
+                    double* loss_acc, void* stream);
+
+/* BCEWithLogitsLoss against ones / zeros (train_gan.py:42,58,60,67): loss_acc += sum l(x, t);
+ * dlogits[i*ld_d] = grad_scale * (sigmoid(x) - t) in bf16 (dlogits may be NULL). */
+int gap_bce_logits_const(const float* logits, int64_t count, float target, float grad_scale, void* dlogits,
+                         int64_t ld_d, double* loss_acc, void* stream);
+
+/* nn.BatchNorm2d training bookkeeping (models.py:179,181,231,239): statistics -> scale/shift,
+ * saved mean / inv-std, running stats (momentum, unbiased var, `repeat` identical updates),
+ * num_batches_tracked += repeat.  Re-zeroes `stats`. */
+int gap_bn_finalize(double* stats, int c, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, int repeat, float* running_mean, float* running_var, int64_t* nbt,
+                    float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+/* eval-mode BatchNorm (generate_synthetic_data.py:55): scale/shift from the running statistics */
+int gap_bn_eval_scale_shift(int c, const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* out1 = act1(y*scale+shift), out2 = act2(y*scale+shift) (optional): BatchNorm apply fused with
+ * LeakyReLU / ReLU and the U-Net skip write into the concat buffer (models.py:178-181,208). */
+int gap_bn_act(const void* y, int64_t ld_y, const float* scale, const float* shift, int64_t pixels, int c,
+               void* out1, int64_t ld1, int act1, void* out2, int64_t ld2, int act2, void* stream);
+/* BatchNorm + activation backward, pass 1 (per-channel sums) and pass 2 (apply); see elementwise.cu.
+ * scale == NULL in gap_bn_bwd_apply selects the activation-only mode. */
+int gap_bn_bwd_reduce(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1, const void* g2, int64_t ld_g2,
+                      float slope, const float* scale, const float* shift, const float* mean,
+                      const float* invstd, int64_t pixels, int c, double* sums, void* stream);
+int gap_bn_bwd_apply(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1, const void* g2, int64_t ld_g2,
+                     float slope, const float* scale, const float* shift, const float* mean, const float* invstd,
+                     int64_t pixels, int c, const double* sums, double count, void* dy, int64_t ld_dy,
+                     void* stream);
+int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* stream);
+/* bias gradient: out[c] += sum over pixels of x[pixel][c] */
+int gap_colsum_bf16(const void* x, int64_t ld, int64_t pixels, int c, float* out, void* stream);
+
+/* optim.Adam / optim.AdamW step on a flat fp32 buffer (train_gan.py:140-141,63,71; train.py:295,144).
+ * grad_scale folds the 1/world_size of the data-parallel gradient all-reduce. */
+int gap_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, int step, float grad_scale, void* stream);
+
+/* fp32 master weights (arbitrary strides) -> bf16 K-major GEMM operand; modes in elementwise.cu. */
+int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows, int rows_pad, int taps_h,
+                     int taps_w, int c, int c_pad, int krow, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
+                     int kdim, void* stream);
 
 /* Debug knobs for bring-up (descriptor conventions); not part of the stable surface. */
 int gap_debug_set(const char* key, int value);
