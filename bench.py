@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the Pix2Pix G+D training iteration (BASELINE.json metric: "Pix2Pix G+D train
+images/sec at 256^2").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours:       one process per GPU (torchrun for N > 1), batch 64 per GPU, 256x256 synthetic RGB pairs,
+            bf16 tensor-core kernels from libgap_b200.so; prints ONE JSON line on rank 0.
+reference:  the CPU restatement of the reference's train_gan_one_epoch iteration (oracle/, a port of
+            train_gan.py:52-74 + models.py; the reference itself is pure Python and cannot travel to
+            the GPU box), timed on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH_PER_GPU = 64
+HW = 256
+GFLOP_PER_IMG = 86.789062656     # 3*G + 8*D - 2*D.0 - G.0, convolutions only
+METRIC = "pix2pix_gd_train_images_per_sec_256"
+UNIT = "images/s"
+
+
+def _peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.rows: list[list[str]] = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = max((float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def _cpu_baseline(seconds_budget: float = 20.0) -> dict:
+    """Oracle port of one train_gan_one_epoch iteration (batch 1, 256^2, fp32) on the host cores."""
+    from oracle import pix2pix_oracle as O
+    from gan_aug_pfa_b200 import spec as MI
+    torch.manual_seed(0)
+    sd_g, sd_d = MI.default_state_dicts()
+    og = O.AdamState(sd_g, O.param_names(sd_g), 1e-4, (0.5, 0.999))
+    od = O.AdamState(sd_d, O.param_names(sd_d), 1e-4, (0.5, 0.999))
+    gen = torch.Generator().manual_seed(1234)
+    A = torch.rand(1, 3, HW, HW, generator=gen) * 2 - 1
+    B = torch.rand(1, 3, HW, HW, generator=gen) * 2 - 1
+    O.gan_train_step(sd_g, sd_d, og, od, A, B)      # warm-up
+    t0 = time.perf_counter()
+    it = 0
+    while True:
+        O.gan_train_step(sd_g, sd_d, og, od, A, B)
+        it += 1
+        el = time.perf_counter() - t0
+        if el > seconds_budget or it >= 40:
+            break
+    return {"value": it / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{it} iterations of batch 1 at 256x256 fp32 (oracle port of train_gan.py:52-74), "
+                      f"{el:.1f} s on {os.cpu_count()} host cpus"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pix2pix_oracle as O
+    from gan_aug_pfa_b200 import spec as MI
+    torch.manual_seed(0)
+    sd_g, sd_d = MI.default_state_dicts()
+    og = O.AdamState(sd_g, O.param_names(sd_g), 1e-4, (0.5, 0.999))
+    od = O.AdamState(sd_d, O.param_names(sd_d), 1e-4, (0.5, 0.999))
+    sample_batch = 2
+    gen = torch.Generator().manual_seed(1234)
+    A = torch.rand(sample_batch, 3, HW, HW, generator=gen) * 2 - 1
+    B = torch.rand(sample_batch, 3, HW, HW, generator=gen) * 2 - 1
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.gan_train_step(sd_g, sd_d, og, od, A, B)
+    steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.gan_train_step(sd_g, sd_d, og, od, A, B)
+    el = time.perf_counter() - t0
+    val = steps * sample_batch / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pix2pix_gan_train_b64_256x256", "sample_batch_per_step": sample_batch,
+                   "note": "CPU oracle port of train_gan_one_epoch; each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} steps of batch {sample_batch} at 256x256 fp32"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    import torch.distributed as dist
+    from gan_aug_pfa_b200 import _lib, ops
+    from gan_aug_pfa_b200.parallel import make_allreduce
+    from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gap_* kernels have no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    tr = Pix2PixTrainer(dev, allreduce=make_allreduce(world) if world > 1 else None, world=world)
+    N = BATCH_PER_GPU
+    gen = torch.Generator().manual_seed(1234 + rank)
+    n_batches = 2
+    host = [(torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory(),
+             torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory()) for _ in range(n_batches)]
+    devb = [(a.to(dev), b.to(dev)) for a, b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        tr.train_step(*devb[i % n_batches])
+    barrier()
+    _lib.LAUNCHES = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            losses = tr.train_step(*devb[i % n_batches])
+        e1.record()
+        barrier()
+    launches = _lib.LAUNCHES
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * N * args.steps / (ms * 1e-3)
+    loss_host = losses.cpu().tolist()
+
+    # ---- end to end: pinned host inputs, H2D inside the timed region, losses read back every step
+    stage = [(torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])) for _ in range(2)]
+    loss_pinned = torch.empty(2, dtype=torch.float64).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        a, b = stage[i % 2]
+        a.copy_(host[i % n_batches][0], non_blocking=True)
+        b.copy_(host[i % n_batches][1], non_blocking=True)
+        out = tr.train_step(a, b)
+        loss_pinned.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller reads the step's losses (train_gan.py:72-74)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * N * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel roofline: time every GEMM launch of a few steps with CUDA events
+    prof_steps = min(2, args.steps)
+    ops.PROFILE = []
+    for i in range(prof_steps):
+        tr.train_step(*devb[i % n_batches])
+    torch.cuda.synchronize()
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    agg: dict = {}
+    for name, flops, ev0, ev1 in prof:
+        d = agg.setdefault(name, [0.0, 0.0, 0])
+        d[0] += flops
+        d[1] += ev0.elapsed_time(ev1) * 1e-3
+        d[2] += 1
+    peaks = _peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    kern = {k: {"tflops": v[0] / v[1] / 1e12 if v[1] > 0 else 0.0, "seconds_per_step": v[1] / prof_steps,
+                "launches_per_step": v[2] // prof_steps} for k, v in agg.items()}
+    dom = max(agg.items(), key=lambda kv: kv[1][1])[0] if agg else None
+    roofline = None
+    if dom is not None:
+        ach = kern[dom]["tflops"]
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "per_kernel": kern,
+                    "step_frac_of_peak": (value / world) * GFLOP_PER_IMG * 1e9 / (peak_tf * 1e12)}
+
+    if rank == 0:
+        cpu = _cpu_baseline() if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "pix2pix_gan_train_b64_256x256", "batch_per_gpu": N, "image": f"{HW}x{HW}x3",
+                       "parallelism": f"dp{world}", "l2": "per-step working set (several GB of activations) >> 126 MB L2; "
+                       "two alternating input batches", "algorithmic_gflop_per_image": GFLOP_PER_IMG},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N * 3 * HW * HW * 4,
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "final_losses": {"loss_d": loss_host[0], "loss_g": loss_host[1]},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

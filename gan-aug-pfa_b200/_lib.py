@@ -104,7 +104,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+LAUNCHES = 0  # gap_* kernel launches issued through this module (bench.py reports it)
+
+
 def check(rc: int, what: str = "gap call") -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = lib().gap_last_error_string().decode(errors="replace")
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")

@@ -16,6 +16,22 @@ from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH  # noqa: F401
 
 
+# bench.py sets PROFILE to a list to time every GEMM launch with CUDA events:
+# entries are (kernel name, algorithmic FLOPs, start event, end event).
+PROFILE = None
+
+
+def _timed(name: str, flops: float, fn) -> None:
+    if PROFILE is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((name, flops, e0, e1))
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -66,8 +82,10 @@ def geom_phase_k4s2p1() -> Geometry:
 def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, out: torch.Tensor,
               n_out: int, grid_hw: tuple[int, int], *, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, act2: int = ACT_NONE,
-              bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
-    """Launch the implicit-GEMM engine.  ``wpk`` is [n_phase, rows, taps*ctot] bf16."""
+              bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+              flops: Optional[float] = None) -> None:
+    """Launch the implicit-GEMM engine.  ``wpk`` is [n_phase, rows, taps*ctot] bf16.  ``flops`` overrides
+    the algorithmic FLOP count reported to the profiler (layers that pad channels pass the true one)."""
     a = _lib.ConvGemmArgs()
     n = ih = iw = None
     for i in range(2):
@@ -130,11 +148,15 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
         a.stats = stats.data_ptr()
     else:
         a.stats = None
-    _lib.check(_lib.lib().gap_conv_gemm(C.byref(a), _stream()), "gap_conv_gemm")
+    if flops is None:
+        flops = 2.0 * n * grid_hw[0] * grid_hw[1] * geom.n_phase * n_out * geom.taps_h * geom.taps_w * ctot
+    _timed("conv_fprop_kernel", flops,
+           lambda: _lib.check(_lib.lib().gap_conv_gemm(C.byref(a), _stream()), "gap_conv_gemm"))
 
 
 def conv_wgrad(mop: torch.Tensor, nop: torch.Tensor, out: torch.Tensor, taps: tuple[int, int], stride: int,
-               off: tuple[int, int], ld_m: int, ld_tap: int, m_rows: int = 0) -> None:
+               off: tuple[int, int], ld_m: int, ld_tap: int, m_rows: int = 0,
+               flops: Optional[float] = None) -> None:
     """out[m*ld_m + tap*ld_tap + c] += sum_pix mop[pix, m] * nop[gather(pix, tap), c]   (fp32 out)."""
     a = _lib.WgradArgs()
     n, gh, gw, mc, mld = _nhwc_view(mop)
@@ -152,7 +174,10 @@ def conv_wgrad(mop: torch.Tensor, nop: torch.Tensor, out: torch.Tensor, taps: tu
     a.off_h, a.off_w = off
     a.out = out.data_ptr()
     a.ld_m, a.ld_tap = ld_m, ld_tap
-    _lib.check(_lib.lib().gap_conv_wgrad(C.byref(a), _stream()), "gap_conv_wgrad")
+    if flops is None:
+        flops = 2.0 * n * gh * gw * (m_rows if m_rows > 0 else mc) * nc * taps[0] * taps[1]
+    _timed("conv_wgrad_kernel", flops,
+           lambda: _lib.check(_lib.lib().gap_conv_wgrad(C.byref(a), _stream()), "gap_conv_wgrad"))
 
 
 # ------------------------------------------------------------------------------------------------

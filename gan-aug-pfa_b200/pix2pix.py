@@ -20,7 +20,6 @@ are not computed.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -28,6 +27,7 @@ import torch
 
 from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH
+from .spec import DiscriminatorSpec, GeneratorSpec
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -211,18 +211,6 @@ class _Net:
             ops.bn_param_grads(bn.sums, None, None)
 
 
-def _kaiming_uniform_(t: torch.Tensor, fan_in: int) -> None:
-    """nn.Conv2d / nn.ConvTranspose2d.reset_parameters: kaiming_uniform_(a=sqrt(5)); torch derives the
-    fan-in from weight.size(1) * kh * kw for both layouts, which equals `fan_in` at every call site."""
-    assert fan_in == t.size(1) * t.size(2) * t.size(3)
-    torch.nn.init.kaiming_uniform_(t, a=math.sqrt(5))
-
-
-def _bias_uniform_(b: torch.Tensor, fan_in: int) -> None:
-    bound = 1 / math.sqrt(fan_in)
-    torch.nn.init.uniform_(b, -bound, bound)
-
-
 # ================================================================================================
 # Generator
 # ================================================================================================
@@ -235,17 +223,10 @@ class GeneratorEngine(_Net):
             raise NotImplementedError("the native generator supports input_nc = output_nc = 3")
         if ngf % 64 != 0 or num_downs < 5:
             raise NotImplementedError("ngf must be a multiple of 64 and num_downs >= 5")
+        self.spec = sp = GeneratorSpec(input_nc, output_nc, num_downs, ngf)
         self.L = L = num_downs
-        self.C = [ngf * min(2 ** j, 8) for j in range(L)]
-        C = self.C
-        # state_dict prefixes of the nested Sequentials (models.py:183-200)
-        pref = ["model.model"]
-        for j in range(1, L):
-            pref.append(pref[-1] + (".1.model" if j == 1 else ".3.model"))
-        self.k_down = [pref[0] + ".0"] + [pref[j] + ".1" for j in range(1, L)]
-        self.k_dbn = [None] + [pref[j] + ".2" for j in range(1, L - 1)] + [None]
-        self.k_up = [pref[0] + ".3"] + [pref[j] + ".5" for j in range(1, L - 1)] + [pref[L - 1] + ".3"]
-        self.k_ubn = [None] + [pref[j] + ".6" for j in range(1, L - 1)] + [pref[L - 1] + ".4"]
+        self.C = C = sp.C
+        self.k_down, self.k_dbn, self.k_up, self.k_ubn = sp.k_down, sp.k_dbn, sp.k_up, sp.k_ubn
         # flat-buffer order = order in which gradients complete in backward (DP buckets)
         self._reg_small(self.k_up[0] + ".weight", 2 * C[0], 3, 64)
         self._reg_vec(self.k_up[0] + ".bias", 3)
@@ -263,7 +244,7 @@ class GeneratorEngine(_Net):
         self.store.allocate(device)
         for bn in self.bns.values():
             bn.allocate(device)
-        self.key_order = self._reference_key_order(pref)
+        self.key_order = sp.key_order()
         # packed bf16 GEMM operands
         bf = dict(device=device, dtype=torch.bfloat16)
         self.w_d_fwd = [torch.empty(1, C[0], 64, **bf)] + [torch.empty(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
@@ -277,51 +258,10 @@ class GeneratorEngine(_Net):
         self._n = None
         self.init_from_torch_default()
 
-    def _reference_key_order(self, pref: List[str]) -> List[str]:
-        """Key order of the reference module's state_dict(): depth-first through the Sequentials."""
-        L = self.L
-        bn_leaves = ["weight", "bias", "running_mean", "running_var", "num_batches_tracked"]
-
-        def block(j: int) -> List[str]:
-            keys = []
-            if j == 0:
-                keys.append(self.k_down[0] + ".weight")
-                keys += block(1)
-                keys += [self.k_up[0] + ".weight", self.k_up[0] + ".bias"]
-                return keys
-            keys.append(self.k_down[j] + ".weight")
-            if j < L - 1:
-                keys += [self.k_dbn[j] + "." + l for l in bn_leaves]
-                keys += block(j + 1)
-            keys.append(self.k_up[j] + ".weight")
-            keys += [self.k_ubn[j] + "." + l for l in bn_leaves]
-            return keys
-
-        return block(0)
-
     def init_from_torch_default(self) -> None:
-        """Consume the global RNG exactly like UNetGenerator.__init__ (models.py:155-161): blocks are
-        constructed innermost first; inside a block downconv, (norms have no RNG), upconv."""
-        L, C = self.L, self.C
-        with torch.no_grad():
-            for bn in self.bns.values():
-                self.param(bn.name + ".weight").fill_(1.0)
-                self.param(bn.name + ".bias").zero_()
-            for j in range(L - 1, -1, -1):
-                cin_d = 3 if j == 0 else C[j - 1]
-                w = torch.empty(C[j], cin_d, 4, 4)
-                _kaiming_uniform_(w, cin_d * 16)
-                self.param(self.k_down[j] + ".weight").copy_(w.to(self.dev))
-                cin_u = C[j] if j == L - 1 else 2 * C[j]
-                cout_u = 3 if j == 0 else C[j - 1]
-                w = torch.empty(cin_u, cout_u, 4, 4)
-                _kaiming_uniform_(w, cout_u * 16)  # ConvTranspose2d fan_in = weight.size(1)*k*k
-                self.param(self.k_up[j] + ".weight").copy_(w.to(self.dev))
-                if j == 0:
-                    b = torch.empty(3)
-                    _bias_uniform_(b, cout_u * 16)
-                    self.param(self.k_up[0] + ".bias").copy_(b.to(self.dev))
-        self.repack()
+        """Default torch init drawn from the global CPU RNG in the reference's construction order
+        (spec.GeneratorSpec.default_state_dict), then copied into the flat buffers."""
+        self.load_state_dict(self.spec.default_state_dict())
 
     def repack(self) -> None:
         L, C, p = self.L, self.C, self.store.p
@@ -462,13 +402,10 @@ class DiscriminatorEngine(_Net):
             raise NotImplementedError("the native discriminator supports input_nc = 6 (cat of two RGB images)")
         if ndf % 64 != 0 or n_layers < 1:
             raise NotImplementedError("ndf must be a multiple of 64")
+        self.spec = sp = DiscriminatorSpec(input_nc, ndf, n_layers)
         self.nl = n_layers
-        self.C = [ndf * min(2 ** k, 8) for k in range(n_layers + 1)]   # conv0..conv_nl output channels
-        C = self.C
-        idx = [0] + [2 + 3 * (k - 1) for k in range(1, n_layers + 2)]    # Sequential indices of the convs
-        self.k_conv = [f"model.{i}" for i in idx]
-        self.k_bn = [None] + [f"model.{i + 1}" for i in idx[1:-1]] + [None]
-        self.n_conv = n_layers + 2
+        self.C = C = sp.C
+        self.k_conv, self.k_bn, self.n_conv = sp.k_conv, sp.k_bn, sp.n_conv
         self._reg_small(self.k_conv[0] + ".weight", C[0], 6, 128)
         self._reg_vec(self.k_conv[0] + ".bias", C[0])
         self.bn: List[Optional[_BN]] = [None] * self.n_conv
@@ -480,14 +417,7 @@ class DiscriminatorEngine(_Net):
         self.store.allocate(device)
         for bn in self.bns.values():
             bn.allocate(device)
-        self.key_order = []
-        bn_leaves = ["weight", "bias", "running_mean", "running_var", "num_batches_tracked"]
-        for k in range(self.n_conv):
-            self.key_order.append(self.k_conv[k] + ".weight")
-            if k == 0 or k == self.n_conv - 1:
-                self.key_order.append(self.k_conv[k] + ".bias")
-            else:
-                self.key_order += [self.k_bn[k] + "." + l for l in bn_leaves]
+        self.key_order = sp.key_order()
         bf = dict(device=device, dtype=torch.bfloat16)
         self.w_fwd = [torch.empty(1, C[0], 128, **bf)] + [torch.empty(1, C[k], 16 * C[k - 1], **bf) for k in range(1, n_layers + 1)]
         self.w_fwd.append(torch.empty(1, 1, 16 * C[-1], **bf))
@@ -505,24 +435,8 @@ class DiscriminatorEngine(_Net):
         return 2 if k < self.nl else 1
 
     def init_from_torch_default(self) -> None:
-        """RNG order of NLayerDiscriminator.__init__ (models.py:223-243): convs in sequence order, each
-        weight then bias."""
-        C = self.C
-        with torch.no_grad():
-            for bn in self.bns.values():
-                self.param(bn.name + ".weight").fill_(1.0)
-                self.param(bn.name + ".bias").zero_()
-            for k in range(self.n_conv):
-                cin = 6 if k == 0 else C[k - 1]
-                cout = 1 if k == self.n_conv - 1 else C[k]
-                w = torch.empty(cout, cin, 4, 4)
-                _kaiming_uniform_(w, cin * 16)
-                self.param(self.k_conv[k] + ".weight").copy_(w.to(self.dev))
-                if k == 0 or k == self.n_conv - 1:
-                    b = torch.empty(cout)
-                    _bias_uniform_(b, cin * 16)
-                    self.param(self.k_conv[k] + ".bias").copy_(b.to(self.dev))
-        self.repack()
+        """RNG order of NLayerDiscriminator.__init__ (models.py:223-243), see spec.DiscriminatorSpec."""
+        self.load_state_dict(self.spec.default_state_dict())
 
     def repack(self) -> None:
         C, p, off = self.C, self.store.p, self.store.off
