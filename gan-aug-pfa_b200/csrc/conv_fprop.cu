@@ -54,8 +54,10 @@ struct alignas(64) FpropParams {
   uint32_t idesc;
   int total_tiles;
   int k_iters;
-  int vec_ok;  // outputs are 16-byte aligned per pixel: use vector stores
+  int vec_ok;  // 1: outputs 16-byte aligned per pixel (128-bit stores); 2: 32-byte aligned (256-bit)
   int out_f32;  // `out` is fp32 (scalar stores; used for the 1-channel logits)
+  int fast_store;  // slope-type activations and 32-byte-aligned bf16 outputs: vector epilogue
+  float slope1, slope2;  // negative-side slope of act / act2 (1 identity, 0.2 LeakyReLU, 0 ReLU)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -126,6 +128,24 @@ __device__ __forceinline__ float transpose_reduce16(const float (&v)[16], uint32
   float w1 = mine + __shfl_xor_sync(0xffffffffu, other, 2);
   w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
   return w1;
+}
+
+// Cold path of the epilogue: partial column chunks, unaligned outputs, fp32 output, Tanh / Sigmoid.
+// Kept out of line so the hot loop stays small (the inlined version was instruction-cache bound).
+__device__ __noinline__ void epilogue_store_generic(const FpropParams& p, const float (&f)[16], long long pix,
+                                                    int col0) {
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < p.n_out) o[j] = apply_act(f[j], p.act);
+    return;
+  }
+  for (int j = 0; j < 16; ++j) {
+    if (col0 + j < p.n_out) {
+      p.out[pix * p.out_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act));
+      if (p.out2 != nullptr) p.out2[pix * p.out2_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act2));
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kFpropThreads, 1)
@@ -286,6 +306,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       const int n_chunks = p.block_n >> 4;
+      const bool fast = valid && p.fast_store;
       for (int c = 0; c < n_chunks; ++c) {
         uint32_t raw[16];
         tmem_ld16(t_row + c * 16, raw);
@@ -293,9 +314,10 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
         const int col0 = tc.n_tile * p.block_n + c * 16;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          f[j] = __uint_as_float(raw[j]);
-          if (p.bias != nullptr && col0 + j < p.n_out) f[j] += __ldg(p.bias + col0 + j);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(raw[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + min(col0 + j, p.n_out - 1));
         }
         if (do_stats) {
           float m[16];
@@ -310,38 +332,25 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
           }
         }
-        if (valid && col0 < p.n_out && p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
+        if (fast && col0 + 16 <= p.n_out) {
+          // common case: slope-type activation (identity / LeakyReLU / ReLU), 256-bit stores
+          uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (col0 + j < p.n_out) o[j] = apply_act(f[j], p.act);
-        } else if (valid && col0 < p.n_out) {
-          if (p.vec_ok && col0 + 16 <= p.n_out) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              pk[j] = pack_bf16x2(apply_act(f[2 * j], p.act), apply_act(f[2 * j + 1], p.act));
-            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + col0);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            if (p.out2 != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                pk[j] = pack_bf16x2(apply_act(f[2 * j], p.act2), apply_act(f[2 * j + 1], p.act2));
-              uint4* dst2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_ld + col0);
-              dst2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              dst2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (col0 + j < p.n_out) {
-                p.out[pix * p.out_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act));
-                if (p.out2 != nullptr)
-                  p.out2[pix * p.out2_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act2));
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float a0 = f[2 * j], a1 = f[2 * j + 1];
+            pk[j] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope1), a1 * (a1 > 0.f ? 1.f : p.slope1));
           }
+          st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
+          if (p.out2 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = f[2 * j], a1 = f[2 * j + 1];
+              pk[j] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope2), a1 * (a1 > 0.f ? 1.f : p.slope2));
+            }
+            st_global_32B(p.out2 + pix * p.out2_ld + col0, pk, true);
+          }
+        } else if (valid && col0 < p.n_out) {
+          epilogue_store_generic(p, f, pix, col0);
         }
       }
       tc_fence_before();
@@ -461,14 +470,20 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.bias = a->bias;
   p.stats = a->stats;
   p.idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
-  p.vec_ok = vec_ok ? 1 : 0;
+  const bool vec32 =
+      vec_ok && a->out_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 31) == 0 &&
+      (!a->out2 || (a->out2_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out2) & 31) == 0));
+  p.vec_ok = vec32 ? 2 : (vec_ok ? 1 : 0);
   p.out_f32 = a->out_f32;
+  auto slope_of = [](int act) { return act == GAP_ACT_NONE ? 1.f : (act == GAP_ACT_LRELU ? 0.2f : 0.f); };
+  p.slope1 = slope_of(a->act);
+  p.slope2 = slope_of(a->act2);
+  p.fast_store = (vec32 && !a->out_f32 && a->act <= GAP_ACT_RELU && a->act2 <= GAP_ACT_RELU) ? 1 : 0;
   GAP_CHECK_ARG(!(a->out_f32 && a->out2), "gap_conv_gemm: out2 is not supported with fp32 output");
 
   const int stage_bytes = kATileBytes + block_n * 128;
   int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
-  stages = std::min(stages, std::max(2, p.k_iters));
   const int force_st = debug_get("fprop_stages", 0);
   if (force_st > 0) stages = std::min(force_st, stages);
   p.num_stages = stages;

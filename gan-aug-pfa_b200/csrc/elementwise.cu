@@ -430,11 +430,24 @@ __global__ void bn_param_grads_kernel(double* __restrict__ sums, int c, float* _
 // per-channel column sums of a bf16 [pixels][c] tensor into fp32 (bias gradients)
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long pixels, int c,
                               float* __restrict__ out) {
-  // blockDim.x threads over channels (c <= 1024 handled by loop), blockIdx over pixel slabs
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+  // 256 threads = (256/cpad) pixel lanes x cpad channel lanes, cpad = pow2 >= min(c, 256)
+  __shared__ float red[256];
+  int cpad = 1;
+  while (cpad < c && cpad < 256) cpad <<= 1;
+  const int lanes = 256 / cpad;
+  const int cl = threadIdx.x % cpad, pl = threadIdx.x / cpad;
+  for (int ch = cl; ch < c; ch += cpad) {
     float s = 0.f;
-    for (long long pix = blockIdx.x; pix < pixels; pix += gridDim.x) s += __bfloat162float(x[pix * ld + ch]);
-    atomicAdd(out + ch, s);
+    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + pl; pix < pixels;
+         pix += static_cast<long long>(gridDim.x) * lanes)
+      s += __bfloat162float(x[pix * ld + ch]);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (pl == 0) {
+      for (int r = 1; r < lanes; ++r) s += red[r * cpad + cl];
+      atomicAdd(out + ch, s);
+    }
+    __syncthreads();
   }
 }
 
@@ -718,8 +731,8 @@ int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* s
 
 int gap_colsum_bf16(const void* x, int64_t ld, int64_t pixels, int c, float* out, void* stream) {
   GAP_CHECK_ARG(x && out && pixels > 0 && c > 0, "gap_colsum_bf16: bad arguments");
-  const int block = c < 256 ? ((c + 31) / 32) * 32 : 256;
-  const int grid = static_cast<int>(pixels < 148 * 4 ? pixels : 148 * 4);
+  const int block = 256;
+  const int grid = static_cast<int>(pixels < 148 * 8 ? pixels : 148 * 8);
   colsum_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld,
                                                                       pixels, c, out);
   GAP_LAUNCH_CHECK();

@@ -204,6 +204,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// 32 contiguous bytes per thread: one 256-bit store (full 32-byte sector, so L2 never has to fetch
+// the sector to merge a partial write) when the address is 32-byte aligned, else two 128-bit stores.
+__device__ __forceinline__ void st_global_32B(void* dst, const uint32_t (&v)[8], bool aligned32) {
+  if (aligned32) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+  } else {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    d[1] = make_uint4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
