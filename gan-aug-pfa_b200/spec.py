@@ -152,3 +152,51 @@ def default_state_dicts(num_downs: int = 7, ngf: int = 64, ndf: int = 64, n_laye
     g = GeneratorSpec(3, 3, num_downs, ngf).default_state_dict()
     d = DiscriminatorSpec(6, ndf, n_layers).default_state_dict()
     return g, d
+
+
+class SiameseSpec:
+    """SiameseUNet(n_channels, n_classes) (models.py:47-145): module construction order = RNG order =
+    state_dict order: dconv_down1..4, bottleneck, att3, att2, att1, att_last, dconv_up3, dconv_up2,
+    dconv_up1, dconv_last, conv_last (maxpool / upsample have no state)."""
+
+    def __init__(self, n_channels: int = 3, n_classes: int = 1) -> None:
+        self.n_channels, self.n_classes = n_channels, n_classes
+        self.double_convs = [("dconv_down1", n_channels, 64), ("dconv_down2", 64, 128), ("dconv_down3", 128, 256),
+                             ("dconv_down4", 256, 512), ("bottleneck", 512, 1024)]
+        # (name, F_g, F_l, F_int)  models.py:76-79
+        self.atts = [("att3", 2048, 1024, 512), ("att2", 512, 512, 256), ("att1", 256, 256, 128),
+                     ("att_last", 128, 128, 64)]
+        self.up_convs = [("dconv_up3", 2048 + 1024, 512), ("dconv_up2", 512 + 512, 256),
+                         ("dconv_up1", 256 + 256, 128), ("dconv_last", 128 + 128, 64)]
+
+    def default_state_dict(self) -> Dict[str, torch.Tensor]:
+        sd: Dict[str, torch.Tensor] = {}
+
+        def dconv(name: str, cin: int, cout: int) -> None:
+            for idx, ci in ((0, cin), (3, cout)):
+                w = torch.empty(cout, ci, 3, 3)
+                _kaiming_uniform_(w)
+                sd[f"{name}.{idx}.weight"] = w
+                _bn_entries(sd, f"{name}.{idx + 1}", cout)
+
+        def conv1x1(prefix: str, cin: int, cout: int) -> None:
+            w = torch.empty(cout, cin, 1, 1)
+            _kaiming_uniform_(w)
+            b = torch.empty(cout)
+            _bias_uniform_(b, w)
+            sd[prefix + ".weight"] = w
+            sd[prefix + ".bias"] = b
+
+        for name, ci, co in self.double_convs:
+            dconv(name, ci, co)
+        for name, fg, fl, fi in self.atts:
+            conv1x1(f"{name}.W_g.0", fg, fi)
+            _bn_entries(sd, f"{name}.W_g.1", fi)
+            conv1x1(f"{name}.W_x.0", fl, fi)
+            _bn_entries(sd, f"{name}.W_x.1", fi)
+            conv1x1(f"{name}.psi.0", fi, 1)
+            _bn_entries(sd, f"{name}.psi.1", 1)
+        for name, ci, co in self.up_convs:
+            dconv(name, ci, co)
+        conv1x1("conv_last", 64, self.n_classes)
+        return sd

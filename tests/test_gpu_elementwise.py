@@ -1,0 +1,190 @@
+"""Parity of the HBM-bound kernels (BatchNorm, losses, Adam, packing, im2col / col2im) against fp32 CPU
+restatements of the same formulas (oracle functions where they exist)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gan_aug_pfa_b200 import ops  # noqa: E402
+from oracle import pix2pix_oracle as O  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def test_bn_finalize_act_and_buffers():
+    g = torch.Generator().manual_seed(0)
+    n, h, c = 3, 10, 64
+    y = (torch.randn(n, h, h, c, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    yf = y.float()
+    stats = torch.cat([yf.double().sum((0, 1, 2)), (yf.double() ** 2).sum((0, 1, 2))]).to(DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    nbt = torch.zeros((), device=DEV, dtype=torch.int64)
+    scale, shift, mean, invstd = (torch.empty(c, device=DEV) for _ in range(4))
+    ops.bn_finalize(stats, n * h * h, gamma.to(DEV), beta.to(DEV), 1e-5, 0.1, 2, rm, rv, nbt, scale, shift, mean, invstd)
+    sd = {"bn.weight": gamma, "bn.bias": beta, "bn.running_mean": torch.zeros(c), "bn.running_var": torch.ones(c),
+          "bn.num_batches_tracked": torch.tensor(0)}
+    nb = {}
+    ref = O.batchnorm2d(yf.permute(0, 3, 1, 2), sd, "bn", True, nb)
+    ref = O.batchnorm2d(yf.permute(0, 3, 1, 2), sd, "bn", True, nb)      # two identical updates (repeat=2)
+    assert torch.allclose(rm.cpu(), nb["bn.running_mean"], atol=1e-5)
+    assert torch.allclose(rv.cpu(), nb["bn.running_var"], atol=1e-5)
+    assert int(nbt) == 2 and float(stats.abs().max()) == 0.0
+    o1 = torch.empty(n, h, h, c, device=DEV, dtype=torch.bfloat16)
+    cat = torch.zeros(n, h, h, 2 * c, device=DEV, dtype=torch.bfloat16)
+    ops.bn_act(y.to(DEV), scale, shift, o1, ops.ACT_LRELU, cat[..., c:], ops.ACT_RELU)
+    refh = ref.permute(0, 2, 3, 1)
+    assert rel(o1.cpu().float(), F.leaky_relu(refh, 0.2)) < 4e-3
+    assert rel(cat[..., c:].cpu().float(), F.relu(refh)) < 4e-3
+    assert float(cat[..., :c].abs().max()) == 0.0
+    # eval mode scale/shift
+    ops.bn_eval_scale_shift(gamma.to(DEV), beta.to(DEV), rm, rv, 1e-5, scale, shift)
+    ref_s = gamma / torch.sqrt(rv.cpu() + 1e-5)
+    assert torch.allclose(scale.cpu(), ref_s, rtol=1e-5)
+
+
+@pytest.mark.parametrize("c,slope,two", [(64, 0.2, True), (512, 0.0, False), (128, 0.2, False)])
+def test_bn_backward(c, slope, two):
+    g = torch.Generator().manual_seed(c)
+    n, h = 2, 6
+    y = (torch.randn(n, h, h, c, generator=g) + 0.2).to(torch.bfloat16)
+    g1 = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16)
+    g2 = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16) if two else None
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    yv = y.float().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    mean = yv.mean((0, 1, 2))
+    var = ((yv - mean) ** 2).mean((0, 1, 2))
+    yhat = (yv - mean) * torch.rsqrt(var + 1e-5) * gm + bt
+    a = F.leaky_relu(yhat, slope) if slope > 0 else F.relu(yhat)
+    loss = (a * g1.float()).sum()
+    if two:
+        loss = loss + (F.relu(a) * g2.float()).sum()
+    dy_ref, dg_ref, db_ref = torch.autograd.grad(loss, [yv, gm, bt])
+    cnt = n * h * h
+    md, vd = mean.detach(), var.detach()
+    invstd = torch.rsqrt(vd + 1e-5)
+    scale = (gamma * invstd).to(DEV)
+    shift = (beta - md * gamma * invstd).to(DEV)
+    sums = torch.zeros(2 * c, device=DEV, dtype=torch.float64)
+    dy = torch.empty(n, h, h, c, device=DEV, dtype=torch.bfloat16)
+    yd, g1d = y.to(DEV), g1.to(DEV)
+    g2d = g2.to(DEV) if two else None
+    ops.bn_bwd_reduce(yd, g1d, g2d, slope, scale, shift, md.to(DEV), invstd.to(DEV), sums)
+    ops.bn_bwd_apply(yd, g1d, g2d, slope, scale, shift, md.to(DEV), invstd.to(DEV), sums, cnt, dy)
+    dgam, dbet = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    ops.bn_param_grads(sums, dgam, dbet)
+    assert rel(dy.cpu().float(), dy_ref) < 6e-3
+    assert rel(dgam.cpu(), dg_ref) < 1e-3 and rel(dbet.cpu(), db_ref) < 1e-3
+    assert float(sums.abs().max()) == 0.0
+    # activation-only mode
+    ops.bn_bwd_apply(yd, g1d, g2d, slope, None, None, None, None, None, 0, dy)
+    yv2 = y.float().requires_grad_(True)
+    a2 = F.leaky_relu(yv2, slope) if slope > 0 else F.relu(yv2)
+    l2 = (a2 * g1.float()).sum() + ((F.relu(a2) * g2.float()).sum() if two else 0)
+    (ref2,) = torch.autograd.grad(l2, yv2)
+    assert rel(dy.cpu().float(), ref2) < 4e-3
+
+
+def test_bce_and_l1_kernels():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 30, 30, 1, generator=g) * 3
+    for t in (0.0, 1.0):
+        acc = torch.zeros(1, device=DEV, dtype=torch.float64)
+        dx = torch.zeros(4, 30, 30, 64, device=DEV, dtype=torch.bfloat16)
+        ops.bce_logits_const(x.to(DEV), t, 0.5 / x.numel(), dx, acc)
+        xv = x.clone().requires_grad_(True)
+        ref = O.bce_with_logits(xv, torch.full_like(xv, t))
+        (gref,) = torch.autograd.grad(0.5 * ref, xv)
+        assert abs(float(acc) / x.numel() - float(ref)) < 1e-5
+        assert rel(dx[..., 0].cpu().float(), gref[..., 0]) < 4e-3
+        assert float(dx[..., 1:].abs().max()) == 0.0
+    # generator output backward: L1 + tanh'
+    n, h = 2, 16
+    fake = torch.tanh(torch.randn(n, h, h, 4, generator=g))
+    real = torch.rand(n, 3, h, h, generator=g) * 2 - 1
+    dfd = torch.randn(n, h, h, 4, generator=g) * 1e-3
+    acc = torch.zeros(1, device=DEV, dtype=torch.float64)
+    dpre = torch.zeros(n, h, h, 4, device=DEV, dtype=torch.bfloat16)
+    lam = 100.0 / (n * 3 * h * h)
+    ops.gen_out_bwd(fake.to(DEV), real.to(DEV), dfd.to(DEV), lam, dpre, acc)
+    f3 = fake[..., :3]
+    r3 = real.permute(0, 2, 3, 1)
+    assert abs(float(acc) - float((f3 - r3).abs().sum())) / float(acc) < 1e-5
+    ref = (dfd[..., :3] + lam * torch.sign(f3 - r3)) * (1 - f3 * f3)
+    assert rel(dpre[..., :3].cpu().float(), ref) < 4e-3
+
+
+def test_adam_kernel_matches_oracle():
+    g = torch.Generator().manual_seed(1)
+    n = 1027                                            # exercises the vector body and the scalar tail
+    p0, m0, v0 = torch.randn(n + 1, generator=g), torch.zeros(n + 1), torch.zeros(n + 1)
+    for decoupled, wd in ((False, 0.0), (True, 0.01)):
+        p, m, v = p0.clone(), m0.clone(), v0.clone()
+        pd, md, vd = (t.clone().to(DEV)[:n] for t in (p0, m0, v0))
+        for step in range(1, 4):
+            grad = torch.randn(n + 1, generator=g)
+            O.adam_update(p, grad / 2, m, v, step, 1e-3, 0.5, 0.999, 1e-8, wd, decoupled)
+            ops.adam_flat(pd, grad.to(DEV)[:n], md, vd, 1e-3, 0.5, 0.999, 1e-8, wd, decoupled, step, grad_scale=0.5)
+        assert torch.allclose(pd.cpu(), p[:n], atol=2e-6)
+        assert torch.allclose(vd.cpu(), v[:n], rtol=1e-4, atol=1e-9)
+
+
+def test_im2col_col2im_roundtrip_against_unfold():
+    g = torch.Generator().manual_seed(2)
+    n, h = 2, 12
+    a = torch.randn(n, 3, h, h, generator=g)
+    b = torch.randn(n, 3, h, h, generator=g)
+    an = torch.zeros(n, h, h, 4, device=DEV, dtype=torch.bfloat16)
+    bn = torch.zeros_like(an)
+    ops.nchw_to_nhwc_bf16(a.to(DEV), an)
+    ops.nchw_to_nhwc_bf16(b.to(DEV), bn)
+    assert torch.equal(an[..., :3].cpu().float(), a.to(torch.bfloat16).float().permute(0, 2, 3, 1))
+    col = torch.empty(n, h // 2, h // 2, 128, device=DEV, dtype=torch.bfloat16)
+    ops.im2col_k4s2p1(an, 3, bn, 3, col)
+    x6 = torch.cat((a, b), 1).to(torch.bfloat16).float()
+    unf = F.unfold(x6, 4, padding=1, stride=2)                          # [n, 6*16, L], index c*16 + tap
+    unf = unf.view(n, 6, 16, h // 2, h // 2).permute(0, 3, 4, 2, 1).reshape(n, h // 2, h // 2, 96)
+    assert torch.equal(col[..., :96].cpu().float(), unf)
+    assert float(col[..., 96:].abs().max()) == 0.0
+    # col2im == fold (transposed-conv overlap-add), channel slice 3..5, + bias + tanh
+    bias = torch.randn(3, generator=g)
+    obf = torch.zeros(n, h, h, 4, device=DEV, dtype=torch.bfloat16)
+    o32 = torch.zeros(n, h, h, 4, device=DEV)
+    ops.col2im_k4s2p1(col, 6, 3, 3, bias.to(DEV), ops.ACT_TANH, obf, o32)
+    cols = col[..., :96].cpu().float().view(n, h // 2, h // 2, 16, 6)[..., 3:6]       # [n,hi,wi,tap,c]
+    cols = cols.permute(0, 4, 3, 1, 2).reshape(n, 3 * 16, -1)
+    ref = torch.tanh(F.fold(cols, (h, h), 4, padding=1, stride=2) + bias.view(1, 3, 1, 1))
+    assert rel(o32[..., :3].cpu(), ref.permute(0, 2, 3, 1)) < 1e-5
+    assert rel(obf[..., :3].cpu().float(), ref.permute(0, 2, 3, 1)) < 4e-3
+    out = torch.empty(n, 3, h, h, device=DEV)
+    ops.nhwc_to_nchw_f32(o32, out, 3)
+    assert rel(out.cpu(), ref) < 1e-5
+
+
+def test_pack_weights_modes():
+    g = torch.Generator().manual_seed(4)
+    co, ci = 96, 64
+    w = torch.randn(co, ci, 4, 4, generator=g)
+    native = w.permute(0, 2, 3, 1).contiguous().view(-1).to(DEV)        # [co][kh][kw][ci]
+    out = torch.empty(1, co, 16 * ci, device=DEV, dtype=torch.bfloat16)
+    ops.pack_weights(native, 0, out, 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
+    assert torch.equal(out.cpu().float().view(co, 4, 4, ci), w.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    ph = torch.empty(4, ci, 4 * co, device=DEV, dtype=torch.bfloat16)
+    ops.pack_weights(native, 0, ph, 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
+    ref = torch.empty(4, ci, 4 * co)
+    for p in range(4):
+        for t in range(4):
+            kh, kw = 3 - (p >> 1) - 2 * (t >> 1), 3 - (p & 1) - 2 * (t & 1)
+            ref[p, :, t * co:(t + 1) * co] = w[:, :, kh, kw].t()
+    assert torch.equal(ph.cpu().float(), ref.to(torch.bfloat16).float())
+    fl = torch.empty(1, ci, 16 * 128, device=DEV, dtype=torch.bfloat16)          # flipped, channel-padded 96 -> 128
+    ops.pack_weights(native, 0, fl, 1, 1, ci, ci, (4, 4), co, 128, 16 * 128, (1, 16 * ci, 4 * ci, ci))
+    got = fl.cpu().float().view(ci, 4, 4, 128)
+    assert torch.equal(got[..., :co], w.flip(2, 3).permute(1, 2, 3, 0).to(torch.bfloat16).float())
+    assert float(got[..., co:].abs().max()) == 0.0
