@@ -70,7 +70,8 @@ _SIGNATURES = {
     "gap_conv_gemm": (C.c_int, [C.POINTER(ConvGemmArgs), C.c_void_p]),
     "gap_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "gap_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _P]),
-    "gap_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _L, _P]),
+    "gap_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _L, _I, _I, _P]),
+    "gap_tanh_bwd": (C.c_int, [_P, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "gap_im2col_k4s2p1": (C.c_int, [_P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _P]),
     "gap_col2im_k4s2p1": (C.c_int, [_P, _L, _I, _I, _I, _P, _I, _P, _L, _P, _L, _I, _I, _I, _P]),
     "gap_gen_out_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _L, _L, _I, _P, _P]),

@@ -45,12 +45,27 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
 
 template <typename T>
 __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restrict__ out, int n, int c,
-                                        long long hw, long long ld) {
+                                        long long hw, long long ld, int c_total, int c_off) {
   const long long total = static_cast<long long>(n) * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long img = i / hw, pix = i - img * hw;
-    for (int ch = 0; ch < c; ++ch) out[(img * c + ch) * hw + pix] = static_cast<float>(x[i * ld + ch]);
+    for (int ch = 0; ch < c; ++ch)
+      out[(img * c_total + c_off + ch) * hw + pix] = static_cast<float>(x[i * ld + ch]);
+  }
+}
+
+// Tanh backward at the model boundary: dpre[nhwc bf16] = gout[nchw f32] * (1 - y[nhwc f32]^2)
+__global__ void tanh_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ y, long long ld_y,
+                                __nv_bfloat16* __restrict__ dpre, long long ld_p, int n, int c, long long hw) {
+  const long long total = static_cast<long long>(n) * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, pix = i - img * hw;
+    for (int ch = 0; ch < c; ++ch) {
+      const float v = y[i * ld_y + ch];
+      dpre[i * ld_p + ch] = __float2bfloat16(gout[(img * c + ch) * hw + pix] * (1.f - v * v));
+    }
   }
 }
 
@@ -569,15 +584,27 @@ int gap_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, int h, in
 }
 
 int gap_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* out, int n, int c, int h, int w, int64_t x_ld,
-                         void* stream) {
-  GAP_CHECK_ARG(x && out && n > 0 && c > 0 && c <= x_ld, "gap_nhwc_to_nchw_f32: bad arguments");
+                         int c_total, int c_off, void* stream) {
+  GAP_CHECK_ARG(x && out && n > 0 && c > 0 && c <= x_ld && c_off >= 0 && c_off + c <= c_total,
+                "gap_nhwc_to_nchw_f32: bad arguments");
   const long long hw = static_cast<long long>(h) * w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_is_f32)
-    nhwc_to_nchw_f32_kernel<float><<<grid_for(n * hw, 256), 256, 0, st>>>(static_cast<const float*>(x), out, n, c, hw, x_ld);
+    nhwc_to_nchw_f32_kernel<float><<<grid_for(n * hw, 256), 256, 0, st>>>(static_cast<const float*>(x), out, n, c, hw,
+                                                                          x_ld, c_total, c_off);
   else
     nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid_for(n * hw, 256), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(x), out, n, c, hw, x_ld);
+        static_cast<const __nv_bfloat16*>(x), out, n, c, hw, x_ld, c_total, c_off);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_tanh_bwd(const float* gout_nchw, const float* y_nhwc, int64_t ld_y, void* dpre, int64_t ld_p, int n, int c,
+                 int h, int w, void* stream) {
+  GAP_CHECK_ARG(gout_nchw && y_nhwc && dpre && n > 0 && c > 0, "gap_tanh_bwd: bad arguments");
+  const long long hw = static_cast<long long>(h) * w;
+  tanh_bwd_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gout_nchw, y_nhwc, ld_y, static_cast<__nv_bfloat16*>(dpre), ld_p, n, c, hw);
   GAP_LAUNCH_CHECK();
   return 0;
 }

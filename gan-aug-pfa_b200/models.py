@@ -1,0 +1,223 @@
+"""Drop-in replacement for the reference's ``models.py`` GAN classes.
+
+Same names, constructor arguments, ``forward`` signatures, parameter/buffer registration order (hence
+the same seeded initial weights) and ``state_dict()`` layout as the reference (models.py:149-247,
+SURVEY.md §8b / App. C), so ``train_gan.py`` and ``generate_synthetic_data.py`` run unchanged with
+``from models import UNetGenerator, NLayerDiscriminator`` pointing here.  The modules hold ordinary
+torch Parameters / buffers; ``forward`` hands them to the native engine (libgap_b200.so through the C
+ABI) and plugs the result into torch autograd with one custom Function per network, so
+``loss.backward()`` and ``torch.optim.Adam`` work as in the reference.
+
+The native kernels exist only for CUDA tensors: calling ``forward`` on CPU tensors raises (there is
+no CPU fallback).  The fastest path is not this module but ``pix2pix.Pix2PixTrainer``, which keeps
+the whole iteration on the device without autograd bookkeeping.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .pix2pix import DiscriminatorEngine, GeneratorEngine
+
+
+# ------------------------------------------------------------------------------------------------
+# module skeletons: identical structure to the reference so that keys and RNG consumption match
+# ------------------------------------------------------------------------------------------------
+class UnetSkipConnectionBlock(nn.Module):
+    """One U-Net level (models.py:167-208).  Kept as a container of the reference's layers; the
+    computation happens in UNetGenerator.forward through the native engine."""
+
+    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
+                 norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super().__init__()
+        self.outermost = outermost
+        if type(norm_layer) == functools.partial:
+            use_bias = norm_layer.func == nn.InstanceNorm2d
+        else:
+            use_bias = norm_layer == nn.InstanceNorm2d
+        if input_nc is None:
+            input_nc = outer_nc
+        downconv = nn.Conv2d(input_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+        downrelu = nn.LeakyReLU(0.2, True)
+        downnorm = norm_layer(inner_nc)
+        uprelu = nn.ReLU(True)
+        upnorm = norm_layer(outer_nc)
+        if outermost:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            layers = [downconv, submodule, uprelu, upconv, nn.Tanh()]
+        elif innermost:
+            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            layers = [downrelu, downconv, uprelu, upconv, upnorm]
+        else:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            layers = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
+            if use_dropout:
+                layers.append(nn.Dropout(0.5))
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, x):  # pragma: no cover - the enclosing generator owns the computation
+        raise RuntimeError("UnetSkipConnectionBlock is executed by UNetGenerator.forward (native engine)")
+
+
+class _NativeModule(nn.Module):
+    """Shared engine management: lazily builds the native engine on the parameters' CUDA device,
+    aliases the BatchNorm buffers, and refreshes the engine's master weights when a Parameter changed."""
+
+    _engine_obj = None
+    _engine_key = None
+    _versions = None
+
+    def _make_engine(self, device):
+        raise NotImplementedError
+
+    def _engine(self):
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise RuntimeError(f"{type(self).__name__}: the native kernels need CUDA tensors; there is no CPU "
+                               "fallback (move the module with .to('cuda'))")
+        key = (p.device, tuple(id(b) for b in self.buffers()))
+        if self._engine_obj is None or self._engine_key != key:
+            eng = self._make_engine(p.device)
+            sd = dict(self.named_buffers())
+            for prefix, bn in eng.bns.items():          # alias: running stats are updated in place
+                bn.running_mean = sd[prefix + ".running_mean"]
+                bn.running_var = sd[prefix + ".running_var"]
+                bn.nbt = sd[prefix + ".num_batches_tracked"]
+            object.__setattr__(self, "_engine_obj", eng)
+            object.__setattr__(self, "_engine_key", key)
+            object.__setattr__(self, "_versions", None)
+        eng = self._engine_obj
+        versions = tuple(q._version for q in self.parameters())
+        if versions != self._versions:
+            with torch.no_grad():
+                for name, q in self.named_parameters():
+                    eng.param(name).copy_(q)
+            eng.repack()
+            object.__setattr__(self, "_versions", versions)
+        eng.training = self.training
+        return eng
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module._engine()
+        if x.requires_grad:
+            raise NotImplementedError("gradient w.r.t. the generator input is not provided (the reference never needs it)")
+        eng.forward(x.detach().contiguous().float())
+        out = eng.output_nchw()
+        ctx.module = module
+        ctx.snap = eng.detach_buffers() if any(p.requires_grad for p in params) else None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        module = ctx.module
+        eng = module._engine_obj
+        eng.attach_buffers(ctx.snap)
+        eng.zero_grad()
+        ops.tanh_bwd(gout.contiguous().float(), eng.fake_f32, eng.dpre)
+        eng.backward()
+        grads = [eng.grad(name).clone() for name, _ in module.named_parameters()]
+        return (None, None, *grads)
+
+
+class UNetGenerator(_NativeModule):
+    """U-Net generator (models.py:149-164) executing on the native sm_100a kernels."""
+
+    def __init__(self, input_nc, output_nc, num_downs=7, ngf=64, norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super().__init__()
+        if norm_layer is not nn.BatchNorm2d:
+            raise NotImplementedError("only norm_layer=nn.BatchNorm2d (the reference default) is implemented natively")
+        if use_dropout:
+            raise NotImplementedError("use_dropout=True is not implemented natively (the reference never enables it)")
+        self._cfg = (input_nc, output_nc, num_downs, ngf)
+        blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=None, norm_layer=norm_layer,
+                                      innermost=True)
+        for _ in range(num_downs - 5):
+            blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=blk, norm_layer=norm_layer,
+                                          use_dropout=use_dropout)
+        blk = UnetSkipConnectionBlock(ngf * 4, ngf * 8, input_nc=None, submodule=blk, norm_layer=norm_layer)
+        blk = UnetSkipConnectionBlock(ngf * 2, ngf * 4, input_nc=None, submodule=blk, norm_layer=norm_layer)
+        blk = UnetSkipConnectionBlock(ngf, ngf * 2, input_nc=None, submodule=blk, norm_layer=norm_layer)
+        self.model = UnetSkipConnectionBlock(output_nc, ngf, input_nc=input_nc, submodule=blk, outermost=True,
+                                             norm_layer=norm_layer)
+
+    def _make_engine(self, device):
+        i, o, n, f = self._cfg
+        return GeneratorEngine(device, i, o, n, f, init=False)
+
+    def forward(self, input):
+        return _GeneratorFn.apply(self, input, *self.parameters())
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module._engine()
+        n, c, h, w = x.shape
+        xd = x.detach().contiguous().float()
+        xa = torch.zeros(n, h, w, 4, device=x.device, dtype=torch.bfloat16)
+        xb = torch.zeros_like(xa)
+        ops.nchw_to_nhwc_bf16(xd[:, :3].contiguous(), xa)
+        ops.nchw_to_nhwc_bf16(xd[:, 3:].contiguous(), xb)
+        logits = eng.forward(xa, xb)
+        out = logits.permute(0, 3, 1, 2).clone()
+        ctx.module = module
+        ctx.shape = (n, h, w)
+        need = x.requires_grad or any(p.requires_grad for p in params)
+        ctx.snap = eng.detach_buffers() if need else None
+        ctx.x_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        module = ctx.module
+        eng = module._engine_obj
+        eng.attach_buffers(ctx.snap)
+        eng.zero_grad()
+        n, h, w = ctx.shape
+        ops.nchw_to_nhwc_bf16(gout.contiguous().float(), eng.dlogits)
+        wgrad = any(p.requires_grad for p in module.parameters())
+        eng.backward(wgrad=wgrad, input_grad=ctx.x_grad, input_grad_a=ctx.x_grad)
+        gx = None
+        if ctx.x_grad:
+            gx = torch.empty(n, 6, h, w, device=gout.device)
+            ops.nhwc_to_nchw_f32(eng.dreal, gx, 3, 6, 0)
+            ops.nhwc_to_nchw_f32(eng.dfake, gx, 3, 6, 3)
+        grads = [eng.grad(name).clone() if wgrad else None for name, _ in module.named_parameters()]
+        return (None, gx, *grads)
+
+
+class NLayerDiscriminator(_NativeModule):
+    """PatchGAN discriminator (models.py:212-247) executing on the native sm_100a kernels."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        if norm_layer is not nn.BatchNorm2d:
+            raise NotImplementedError("only norm_layer=nn.BatchNorm2d (the reference default) is implemented natively")
+        self._cfg = (input_nc, ndf, n_layers)
+        use_bias = False
+        kw, padw = 4, 1
+        sequence = [nn.Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), nn.LeakyReLU(0.2, True)]
+        nf_mult = 1
+        for n in range(1, n_layers):
+            nf_prev, nf_mult = nf_mult, min(2 ** n, 8)
+            sequence += [nn.Conv2d(ndf * nf_prev, ndf * nf_mult, kernel_size=kw, stride=2, padding=padw, bias=use_bias),
+                         norm_layer(ndf * nf_mult), nn.LeakyReLU(0.2, True)]
+        nf_prev, nf_mult = nf_mult, min(2 ** n_layers, 8)
+        sequence += [nn.Conv2d(ndf * nf_prev, ndf * nf_mult, kernel_size=kw, stride=1, padding=padw, bias=use_bias),
+                     norm_layer(ndf * nf_mult), nn.LeakyReLU(0.2, True)]
+        sequence += [nn.Conv2d(ndf * nf_mult, 1, kernel_size=kw, stride=1, padding=padw)]
+        self.model = nn.Sequential(*sequence)
+
+    def _make_engine(self, device):
+        i, d, n = self._cfg
+        return DiscriminatorEngine(device, i, d, n, init=False)
+
+    def forward(self, input):
+        return _DiscriminatorFn.apply(self, input, *self.parameters())

@@ -202,10 +202,17 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
                "gap_nchw_f32_to_nhwc_bf16")
 
 
-def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor, c: int) -> None:
+def nhwc_to_nchw_f32(x: torch.Tensor, out: torch.Tensor, c: int, c_total: Optional[int] = None, c_off: int = 0) -> None:
     n, h, w, _ = x.shape
     _lib.check(_lib.lib().gap_nhwc_to_nchw_f32(_ptr(x), 1 if x.dtype == torch.float32 else 0, _ptr(out), n, c, h, w,
-                                               x.stride(2), _stream()), "gap_nhwc_to_nchw_f32")
+                                               x.stride(2), c if c_total is None else c_total, c_off, _stream()),
+               "gap_nhwc_to_nchw_f32")
+
+
+def tanh_bwd(gout_nchw: torch.Tensor, y_nhwc_f32: torch.Tensor, dpre: torch.Tensor) -> None:
+    n, c, h, w = gout_nchw.shape
+    _lib.check(_lib.lib().gap_tanh_bwd(_ptr(gout_nchw), _ptr(y_nhwc_f32), y_nhwc_f32.stride(2), _ptr(dpre),
+                                       dpre.stride(2), n, c, h, w, _stream()), "gap_tanh_bwd")
 
 
 def im2col_k4s2p1(s0: torch.Tensor, c0: int, s1: Optional[torch.Tensor], c1: int, col: torch.Tensor) -> None:

@@ -182,6 +182,28 @@ class _Net:
     def zero_grad(self) -> None:
         self.store.g.zero_()
 
+    # -- in-flight activation sets (autograd path: several forwards may precede one backward) --------
+    _BUFFER_ATTRS: Tuple[str, ...] = ()
+
+    def detach_buffers(self) -> dict:
+        """Hand the current activation set (and the BatchNorm statistics saved for backward) to the
+        caller; the next forward allocates a fresh set."""
+        snap = {a: getattr(self, a) for a in self._BUFFER_ATTRS if hasattr(self, a)}
+        snap["_bn"] = {k: (b.scale.clone(), b.shift.clone(), b.mean.clone(), b.invstd.clone())
+                       for k, b in self.bns.items()}
+        snap["_n"] = self._n
+        self._n = None
+        return snap
+
+    def attach_buffers(self, snap: dict) -> None:
+        for a, v in snap.items():
+            if a == "_bn":
+                for k, (sc, sh, mu, iv) in v.items():
+                    b = self.bns[k]
+                    b.scale, b.shift, b.mean, b.invstd = sc, sh, mu, iv
+            else:
+                setattr(self, a, v)
+
     def adam_step(self, lr: float, betas=(0.5, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                   decoupled: bool = False, grad_scale: float = 1.0) -> None:
         s = self.store
@@ -217,7 +239,11 @@ class _Net:
 class GeneratorEngine(_Net):
     """UNetGenerator(input_nc=3, output_nc=3, num_downs, ngf, BatchNorm2d, use_dropout=False)."""
 
-    def __init__(self, device, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64) -> None:
+    _BUFFER_ATTRS = ("S", "x_nhwc", "col0", "A", "R", "Rin", "yd", "yu", "ycol", "fake_bf", "fake_f32", "dpre",
+                     "dycol", "gR", "gRin", "gA", "dyu", "dyd")
+
+    def __init__(self, device, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64,
+                 init: bool = True) -> None:
         super().__init__(device)
         if input_nc != 3 or output_nc != 3:
             raise NotImplementedError("the native generator supports input_nc = output_nc = 3")
@@ -256,7 +282,8 @@ class GeneratorEngine(_Net):
             self.w_u_fwd.append(torch.empty(4, C[j - 1], 4 * cin, **bf))
             self.w_u_dg.append(torch.empty(1, cin, 16 * C[j - 1], **bf))
         self._n = None
-        self.init_from_torch_default()
+        if init:
+            self.init_from_torch_default()
 
     def init_from_torch_default(self) -> None:
         """Default torch init drawn from the global CPU RNG in the reference's construction order
@@ -396,7 +423,9 @@ class GeneratorEngine(_Net):
 class DiscriminatorEngine(_Net):
     """NLayerDiscriminator(input_nc=6, ndf, n_layers, BatchNorm2d)."""
 
-    def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3) -> None:
+    _BUFFER_ATTRS = ("hs", "ws", "col", "H", "y", "logits", "dlogits", "gH", "dy", "dcol", "dfake")
+
+    def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3, init: bool = True) -> None:
         super().__init__(device)
         if input_nc != 6:
             raise NotImplementedError("the native discriminator supports input_nc = 6 (cat of two RGB images)")
@@ -429,7 +458,8 @@ class DiscriminatorEngine(_Net):
                 self.w_dg.append(torch.empty(1, C[k - 1], 16 * C[k], **bf))    # stride 1: flipped taps
         self.w_dg.append(torch.empty(1, C[-1], 16 * 64, **bf))                 # Cout = 1 padded to 64 channels
         self._n = None
-        self.init_from_torch_default()
+        if init:
+            self.init_from_torch_default()
 
     def stride(self, k: int) -> int:
         return 2 if k < self.nl else 1
@@ -498,7 +528,7 @@ class DiscriminatorEngine(_Net):
                       (self.hs[k], self.ws[k]), bias=self.param(self.k_conv[k] + ".bias"))
         return self.logits
 
-    def backward(self, wgrad: bool, input_grad: bool) -> Optional[torch.Tensor]:
+    def backward(self, wgrad: bool, input_grad: bool, input_grad_a: bool = False) -> Optional[torch.Tensor]:
         """Consumes self.dlogits (bf16, channel 0 of a 64-channel-padded map).  wgrad=False skips
         every parameter gradient (the G step); input_grad=True returns d(loss)/d(xb) as fp32 NHWC."""
         C = self.C
@@ -528,6 +558,9 @@ class DiscriminatorEngine(_Net):
             ops.conv_gemm([self.dy[0]], self.w_dg[0], ops.geom_conv_fwd(1, 1, 0), self.dcol, 128,
                           (self.hs[0], self.ws[0]))
             ops.col2im_k4s2p1(self.dcol, 6, 3, 3, None, ACT_NONE, None, self.dfake)
+            if input_grad_a:
+                self.dreal = torch.zeros_like(self.dfake)
+                ops.col2im_k4s2p1(self.dcol, 6, 0, 3, None, ACT_NONE, None, self.dreal)
             return self.dfake
         return None
 

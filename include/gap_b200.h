@@ -132,8 +132,12 @@ int gap_conv_wgrad(const gap_wgrad_args* args, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int gap_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, int h, int w, int64_t out_ld,
                               void* stream);
+/* writes channels [c_off, c_off+c) of an NCHW fp32 tensor that has c_total channels */
 int gap_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* out, int n, int c, int h, int w, int64_t x_ld,
-                         void* stream);
+                         int c_total, int c_off, void* stream);
+/* Tanh backward at the model boundary (models.py:186): dpre = gout * (1 - y^2), NCHW fp32 -> NHWC bf16 */
+int gap_tanh_bwd(const float* gout_nchw, const float* y_nhwc, int64_t ld_y, void* dpre, int64_t ld_p, int n, int c,
+                 int h, int w, void* stream);
 
 /* First-layer im2col for Conv2d(k4,s2,p1) with 3 or 6 input channels (models.py:177 outermost,
  * models.py:223; the 6-channel input is torch.cat((real_A, B), 1), train_gan.py:57,59,66):
