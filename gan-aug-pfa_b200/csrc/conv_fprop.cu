@@ -54,6 +54,10 @@ struct alignas(64) FpropParams {
   uint32_t idesc;
   int total_tiles;
   int k_iters;
+  int mt;          // M tiles (128 rows each) per CTA work item: they share every B tile fetched from L2
+  int sm_tiles;    // work items along M per phase = ceil(m_tiles_pp / mt)
+  int m_tiles_pp;  // M tiles per phase
+  int acc_stages;  // TMEM accumulator buffers (2 when mt*block_n <= 256, else 1)
   int vec_ok;  // 1: outputs 16-byte aligned per pixel (128-bit stores); 2: 32-byte aligned (256-bit)
   int out_f32;  // `out` is fp32 (scalar stores; used for the 1-channel logits)
   int fast_store;  // slope-type activations and 32-byte-aligned bf16 outputs: vector epilogue
@@ -75,23 +79,32 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-struct TileCoord {
-  int n_tile, tw, th, tn, ph, pw, phase;
+struct WorkCoord {
+  int n_tile, sm, ph, pw, phase;
+};
+struct MTile {
+  int tw, th, tn;
+  bool exists;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const FpropParams& p, int t) {
-  TileCoord c;
+__device__ __forceinline__ WorkCoord decode_work(const FpropParams& p, int t) {
+  WorkCoord c;
   c.n_tile = t % p.n_tiles;
   t /= p.n_tiles;
-  c.tw = t % p.tiles_w;
-  t /= p.tiles_w;
-  c.th = t % p.tiles_h;
-  t /= p.tiles_h;
-  c.tn = t % p.tiles_n;
-  c.phase = t / p.tiles_n;
+  c.sm = t % p.sm_tiles;
+  c.phase = t / p.sm_tiles;
   c.ph = c.phase >> 1;
   c.pw = c.phase & 1;
   return c;
+}
+__device__ __forceinline__ MTile decode_mtile(const FpropParams& p, int mi) {
+  MTile m;
+  m.exists = mi < p.m_tiles_pp;
+  m.tw = mi % p.tiles_w;
+  mi /= p.tiles_w;
+  m.th = mi % p.tiles_h;
+  m.tn = mi / p.tiles_h;
+  return m;
 }
 
 // Sum the 16 per-row values of v across the 32 lanes of the warp.  On return lane l holds in its
@@ -154,7 +167,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int stage_bytes = kATileBytes + p.block_n * 128;
+  const int a_bytes = p.mt * kATileBytes;
+  const int stage_bytes = a_bytes + p.block_n * 128;
   const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
   // barrier slots (8 bytes each): full[0..7], empty[8..15], tfull[16..17], tempty[18..19]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -200,12 +214,19 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int x_base = tc.tw * BW * p.in_stride + p.in_off_w[tc.pw];
-        const int y_base = tc.th * BH * p.in_stride + p.in_off_h[tc.ph];
-        const int n_base = tc.tn * BNI;
+        const WorkCoord wc = decode_work(p, tile);
+        int x_base[2], y_base[2], n_base[2];
+        bool exists[2] = {false, false};
+        uint32_t tx_bytes = static_cast<uint32_t>(p.block_n * 128);
+        for (int j = 0; j < p.mt; ++j) {
+          const MTile m = decode_mtile(p, wc.sm * p.mt + j);
+          exists[j] = m.exists;
+          x_base[j] = m.tw * BW * p.in_stride + p.in_off_w[wc.pw];
+          y_base[j] = m.th * BH * p.in_stride + p.in_off_h[wc.ph];
+          n_base[j] = m.tn * BNI;
+          if (m.exists) tx_bytes += kATileBytes;
+        }
         int kcol = 0;
         for (int tap = 0; tap < n_taps; ++tap) {
           const int t_h = tap / p.taps_w, t_w = tap - t_h * p.taps_w;
@@ -214,10 +235,11 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               mbar_expect_tx(full_bar(stage), tx_bytes);
               const uint32_t a_dst = smem_base + stage * stage_bytes;
-              tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x_base + t_w,
-                          y_base + t_h, n_base);
-              tma_load_3d(a_dst + kATileBytes, &p.tmB, full_bar(stage), kcol,
-                          tc.n_tile * p.block_n, tc.phase);
+              for (int j = 0; j < p.mt; ++j)
+                if (exists[j])
+                  tma_load_4d(a_dst + j * kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x_base[j] + t_w,
+                              y_base[j] + t_h, n_base[j]);
+              tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kcol, wc.n_tile * p.block_n, wc.phase);
               kcol += kBlockK;
               if (++stage == p.num_stages) {
                 stage = 0;
@@ -236,6 +258,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const WorkCoord wc = decode_work(p, tile);
+        const int mt_eff = min(p.mt, p.m_tiles_pp - wc.sm * p.mt);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -243,12 +267,14 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint32_t b_addr = a_addr + kATileBytes;
+          const uint32_t b_addr = a_addr + a_bytes;
+          for (int j = 0; j < mt_eff; ++j) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (k_iter | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t adesc = make_sw128_desc(a_addr + j * kATileBytes + k * 32, 16, 1024);
+              const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == p.num_stages) {
@@ -257,8 +283,10 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           }
         }
         umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
   } else {
@@ -286,78 +314,83 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     };
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      if (do_stats && tc.n_tile != cur_ntile) {
+      const WorkCoord wc = decode_work(p, tile);
+      if (do_stats && wc.n_tile != cur_ntile) {
         if (cur_ntile >= 0) flush_stats(cur_ntile);
         for (int c = lane; c < 512; c += 32) my_stats[c] = 0.0;
         __syncwarp();
-        cur_ntile = tc.n_tile;
+        cur_ntile = wc.n_tile;
       }
-      const int wi = row & (BW - 1);
-      const int hi = (row >> p.log_bw) & (BH - 1);
-      const int ni = row >> (p.log_bw + p.log_bh);
-      const int gx = tc.tw * BW + wi, gy = tc.th * BH + hi, n = tc.tn * BNI + ni;
-      const bool valid = (gx < p.gw) && (gy < p.gh) && (n < p.n_img);
-      const long long pix =
-          (static_cast<long long>(n) * p.OH + (gy * p.out_stride + tc.ph)) * p.OW +
-          (gx * p.out_stride + tc.pw);
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       const int n_chunks = p.block_n >> 4;
-      const bool fast = valid && p.fast_store;
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t raw[16];
-        tmem_ld16(t_row + c * 16, raw);
-        tmem_ld_wait();
-        const int col0 = tc.n_tile * p.block_n + c * 16;
-        float f[16];
+      for (int j = 0; j < p.mt; ++j) {
+        const MTile mtile = decode_mtile(p, wc.sm * p.mt + j);
+        const int wi = row & (BW - 1);
+        const int hi = (row >> p.log_bw) & (BH - 1);
+        const int ni = row >> (p.log_bw + p.log_bh);
+        const int gx = mtile.tw * BW + wi, gy = mtile.th * BH + hi, n = mtile.tn * BNI + ni;
+        const bool valid = mtile.exists && (gx < p.gw) && (gy < p.gh) && (n < p.n_img);
+        const long long pix =
+            (static_cast<long long>(n) * p.OH + (gy * p.out_stride + wc.ph)) * p.OW + (gx * p.out_stride + wc.pw);
+        const uint32_t t_row =
+            tmem_base + acc * kAccStride + j * p.block_n + (static_cast<uint32_t>(q * 32) << 16);
+        if (!mtile.exists) continue;
+        const bool fast = valid && p.fast_store;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t raw[16];
+          tmem_ld16(t_row + c * 16, raw);
+          tmem_ld_wait();
+          const int col0 = wc.n_tile * p.block_n + c * 16;
+          float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(raw[j]);
-        if (p.bias != nullptr) {
+          for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(raw[jj]);
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + min(col0 + j, p.n_out - 1));
-        }
-        if (do_stats) {
-          float m[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = valid ? f[j] : 0.f;
-          const float s = transpose_reduce16(m, lane);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = m[j] * m[j];
-          const float s2 = transpose_reduce16(m, lane);
-          if ((lane & 1) == 0) {
-            my_stats[c * 16 + stat_col] += static_cast<double>(s);
-            my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
+            for (int jj = 0; jj < 16; ++jj) f[jj] += __ldg(p.bias + min(col0 + jj, p.n_out - 1));
           }
-        }
-        if (fast && col0 + 16 <= p.n_out) {
-          // common case: slope-type activation (identity / LeakyReLU / ReLU), 256-bit stores
-          uint32_t pk[8];
+          if (do_stats) {
+            float m[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float a0 = f[2 * j], a1 = f[2 * j + 1];
-            pk[j] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope1), a1 * (a1 > 0.f ? 1.f : p.slope1));
-          }
-          st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
-          if (p.out2 != nullptr) {
+            for (int jj = 0; jj < 16; ++jj) m[jj] = valid ? f[jj] : 0.f;
+            const float s = transpose_reduce16(m, lane);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a0 = f[2 * j], a1 = f[2 * j + 1];
-              pk[j] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope2), a1 * (a1 > 0.f ? 1.f : p.slope2));
+            for (int jj = 0; jj < 16; ++jj) m[jj] = m[jj] * m[jj];
+            const float s2 = transpose_reduce16(m, lane);
+            if ((lane & 1) == 0) {
+              my_stats[c * 16 + stat_col] += static_cast<double>(s);
+              my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
             }
-            st_global_32B(p.out2 + pix * p.out2_ld + col0, pk, true);
           }
-        } else if (valid && col0 < p.n_out) {
-          epilogue_store_generic(p, f, pix, col0);
+          if (fast && col0 + 16 <= p.n_out) {
+            // common case: slope-type activation (identity / LeakyReLU / ReLU), 256-bit stores
+            uint32_t pk[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float a0 = f[2 * jj], a1 = f[2 * jj + 1];
+              pk[jj] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope1), a1 * (a1 > 0.f ? 1.f : p.slope1));
+            }
+            st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
+            if (p.out2 != nullptr) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float a0 = f[2 * jj], a1 = f[2 * jj + 1];
+                pk[jj] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope2), a1 * (a1 > 0.f ? 1.f : p.slope2));
+              }
+              st_global_32B(p.out2 + pix * p.out2_ld + col0, pk, true);
+            }
+          } else if (valid && col0 < p.n_out) {
+            epilogue_store_generic(p, f, pix, col0);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
     if (do_stats && cur_ntile >= 0) flush_stats(cur_ntile);
   }
@@ -423,7 +456,8 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.tiles_w = (a->gw + BW - 1) / BW;
   p.tiles_h = (a->gh + BH - 1) / BH;
   p.tiles_n = (a->n + BNI - 1) / BNI;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n * a->n_phase;
+  const int m_tiles_pp = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_tiles = m_tiles_pp * a->n_phase;
   // ---- N tile
   const int n_pad = (a->n_out + 15) / 16 * 16;
   int n_tiles = (n_pad + 255) / 256;
@@ -439,9 +473,18 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
       n_tiles = (n_pad + block_n - 1) / block_n;
     }
   }
+  // Two M tiles per work item share each B tile (halves the weight traffic from L2) when there is
+  // still at least ~2 waves of work items left.
+  int mt = (m_tiles_pp >= 2 && (m_tiles / 2) * n_tiles >= 2 * sms) ? 2 : 1;
+  const int force_mt = debug_get("fprop_mt", 0);
+  if (force_mt > 0) mt = std::min(force_mt, 2);
+  p.mt = mt;
+  p.m_tiles_pp = m_tiles_pp;
+  p.sm_tiles = (m_tiles_pp + mt - 1) / mt;
+  p.acc_stages = (mt * block_n <= kAccStride) ? 2 : 1;
   p.block_n = block_n;
   p.n_tiles = n_tiles;
-  p.total_tiles = m_tiles * n_tiles;
+  p.total_tiles = p.sm_tiles * a->n_phase * n_tiles;
   const int ctot = a->src_c[0] + a->src_c[1];
   p.src_chunks[0] = a->src_c[0] / 64;
   p.src_chunks[1] = a->src_c[1] / 64;
@@ -481,7 +524,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.fast_store = (vec32 && !a->out_f32 && a->act <= GAP_ACT_RELU && a->act2 <= GAP_ACT_RELU) ? 1 : 0;
   GAP_CHECK_ARG(!(a->out_f32 && a->out2), "gap_conv_gemm: out2 is not supported with fp32 output");
 
-  const int stage_bytes = kATileBytes + block_n * 128;
+  const int stage_bytes = mt * kATileBytes + block_n * 128;
   int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);

@@ -110,33 +110,42 @@ def bench(n, cin, cout, h, k, s, p, iters=20):
     print(f"bench conv n{n} {cin}->{cout} h{h} k{k}s{s}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
-if __name__ == "__main__":
-    t0 = time.time()
+def run_all():
     allok = True
-    # 1x1 conv == plain GEMM: isolates descriptor / TMEM conventions from the gather geometry
     allok &= test_conv(2, 64, 64, 8, 1, 1, 0, tag="[1x1]")
     allok &= test_conv(2, 128, 128, 16, 1, 1, 0, tag="[1x1]")
     allok &= test_conv(4, 256, 512, 16, 1, 1, 0, tag="[1x1]")
-    # stride-1 3x3 (zero padding through TMA OOB fill)
     allok &= test_conv(2, 64, 64, 16, 3, 1, 1)
-    # stride-2 4x4 (traversal stride)
     allok &= test_conv(2, 64, 128, 32, 4, 2, 1)
     allok &= test_conv(4, 128, 256, 16, 4, 2, 1, stats=True)
     allok &= test_conv(8, 512, 512, 4, 4, 2, 1)
-    allok &= test_conv(3, 64, 128, 256, 4, 2, 1, act=ops.ACT_LRELU)
-    # PatchGAN tail: k4 s1 p1 on 32 -> 31 -> 30, Cout 512 / 1, bias
+    allok &= test_conv(3, 64, 128, 256, 4, 2, 1, act=ops.ACT_LRELU, stats=True)
     allok &= test_conv(2, 256, 512, 32, 4, 1, 1, stats=True)
     allok &= test_conv(2, 512, 1, 31, 4, 1, 1, bias=True)
-    # concat of two sources
+    allok &= test_conv(3, 64, 64, 31, 4, 1, 1, bias=True, stats=True)
     allok &= test_conv(2, 128, 64, 16, 4, 2, 1, split=64)
-    # transposed conv via 4 phases
     allok &= test_convT(2, 64, 64, 4)
     allok &= test_convT(2, 128, 64, 16, split=64)
     allok &= test_convT(4, 1024, 512, 8, split=512)
+    allok &= test_convT(3, 256, 64, 32)
+    return allok
+
+
+if __name__ == "__main__":
+    from gan_aug_pfa_b200 import _lib
+    t0 = time.time()
+    allok = True
+    for mt in (1, 2):
+        print("=== forced mt", mt)
+        _lib.debug_set("fprop_mt", mt)
+        allok &= run_all()
     print("ALL OK" if allok else "SOME FAILED", f"({time.time()-t0:.1f}s)", flush=True)
     if allok:
-        bench(64, 64, 128, 128, 4, 2, 1)
-        bench(64, 128, 256, 64, 4, 2, 1)
-        bench(64, 256, 512, 32, 4, 2, 1)
-        bench(64, 256, 512, 32, 4, 1, 1)
-        bench(64, 512, 512, 16, 4, 2, 1)
+        for mt in (1, 2):
+            print("=== bench mt", mt)
+            _lib.debug_set("fprop_mt", mt)
+            bench(64, 64, 128, 128, 4, 2, 1)
+            bench(64, 128, 256, 64, 4, 2, 1)
+            bench(64, 256, 512, 32, 4, 2, 1)
+            bench(64, 256, 512, 32, 4, 1, 1)
+            bench(64, 512, 512, 16, 4, 2, 1)
