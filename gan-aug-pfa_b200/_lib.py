@@ -57,6 +57,18 @@ class WgradArgs(C.Structure):
     ]
 
 
+class PackEntry(C.Structure):
+    """Mirror of ``gap_pack_entry``."""
+
+    _fields_ = [
+        ("w", C.c_void_p), ("out", C.c_void_p),
+        ("mode", C.c_int), ("n_phase", C.c_int), ("rows", C.c_int), ("rows_pad", C.c_int),
+        ("taps_h", C.c_int), ("taps_w", C.c_int), ("c", C.c_int), ("c_pad", C.c_int), ("krow", C.c_int),
+        ("tile_begin", C.c_int), ("tiles_r", C.c_int), ("tiles_c", C.c_int),
+        ("s_r", C.c_int64), ("s_c", C.c_int64), ("s_kh", C.c_int64), ("s_kw", C.c_int64),
+    ]
+
+
 _lib = None
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
@@ -85,6 +97,7 @@ _SIGNATURES = {
     "gap_colsum_bf16": (C.c_int, [_P, _L, _L, _I, _P, _P]),
     "gap_adam_flat": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _F, _P]),
     "gap_pack_weights": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P]),
+    "gap_pack_weights_multi": (C.c_int, [_P, _I, _I, _P]),
 }
 
 

@@ -562,6 +562,70 @@ __global__ void pack_weights_kernel(const PackArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-tensor weight packing: every fp32 master -> bf16 GEMM operand of a network in ONE launch.
+// One CTA = one 32 x 32 (row, channel) tile of one (phase, tap) slice of one table entry; reads run
+// along whichever of (row, channel) is contiguous in the master, writes along the channel (K) axis
+// of the operand, through a padded shared-memory tile when the two differ.  Padding elements of the
+// operand are never written: the caller zero-fills the operand buffers once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const gap_pack_entry* __restrict__ table,
+                                                                 int n_entries) {
+  __shared__ float tile[32][33];
+  __shared__ int s_entry;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int e = 0;
+    while (e + 1 < n_entries && table[e + 1].tile_begin <= static_cast<int>(blockIdx.x)) ++e;
+    s_entry = e;
+  }
+  __syncthreads();
+  const gap_pack_entry a = table[s_entry];
+  int t = blockIdx.x - a.tile_begin;
+  const int tc = t % a.tiles_c;
+  t /= a.tiles_c;
+  const int tr = t % a.tiles_r;
+  t /= a.tiles_r;
+  const int n_taps = a.taps_h * a.taps_w;
+  const int tap = t % n_taps;
+  const int ph = t / n_taps;
+  const int th = tap / a.taps_w, tw = tap - th * a.taps_w;
+  int kh = th, kw = tw;
+  if (a.mode == 1) {
+    kh = a.taps_h - 1 - th;
+    kw = a.taps_w - 1 - tw;
+  } else if (a.mode == 2) {
+    kh = 3 - (ph >> 1) - 2 * th;
+    kw = 3 - (ph & 1) - 2 * tw;
+  }
+  const float* __restrict__ w = a.w + kh * a.s_kh + kw * a.s_kw;
+  __nv_bfloat16* __restrict__ out = static_cast<__nv_bfloat16*>(a.out) +
+                                    static_cast<long long>(ph) * a.rows_pad * a.krow + tap * a.c_pad;
+  const int r0 = tr * 32, c0 = tc * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (a.s_r == 1 && a.s_c != 1) {
+    // master is contiguous along rows: transpose through shared memory
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, r = r0 + tx;
+      tile[ty + 8 * i][tx] = (r < a.rows && c < a.c) ? w[r + c * a.s_c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      if (r < a.rows && c < a.c) out[static_cast<long long>(r) * a.krow + c] = __float2bfloat16(tile[tx][ty + 8 * i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      if (r < a.rows && c < a.c)
+        out[static_cast<long long>(r) * a.krow + c] = __float2bfloat16(w[r * a.s_r + c * a.s_c]);
+    }
+  }
+}
+
 }  // namespace gap
 
 using namespace gap;
@@ -793,6 +857,13 @@ int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows,
              s_r, s_c, s_kh, s_kw, kdim};
   const long long total = static_cast<long long>(n_phase) * rows_pad * krow;
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_pack_weights_multi(const gap_pack_entry* table_dev, int n_entries, int total_tiles, void* stream) {
+  GAP_CHECK_ARG(table_dev != nullptr && n_entries > 0 && total_tiles > 0, "gap_pack_weights_multi: empty table");
+  pack_weights_multi_kernel<<<total_tiles, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries);
   GAP_LAUNCH_CHECK();
   return 0;
 }

@@ -218,6 +218,11 @@ __device__ __forceinline__ void st_global_32B(void* dst, const uint32_t (&v)[8],
   }
 }
 
+// fp32 vector reduction into global memory (no return value): 4 consecutive floats, 16-byte aligned.
+__device__ __forceinline__ void red_add_v4_f32(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

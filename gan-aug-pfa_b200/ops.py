@@ -309,3 +309,46 @@ def pack_weights(w: torch.Tensor, w_off: int, out: torch.Tensor, mode: int, n_ph
     _lib.check(_lib.lib().gap_pack_weights(src, _ptr(out), mode, n_phase, rows, rows_pad, taps[0], taps[1], c, c_pad,
                                            krow, strides[0], strides[1], strides[2], strides[3], kdim, _stream()),
                "gap_pack_weights")
+
+
+class PackPlan:
+    """All fp32-master -> bf16-operand repacks of one network as ONE launch (gap_pack_weights_multi).
+
+    ``add`` takes the arguments of :func:`pack_weights`; ``run`` launches.  Padding elements of the
+    operands are never written, so the operand buffers must be zero-initialised by the owner."""
+
+    def __init__(self) -> None:
+        self.entries: list[_lib.PackEntry] = []
+        self.total_tiles = 0
+        self._table = None
+        self._keep = []
+
+    def add(self, w: torch.Tensor, w_off: int, out: torch.Tensor, mode: int, n_phase: int, rows: int, rows_pad: int,
+            taps: tuple[int, int], c: int, c_pad: int, krow: int, strides: tuple[int, int, int, int]) -> None:
+        if mode not in (0, 1, 2):
+            raise ValueError("PackPlan supports modes 0-2")
+        if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.numel() != n_phase * rows_pad * krow:
+            raise ValueError("operand buffer does not match n_phase*rows_pad*krow")
+        e = _lib.PackEntry()
+        e.w = w.data_ptr() + 4 * w_off
+        e.out = out.data_ptr()
+        e.mode, e.n_phase, e.rows, e.rows_pad = mode, n_phase, rows, rows_pad
+        e.taps_h, e.taps_w, e.c, e.c_pad, e.krow = taps[0], taps[1], c, c_pad, krow
+        e.tiles_r, e.tiles_c = (rows + 31) // 32, (c + 31) // 32
+        e.tile_begin = self.total_tiles
+        e.s_r, e.s_c, e.s_kh, e.s_kw = strides
+        self.total_tiles += n_phase * taps[0] * taps[1] * e.tiles_r * e.tiles_c
+        self.entries.append(e)
+        self._keep.append((w, out))
+        self._table = None
+
+    def run(self) -> None:
+        if not self.entries:
+            return
+        if self._table is None:
+            arr = (_lib.PackEntry * len(self.entries))(*self.entries)
+            raw = bytes(arr)
+            dev = self._keep[0][1].device
+            self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        _lib.check(_lib.lib().gap_pack_weights_multi(_ptr(self._table), len(self.entries), self.total_tiles, _stream()),
+                   "gap_pack_weights_multi")

@@ -273,15 +273,17 @@ class GeneratorEngine(_Net):
         self.key_order = sp.key_order()
         # packed bf16 GEMM operands
         bf = dict(device=device, dtype=torch.bfloat16)
-        self.w_d_fwd = [torch.empty(1, C[0], 64, **bf)] + [torch.empty(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
-        self.w_d_dg = [None] + [torch.empty(4, C[j - 1], 4 * C[j], **bf) for j in range(1, L)]
-        self.w_u_fwd = [torch.empty(1, 64, 2 * C[0], **bf)]
-        self.w_u_dg = [torch.empty(1, 2 * C[0], 64, **bf)]
+        # (zero-filled once: the packer never writes padding elements)
+        self.w_d_fwd = [torch.zeros(1, C[0], 64, **bf)] + [torch.zeros(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
+        self.w_d_dg = [None] + [torch.zeros(4, C[j - 1], 4 * C[j], **bf) for j in range(1, L)]
+        self.w_u_fwd = [torch.zeros(1, 64, 2 * C[0], **bf)]
+        self.w_u_dg = [torch.zeros(1, 2 * C[0], 64, **bf)]
         for j in range(1, L):
             cin = C[j] if j == L - 1 else 2 * C[j]
-            self.w_u_fwd.append(torch.empty(4, C[j - 1], 4 * cin, **bf))
-            self.w_u_dg.append(torch.empty(1, cin, 16 * C[j - 1], **bf))
+            self.w_u_fwd.append(torch.zeros(4, C[j - 1], 4 * cin, **bf))
+            self.w_u_dg.append(torch.zeros(1, cin, 16 * C[j - 1], **bf))
         self._n = None
+        self._plan = None
         if init:
             self.init_from_torch_default()
 
@@ -291,25 +293,33 @@ class GeneratorEngine(_Net):
         self.load_state_dict(self.spec.default_state_dict())
 
     def repack(self) -> None:
+        """fp32 masters -> bf16 GEMM operands (one launch for the whole network)."""
+        if self._plan is None:
+            self._plan = self._build_pack_plan()
+        self._plan.run()
+
+    def _build_pack_plan(self) -> ops.PackPlan:
         L, C, p = self.L, self.C, self.store.p
         off = self.store.off
-        ops.pack_weights(p, off(self.k_down[0] + ".weight"), self.w_d_fwd[0], 0, 1, C[0], C[0], (1, 1), 64, 64, 64,
+        plan = ops.PackPlan()
+        plan.add(p, off(self.k_down[0] + ".weight"), self.w_d_fwd[0], 0, 1, C[0], C[0], (1, 1), 64, 64, 64,
                          (64, 1, 0, 0))
         for j in range(1, L):
             ci, co = C[j - 1], C[j]
             o = off(self.k_down[j] + ".weight")
-            ops.pack_weights(p, o, self.w_d_fwd[j], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
-            ops.pack_weights(p, o, self.w_d_dg[j], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
+            plan.add(p, o, self.w_d_fwd[j], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
+            plan.add(p, o, self.w_d_dg[j], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
         k0 = off(self.k_up[0] + ".weight")
         c2 = 2 * C[0]
-        ops.pack_weights(p, k0, self.w_u_fwd[0], 0, 1, 64, 64, (1, 1), c2, c2, c2, (1, 64, 0, 0))
-        ops.pack_weights(p, k0, self.w_u_dg[0], 0, 1, c2, c2, (1, 1), 64, 64, 64, (64, 1, 0, 0))
+        plan.add(p, k0, self.w_u_fwd[0], 0, 1, 64, 64, (1, 1), c2, c2, c2, (1, 64, 0, 0))
+        plan.add(p, k0, self.w_u_dg[0], 0, 1, c2, c2, (1, 1), 64, 64, 64, (64, 1, 0, 0))
         for j in range(1, L):
             ci = C[j] if j == L - 1 else 2 * C[j]
             co = C[j - 1]
             o = off(self.k_up[j] + ".weight")
-            ops.pack_weights(p, o, self.w_u_fwd[j], 2, 4, co, co, (2, 2), ci, ci, 4 * ci, (1, 16 * co, 4 * co, co))
-            ops.pack_weights(p, o, self.w_u_dg[j], 0, 1, ci, ci, (4, 4), co, co, 16 * co, (16 * co, 1, 4 * co, co))
+            plan.add(p, o, self.w_u_fwd[j], 2, 4, co, co, (2, 2), ci, ci, 4 * ci, (1, 16 * co, 4 * co, co))
+            plan.add(p, o, self.w_u_dg[j], 0, 1, ci, ci, (4, 4), co, co, 16 * co, (16 * co, 1, 4 * co, co))
+        return plan
 
     # -- activation buffers ---------------------------------------------------------------------
     def _alloc(self, n: int, h: int, w: int) -> None:
@@ -448,16 +458,17 @@ class DiscriminatorEngine(_Net):
             bn.allocate(device)
         self.key_order = sp.key_order()
         bf = dict(device=device, dtype=torch.bfloat16)
-        self.w_fwd = [torch.empty(1, C[0], 128, **bf)] + [torch.empty(1, C[k], 16 * C[k - 1], **bf) for k in range(1, n_layers + 1)]
-        self.w_fwd.append(torch.empty(1, 1, 16 * C[-1], **bf))
-        self.w_dg = [torch.empty(1, 128, C[0], **bf)]
+        self.w_fwd = [torch.zeros(1, C[0], 128, **bf)] + [torch.zeros(1, C[k], 16 * C[k - 1], **bf) for k in range(1, n_layers + 1)]
+        self.w_fwd.append(torch.zeros(1, 1, 16 * C[-1], **bf))
+        self.w_dg = [torch.zeros(1, 128, C[0], **bf)]
         for k in range(1, n_layers + 1):
             if k < n_layers:
-                self.w_dg.append(torch.empty(4, C[k - 1], 4 * C[k], **bf))     # stride 2: four phases
+                self.w_dg.append(torch.zeros(4, C[k - 1], 4 * C[k], **bf))     # stride 2: four phases
             else:
-                self.w_dg.append(torch.empty(1, C[k - 1], 16 * C[k], **bf))    # stride 1: flipped taps
-        self.w_dg.append(torch.empty(1, C[-1], 16 * 64, **bf))                 # Cout = 1 padded to 64 channels
+                self.w_dg.append(torch.zeros(1, C[k - 1], 16 * C[k], **bf))    # stride 1: flipped taps
+        self.w_dg.append(torch.zeros(1, C[-1], 16 * 64, **bf))                 # Cout = 1 padded to 64 channels
         self._n = None
+        self._plan = None
         if init:
             self.init_from_torch_default()
 
@@ -469,20 +480,27 @@ class DiscriminatorEngine(_Net):
         self.load_state_dict(self.spec.default_state_dict())
 
     def repack(self) -> None:
+        if self._plan is None:
+            self._plan = self._build_pack_plan()
+        self._plan.run()
+
+    def _build_pack_plan(self) -> ops.PackPlan:
         C, p, off = self.C, self.store.p, self.store.off
+        plan = ops.PackPlan()
         o = off(self.k_conv[0] + ".weight")
-        ops.pack_weights(p, o, self.w_fwd[0], 0, 1, C[0], C[0], (1, 1), 128, 128, 128, (128, 1, 0, 0))
-        ops.pack_weights(p, o, self.w_dg[0], 0, 1, 128, 128, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0))
+        plan.add(p, o, self.w_fwd[0], 0, 1, C[0], C[0], (1, 1), 128, 128, 128, (128, 1, 0, 0))
+        plan.add(p, o, self.w_dg[0], 0, 1, 128, 128, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0))
         for k in range(1, self.n_conv):
             ci = C[k - 1]
             co = 1 if k == self.n_conv - 1 else C[k]
             o = off(self.k_conv[k] + ".weight")
-            ops.pack_weights(p, o, self.w_fwd[k], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
+            plan.add(p, o, self.w_fwd[k], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
             if self.stride(k) == 2:
-                ops.pack_weights(p, o, self.w_dg[k], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
+                plan.add(p, o, self.w_dg[k], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
             else:
                 cp = max(co, 64)
-                ops.pack_weights(p, o, self.w_dg[k], 1, 1, ci, ci, (4, 4), co, cp, 16 * cp, (1, 16 * ci, 4 * ci, ci))
+                plan.add(p, o, self.w_dg[k], 1, 1, ci, ci, (4, 4), co, cp, 16 * cp, (1, 16 * ci, 4 * ci, ci))
+        return plan
 
     def _alloc(self, n: int, h: int, w: int) -> None:
         if self._n == (n, h, w):

@@ -199,6 +199,19 @@ int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows,
                      int taps_w, int c, int c_pad, int krow, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,
                      int kdim, void* stream);
 
+/* All operands of a network in one launch.  `table` lives in DEVICE memory; the host fills tile_begin
+ * (exclusive prefix sum of n_phase*taps_h*taps_w*tiles_r*tiles_c), tiles_r = ceil(rows/32),
+ * tiles_c = ceil(c/32).  Same element mapping as gap_pack_weights modes 0-2, except that padding
+ * elements (c >= C, rows >= R, k >= taps*c_pad) are not written: zero the operand buffers once. */
+typedef struct gap_pack_entry {
+  const float* w;
+  void* out;
+  int mode, n_phase, rows, rows_pad, taps_h, taps_w, c, c_pad, krow;
+  int tile_begin, tiles_r, tiles_c;
+  int64_t s_r, s_c, s_kh, s_kw;
+} gap_pack_entry;
+int gap_pack_weights_multi(const gap_pack_entry* table, int n_entries, int total_tiles, void* stream);
+
 /* Debug knobs for bring-up (descriptor conventions); not part of the stable surface. */
 int gap_debug_set(const char* key, int value);
 

@@ -188,3 +188,32 @@ def test_pack_weights_modes():
     got = fl.cpu().float().view(ci, 4, 4, 128)
     assert torch.equal(got[..., :co], w.flip(2, 3).permute(1, 2, 3, 0).to(torch.bfloat16).float())
     assert float(got[..., co:].abs().max()) == 0.0
+
+
+def test_pack_plan_matches_single_tensor_pack():
+    """gap_pack_weights_multi (one launch, tiled transposes) == gap_pack_weights on every mode the engines use."""
+    g = torch.Generator().manual_seed(5)
+    co, ci = 96, 72
+    flat = torch.randn(2 * co * ci * 16 + 40, generator=g).to(DEV)
+    off2 = co * ci * 16 + 24
+    cases = [  # (w_off, mode, n_phase, rows, rows_pad, taps, c, c_pad, krow, strides)
+        (0, 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci)),
+        (0, 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci)),
+        (off2, 1, 1, ci, ci, (4, 4), co, 128, 16 * 128, (1, 16 * ci, 4 * ci, ci)),
+        (off2, 0, 1, 64, 64, (1, 1), 128, 128, 128, (1, 64, 0, 0)),
+        (off2, 1, 1, ci, 80, (4, 4), 1, 64, 16 * 64, (1, 16 * ci, 4 * ci, ci)),
+    ]
+    plan = ops.PackPlan()
+    outs, refs = [], []
+    for (o, mode, nph, rows, rpad, taps, c, cpad, krow, st) in cases:
+        a = torch.zeros(nph, rpad, krow, device=DEV, dtype=torch.bfloat16)
+        b = torch.full((nph, rpad, krow), 7.0, device=DEV, dtype=torch.bfloat16)
+        plan.add(flat, o, a, mode, nph, rows, rpad, taps, c, cpad, krow, st)
+        ops.pack_weights(flat, o, b, mode, nph, rows, rpad, taps, c, cpad, krow, st)
+        outs.append(a)
+        refs.append(b)
+    plan.run()
+    plan.run()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, refs):
+        assert torch.equal(a.cpu().float(), b.cpu().float())
