@@ -214,40 +214,39 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const WorkCoord wc = decode_work(p, tile);
-      const MTile m0 = decode_mtile(p, wc.sm * p.mt);
-      const MTile m1 = decode_mtile(p, wc.sm * p.mt + 1);
-      const bool has1 = p.mt > 1 && m1.exists;
-      const int x0 = m0.tw * BW * p.in_stride + p.in_off_w[wc.pw];
-      const int y0 = m0.th * BH * p.in_stride + p.in_off_h[wc.ph];
-      const int n0 = m0.tn * BNI;
-      const int x1 = m1.tw * BW * p.in_stride + p.in_off_w[wc.pw];
-      const int y1 = m1.th * BH * p.in_stride + p.in_off_h[wc.ph];
-      const int n1 = m1.tn * BNI;
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.block_n * 128 + (has1 ? 2 : 1) * kATileBytes);
-      const int b_row = wc.n_tile * p.block_n;
-      int kcol = 0;
-      for (int t_h = 0; t_h < p.taps_h; ++t_h) {
-        for (int t_w = 0; t_w < p.taps_w; ++t_w) {
-          for (int s = 0; s < 2; ++s) {
-            for (int c = 0; c < p.src_chunks[s]; ++c) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              if (elect_one()) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const WorkCoord wc = decode_work(p, tile);
+        const MTile m0 = decode_mtile(p, wc.sm * p.mt);
+        const MTile m1 = decode_mtile(p, wc.sm * p.mt + 1);
+        const bool has1 = p.mt > 1 && m1.exists;
+        const int x0 = m0.tw * BW * p.in_stride + p.in_off_w[wc.pw];
+        const int y0 = m0.th * BH * p.in_stride + p.in_off_h[wc.ph];
+        const int n0 = m0.tn * BNI;
+        const int x1 = m1.tw * BW * p.in_stride + p.in_off_w[wc.pw];
+        const int y1 = m1.th * BH * p.in_stride + p.in_off_h[wc.ph];
+        const int n1 = m1.tn * BNI;
+        const uint32_t tx_bytes = static_cast<uint32_t>(p.block_n * 128 + (has1 ? 2 : 1) * kATileBytes);
+        const int b_row = wc.n_tile * p.block_n;
+        int kcol = 0;
+        for (int t_h = 0; t_h < p.taps_h; ++t_h) {
+          for (int t_w = 0; t_w < p.taps_w; ++t_w) {
+            for (int s = 0; s < 2; ++s) {
+              for (int c = 0; c < p.src_chunks[s]; ++c) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_expect_tx(full_bar(stage), tx_bytes);
                 const uint32_t a_dst = smem_base + stage * stage_bytes;
                 tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
                 if (has1)
                   tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
                 tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kcol, b_row, wc.phase);
-              }
-              __syncwarp();
-              kcol += kBlockK;
-              if (++stage == p.num_stages) {
-                stage = 0;
-                phase ^= 1u;
+                kcol += kBlockK;
+                if (++stage == p.num_stages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
               }
             }
           }
@@ -256,20 +255,20 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const WorkCoord wc = decode_work(p, tile);
-      const int mt_eff = min(p.mt, p.m_tiles_pp - wc.sm * p.mt);
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kAccStride;
-      for (int k_iter = 0; k_iter < p.k_iters; ++k_iter) {
-        mbar_wait(full_bar(stage), phase);
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const WorkCoord wc = decode_work(p, tile);
+        const int mt_eff = min(p.mt, p.m_tiles_pp - wc.sm * p.mt);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int k_iter = 0; k_iter < p.k_iters; ++k_iter) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
           const uint32_t b_addr = a_addr + a_bytes;
           for (int j = 0; j < mt_eff; ++j) {
@@ -281,18 +280,16 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             }
           }
           umma_commit(empty_bar(stage));
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        __syncwarp();
-        if (++stage == p.num_stages) {
-          stage = 0;
-          phase ^= 1u;
+        umma_commit(tfull_bar(acc));
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1u;
         }
-      }
-      if (elect_one()) umma_commit(tfull_bar(acc));
-      __syncwarp();
-      if (++acc == p.acc_stages) {
-        acc = 0;
-        acc_phase ^= 1u;
       }
     }
   } else {

@@ -181,8 +181,10 @@ class _DiscriminatorFn(torch.autograd.Function):
         eng.attach_buffers(ctx.snap)
         eng.zero_grad()
         n, h, w = ctx.shape
-        ops.nchw_to_nhwc_bf16(gout.contiguous().float(), eng.dlogits)
+        eng.dlogits.copy_(gout.reshape(eng.dlogits.shape))
         wgrad = any(p.requires_grad for p in module.parameters())
+        if wgrad:
+            ops.sum_f32(eng.dlogits, eng.grad(eng.k_conv[-1] + ".bias"))
         eng.backward(wgrad=wgrad, input_grad=ctx.x_grad, input_grad_a=ctx.x_grad)
         gx = None
         if ctx.x_grad:

@@ -247,6 +247,55 @@ def bce_logits_const(logits: torch.Tensor, target: float, grad_scale: float, dlo
                "gap_bce_logits_const")
 
 
+def bce_logits_const_f32(logits: torch.Tensor, target: float, grad_scale: float, dlogits: Optional[torch.Tensor],
+                         loss_acc: torch.Tensor, dbias: Optional[torch.Tensor] = None) -> None:
+    """BCEWithLogitsLoss vs a constant target (train_gan.py:58,60,67): fp32 gradient (+ the producing conv's
+    bias gradient)."""
+    if dlogits is not None and (dlogits.dtype != torch.float32 or dlogits.numel() != logits.numel()):
+        raise ValueError("dlogits must be fp32 with the shape of logits")
+    _lib.check(_lib.lib().gap_bce_logits_const_f32(_ptr(logits), logits.numel(), target, grad_scale, _ptr(dlogits),
+                                                   _ptr(loss_acc), _ptr(dbias), _stream()), "gap_bce_logits_const_f32")
+
+
+def sum_f32(x: torch.Tensor, out: torch.Tensor) -> None:
+    _lib.check(_lib.lib().gap_sum_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "gap_sum_f32")
+
+
+def cout1_conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], z_ws: torch.Tensor,
+                   logits: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:
+    """Conv2d(C -> 1, k4, s1, p1) + bias (models.py:243): x NHWC bf16, w bf16 [16*C] ([kh][kw][c]), logits fp32
+    [n, oh, ow(, 1)]."""
+    n, ih, iw, c, ld = _nhwc_view(x)
+    if z_ws.dtype != torch.float32 or z_ws.numel() < n * ih * iw * 16 or logits.dtype != torch.float32:
+        raise ValueError("z_ws / logits must be fp32 (z_ws >= n*ih*iw*16 elements)")
+    if w.dtype != torch.bfloat16 or w.numel() != ksize * ksize * c:
+        raise ValueError("w must be bf16 [k*k*C]")
+    if logits.numel() != n * (ih + 2 * pad - ksize + 1) * (iw + 2 * pad - ksize + 1):
+        raise ValueError("logits shape mismatch")
+    _lib.check(_lib.lib().gap_cout1_conv_fwd(_ptr(x), ld, n, ih, iw, c, _ptr(w), _ptr(bias), ksize, pad, _ptr(z_ws),
+                                             _ptr(logits), _stream()), "gap_cout1_conv_fwd")
+
+
+def cout1_conv_dgrad(dlogits: torch.Tensor, w: torch.Tensor, gx: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:
+    n, ih, iw, c, ld = _nhwc_view(gx)
+    oh, ow = ih + 2 * pad - ksize + 1, iw + 2 * pad - ksize + 1
+    if dlogits.dtype != torch.float32 or dlogits.numel() != n * oh * ow:
+        raise ValueError("dlogits must be fp32 [n, oh, ow]")
+    _lib.check(_lib.lib().gap_cout1_conv_dgrad(_ptr(dlogits), n, oh, ow, _ptr(w), ksize, pad, c, _ptr(gx), ld, ih, iw,
+                                               _stream()), "gap_cout1_conv_dgrad")
+
+
+def cout1_conv_wgrad(dlogits: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:
+    n, ih, iw, c, ld = _nhwc_view(x)
+    oh, ow = ih + 2 * pad - ksize + 1, iw + 2 * pad - ksize + 1
+    if dlogits.dtype != torch.float32 or dlogits.numel() != n * oh * ow:
+        raise ValueError("dlogits must be fp32 [n, oh, ow]")
+    if dw.dtype != torch.float32 or dw.numel() != ksize * ksize * c:
+        raise ValueError("dw must be fp32 [k*k*C]")
+    _lib.check(_lib.lib().gap_cout1_conv_wgrad(_ptr(dlogits), n, oh, ow, _ptr(x), ld, ih, iw, c, ksize, pad, _ptr(dw),
+                                               _stream()), "gap_cout1_conv_wgrad")
+
+
 def bn_finalize(stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, nbt, scale, shift,
                 save_mean, save_invstd) -> None:
     c = scale.numel()

@@ -433,7 +433,7 @@ class GeneratorEngine(_Net):
 class DiscriminatorEngine(_Net):
     """NLayerDiscriminator(input_nc=6, ndf, n_layers, BatchNorm2d)."""
 
-    _BUFFER_ATTRS = ("hs", "ws", "col", "H", "y", "logits", "dlogits", "gH", "dy", "dcol", "dfake")
+    _BUFFER_ATTRS = ("hs", "ws", "col", "H", "y", "logits", "z_ws", "dlogits", "gH", "dy", "dcol", "dfake")
 
     def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3, init: bool = True) -> None:
         super().__init__(device)
@@ -466,7 +466,7 @@ class DiscriminatorEngine(_Net):
                 self.w_dg.append(torch.zeros(4, C[k - 1], 4 * C[k], **bf))     # stride 2: four phases
             else:
                 self.w_dg.append(torch.zeros(1, C[k - 1], 16 * C[k], **bf))    # stride 1: flipped taps
-        self.w_dg.append(torch.zeros(1, C[-1], 16 * 64, **bf))                 # Cout = 1 padded to 64 channels
+        self.w_dg.append(None)                                                  # Cout = 1: direct kernels, no operand
         self._n = None
         self._plan = None
         if init:
@@ -495,6 +495,8 @@ class DiscriminatorEngine(_Net):
             co = 1 if k == self.n_conv - 1 else C[k]
             o = off(self.k_conv[k] + ".weight")
             plan.add(p, o, self.w_fwd[k], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
+            if k == self.n_conv - 1:
+                continue            # Cout = 1: the direct kernels read the forward operand
             if self.stride(k) == 2:
                 plan.add(p, o, self.w_dg[k], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
             else:
@@ -520,7 +522,8 @@ class DiscriminatorEngine(_Net):
         self.H = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
         self.y = [None] + [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(1, self.n_conv - 1)]
         self.logits = torch.empty(n, hs[-1], ws[-1], 1, device=self.dev)
-        self.dlogits = torch.zeros(n, hs[-1], ws[-1], 64, **bf)
+        self.z_ws = torch.empty(n * hs[-2] * ws[-2], 16, device=self.dev)      # per-pixel tap products of the last conv
+        self.dlogits = torch.zeros(n, hs[-1], ws[-1], device=self.dev)            # fp32 d(loss)/d(logits)
         self.gH = [torch.empty_like(t) for t in self.H]
         self.dy = [torch.empty_like(t) for t in self.H]
         self.dcol = torch.empty(n, hs[0], ws[0], 128, **bf)
@@ -542,22 +545,20 @@ class DiscriminatorEngine(_Net):
                           (self.hs[k], self.ws[k]), stats=bn.stats if self.training else None)
             self._bn_forward(bn, self.y[k], self.H[k], ACT_LRELU)
         k = self.n_conv - 1
-        ops.conv_gemm([self.H[k - 1]], self.w_fwd[k], ops.geom_conv_fwd(4, 1, 1), self.logits, 1,
-                      (self.hs[k], self.ws[k]), bias=self.param(self.k_conv[k] + ".bias"))
+        ops.cout1_conv_fwd(self.H[k - 1], self.w_fwd[k].view(-1), self.param(self.k_conv[k] + ".bias"), self.z_ws,
+                           self.logits)
         return self.logits
 
     def backward(self, wgrad: bool, input_grad: bool, input_grad_a: bool = False) -> Optional[torch.Tensor]:
-        """Consumes self.dlogits (bf16, channel 0 of a 64-channel-padded map).  wgrad=False skips
-        every parameter gradient (the G step); input_grad=True returns d(loss)/d(xb) as fp32 NHWC."""
+        """Consumes self.dlogits (fp32 [n, h', w']).  wgrad=False skips every parameter gradient (the G step);
+        input_grad=True returns d(loss)/d(xb) as fp32 NHWC.  The last conv's bias gradient (sum of dlogits) is
+        produced by whoever wrote dlogits (gap_bce_logits_const_f32 / gap_sum_f32)."""
         C = self.C
         last = self.n_conv - 1
         g = self.store.g
         if wgrad:
-            ops.conv_wgrad(self.dlogits, self.H[last - 1], self.store.seg(g, self.k_conv[last] + ".weight"), (4, 4), 1,
-                           (-1, -1), 16 * C[last - 1], C[last - 1], m_rows=1)
-            ops.colsum_bf16(self.dlogits, 1, self.grad(self.k_conv[last] + ".bias"))
-        ops.conv_gemm([self.dlogits], self.w_dg[last], ops.geom_conv_dgrad_s1(4, 1), self.gH[last - 1], C[last - 1],
-                      (self.hs[last - 1], self.ws[last - 1]))
+            ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1], self.store.seg(g, self.k_conv[last] + ".weight"))
+        ops.cout1_conv_dgrad(self.dlogits, self.w_fwd[last].view(-1), self.gH[last - 1])
         for k in range(last - 1, 0, -1):
             self._bn_backward(self.bn[k], self.y[k], self.gH[k], None, 0.2, self.dy[k], param_grads=wgrad)
             s = self.stride(k)
@@ -619,10 +620,11 @@ class Pix2PixTrainer:
         a_nhwc = G.x_nhwc
         logits = D.forward(a_nhwc, self.b_nhwc)            # :57
         cnt = logits.numel()
-        ops.bce_logits_const(logits, 1.0, 0.5 / cnt, D.dlogits, self.loss_acc[0:1])   # :58,61
+        d_bias_last = D.grad(D.k_conv[-1] + ".bias")
+        ops.bce_logits_const_f32(logits, 1.0, 0.5 / cnt, D.dlogits, self.loss_acc[0:1], d_bias_last)   # :58,61
         D.backward(wgrad=True, input_grad=False)
         logits = D.forward(a_nhwc, G.fake_bf)              # :59
-        ops.bce_logits_const(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2])   # :60,61
+        ops.bce_logits_const_f32(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2], d_bias_last)   # :60,61
         D.backward(wgrad=True, input_grad=False)           # :62
         if self.allreduce is not None:
             self.allreduce(D.store.g)
@@ -630,7 +632,7 @@ class Pix2PixTrainer:
         # ---- G step (train_gan.py:64-71)
         G.zero_grad()
         logits = D.forward(a_nhwc, G.fake_bf)              # :66 (updated D)
-        ops.bce_logits_const(logits, 1.0, 1.0 / cnt, D.dlogits, self.loss_acc[2:3])   # :67
+        ops.bce_logits_const_f32(logits, 1.0, 1.0 / cnt, D.dlogits, self.loss_acc[2:3])   # :67
         dfake = D.backward(wgrad=False, input_grad=True)
         numel = n * 3 * h * w
         ops.gen_out_bwd(G.fake_f32, real_B, dfake, LAMBDA_L1 / numel, G.dpre, self.loss_acc[3:4])  # :68-70

@@ -163,6 +163,29 @@ int gap_gen_out_bwd(const float* fake, int64_t ld_f, const float* real_nchw, int
 int gap_bce_logits_const(const float* logits, int64_t count, float target, float grad_scale, void* dlogits,
                          int64_t ld_d, double* loss_acc, void* stream);
 
+/* Same loss with an fp32 gradient and the bias gradient of the conv that produced the logits
+ * (dbias += sum dlogits; dlogits / dbias may be NULL). */
+int gap_bce_logits_const_f32(const float* logits, int64_t count, float target, float grad_scale, float* dlogits,
+                             double* loss_acc, float* dbias, void* stream);
+/* out[0] += sum x[i] (fp32) */
+int gap_sum_f32(const float* x, int64_t count, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv2d(C -> 1, k4, s1, pad) + bias: the PatchGAN's last layer (models.py:243) as direct warp-MMA
+ * kernels that read every activation once (the layer is HBM-bound: 8192 MACs per 1 KiB pixel).
+ *   fwd:   z_ws[pix][16] = x[pix][:] . w[tap][:]  then  logits[n][oy][ox] = bias + sum_taps z[...]
+ *   dgrad: gx[pix][c]  = sum_taps dlogits[n][y-kh+pad][x-kw+pad] * w[tap][c]            (bf16 out)
+ *   wgrad: dw[tap][c] += sum_pix  dlogits[n][y-kh+pad][x-kw+pad] * x[pix][c]            (fp32)
+ * x / gx: NHWC bf16 (pixel stride ld, multiple of 8); w: bf16 [16][c] ([kh][kw][c], the packed
+ * forward operand); logits / dlogits: fp32 [n][oh][ow]; z_ws: fp32 workspace [n*ih*iw*16].
+ * ---------------------------------------------------------------------------------------------- */
+int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c, const void* w, const float* bias,
+                       int ksize, int pad, float* z_ws, float* logits, void* stream);
+int gap_cout1_conv_dgrad(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
+                         int64_t ld_gx, int ih, int iw, void* stream);
+int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void* x, int64_t ld_x, int ih, int iw, int c,
+                         int ksize, int pad, float* dw, void* stream);
+
 /* nn.BatchNorm2d training bookkeeping (models.py:179,181,231,239): statistics -> scale/shift,
  * saved mean / inv-std, running stats (momentum, unbiased var, `repeat` identical updates),
  * num_batches_tracked += repeat.  Re-zeroes `stats`. */
