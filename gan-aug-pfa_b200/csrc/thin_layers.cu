@@ -14,6 +14,15 @@ namespace gap {
 typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// 8-byte asynchronous global -> shared copy; src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // Cout = 1 forward, stage 1: z[pix][tap] = sum_c x[pix][c] * w[tap][c] for the 16 taps of a 4x4
@@ -224,6 +233,195 @@ __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Thin-input Conv2d(k4, s2, p1): out[pix][cw] = sum_{tap, slot} in[2*pix + tap - 1][slot] * w[cw][tap][slot]
+// for inputs of 3 channels (one NHWC source with 4 channel slots, CT = 4) or 6 channels (two such
+// sources concatenated, CT = 8): the generator's first conv (models.py:177 outermost), the
+// discriminator's first conv on cat(A, B) (models.py:223, train_gan.py:57) and the input gradient of the
+// generator's last ConvTranspose2d (models.py:184).  The input patch of an 8 x 16 output tile is staged in
+// shared memory once and the im2col matrix only ever exists as MMA fragments.
+// CTA = 128 output pixels; warp = 2 output rows (2 x m16) x 64 output channels.
+// dynamic smem: patch[2][18][34][CT] (double-buffered with cp.async) | ws[cw][16*CT + 8] | out_s[128][cw + 8]
+// ------------------------------------------------------------------------------------------------
+struct ThinFwdParams {
+  const bf16* s0;
+  long long ld0;
+  const bf16* s1;
+  long long ld1;
+  const bf16* w;
+  const float* bias;
+  int n, h, w_in, oh, ow, cw;
+  bf16* out1;
+  long long ldo1;
+  float slope1;
+  bf16* out2;
+  long long ldo2;
+  float slope2;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+  int skip;  // bring-up ablation: 1 no MMA loop, 2 no global stores, 4 no patch loads
+};
+
+template <int CT>
+__global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams p) {
+  constexpr int K = 16 * CT;
+  constexpr int WSTRIDE = K + 8;      // bf16 elements per weight row in smem
+  constexpr int PW = CT / 2;          // 32-bit words per patch pixel
+  extern __shared__ __align__(16) uint8_t dsm[];
+  constexpr int PATCH_WORDS = 18 * 34 * PW;
+  uint32_t* patch_buf = reinterpret_cast<uint32_t*>(dsm);                  // [2][18][34][PW]
+  bf16* ws = reinterpret_cast<bf16*>(dsm + 2 * PATCH_WORDS * 4);
+  bf16* out_s = ws + static_cast<size_t>(p.cw) * WSTRIDE;
+  const int ostride = p.cw + 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int mp = warp & 3, nh = warp >> 2;
+  const int nthr = blockDim.x;
+
+  for (int idx = tid; idx < p.cw * (K / 8); idx += nthr) {
+    const int r = idx / (K / 8), seg = idx - r * (K / 8);
+    *reinterpret_cast<uint4*>(ws + r * WSTRIDE + seg * 8) = ldg128(p.w + static_cast<long long>(r) * K + seg * 8);
+  }
+  const uint32_t ws_a = smem_u32(ws);
+
+  // asynchronous (cp.async) load of the input patch of one tile into a patch buffer
+  auto issue_patch = [&](long long tile, int buf) {
+    const int tx = static_cast<int>(tile % p.tiles_x);
+    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
+    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int oy0 = ty * 8, ox0 = tx * 16;
+    const bf16* s0i = p.s0 + img * p.h * p.w_in * p.ld0;
+    const bf16* s1i = CT == 8 ? p.s1 + img * p.h * p.w_in * p.ld1 : p.s0;
+    const int ld0 = static_cast<int>(p.ld0), ld1 = static_cast<int>(p.ld1);
+    const uint32_t dst0 = smem_u32(patch_buf + buf * PATCH_WORDS);
+    for (int idx = tid; idx < 18 * 34; idx += nthr) {
+      const int py = idx / 34, px = idx - py * 34;
+      const int iy = 2 * oy0 - 1 + py, ix = 2 * ox0 - 1 + px;
+      const bool ok = static_cast<unsigned>(iy) < static_cast<unsigned>(p.h) &&
+                      static_cast<unsigned>(ix) < static_cast<unsigned>(p.w_in) && !(p.skip & 4);
+      const int pix = ok ? iy * p.w_in + ix : 0;
+      cp_async8(dst0 + idx * PW * 4, s0i + pix * ld0, ok ? 8 : 0);
+      if (CT == 8) cp_async8(dst0 + idx * PW * 4 + 8, s1i + pix * ld1, ok ? 8 : 0);
+    }
+    cp_async_commit();
+  };
+
+  if (static_cast<long long>(blockIdx.x) < p.total_tiles) issue_patch(blockIdx.x, 0);
+  int buf = 0;
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
+    const int tx = static_cast<int>(tile % p.tiles_x);
+    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
+    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int oy0 = ty * 8, ox0 = tx * 16;
+    const uint32_t* patch = patch_buf + buf * PATCH_WORDS;
+    const long long next = tile + gridDim.x;
+    // the other patch buffer was last read two iterations ago (a __syncthreads lies in between)
+    if (next < p.total_tiles) {
+      issue_patch(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();  // this tile's patch has landed for every thread; out_s of the previous tile is free; ws loaded
+
+    float acc[2][8][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[m][nt][j] = 0.f;
+
+    if (!(p.skip & 1))
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int oyl = 2 * mp + m;
+        if (CT == 8) {
+          const int tap0 = 2 * ks, kh = tap0 >> 2, kw = tap0 & 3;
+          const int base = ((2 * oyl + kh) * 34 + kw) * PW + t;
+          a[m][0] = patch[base + (2 * g) * PW];
+          a[m][1] = patch[base + (2 * (g + 8)) * PW];
+          a[m][2] = patch[base + (2 * g + 1) * PW];
+          a[m][3] = patch[base + (2 * (g + 8) + 1) * PW];
+        } else {
+          const int kh = ks, kw = t >> 1;
+          const int base = ((2 * oyl + kh) * 34 + kw) * PW + (t & 1);
+          a[m][0] = patch[base + (2 * g) * PW];
+          a[m][1] = patch[base + (2 * (g + 8)) * PW];
+          a[m][2] = patch[base + (2 * g + 2) * PW];
+          a[m][3] = patch[base + (2 * (g + 8) + 2) * PW];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t b[4];
+        ldb_16x16(b, ws_a + ((nh * 64 + j * 16) * WSTRIDE + ks * 16) * 2, WSTRIDE * 2, lane);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_bf16_16816(acc[m][2 * j], a[m], b[0], b[1]);
+          mma_bf16_16816(acc[m][2 * j + 1], a[m], b[2], b[3]);
+        }
+      }
+    }
+
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = nh * 64 + nt * 8 + 2 * t;
+        const float b0 = __ldg(p.bias + col), b1 = __ldg(p.bias + col + 1);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          acc[m][nt][0] += b0;
+          acc[m][nt][1] += b1;
+          acc[m][nt][2] += b0;
+          acc[m][nt][3] += b1;
+        }
+      }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      bf16* outp = pass == 0 ? p.out1 : p.out2;
+      if (outp == nullptr) break;
+      const float slope = pass == 0 ? p.slope1 : p.slope2;
+      const int ldo = static_cast<int>(pass == 0 ? p.ldo1 : p.ldo2);
+      const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
+      const bool ident = slope == 1.f;
+      if (pass == 1) __syncthreads();
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        bf16* row0 = out_s + ((2 * mp + m) * 16 + g) * ostride + nh * 64 + 2 * t;
+        bf16* row1 = row0 + 8 * ostride;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          // act(v) = max(v, slope*v) for slope in [0,1], applied to the packed bf16 pair
+          __nv_bfloat162 lo = __floats2bfloat162_rn(acc[m][nt][0], acc[m][nt][1]);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(acc[m][nt][2], acc[m][nt][3]);
+          if (!ident) {
+            lo = __hmax2(lo, __hmul2(lo, slope2));
+            hi = __hmax2(hi, __hmul2(hi, slope2));
+          }
+          *reinterpret_cast<__nv_bfloat162*>(row0 + nt * 8) = lo;
+          *reinterpret_cast<__nv_bfloat162*>(row1 + nt * 8) = hi;
+        }
+      }
+      __syncthreads();
+      // 128 pixels x (cw/8) 16-byte vectors; cw/8 is 8 or 16
+      const int vshift = p.cw == 64 ? 3 : 4;
+      bf16* out_img = outp + img * p.oh * p.ow * ldo;
+      for (int idx = tid; idx < (128 << vshift); idx += nthr) {
+        const int px = idx >> vshift, seg = idx & ((1 << vshift) - 1);
+        const int oy = oy0 + (px >> 4), ox = ox0 + (px & 15);
+        if (oy < p.oh && ox < p.ow && !(p.skip & 2))
+          *reinterpret_cast<uint4*>(out_img + (oy * p.ow + ox) * ldo + seg * 8) =
+              *reinterpret_cast<const uint4*>(out_s + px * ostride + seg * 8);
+      }
+    }
+  }
+}
+
 // BCE-with-logits against a constant target with an fp32 gradient and the bias gradient of the
 // producing Cout = 1 conv:  dlogits = grad_scale*(sigmoid(x) - t);  dbias += sum dlogits
 __global__ void bce_logits_const_f32_kernel(const float* __restrict__ x, long long count, float t, float grad_scale,
@@ -359,6 +557,67 @@ int gap_bce_logits_const_f32(const float* logits, int64_t count, float target, f
   const int blocks = static_cast<int>(std::min<int64_t>((count + 255) / 256, 148));
   bce_logits_const_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, count, target, grad_scale,
                                                                                      dlogits, loss_acc, dbias);
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t ld1, int n, int h, int w, const void* wpk,
+                      const float* bias, int cw, void* out1, int64_t ldo1, int act1, void* out2, int64_t ldo2, int act2,
+                      void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GAP_CHECK_ARG(src0 && wpk && out1 && n > 0 && h > 1 && w > 1, "gap_thin_conv_fwd: bad arguments");
+  GAP_CHECK_ARG(act1 >= GAP_ACT_NONE && act1 <= GAP_ACT_RELU && act2 >= GAP_ACT_NONE && act2 <= GAP_ACT_RELU,
+                "gap_thin_conv_fwd: activations must be none / LeakyReLU / ReLU");
+  if ((cw != 64 && cw != 128) || h % 2 || w % 2 || ld0 % 4 || (src1 && ld1 % 4) || ldo1 % 8 || (out2 && ldo2 % 8) ||
+      (reinterpret_cast<uintptr_t>(src0) & 7) || (reinterpret_cast<uintptr_t>(src1) & 7) ||
+      (reinterpret_cast<uintptr_t>(out1) & 15) || (reinterpret_cast<uintptr_t>(out2) & 15) ||
+      (reinterpret_cast<uintptr_t>(wpk) & 15)) {
+    set_error("gap_thin_conv_fwd: needs cw in {64,128}, even h/w, 4-slot sources (ld %% 4), 16-byte aligned outputs");
+    return GAP_ERR_UNSUPPORTED;
+  }
+  ThinFwdParams p;
+  p.s0 = static_cast<const bf16*>(src0);
+  p.ld0 = ld0;
+  p.s1 = static_cast<const bf16*>(src1);
+  p.ld1 = ld1;
+  p.w = static_cast<const bf16*>(wpk);
+  p.bias = bias;
+  p.n = n;
+  p.h = h;
+  p.w_in = w;
+  p.oh = h / 2;
+  p.ow = w / 2;
+  p.cw = cw;
+  auto slope_of = [](int act) { return act == GAP_ACT_NONE ? 1.f : (act == GAP_ACT_LRELU ? 0.2f : 0.f); };
+  p.out1 = static_cast<bf16*>(out1);
+  p.ldo1 = ldo1;
+  p.slope1 = slope_of(act1);
+  p.out2 = static_cast<bf16*>(out2);
+  p.ldo2 = ldo2;
+  p.slope2 = slope_of(act2);
+  p.tiles_x = (p.ow + 15) / 16;
+  p.tiles_y = (p.oh + 7) / 8;
+  p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  p.skip = debug_get("thin_skip", 0);
+  const int ct = src1 ? 8 : 4;
+  const size_t smem = 2 * 18 * 34 * ct * 2 + static_cast<size_t>(cw) * (16 * ct + 8) * 2 + 128 * static_cast<size_t>(cw + 8) * 2;
+  const int threads = 128 * (cw / 64);
+  const int grid = static_cast<int>(std::min<long long>(p.total_tiles, static_cast<long long>(debug_get("thin_ctas_per_sm", 4)) * sm_count()));
+  if (ct == 8) {
+    static bool set8 = false;
+    if (!set8) {
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      set8 = true;
+    }
+    thin_conv_fwd_kernel<8><<<grid, threads, smem, st>>>(p);
+  } else {
+    static bool set4 = false;
+    if (!set4) {
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      set4 = true;
+    }
+    thin_conv_fwd_kernel<4><<<grid, threads, smem, st>>>(p);
+  }
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

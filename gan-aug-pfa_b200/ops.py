@@ -296,6 +296,35 @@ def cout1_conv_wgrad(dlogits: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, k
                                                _stream()), "gap_cout1_conv_wgrad")
 
 
+def thin_conv_fwd(s0: torch.Tensor, s1: Optional[torch.Tensor], wpk: torch.Tensor, bias: Optional[torch.Tensor],
+                  out1: torch.Tensor, act1: int = ACT_NONE, out2: Optional[torch.Tensor] = None,
+                  act2: int = ACT_NONE) -> None:
+    """Conv2d(k4,s2,p1) over one or two 4-slot NHWC sources (3 channels + a zero slot each) -> cw = 64/128
+    channels, fused bias + activation(s); wpk bf16 [cw, 16*CT] with CT = 4 (one source) or 8 (two)."""
+    n, h, w, _, ld0 = _nhwc_view(s0)
+    ld1 = 0
+    if s1 is not None:
+        n1, h1, w1, _, ld1 = _nhwc_view(s1)
+        if (n1, h1, w1) != (n, h, w):
+            raise ValueError("sources must share n/h/w")
+    on, oh, ow, cw, ldo1 = _nhwc_view(out1)
+    if (on, oh, ow) != (n, h // 2, w // 2):
+        raise ValueError("out1 shape mismatch")
+    ct = 8 if s1 is not None else 4
+    if wpk.dtype != torch.bfloat16 or wpk.numel() != cw * 16 * ct or not wpk.is_contiguous():
+        raise ValueError(f"wpk must be contiguous bf16 [{cw}, {16 * ct}]")
+    ldo2 = 0
+    if out2 is not None:
+        o2 = _nhwc_view(out2)
+        if o2[:4] != (on, oh, ow, cw):
+            raise ValueError("out2 shape mismatch")
+        ldo2 = o2[4]
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() < cw):
+        raise ValueError("bias must be fp32 [cw]")
+    _lib.check(_lib.lib().gap_thin_conv_fwd(_ptr(s0), ld0, _ptr(s1), ld1, n, h, w, _ptr(wpk), _ptr(bias), cw, _ptr(out1),
+                                            ldo1, act1, _ptr(out2), ldo2, act2, _stream()), "gap_thin_conv_fwd")
+
+
 def bn_finalize(stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, nbt, scale, shift,
                 save_mean, save_invstd) -> None:
     c = scale.numel()
@@ -373,14 +402,16 @@ class PackPlan:
         self._keep = []
 
     def add(self, w: torch.Tensor, w_off: int, out: torch.Tensor, mode: int, n_phase: int, rows: int, rows_pad: int,
-            taps: tuple[int, int], c: int, c_pad: int, krow: int, strides: tuple[int, int, int, int]) -> None:
+            taps: tuple[int, int], c: int, c_pad: int, krow: int, strides: tuple[int, int, int, int],
+            out_off: int = 0) -> None:
+        """``out_off`` (elements) shifts the destination inside each operand row (channel-slot packing)."""
         if mode not in (0, 1, 2):
             raise ValueError("PackPlan supports modes 0-2")
         if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.numel() != n_phase * rows_pad * krow:
             raise ValueError("operand buffer does not match n_phase*rows_pad*krow")
         e = _lib.PackEntry()
         e.w = w.data_ptr() + 4 * w_off
-        e.out = out.data_ptr()
+        e.out = out.data_ptr() + 2 * out_off
         e.mode, e.n_phase, e.rows, e.rows_pad = mode, n_phase, rows, rows_pad
         e.taps_h, e.taps_w, e.c, e.c_pad, e.krow = taps[0], taps[1], c, c_pad, krow
         e.tiles_r, e.tiles_c = (rows + 31) // 32, (c + 31) // 32

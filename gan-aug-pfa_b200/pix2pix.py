@@ -277,7 +277,10 @@ class GeneratorEngine(_Net):
         self.w_d_fwd = [torch.zeros(1, C[0], 64, **bf)] + [torch.zeros(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
         self.w_d_dg = [None] + [torch.zeros(4, C[j - 1], 4 * C[j], **bf) for j in range(1, L)]
         self.w_u_fwd = [torch.zeros(1, 64, 2 * C[0], **bf)]
-        self.w_u_dg = [torch.zeros(1, 2 * C[0], 64, **bf)]
+        self.w_u_dg = [None]
+        # thin-layer operands [rows][16 taps x 4 channel slots] (3 channels + a zero slot)
+        self.w_d_thin = torch.zeros(C[0], 64, **bf)          # first conv, models.py:177
+        self.w_u_thin = torch.zeros(2 * C[0], 64, **bf)      # last ConvTranspose2d seen from its dgrad
         for j in range(1, L):
             cin = C[j] if j == L - 1 else 2 * C[j]
             self.w_u_fwd.append(torch.zeros(4, C[j - 1], 4 * cin, **bf))
@@ -312,7 +315,8 @@ class GeneratorEngine(_Net):
         k0 = off(self.k_up[0] + ".weight")
         c2 = 2 * C[0]
         plan.add(p, k0, self.w_u_fwd[0], 0, 1, 64, 64, (1, 1), c2, c2, c2, (1, 64, 0, 0))
-        plan.add(p, k0, self.w_u_dg[0], 0, 1, c2, c2, (1, 1), 64, 64, 64, (64, 1, 0, 0))
+        plan.add(p, off(self.k_down[0] + ".weight"), self.w_d_thin, 0, 1, C[0], C[0], (4, 4), 3, 4, 64, (64, 1, 12, 3))
+        plan.add(p, k0, self.w_u_thin, 0, 1, c2, c2, (4, 4), 3, 4, 64, (64, 1, 12, 3))
         for j in range(1, L):
             ci = C[j] if j == L - 1 else 2 * C[j]
             co = C[j - 1]
@@ -362,9 +366,7 @@ class GeneratorEngine(_Net):
         g_1x1 = ops.geom_conv_fwd(1, 1, 0)
         g_ph = ops.geom_phase_k4s2p1()
         ops.nchw_to_nhwc_bf16(x_nchw, self.x_nhwc)
-        ops.im2col_k4s2p1(self.x_nhwc, 3, None, 0, self.col0)
-        ops.conv_gemm([self.col0], self.w_d_fwd[0], g_1x1, self.A[0], C[0], S[0], act=ACT_LRELU,
-                      out2=self.R[0][..., :C[0]], act2=ACT_RELU)
+        ops.thin_conv_fwd(self.x_nhwc, None, self.w_d_thin, None, self.A[0], ACT_LRELU, self.R[0][..., :C[0]], ACT_RELU)
         for j in range(1, L - 1):
             bn = self.dbn[j]
             ops.conv_gemm([self.A[j - 1]], self.w_d_fwd[j], g_s2, self.yd[j], C[j], S[j],
@@ -399,7 +401,7 @@ class GeneratorEngine(_Net):
         ops.conv_wgrad(self.R[0], self.dycol, self.store.seg(self.store.g, self.k_up[0] + ".weight"), (1, 1), 1,
                        (0, 0), 64, 0)
         ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
-        ops.conv_gemm([self.dycol], self.w_u_dg[0], g_1x1, self.gR[0], 2 * C[0], S[0])
+        ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
         # up path, outer -> inner
         for j in range(1, L):
             bn = self.ubn[j]
@@ -423,6 +425,7 @@ class GeneratorEngine(_Net):
             else:
                 ops.bn_bwd_apply(self.A[0], self.gA[0], self.gR[0][..., :C[0]], 0.2, None, None, None, None, None, 0,
                                  self.dyd[0])
+        ops.im2col_k4s2p1(self.x_nhwc, 3, None, 0, self.col0)
         ops.conv_wgrad(self.dyd[0], self.col0, self.store.seg(self.store.g, self.k_down[0] + ".weight"), (1, 1), 1,
                        (0, 0), 64, 0)
 
@@ -433,7 +436,8 @@ class GeneratorEngine(_Net):
 class DiscriminatorEngine(_Net):
     """NLayerDiscriminator(input_nc=6, ndf, n_layers, BatchNorm2d)."""
 
-    _BUFFER_ATTRS = ("hs", "ws", "col", "H", "y", "logits", "z_ws", "dlogits", "gH", "dy", "dcol", "dfake")
+    _BUFFER_ATTRS = ("hs", "ws", "col", "H", "y", "logits", "z_ws", "dlogits", "gH", "dy", "dcol", "dfake", "_xa",
+                     "_xb")
 
     def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3, init: bool = True) -> None:
         super().__init__(device)
@@ -467,6 +471,7 @@ class DiscriminatorEngine(_Net):
             else:
                 self.w_dg.append(torch.zeros(1, C[k - 1], 16 * C[k], **bf))    # stride 1: flipped taps
         self.w_dg.append(None)                                                  # Cout = 1: direct kernels, no operand
+        self.w_thin = torch.zeros(C[0], 128, **bf)   # first conv: [64][16 taps x (A slots 0-3 | B slots 4-7)]
         self._n = None
         self._plan = None
         if init:
@@ -489,6 +494,8 @@ class DiscriminatorEngine(_Net):
         plan = ops.PackPlan()
         o = off(self.k_conv[0] + ".weight")
         plan.add(p, o, self.w_fwd[0], 0, 1, C[0], C[0], (1, 1), 128, 128, 128, (128, 1, 0, 0))
+        plan.add(p, o, self.w_thin, 0, 1, C[0], C[0], (4, 4), 3, 8, 128, (128, 1, 24, 6))
+        plan.add(p, o + 3, self.w_thin, 0, 1, C[0], C[0], (4, 4), 3, 8, 128, (128, 1, 24, 6), out_off=4)
         plan.add(p, o, self.w_dg[0], 0, 1, 128, 128, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0))
         for k in range(1, self.n_conv):
             ci = C[k - 1]
@@ -536,9 +543,8 @@ class DiscriminatorEngine(_Net):
         n, h, w, _ = xa.shape
         self._alloc(n, h, w)
         C = self.C
-        ops.im2col_k4s2p1(xa, 3, xb, 3, self.col)
-        ops.conv_gemm([self.col], self.w_fwd[0], ops.geom_conv_fwd(1, 1, 0), self.H[0], C[0], (self.hs[0], self.ws[0]),
-                      act=ACT_LRELU, bias=self.param(self.k_conv[0] + ".bias"))
+        self._xa, self._xb = xa, xb
+        ops.thin_conv_fwd(xa, xb, self.w_thin, self.param(self.k_conv[0] + ".bias"), self.H[0], ACT_LRELU)
         for k in range(1, self.n_conv - 1):
             bn = self.bn[k]
             ops.conv_gemm([self.H[k - 1]], self.w_fwd[k], ops.geom_conv_fwd(4, self.stride(k), 1), self.y[k], C[k],
@@ -570,6 +576,7 @@ class DiscriminatorEngine(_Net):
             ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.gH[k - 1], C[k - 1], grid)
         ops.bn_bwd_apply(self.H[0], self.gH[0], None, 0.2, None, None, None, None, None, 0, self.dy[0])
         if wgrad:
+            ops.im2col_k4s2p1(self._xa, 3, self._xb, 3, self.col)
             ops.conv_wgrad(self.dy[0], self.col, self.store.seg(g, self.k_conv[0] + ".weight"), (1, 1), 1, (0, 0),
                            128, 0)
             ops.colsum_bf16(self.dy[0], C[0], self.grad(self.k_conv[0] + ".bias"))

@@ -186,6 +186,19 @@ int gap_cout1_conv_dgrad(const float* dlogits, int n, int oh, int ow, const void
 int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void* x, int64_t ld_x, int ih, int iw, int c,
                          int ksize, int pad, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Thin-input Conv2d(k4, s2, p1) as one fused warp-MMA kernel (no im2col buffer): the generator's first
+ * conv (models.py:177, outermost block), the discriminator's first conv over cat(A, B) (models.py:223,
+ * train_gan.py:57,59,66) and the input gradient of the generator's last ConvTranspose2d (models.py:184).
+ *   out1[pix][co] = act1(bias[co] + sum_{tap,slot} in[2*pix+tap-1][slot] * wpk[co][tap*CT + slot]),  out2 likewise
+ * src0 / src1: NHWC bf16 with 4 channel slots used per pixel (3 channels + a zero slot; ld % 4 == 0);
+ * src1 == NULL -> CT = 4, else CT = 8 with src1's slots at 4..7.  wpk: bf16 [cw][16*CT]; cw = 64 or 128;
+ * activations: none / LeakyReLU / ReLU.  out2 may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t ld1, int n, int h, int w, const void* wpk,
+                      const float* bias, int cw, void* out1, int64_t ldo1, int act1, void* out2, int64_t ldo2, int act2,
+                      void* stream);
+
 /* nn.BatchNorm2d training bookkeeping (models.py:179,181,231,239): statistics -> scale/shift,
  * saved mean / inv-std, running stats (momentum, unbiased var, `repeat` identical updates),
  * num_batches_tracked += repeat.  Re-zeroes `stats`. */

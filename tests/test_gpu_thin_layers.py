@@ -82,3 +82,44 @@ def test_bce_logits_const_f32_loss_grad_and_bias_grad():
     s = torch.zeros(1, device=DEV)
     ops.sum_f32(x.to(DEV), s)
     assert abs(float(s) - float(x.sum())) < 1e-2
+
+
+def _slots(x):
+    """NCHW (3 channels) -> NHWC bf16 with 4 channel slots (slot 3 = 0)."""
+    n, c, h, w = x.shape
+    out = torch.zeros(n, h, w, 4, dtype=torch.bfloat16)
+    out[..., :c] = nhwc(x).to(torch.bfloat16)
+    return out
+
+
+def _pack_thin(w, groups):
+    """(cw, 3*groups, 4, 4) -> [cw][16 taps][4*groups slots] bf16, each group's 3 channels + a zero slot."""
+    cw = w.shape[0]
+    out = torch.zeros(cw, 16, 4 * groups, dtype=torch.bfloat16)
+    for gi in range(groups):
+        out[:, :, 4 * gi:4 * gi + 3] = w[:, 3 * gi:3 * gi + 3].permute(0, 2, 3, 1).reshape(cw, 16, 3).to(torch.bfloat16)
+    return out.reshape(cw, -1).contiguous()
+
+
+@pytest.mark.parametrize("n,h,w,cw,groups,bias,two_out", [
+    (2, 32, 64, 64, 1, False, True),      # generator first conv: LeakyReLU + ReLU outputs (models.py:177,178,208)
+    (3, 48, 32, 64, 2, True, False),      # discriminator first conv on cat(A, B) (models.py:223)
+    (2, 20, 36, 128, 1, False, False),    # generator last ConvT seen from its dgrad; partial tiles
+    (1, 256, 256, 64, 2, True, False),
+])
+def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
+    g = torch.Generator().manual_seed(h + cw)
+    xs = [torch.randn(n, 3, h, w, generator=g).to(torch.bfloat16).float() for _ in range(groups)]
+    wt = (torch.randn(cw, 3 * groups, 4, 4, generator=g) / (48 * groups) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(cw, generator=g) if bias else None
+    ref = F.conv2d(torch.cat(xs, 1), wt, b, stride=2, padding=1)
+    srcs = [_slots(x).to(DEV) for x in xs]
+    wide = torch.full((n, h // 2, w // 2, 2 * cw), float("nan"), device=DEV, dtype=torch.bfloat16)
+    out1 = wide[..., :cw]                                  # a channel slot of a wider buffer
+    out2 = torch.full((n, h // 2, w // 2, cw), float("nan"), device=DEV, dtype=torch.bfloat16) if two_out else None
+    ops.thin_conv_fwd(srcs[0], srcs[1] if groups == 2 else None, _pack_thin(wt, groups).to(DEV),
+                      b.to(DEV) if bias else None, out1, ops.ACT_LRELU, out2, ops.ACT_RELU)
+    assert rel(out1.cpu().float(), nhwc(F.leaky_relu(ref, 0.2))) < 4e-3
+    assert torch.isnan(wide[..., cw:].float()).all()       # the neighbouring slot is untouched
+    if two_out:
+        assert rel(out2.cpu().float(), nhwc(F.relu(ref))) < 4e-3
