@@ -575,9 +575,13 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const gap_pack_
   __shared__ float tile[32][33];
   __shared__ int s_entry;
   if (threadIdx.x == 0 && threadIdx.y == 0) {
-    int e = 0;
-    while (e + 1 < n_entries && table[e + 1].tile_begin <= static_cast<int>(blockIdx.x)) ++e;
-    s_entry = e;
+    int lo = 0, hi = n_entries - 1;   // last entry whose tile_begin <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].tile_begin <= static_cast<int>(blockIdx.x)) lo = mid;
+      else hi = mid - 1;
+    }
+    s_entry = lo;
   }
   __syncthreads();
   const gap_pack_entry a = table[s_entry];

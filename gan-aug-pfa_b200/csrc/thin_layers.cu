@@ -422,6 +422,305 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Thin-input Conv2d(k4, s2, p1) weight gradient (and the last ConvTranspose2d's, with roles swapped):
+//   dw[cw][tap][ch] += sum_pix wide[pix][cw] * thin[2*pix + tap - 1][ch];   dbias[cw] += sum_pix wide[pix][cw]
+// wide = the 64/128-channel tensor at the coarse resolution (dY of the first convs, X of the last ConvT),
+// thin = the 3-channel tensor(s) at twice the resolution (4 channel slots each).  K = pixels: per k-step one
+// row of 16 coarse pixels; A fragments come from the wide tile with ldmatrix.trans, B fragments straight from
+// the thin patch with ldmatrix.trans (a patch pixel is one 8/16-byte row of the im2col matrix that never
+// exists).  CTA = persistent over 8 x 16 tiles with register accumulators, one atomic flush at the end.
+// warp = (kernel row kh, 64-channel group).
+// dynamic smem: patch[2][18][34][CT] | wide_s[2][128][cw + 8]   (bf16, cp.async double buffers)
+// ------------------------------------------------------------------------------------------------
+struct ThinWgradParams {
+  const bf16* wide;
+  long long ld_w;
+  const bf16* s0;
+  long long ld0;
+  const bf16* s1;
+  long long ld1;
+  int n, h, w_in, oh, ow, cw;
+  float* dw;
+  long long ld_m;
+  int c_real;   // 3 (CT = 4) or 6 (CT = 8): channels per tap in the master layout
+  float* dbias;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradParams p) {
+  constexpr int PW = CT / 2;
+  constexpr int PATCH_WORDS = 18 * 34 * PW;
+  constexpr int NT = CT / 2;             // n-tiles (8 columns) per kernel row: 4 taps * CT / 8
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint32_t* patch_buf = reinterpret_cast<uint32_t*>(dsm);
+  bf16* wide_buf = reinterpret_cast<bf16*>(dsm + 2 * PATCH_WORDS * 4);
+  const int wstride = p.cw + 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int kh = warp & 3, mh = warp >> 2;
+  const int nthr = blockDim.x;
+
+  auto issue_tile = [&](long long tile, int buf) {
+    const int tx = static_cast<int>(tile % p.tiles_x);
+    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
+    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int oy0 = ty * 8, ox0 = tx * 16;
+    const bf16* s0i = p.s0 + img * p.h * p.w_in * p.ld0;
+    const bf16* s1i = CT == 8 ? p.s1 + img * p.h * p.w_in * p.ld1 : p.s0;
+    const int ld0 = static_cast<int>(p.ld0), ld1 = static_cast<int>(p.ld1);
+    const uint32_t dst0 = smem_u32(patch_buf + buf * PATCH_WORDS);
+    for (int idx = tid; idx < 18 * 34; idx += nthr) {
+      const int py = idx / 34, px = idx - py * 34;
+      const int iy = 2 * oy0 - 1 + py, ix = 2 * ox0 - 1 + px;
+      const bool ok = static_cast<unsigned>(iy) < static_cast<unsigned>(p.h) &&
+                      static_cast<unsigned>(ix) < static_cast<unsigned>(p.w_in);
+      const int pix = ok ? iy * p.w_in + ix : 0;
+      cp_async8(dst0 + idx * PW * 4, s0i + pix * ld0, ok ? 8 : 0);
+      if (CT == 8) cp_async8(dst0 + idx * PW * 4 + 8, s1i + pix * ld1, ok ? 8 : 0);
+    }
+    const bf16* wi = p.wide + img * p.oh * p.ow * p.ld_w;
+    const int ldw = static_cast<int>(p.ld_w);
+    const uint32_t wdst = smem_u32(wide_buf + buf * 128 * wstride);
+    const int vshift = p.cw == 64 ? 3 : 4;
+    for (int idx = tid; idx < (128 << vshift); idx += nthr) {
+      const int px = idx >> vshift, seg = idx & ((1 << vshift) - 1);
+      const int oy = oy0 + (px >> 4), ox = ox0 + (px & 15);
+      const bool ok = oy < p.oh && ox < p.ow;
+      cp_async16(wdst + (px * wstride + seg * 8) * 2, wi + (ok ? (oy * p.ow + ox) * ldw + seg * 8 : 0), ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  float acc[4][NT][4];
+  float accb[4][4];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[mi][ni][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accb[mi][j] = 0.f;
+  }
+  const bool do_bias = p.dbias != nullptr && kh == 0;
+
+  if (static_cast<long long>(blockIdx.x) < p.total_tiles) issue_tile(blockIdx.x, 0);
+  int buf = 0;
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
+    const long long next = tile + gridDim.x;
+    __syncthreads();  // everyone finished reading buffer buf^1 (previous tile)
+    if (next < p.total_tiles) {
+      issue_tile(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t patch_a = smem_u32(patch_buf + buf * PATCH_WORDS);
+    const uint32_t wide_a = smem_u32(wide_buf + buf * 128 * wstride);
+#pragma unroll 2
+    for (int r = 0; r < 8; ++r) {     // k-step: output row r of the tile, 16 pixels
+      // A (m = channels, k = pixels): wide_s[px][cw] read transposed
+      uint32_t a[4][4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int px = r * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int col = mh * 64 + mi * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4_trans(a[mi], wide_a + (px * wstride + col) * 2);
+      }
+      // B (k = pixels, n = (tap, slot)): patch pixels (2r + kh, 2*ox + kw) are the rows
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        // CT = 8: n-tile = tap kw = ni (16 B per pixel);  CT = 4: n-tile = taps kw = 2ni, 2ni+1 (two 8 B pixels)
+        const int kw = CT == 8 ? ni : 2 * ni;
+        const int ox = lane & 15;
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, patch_a + (((2 * r + kh) * 34 + 2 * ox + kw) * PW) * 4);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) mma_bf16_16816(acc[mi][ni], a[mi], b0, b1);
+      }
+      if (do_bias) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) mma_bf16_16816(accb[mi], a[mi], 0x3F803F80u, 0x3F803F80u);
+      }
+    }
+  }
+
+  // flush: rows = channels mh*64 + mi*16 + g (+8); columns n = ni*8 + 2t (+1) -> (tap, slot)
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int c0 = mh * 64 + mi * 16 + g;
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ncol = 2 * t + e;
+        int tap, slot;
+        if (CT == 8) {
+          tap = kh * 4 + ni;
+          slot = ncol;
+        } else {
+          tap = kh * 4 + 2 * ni + (ncol >> 2);
+          slot = ncol & 3;
+        }
+        if ((slot & 3) == 3) continue;
+        const int ch = (slot & 3) + (slot >> 2) * 3;
+        atomicAdd(p.dw + static_cast<long long>(c0) * p.ld_m + tap * p.c_real + ch, acc[mi][ni][e]);
+        atomicAdd(p.dw + static_cast<long long>(c0 + 8) * p.ld_m + tap * p.c_real + ch, acc[mi][ni][2 + e]);
+      }
+    }
+    if (do_bias && t == 0) {
+      atomicAdd(p.dbias + c0, accb[mi][0]);
+      atomicAdd(p.dbias + c0 + 8, accb[mi][2]);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Thin-output ConvTranspose2d(cw -> 3, k4, s2, p1): the generator's last layer (+bias, Tanh; models.py:184,186)
+// and the input gradient of the discriminator's first conv.  Per CTA: a 10 x 18 halo tile of `wide` (8 x 16
+// source pixels + 1 ring) is multiplied by wcol[48 = tap*3 + co][cw] into col[halo pixel][48] (fp32, shared
+// memory) with warp MMAs, then every output pixel of the 16 x 32 output tile sums its 4 taps (col2im inside
+// the CTA; the ring makes the tile self-contained), adds the bias, applies Tanh and is written once.
+// dynamic smem: wide_s[192][cw+8] (bf16) | w_s[48][cw+8] (bf16) | col_s[192][COLS] (fp32)
+// ------------------------------------------------------------------------------------------------
+struct ThinConvTParams {
+  const bf16* wide;
+  long long ld_w;
+  const bf16* wcol;
+  const float* bias;
+  int n, ih, iw, cw, act;
+  bf16* out_bf;
+  long long ld_bf;
+  float* out_f32;
+  long long ld_f;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+};
+
+constexpr int kColStride = 52;  // fp32 per col_s row (48 used)
+
+__global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTParams p) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int wstride = p.cw + 8;
+  bf16* wide_s = reinterpret_cast<bf16*>(dsm);
+  bf16* w_s = wide_s + 192 * wstride;
+  float* col_s = reinterpret_cast<float*>(w_s + 48 * wstride);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int vshift = p.cw == 64 ? 3 : 4;
+  const int oh = 2 * p.ih, ow = 2 * p.iw;
+  const int mg = warp >> 1, nh = warp & 1;   // warp = 3 m-tiles (48 halo pixels) x 3 n-tiles (24 columns)
+
+  for (int idx = tid; idx < (48 << vshift); idx += 256) {
+    const int r = idx >> vshift, seg = idx & ((1 << vshift) - 1);
+    *reinterpret_cast<uint4*>(w_s + r * wstride + seg * 8) = ldg128(p.wcol + static_cast<long long>(r) * p.cw + seg * 8);
+  }
+  float bias3[3] = {0.f, 0.f, 0.f};
+  if (p.bias != nullptr) {
+    bias3[0] = __ldg(p.bias);
+    bias3[1] = __ldg(p.bias + 1);
+    bias3[2] = __ldg(p.bias + 2);
+  }
+  const uint32_t wide_a = smem_u32(wide_s), w_a = smem_u32(w_s);
+  const int kchunks = p.cw >> 4;
+
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int tx = static_cast<int>(tile % p.tiles_x);
+    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
+    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int i0 = ty * 8, j0 = tx * 16;
+    __syncthreads();  // previous tile finished with wide_s / col_s; w_s loaded
+    {
+      const bf16* wi = p.wide + img * p.ih * p.iw * p.ld_w;
+      const int ldw = static_cast<int>(p.ld_w);
+      for (int idx = tid; idx < (192 << vshift); idx += 256) {
+        const int pix = idx >> vshift, seg = idx & ((1 << vshift) - 1);
+        const int r = pix / 18, c = pix - r * 18;
+        const int gy = i0 - 1 + r, gx = j0 - 1 + c;
+        const bool ok = pix < 180 && static_cast<unsigned>(gy) < static_cast<unsigned>(p.ih) &&
+                        static_cast<unsigned>(gx) < static_cast<unsigned>(p.iw);
+        cp_async16(wide_a + (pix * wstride + seg * 8) * 2, wi + (ok ? (gy * p.iw + gx) * ldw + seg * 8 : 0), ok ? 16 : 0);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    // ---- col = wide_s (192 x cw) * wcol^T (cw x 48)
+    float acc[3][3][4];
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 3; ++ni)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mi][ni][j] = 0.f;
+    for (int kc = 0; kc < kchunks; ++kc) {
+      uint32_t a[3][4], b[4], b4, b5;
+#pragma unroll
+      for (int mi = 0; mi < 3; ++mi)
+        ldmatrix_x4(a[mi], wide_a + (((mg * 3 + mi) * 16 + (lane & 15)) * wstride + kc * 16 + (lane >> 4) * 8) * 2);
+      ldb_16x16(b, w_a + ((nh * 24) * wstride + kc * 16) * 2, wstride * 2, lane);
+      ldmatrix_x2(b4, b5, w_a + ((nh * 24 + 16 + (lane & 7)) * wstride + kc * 16 + ((lane >> 3) & 1) * 8) * 2);
+#pragma unroll
+      for (int mi = 0; mi < 3; ++mi) {
+        mma_bf16_16816(acc[mi][0], a[mi], b[0], b[1]);
+        mma_bf16_16816(acc[mi][1], a[mi], b[2], b[3]);
+        mma_bf16_16816(acc[mi][2], a[mi], b4, b5);
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi) {
+      const int px0 = (mg * 3 + mi) * 16 + g;
+#pragma unroll
+      for (int ni = 0; ni < 3; ++ni) {
+        const int col = nh * 24 + ni * 8 + 2 * t;
+        *reinterpret_cast<float2*>(col_s + px0 * kColStride + col) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
+        *reinterpret_cast<float2*>(col_s + (px0 + 8) * kColStride + col) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
+      }
+    }
+    __syncthreads();
+    // ---- col2im inside the tile: output (yl, xl) sums its 2 x 2 taps
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pix = tid + k * 256, yl = pix >> 5, xl = pix & 31;
+      const int y = 2 * i0 + yl, x = 2 * j0 + xl;
+      if (y >= oh || x >= ow) continue;
+      float v[3] = {bias3[0], bias3[1], bias3[2]};
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const int kh = ((yl + 1) & 1) + 2 * a2;          // taps with (yl + 1 - kh) even
+        const int r = ((yl + 1 - kh) >> 1) + 1;          // halo row of the source pixel
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          const int kw = ((xl + 1) & 1) + 2 * b2;
+          const int c = ((xl + 1 - kw) >> 1) + 1;
+          const float* src = col_s + (r * 18 + c) * kColStride + (kh * 4 + kw) * 3;
+          v[0] += src[0];
+          v[1] += src[1];
+          v[2] += src[2];
+        }
+      }
+      if (p.act == GAP_ACT_TANH) {
+        v[0] = tanhf(v[0]);
+        v[1] = tanhf(v[1]);
+        v[2] = tanhf(v[2]);
+      }
+      const long long o = (img * oh + y) * ow + x;
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o * p.ld_f) = make_float4(v[0], v[1], v[2], 0.f);
+      if (p.out_bf) *reinterpret_cast<uint2*>(p.out_bf + o * p.ld_bf) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
+    }
+  }
+}
+
 // BCE-with-logits against a constant target with an fp32 gradient and the bias gradient of the
 // producing Cout = 1 conv:  dlogits = grad_scale*(sigmoid(x) - t);  dbias += sum dlogits
 __global__ void bce_logits_const_f32_kernel(const float* __restrict__ x, long long count, float t, float grad_scale,
@@ -618,6 +917,99 @@ int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t l
     }
     thin_conv_fwd_kernel<4><<<grid, threads, smem, st>>>(p);
   }
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_t ld0, const void* src1, int64_t ld1,
+                        int n, int h, int w, int cw, float* dw, int64_t ld_m, float* dbias, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GAP_CHECK_ARG(wide && src0 && dw && n > 0 && h > 1 && w > 1, "gap_thin_conv_wgrad: bad arguments");
+  if ((cw != 64 && cw != 128) || h % 2 || w % 2 || ld0 % 4 || (src1 && ld1 % 4) || ld_w % 8 ||
+      (reinterpret_cast<uintptr_t>(src0) & 7) || (reinterpret_cast<uintptr_t>(src1) & 7) ||
+      (reinterpret_cast<uintptr_t>(wide) & 15)) {
+    set_error("gap_thin_conv_wgrad: needs cw in {64,128}, even h/w, 4-slot sources (ld %% 4), 16-byte aligned wide rows");
+    return GAP_ERR_UNSUPPORTED;
+  }
+  ThinWgradParams p;
+  p.wide = static_cast<const bf16*>(wide);
+  p.ld_w = ld_w;
+  p.s0 = static_cast<const bf16*>(src0);
+  p.ld0 = ld0;
+  p.s1 = static_cast<const bf16*>(src1);
+  p.ld1 = ld1;
+  p.n = n;
+  p.h = h;
+  p.w_in = w;
+  p.oh = h / 2;
+  p.ow = w / 2;
+  p.cw = cw;
+  p.dw = dw;
+  p.ld_m = ld_m;
+  p.c_real = src1 ? 6 : 3;
+  p.dbias = dbias;
+  p.tiles_x = (p.ow + 15) / 16;
+  p.tiles_y = (p.oh + 7) / 8;
+  p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  const int ct = src1 ? 8 : 4;
+  const size_t smem = 2 * 18 * 34 * ct * 2 + 2 * 128 * static_cast<size_t>(cw + 8) * 2;
+  const int threads = 128 * (cw / 64);
+  const int grid = static_cast<int>(std::min<long long>(p.total_tiles, static_cast<long long>(debug_get("thin_wgrad_ctas_per_sm", 3)) * sm_count()));
+  if (ct == 8) {
+    static bool set8 = false;
+    if (!set8) {
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      set8 = true;
+    }
+    thin_conv_wgrad_kernel<8><<<grid, threads, smem, st>>>(p);
+  } else {
+    static bool set4 = false;
+    if (!set4) {
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      set4 = true;
+    }
+    thin_conv_wgrad_kernel<4><<<grid, threads, smem, st>>>(p);
+  }
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, int cw, const void* wcol, const float* bias,
+                       int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GAP_CHECK_ARG(wide && wcol && (out_bf16 || out_f32) && n > 0 && ih > 0 && iw > 0, "gap_thin_convT_fwd: bad arguments");
+  GAP_CHECK_ARG(act == GAP_ACT_NONE || act == GAP_ACT_TANH, "gap_thin_convT_fwd: activation must be none or Tanh");
+  if ((cw != 64 && cw != 128) || ld_w % 8 || (out_bf16 && ld_bf % 4) || (out_f32 && ld_f % 4) ||
+      (reinterpret_cast<uintptr_t>(wide) & 15) || (reinterpret_cast<uintptr_t>(wcol) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_bf16) & 7) || (reinterpret_cast<uintptr_t>(out_f32) & 15)) {
+    set_error("gap_thin_convT_fwd: needs cw in {64,128}, 16-byte aligned wide rows and 4-slot outputs");
+    return GAP_ERR_UNSUPPORTED;
+  }
+  ThinConvTParams p;
+  p.wide = static_cast<const bf16*>(wide);
+  p.ld_w = ld_w;
+  p.wcol = static_cast<const bf16*>(wcol);
+  p.bias = bias;
+  p.n = n;
+  p.ih = ih;
+  p.iw = iw;
+  p.cw = cw;
+  p.act = act;
+  p.out_bf = static_cast<bf16*>(out_bf16);
+  p.ld_bf = ld_bf;
+  p.out_f32 = out_f32;
+  p.ld_f = ld_f;
+  p.tiles_x = (iw + 15) / 16;
+  p.tiles_y = (ih + 7) / 8;
+  p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  const size_t smem = (192 + 48) * static_cast<size_t>(cw + 8) * 2 + 192 * kColStride * 4;
+  static bool set = false;
+  if (!set) {
+    GAP_CUDA(cudaFuncSetAttribute(thin_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    set = true;
+  }
+  const int grid = static_cast<int>(std::min<long long>(p.total_tiles, static_cast<long long>(debug_get("thin_convT_ctas_per_sm", cw == 64 ? 3 : 2)) * sm_count()));
+  thin_convT_fwd_kernel<<<grid, 256, smem, st>>>(p);
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -325,6 +325,41 @@ def thin_conv_fwd(s0: torch.Tensor, s1: Optional[torch.Tensor], wpk: torch.Tenso
                                             ldo1, act1, _ptr(out2), ldo2, act2, _stream()), "gap_thin_conv_fwd")
 
 
+def thin_conv_wgrad(wide: torch.Tensor, s0: torch.Tensor, s1: Optional[torch.Tensor], dw: torch.Tensor, ld_m: int,
+                    dbias: Optional[torch.Tensor] = None) -> None:
+    """dw[cw][(kh*4+kw)*c + ch] += sum_pix wide[pix][cw] * thin[2*pix+tap-1][ch] (fp32 master layout, row stride
+    ld_m); dbias[cw] += sum_pix wide[pix][cw]."""
+    n, oh, ow, cw, ldw = _nhwc_view(wide)
+    n0, h, w, _, ld0 = _nhwc_view(s0)
+    if (n0, h, w) != (n, 2 * oh, 2 * ow):
+        raise ValueError("thin source must be at twice the resolution of the wide tensor")
+    ld1 = 0
+    if s1 is not None:
+        n1, h1, w1, _, ld1 = _nhwc_view(s1)
+        if (n1, h1, w1) != (n, h, w):
+            raise ValueError("sources must share n/h/w")
+    c = 6 if s1 is not None else 3
+    if dw.dtype != torch.float32 or dw.numel() < (cw - 1) * ld_m + 16 * c:
+        raise ValueError("dw too small")
+    _lib.check(_lib.lib().gap_thin_conv_wgrad(_ptr(wide), ldw, _ptr(s0), ld0, _ptr(s1), ld1, n, h, w, cw, _ptr(dw), ld_m,
+                                              _ptr(dbias), _stream()), "gap_thin_conv_wgrad")
+
+
+def thin_convT_fwd(wide: torch.Tensor, wcol: torch.Tensor, bias: Optional[torch.Tensor], act: int,
+                   out_bf16: Optional[torch.Tensor], out_f32: Optional[torch.Tensor]) -> None:
+    """ConvTranspose2d(cw -> 3, k4, s2, p1) (+bias, Tanh) into 4-slot NHWC outputs; wcol bf16 [48 = tap*3+co, cw]."""
+    n, ih, iw, cw, ldw = _nhwc_view(wide)
+    if wcol.dtype != torch.bfloat16 or tuple(wcol.shape) != (48, cw) or not wcol.is_contiguous():
+        raise ValueError(f"wcol must be contiguous bf16 [48, {cw}]")
+    for o, dt in ((out_bf16, torch.bfloat16), (out_f32, torch.float32)):
+        if o is not None and (o.dtype != dt or tuple(o.shape[:3]) != (n, 2 * ih, 2 * iw) or o.shape[3] < 4):
+            raise ValueError("output must be [n, 2ih, 2iw, >=4]")
+    _lib.check(_lib.lib().gap_thin_convT_fwd(_ptr(wide), ldw, n, ih, iw, cw, _ptr(wcol), _ptr(bias), act, _ptr(out_bf16),
+                                             0 if out_bf16 is None else out_bf16.stride(2), _ptr(out_f32),
+                                             0 if out_f32 is None else out_f32.stride(2), _stream()),
+               "gap_thin_convT_fwd")
+
+
 def bn_finalize(stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, nbt, scale, shift,
                 save_mean, save_invstd) -> None:
     c = scale.numel()
@@ -407,8 +442,9 @@ class PackPlan:
         """``out_off`` (elements) shifts the destination inside each operand row (channel-slot packing)."""
         if mode not in (0, 1, 2):
             raise ValueError("PackPlan supports modes 0-2")
-        if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.numel() != n_phase * rows_pad * krow:
-            raise ValueError("operand buffer does not match n_phase*rows_pad*krow")
+        last = out_off + ((n_phase - 1) * rows_pad + rows - 1) * krow + (taps[0] * taps[1] - 1) * c_pad + c - 1
+        if out.dtype != torch.bfloat16 or not out.is_contiguous() or last >= out.numel():
+            raise ValueError("operand buffer is too small for this entry")
         e = _lib.PackEntry()
         e.w = w.data_ptr() + 4 * w_off
         e.out = out.data_ptr() + 2 * out_off

@@ -239,8 +239,8 @@ class _Net:
 class GeneratorEngine(_Net):
     """UNetGenerator(input_nc=3, output_nc=3, num_downs, ngf, BatchNorm2d, use_dropout=False)."""
 
-    _BUFFER_ATTRS = ("S", "x_nhwc", "col0", "A", "R", "Rin", "yd", "yu", "ycol", "fake_bf", "fake_f32", "dpre",
-                     "dycol", "gR", "gRin", "gA", "dyu", "dyd")
+    _BUFFER_ATTRS = ("S", "x_nhwc", "A", "R", "Rin", "yd", "yu", "fake_bf", "fake_f32", "dpre", "gR", "gRin", "gA",
+                     "dyu", "dyd")
 
     def __init__(self, device, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64,
                  init: bool = True) -> None:
@@ -274,10 +274,11 @@ class GeneratorEngine(_Net):
         # packed bf16 GEMM operands
         bf = dict(device=device, dtype=torch.bfloat16)
         # (zero-filled once: the packer never writes padding elements)
-        self.w_d_fwd = [torch.zeros(1, C[0], 64, **bf)] + [torch.zeros(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
+        self.w_d_fwd = [None] + [torch.zeros(1, C[j], 16 * C[j - 1], **bf) for j in range(1, L)]
         self.w_d_dg = [None] + [torch.zeros(4, C[j - 1], 4 * C[j], **bf) for j in range(1, L)]
-        self.w_u_fwd = [torch.zeros(1, 64, 2 * C[0], **bf)]
+        self.w_u_fwd = [None]
         self.w_u_dg = [None]
+        self.w_u_T2 = torch.zeros(48, 2 * C[0], **bf)        # last ConvTranspose2d, forward: [(kh*4+kw)*3 + co][Cin]
         # thin-layer operands [rows][16 taps x 4 channel slots] (3 channels + a zero slot)
         self.w_d_thin = torch.zeros(C[0], 64, **bf)          # first conv, models.py:177
         self.w_u_thin = torch.zeros(2 * C[0], 64, **bf)      # last ConvTranspose2d seen from its dgrad
@@ -305,8 +306,6 @@ class GeneratorEngine(_Net):
         L, C, p = self.L, self.C, self.store.p
         off = self.store.off
         plan = ops.PackPlan()
-        plan.add(p, off(self.k_down[0] + ".weight"), self.w_d_fwd[0], 0, 1, C[0], C[0], (1, 1), 64, 64, 64,
-                         (64, 1, 0, 0))
         for j in range(1, L):
             ci, co = C[j - 1], C[j]
             o = off(self.k_down[j] + ".weight")
@@ -314,7 +313,7 @@ class GeneratorEngine(_Net):
             plan.add(p, o, self.w_d_dg[j], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
         k0 = off(self.k_up[0] + ".weight")
         c2 = 2 * C[0]
-        plan.add(p, k0, self.w_u_fwd[0], 0, 1, 64, 64, (1, 1), c2, c2, c2, (1, 64, 0, 0))
+        plan.add(p, k0, self.w_u_T2, 0, 1, 48, 48, (1, 1), c2, c2, c2, (1, 64, 0, 0))
         plan.add(p, off(self.k_down[0] + ".weight"), self.w_d_thin, 0, 1, C[0], C[0], (4, 4), 3, 4, 64, (64, 1, 12, 3))
         plan.add(p, k0, self.w_u_thin, 0, 1, c2, c2, (4, 4), 3, 4, 64, (64, 1, 12, 3))
         for j in range(1, L):
@@ -336,18 +335,15 @@ class GeneratorEngine(_Net):
         S = [(h >> (j + 1), w >> (j + 1)) for j in range(L)]
         self.S = S
         self.x_nhwc = torch.zeros(n, h, w, 4, **bf)
-        self.col0 = torch.empty(n, S[0][0], S[0][1], 64, **bf)
         self.A = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
         self.R = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
         self.Rin = torch.empty(n, S[L - 1][0], S[L - 1][1], C[L - 1], **bf)
         self.yd = [None] + [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(1, L - 1)] + [None]
         self.yu = [None] + [torch.empty(n, S[j - 1][0], S[j - 1][1], C[j - 1], **bf) for j in range(1, L)]
-        self.ycol = torch.empty(n, S[0][0], S[0][1], 64, **bf)
         self.fake_bf = torch.zeros(n, h, w, 4, **bf)
         self.fake_f32 = torch.zeros(n, h, w, 4, device=self.dev)
         # backward scratch
         self.dpre = torch.zeros(n, h, w, 4, **bf)
-        self.dycol = torch.empty(n, S[0][0], S[0][1], 64, **bf)
         self.gR = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
         self.gRin = torch.empty_like(self.Rin)
         self.gA = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
@@ -378,8 +374,7 @@ class GeneratorEngine(_Net):
             bn = self.ubn[j]
             ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats if self.training else None)
             self._bn_forward(bn, self.yu[j], self.R[j - 1][..., C[j - 1]:], ACT_RELU, repeat=bn_repeat)
-        ops.conv_gemm([self.R[0]], self.w_u_fwd[0], g_1x1, self.ycol, 64, S[0])
-        ops.col2im_k4s2p1(self.ycol, 3, 0, 3, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32)
+        ops.thin_convT_fwd(self.R[0], self.w_u_T2, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32)
         return self.fake_f32
 
     def output_nchw(self) -> torch.Tensor:
@@ -397,9 +392,7 @@ class GeneratorEngine(_Net):
         g_1x1 = ops.geom_conv_fwd(1, 1, 0)
         g_ph = ops.geom_phase_k4s2p1()
         # outermost up-conv (GEMM + col2im form)
-        ops.im2col_k4s2p1(self.dpre, 3, None, 0, self.dycol)
-        ops.conv_wgrad(self.R[0], self.dycol, self.store.seg(self.store.g, self.k_up[0] + ".weight"), (1, 1), 1,
-                       (0, 0), 64, 0)
+        ops.thin_conv_wgrad(self.R[0], self.dpre, None, self.store.seg(self.store.g, self.k_up[0] + ".weight"), 64)
         ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
         ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
         # up path, outer -> inner
@@ -425,9 +418,7 @@ class GeneratorEngine(_Net):
             else:
                 ops.bn_bwd_apply(self.A[0], self.gA[0], self.gR[0][..., :C[0]], 0.2, None, None, None, None, None, 0,
                                  self.dyd[0])
-        ops.im2col_k4s2p1(self.x_nhwc, 3, None, 0, self.col0)
-        ops.conv_wgrad(self.dyd[0], self.col0, self.store.seg(self.store.g, self.k_down[0] + ".weight"), (1, 1), 1,
-                       (0, 0), 64, 0)
+        ops.thin_conv_wgrad(self.dyd[0], self.x_nhwc, None, self.store.seg(self.store.g, self.k_down[0] + ".weight"), 64)
 
 
 # ================================================================================================
@@ -436,8 +427,7 @@ class GeneratorEngine(_Net):
 class DiscriminatorEngine(_Net):
     """NLayerDiscriminator(input_nc=6, ndf, n_layers, BatchNorm2d)."""
 
-    _BUFFER_ATTRS = ("hs", "ws", "col", "H", "y", "logits", "z_ws", "dlogits", "gH", "dy", "dcol", "dfake", "_xa",
-                     "_xb")
+    _BUFFER_ATTRS = ("hs", "ws", "H", "y", "logits", "z_ws", "dlogits", "gH", "dy", "dfake", "_xa", "_xb")
 
     def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3, init: bool = True) -> None:
         super().__init__(device)
@@ -462,9 +452,12 @@ class DiscriminatorEngine(_Net):
             bn.allocate(device)
         self.key_order = sp.key_order()
         bf = dict(device=device, dtype=torch.bfloat16)
-        self.w_fwd = [torch.zeros(1, C[0], 128, **bf)] + [torch.zeros(1, C[k], 16 * C[k - 1], **bf) for k in range(1, n_layers + 1)]
+        self.w_fwd = [None] + [torch.zeros(1, C[k], 16 * C[k - 1], **bf) for k in range(1, n_layers + 1)]
         self.w_fwd.append(torch.zeros(1, 1, 16 * C[-1], **bf))
-        self.w_dg = [torch.zeros(1, 128, C[0], **bf)]
+        self.w_dg = [None]
+        # first conv seen from its input gradient: [(kh*4+kw)*3 + ch][64]; B half (channels 3..5) and A half
+        self.w_T2 = torch.zeros(48, C[0], **bf)
+        self.w_T2a = torch.zeros(48, C[0], **bf)
         for k in range(1, n_layers + 1):
             if k < n_layers:
                 self.w_dg.append(torch.zeros(4, C[k - 1], 4 * C[k], **bf))     # stride 2: four phases
@@ -493,10 +486,11 @@ class DiscriminatorEngine(_Net):
         C, p, off = self.C, self.store.p, self.store.off
         plan = ops.PackPlan()
         o = off(self.k_conv[0] + ".weight")
-        plan.add(p, o, self.w_fwd[0], 0, 1, C[0], C[0], (1, 1), 128, 128, 128, (128, 1, 0, 0))
         plan.add(p, o, self.w_thin, 0, 1, C[0], C[0], (4, 4), 3, 8, 128, (128, 1, 24, 6))
         plan.add(p, o + 3, self.w_thin, 0, 1, C[0], C[0], (4, 4), 3, 8, 128, (128, 1, 24, 6), out_off=4)
-        plan.add(p, o, self.w_dg[0], 0, 1, 128, 128, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0))
+        for tap in range(16):
+            plan.add(p, o + 6 * tap + 3, self.w_T2, 0, 1, 3, 3, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0), out_off=3 * tap * C[0])
+            plan.add(p, o + 6 * tap, self.w_T2a, 0, 1, 3, 3, (1, 1), C[0], C[0], C[0], (1, 128, 0, 0), out_off=3 * tap * C[0])
         for k in range(1, self.n_conv):
             ci = C[k - 1]
             co = 1 if k == self.n_conv - 1 else C[k]
@@ -525,7 +519,6 @@ class DiscriminatorEngine(_Net):
                 hs.append(hs[-1] - 1)
                 ws.append(ws[-1] - 1)
         self.hs, self.ws = hs, ws
-        self.col = torch.empty(n, hs[0], ws[0], 128, **bf)
         self.H = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
         self.y = [None] + [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(1, self.n_conv - 1)]
         self.logits = torch.empty(n, hs[-1], ws[-1], 1, device=self.dev)
@@ -533,7 +526,6 @@ class DiscriminatorEngine(_Net):
         self.dlogits = torch.zeros(n, hs[-1], ws[-1], device=self.dev)            # fp32 d(loss)/d(logits)
         self.gH = [torch.empty_like(t) for t in self.H]
         self.dy = [torch.empty_like(t) for t in self.H]
-        self.dcol = torch.empty(n, hs[0], ws[0], 128, **bf)
         self.dfake = torch.zeros(n, h, w, 4, device=self.dev)
         self._n = (n, h, w)
 
@@ -576,17 +568,13 @@ class DiscriminatorEngine(_Net):
             ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.gH[k - 1], C[k - 1], grid)
         ops.bn_bwd_apply(self.H[0], self.gH[0], None, 0.2, None, None, None, None, None, 0, self.dy[0])
         if wgrad:
-            ops.im2col_k4s2p1(self._xa, 3, self._xb, 3, self.col)
-            ops.conv_wgrad(self.dy[0], self.col, self.store.seg(g, self.k_conv[0] + ".weight"), (1, 1), 1, (0, 0),
-                           128, 0)
-            ops.colsum_bf16(self.dy[0], C[0], self.grad(self.k_conv[0] + ".bias"))
+            ops.thin_conv_wgrad(self.dy[0], self._xa, self._xb, self.store.seg(g, self.k_conv[0] + ".weight"), 128,
+                                dbias=self.grad(self.k_conv[0] + ".bias"))
         if input_grad:
-            ops.conv_gemm([self.dy[0]], self.w_dg[0], ops.geom_conv_fwd(1, 1, 0), self.dcol, 128,
-                          (self.hs[0], self.ws[0]))
-            ops.col2im_k4s2p1(self.dcol, 6, 3, 3, None, ACT_NONE, None, self.dfake)
+            ops.thin_convT_fwd(self.dy[0], self.w_T2, None, ACT_NONE, None, self.dfake)
             if input_grad_a:
                 self.dreal = torch.zeros_like(self.dfake)
-                ops.col2im_k4s2p1(self.dcol, 6, 0, 3, None, ACT_NONE, None, self.dreal)
+                ops.thin_convT_fwd(self.dy[0], self.w_T2a, None, ACT_NONE, None, self.dreal)
             return self.dfake
         return None
 

@@ -199,6 +199,22 @@ int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t l
                       const float* bias, int cw, void* out1, int64_t ldo1, int act1, void* out2, int64_t ldo2, int act2,
                       void* stream);
 
+/* Weight (and bias) gradient of the same thin layers, accumulated straight into the fp32 master layout
+ * [cw][(kh*4+kw)*c + ch] (row stride ld_m, c = 3 or 6):
+ *   dw[cw][tap][ch] += sum_pix wide[pix][cw] * thin[2*pix+tap-1][ch];   dbias[cw] += sum_pix wide[pix][cw]
+ * wide: NHWC bf16 [n, h/2, w/2, cw] (dY of the first convs; X of the generator's last ConvTranspose2d, whose
+ * weight (Cin, 3, 4, 4) has this same form with thin = dY); thin sources as in gap_thin_conv_fwd.
+ * dbias may be NULL. */
+int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_t ld0, const void* src1, int64_t ld1,
+                        int n, int h, int w, int cw, float* dw, int64_t ld_m, float* dbias, void* stream);
+
+/* Thin-output ConvTranspose2d(cw -> 3, k4, s2, p1) (+bias, Tanh): the generator's last layer
+ * (models.py:184,186), and — with the first conv's weights — the input gradient of the discriminator's first
+ * conv (models.py:223).  wide: NHWC bf16 [n, ih, iw, cw]; wcol: bf16 [48 = (kh*4+kw)*3 + co][cw]; outputs
+ * [n, 2ih, 2iw, 4 slots] in bf16 and / or fp32 (slot 3 is written as zero); act = GAP_ACT_NONE or GAP_ACT_TANH. */
+int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, int cw, const void* wcol, const float* bias,
+                       int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, void* stream);
+
 /* nn.BatchNorm2d training bookkeeping (models.py:179,181,231,239): statistics -> scale/shift,
  * saved mean / inv-std, running stats (momentum, unbiased var, `repeat` identical updates),
  * num_batches_tracked += repeat.  Re-zeroes `stats`. */

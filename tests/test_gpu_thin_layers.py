@@ -123,3 +123,53 @@ def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
     assert torch.isnan(wide[..., cw:].float()).all()       # the neighbouring slot is untouched
     if two_out:
         assert rel(out2.cpu().float(), nhwc(F.relu(ref))) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,cw,groups,bias", [
+    (2, 32, 64, 64, 1, False),       # generator first conv wgrad
+    (3, 48, 32, 64, 2, True),        # discriminator first conv wgrad + bias grad
+    (2, 20, 36, 128, 1, False),      # generator last ConvT wgrad (wide = its input); partial tiles
+    (5, 64, 64, 64, 2, True),
+])
+def test_thin_conv_wgrad(n, h, w, cw, groups, bias):
+    g = torch.Generator().manual_seed(h * 3 + cw)
+    xs = [torch.randn(n, 3, h, w, generator=g).to(torch.bfloat16).float() for _ in range(groups)]
+    dy = torch.randn(n, cw, h // 2, w // 2, generator=g).to(torch.bfloat16).float()
+    wt = torch.zeros(cw, 3 * groups, 4, 4, requires_grad=True)
+    bt = torch.zeros(cw, requires_grad=True)
+    out = F.conv2d(torch.cat(xs, 1), wt, bt, stride=2, padding=1)
+    out.backward(dy)
+    c = 3 * groups
+    krow = 64 if groups == 1 else 128
+    dw = torch.zeros(cw, krow, device=DEV)
+    db = torch.zeros(cw, device=DEV) if bias else None
+    srcs = [_slots(x).to(DEV) for x in xs]
+    ops.thin_conv_wgrad(nhwc(dy).to(torch.bfloat16).to(DEV), srcs[0], srcs[1] if groups == 2 else None, dw.view(-1), krow, db)
+    ref = wt.grad.permute(0, 2, 3, 1).reshape(cw, 16 * c)                      # [cw][(kh*4+kw)*c + ch]
+    assert rel(dw.cpu()[:, :16 * c], ref) < 2e-4
+    assert float(dw.cpu()[:, 16 * c:].abs().max()) == 0.0
+    if bias:
+        assert rel(db.cpu(), bt.grad) < 2e-4
+
+
+@pytest.mark.parametrize("n,ih,iw,cw,bias,act", [
+    (2, 16, 32, 128, True, "tanh"),     # generator last layer (models.py:184,186)
+    (3, 24, 16, 64, False, "none"),     # discriminator first conv, input gradient
+    (2, 10, 18, 64, True, "tanh"),      # partial tiles
+])
+def test_thin_convT_fwd(n, ih, iw, cw, bias, act):
+    g = torch.Generator().manual_seed(ih + cw)
+    x = torch.randn(n, cw, ih, iw, generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn(cw, 3, 4, 4, generator=g) / (4 * cw) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(3, generator=g) if bias else None
+    ref = F.conv_transpose2d(x, wt, b, stride=2, padding=1)
+    if act == "tanh":
+        ref = torch.tanh(ref)
+    w2 = wt.permute(2, 3, 1, 0).reshape(48, cw).to(torch.bfloat16).contiguous()       # [(kh*4+kw)*3 + co][ci]
+    obf = torch.full((n, 2 * ih, 2 * iw, 4), float("nan"), device=DEV, dtype=torch.bfloat16)
+    o32 = torch.full((n, 2 * ih, 2 * iw, 4), float("nan"), device=DEV)
+    ops.thin_convT_fwd(nhwc(x).to(torch.bfloat16).to(DEV), w2.to(DEV), b.to(DEV) if bias else None,
+                       ops.ACT_TANH if act == "tanh" else ops.ACT_NONE, obf, o32)
+    assert rel(o32.cpu()[..., :3], nhwc(ref)) < 1e-4
+    assert rel(obf.cpu().float()[..., :3], nhwc(ref)) < 4e-3
+    assert float(o32.cpu()[..., 3].abs().max()) == 0.0
