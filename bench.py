@@ -149,7 +149,6 @@ def run_reference(args) -> None:
 def run_ours(args) -> None:
     import torch.distributed as dist
     from gan_aug_pfa_b200 import _lib, ops
-    from gan_aug_pfa_b200.parallel import make_allreduce
     from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,7 +161,7 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    tr = Pix2PixTrainer(dev, allreduce=make_allreduce(world) if world > 1 else None, world=world)
+    tr = Pix2PixTrainer(dev, world=world)     # world > 1: bucketed NCCL all-reduce overlapped with the backward pass
     N = BATCH_PER_GPU
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 2

@@ -105,6 +105,16 @@ class _Net:
         self.views: Dict[str, Tuple[str, Tuple[int, ...], Tuple[int, ...]]] = {}
         self.key_order: List[str] = []
         self.training = True
+        self.grad_hook = None     # callable(segment name) fired when a gradient segment is final (data-parallel buckets)
+
+    def _ready(self, *keys: str) -> None:
+        if self.grad_hook is not None:
+            for k in keys:
+                self.grad_hook(k)
+
+    def grad_segments(self) -> List[Tuple[str, int, int]]:
+        """(name, offset, numel) of every gradient segment in flat-buffer (= backward-completion) order."""
+        return [(k, off, n) for k, (off, n) in self.store.segs.items()]
 
     # -- registration helpers -------------------------------------------------------------------
     def _reg(self, key: str, numel: int, shape, strides) -> None:
@@ -229,6 +239,7 @@ class _Net:
         ops.bn_bwd_apply(y, g1, g2, slope, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums, count, dy)
         if param_grads:
             ops.bn_param_grads(bn.sums, self.grad(bn.name + ".weight"), self.grad(bn.name + ".bias"))
+            self._ready(bn.name + ".weight", bn.name + ".bias")
         else:
             ops.bn_param_grads(bn.sums, None, None)
 
@@ -394,6 +405,7 @@ class GeneratorEngine(_Net):
         # outermost up-conv (GEMM + col2im form)
         ops.thin_conv_wgrad(self.R[0], self.dpre, None, self.store.seg(self.store.g, self.k_up[0] + ".weight"), 64)
         ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
+        self._ready(self.k_up[0] + ".weight", self.k_up[0] + ".bias")
         ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
         # up path, outer -> inner
         for j in range(1, L):
@@ -404,6 +416,7 @@ class GeneratorEngine(_Net):
             ci = src.shape[-1]
             ops.conv_wgrad(src, self.dyu[j], self.store.seg(self.store.g, self.k_up[j] + ".weight"), (4, 4), 2,
                            (-1, -1), 16 * co, co)
+            self._ready(self.k_up[j] + ".weight")
             dst = self.gRin if j == L - 1 else self.gR[j]
             ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, dst, ci, S[j])
         # innermost down conv: ReLU backward, wgrad, dgrad
@@ -411,6 +424,7 @@ class GeneratorEngine(_Net):
         for j in range(L - 1, 0, -1):
             ops.conv_wgrad(self.dyd[j], self.A[j - 1], self.store.seg(self.store.g, self.k_down[j] + ".weight"),
                            (4, 4), 2, (-1, -1), 16 * C[j - 1], C[j - 1])
+            self._ready(self.k_down[j] + ".weight")
             ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.gA[j - 1], C[j - 1], S[j])
             jj = j - 1
             if jj >= 1:
@@ -419,6 +433,7 @@ class GeneratorEngine(_Net):
                 ops.bn_bwd_apply(self.A[0], self.gA[0], self.gR[0][..., :C[0]], 0.2, None, None, None, None, None, 0,
                                  self.dyd[0])
         ops.thin_conv_wgrad(self.dyd[0], self.x_nhwc, None, self.store.seg(self.store.g, self.k_down[0] + ".weight"), 64)
+        self._ready(self.k_down[0] + ".weight")
 
 
 # ================================================================================================
@@ -587,7 +602,8 @@ class Pix2PixTrainer:
     data-parallel gradient all-reduce (see parallel.py)."""
 
     def __init__(self, device, lr_g: float = 1e-4, lr_d: float = 1e-4, beta1: float = 0.5, num_downs: int = 7,
-                 ngf: int = 64, ndf: int = 64, n_layers: int = 3, allreduce=None, world: int = 1) -> None:
+                 ngf: int = 64, ndf: int = 64, n_layers: int = 3, allreduce=None, world: int = 1,
+                 bucket_elems: int = 8 << 20) -> None:
         self.dev = torch.device(device)
         # construction order G then D fixes the seeded weights (train_gan.py:138-139)
         self.G = GeneratorEngine(self.dev, 3, 3, num_downs, ngf)
@@ -597,6 +613,15 @@ class Pix2PixTrainer:
         self.allreduce = allreduce
         self.world = world
         self.a_nhwc = None
+        # data parallel: bucketed all-reduce of the flat gradient buffers; the generator's buckets are reduced
+        # on a side stream while its backward pass is still running (buffer order = completion order)
+        self.g_reducer = self.d_reducer = None
+        if world > 1 and allreduce is None:
+            from .parallel import GradBucketReducer
+            self.g_reducer = GradBucketReducer(self.G.store.g, self.G.grad_segments(), bucket_elems=bucket_elems)
+            self.d_reducer = GradBucketReducer(self.D.store.g, self.D.grad_segments(), bucket_elems=1 << 30,
+                                               comm_stream=self.g_reducer.comm_stream)
+            self.G.grad_hook = self.g_reducer.mark_ready
 
     def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
         """real_A / real_B: fp32 NCHW on the device.  Returns a device tensor [loss_d, loss_g] (fp64);
@@ -621,7 +646,10 @@ class Pix2PixTrainer:
         logits = D.forward(a_nhwc, G.fake_bf)              # :59
         ops.bce_logits_const_f32(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2], d_bias_last)   # :60,61
         D.backward(wgrad=True, input_grad=False)           # :62
-        if self.allreduce is not None:
+        if self.d_reducer is not None:
+            self.d_reducer.begin()
+            self.d_reducer.finish()
+        elif self.allreduce is not None:
             self.allreduce(D.store.g)
         D.adam_step(self.lr_d, self.betas, grad_scale=1.0 / self.world)   # :63
         # ---- G step (train_gan.py:64-71)
@@ -631,8 +659,12 @@ class Pix2PixTrainer:
         dfake = D.backward(wgrad=False, input_grad=True)
         numel = n * 3 * h * w
         ops.gen_out_bwd(G.fake_f32, real_B, dfake, LAMBDA_L1 / numel, G.dpre, self.loss_acc[3:4])  # :68-70
+        if self.g_reducer is not None:
+            self.g_reducer.begin()
         G.backward()
-        if self.allreduce is not None:
+        if self.g_reducer is not None:
+            self.g_reducer.finish()
+        elif self.allreduce is not None:
             self.allreduce(G.store.g)
         G.adam_step(self.lr_g, self.betas, grad_scale=1.0 / self.world)   # :71
         la = self.loss_acc

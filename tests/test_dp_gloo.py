@@ -82,3 +82,62 @@ def test_grad_scale_equals_averaging():
     pb, mb, vb = p.clone(), torch.zeros(100), torch.zeros(100)
     O.adam_update(pb, (g1 + g2) * 0.5, mb, vb, 1, 1e-4, 0.5, 0.999)
     assert torch.equal(pa, pb)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GradBucketReducer: bucket planning and the overlapped launch protocol (CPU tensors, gloo)
+# ---------------------------------------------------------------------------------------------------
+def test_plan_buckets_tiles_the_buffer_on_segment_boundaries():
+    from gan_aug_pfa_b200.parallel import plan_buckets
+    segs = [("a", 0, 10), ("b", 12, 100), ("c", 112, 5), ("d", 120, 300), ("e", 420, 7)]
+    buckets = plan_buckets(segs, 428, 100)
+    assert buckets[0][0] == 0 and buckets[-1][1] == 428
+    for (b0, e0, _), (b1, _, _) in zip(buckets, buckets[1:]):
+        assert e0 == b1
+    assert [n for _, _, names in buckets for n in names] == ["a", "b", "c", "d", "e"]
+    assert all(e - b >= 100 for b, e, _ in buckets[:-1])
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gan_aug_pfa_b200.parallel import GradBucketReducer
+        segs, off = [], 0
+        for i, n in enumerate([50, 7, 300, 120, 3, 64, 900, 11]):
+            segs.append((f"s{i}", off, n))
+            off += (n + 3) // 4 * 4
+        g = torch.Generator().manual_seed(100 + rank)
+        flat = torch.randn(off, generator=g)
+        local = flat.clone()
+        red = GradBucketReducer(flat, segs, bucket_elems=200)
+        red.begin()
+        order = ["s0", "s2", "s1", "s3", "s4", "s5", "s6"]        # s1 late: bucket 0 waits for it; s7 never marked
+        launched = []
+        for name in order:
+            red.mark_ready(name)
+            launched.append(red.launched_before_finish)
+        red.finish()
+        q.put((rank, local, flat, launched, len(red.buckets)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_bucket_reducer_world2_overlapped_protocol():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = res[0][1] + res[1][1]
+    for _, _, reduced, launched, n_buckets in res:
+        assert torch.allclose(reduced, total, rtol=1e-6, atol=1e-9)      # every element reduced exactly once
+        assert launched[0] == 0 and launched[1] == 0                      # bucket 0 = {s0,s1,s2} not complete yet
+        assert launched[2] >= 1                                           # ... until s1 arrives
+        assert launched[-1] >= 2 and launched[-1] < n_buckets             # buckets went out during "backward"
