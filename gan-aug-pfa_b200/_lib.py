@@ -41,6 +41,10 @@ class ConvGemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("stats", C.c_void_p),
         ("out_f32", C.c_int),
+        ("bwd_y", C.c_void_p), ("bwd_y_ld", C.c_int64),
+        ("bwd_scale", C.c_void_p), ("bwd_shift", C.c_void_p),
+        ("bwd_g2", C.c_void_p), ("bwd_g2_ld", C.c_int64),
+        ("bwd_slope", C.c_float), ("bwd_c0", C.c_int),
     ]
 
 
@@ -102,6 +106,7 @@ _SIGNATURES = {
     "gap_bn_bwd_reduce": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _P, _P, _P, _L, _I, _P, _P]),
     "gap_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _P, _P, _P, _L, _I, _P, _D, _P, _L, _P]),
     "gap_bn_param_grads": (C.c_int, [_P, _I, _P, _P, _P]),
+    "gap_bn_bwd_finalize": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "gap_colsum_bf16": (C.c_int, [_P, _L, _L, _I, _P, _P]),
     "gap_adam_flat": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _F, _P]),
     "gap_pack_weights": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P]),

@@ -22,12 +22,14 @@ namespace gap {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kFpropThreads = 192;
+constexpr int kEpiWarps = 8;   // two warps per TMEM lane quarter: one warp per scheduler is latency-bound in the epilogue
+constexpr int kFpropThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
 constexpr int kTmemCols = 512;
 constexpr int kStatsBytes = 4 * 256 * 2 * 8;  // per-epilogue-warp fp64 partial sums
 constexpr int kBarrierBytes = 256;
+constexpr int kParamBytes = 2 * 256 * 4;  // per-N-tile scale / shift of the backward-fused epilogue
 constexpr int kSmemBudget = 227 * 1024;
 
 struct alignas(64) FpropParams {
@@ -62,6 +64,16 @@ struct alignas(64) FpropParams {
   int out_f32;  // `out` is fp32 (scalar stores; used for the 1-channel logits)
   int fast_store;  // slope-type activations and 32-byte-aligned bf16 outputs: vector epilogue
   float slope1, slope2;  // negative-side slope of act / act2 (1 identity, 0.2 LeakyReLU, 0 ReLU)
+  // backward-fused epilogue (kEpi = 1): activation (+BatchNorm) backward applied to output channels >= bwd_c0
+  const __nv_bfloat16* bwd_y;
+  long long bwd_y_ld;
+  const float* bwd_scale;
+  const float* bwd_shift;
+  const __nv_bfloat16* bwd_g2;
+  long long bwd_g2_ld;
+  float bwd_slope;
+  int bwd_c0;
+  int skip;  // bring-up ablation: 1 no global stores, 2 no y / g2 loads, 4 no statistics
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -161,6 +173,7 @@ __device__ __noinline__ void epilogue_store_generic(const FpropParams& p, const 
   }
 }
 
+template <int kEpi>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -178,6 +191,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   uint8_t* bar_gen = smem_gen + p.num_stages * stage_bytes;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 20);
   double* stats_sm = reinterpret_cast<double*>(bar_gen + kBarrierBytes);
+  float* par_sm = reinterpret_cast<float*>(bar_gen + kBarrierBytes + kStatsBytes);  // [2][256] scale | shift
 
   // Warp index broadcast from lane 0: the role dispatch and the producer / MMA loops are then
   // warp-uniform for the compiler, so TMA / MMA operands stay in uniform registers (a per-lane
@@ -195,7 +209,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -293,34 +307,55 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter take the even / odd 16-column chunks
     const int row = q * 32 + lane;
-    const int e_tid = threadIdx.x - 64;  // 0..127
+    const int e_tid = threadIdx.x - 64;  // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_ntile = -1;
     double* my_stats = stats_sm + q * 512;  // [256 sum][256 sumsq]
-    const bool do_stats = p.stats != nullptr;
+    const bool do_stats = p.stats != nullptr && !(p.skip & 4);
     const int stat_col = ((lane >> 1) & 15);
 
     auto flush_stats = [&](int n_tile) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = e_tid; c < 2 * p.block_n; c += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = e_tid; c < 2 * p.block_n; c += 32 * kEpiWarps) {
         const int which = c / p.block_n, col = c - which * p.block_n;
         const int gcol = n_tile * p.block_n + col;
         const int idx = which * 256 + col;
         double tot = stats_sm[idx] + stats_sm[512 + idx] + stats_sm[1024 + idx] + stats_sm[1536 + idx];
-        if (gcol < p.n_out) atomicAdd(p.stats + which * p.n_out + gcol, tot);
+        if (kEpi == 1) {
+          const int n_stats = p.n_out - p.bwd_c0;
+          if (gcol >= p.bwd_c0 && gcol < p.n_out) atomicAdd(p.stats + which * n_stats + (gcol - p.bwd_c0), tot);
+        } else if (gcol < p.n_out) {
+          atomicAdd(p.stats + which * p.n_out + gcol, tot);
+        }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     };
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const WorkCoord wc = decode_work(p, tile);
-      if (do_stats && wc.n_tile != cur_ntile) {
-        if (cur_ntile >= 0) flush_stats(cur_ntile);
-        for (int c = lane; c < 512; c += 32) my_stats[c] = 0.0;
+      if ((do_stats || kEpi == 1) && wc.n_tile != cur_ntile) {
+        if (do_stats && cur_ntile >= 0) flush_stats(cur_ntile);
+        if (do_stats) {
+          if (half == 0)
+            for (int c = lane; c < 512; c += 32) my_stats[c] = 0.0;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        if (kEpi == 1) {
+          // stage this N tile's BatchNorm scale / shift (identity when the layer has no BatchNorm)
+          if (!do_stats) asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+          for (int c = e_tid; c < p.block_n; c += 32 * kEpiWarps) {
+            const int gcol = wc.n_tile * p.block_n + c;
+            const bool on = p.bwd_scale != nullptr && gcol >= p.bwd_c0 && gcol < p.n_out;
+            par_sm[c] = on ? __ldg(p.bwd_scale + gcol - p.bwd_c0) : 1.f;
+            par_sm[256 + c] = on ? __ldg(p.bwd_shift + gcol - p.bwd_c0) : 0.f;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         __syncwarp();
         cur_ntile = wc.n_tile;
       }
@@ -340,7 +375,31 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             tmem_base + acc * kAccStride + j * p.block_n + (static_cast<uint32_t>(q * 32) << 16);
         if (!mtile.exists) continue;
         const bool fast = valid && p.fast_store;
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int cg = half; cg < n_chunks; cg += 8) {
+          // backward-fused epilogue: issue the y / g2 loads of up to four chunks before touching TMEM, so their
+          // latency overlaps (the epilogue is latency-bound otherwise: only four warps per CTA)
+          uint4 yq[4][2], gq[4][2];
+          if (kEpi == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              yq[i][0] = yq[i][1] = gq[i][0] = gq[i][1] = make_uint4(0, 0, 0, 0);
+              const int colp = wc.n_tile * p.block_n + (cg + 2 * i) * 16;
+              if (valid && cg + 2 * i < n_chunks && colp >= p.bwd_c0 && colp < p.n_out && !(p.skip & 2)) {
+                const uint4* yp = reinterpret_cast<const uint4*>(p.bwd_y + pix * p.bwd_y_ld + (colp - p.bwd_c0));
+                yq[i][0] = __ldg(yp);
+                yq[i][1] = __ldg(yp + 1);
+                if (p.bwd_g2 != nullptr) {
+                  const uint4* gp = reinterpret_cast<const uint4*>(p.bwd_g2 + pix * p.bwd_g2_ld + (colp - p.bwd_c0));
+                  gq[i][0] = __ldg(gp);
+                  gq[i][1] = __ldg(gp + 1);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+          const int c = cg + 2 * ci;
+          if (c >= n_chunks) break;
           uint32_t raw[16];
           tmem_ld16(t_row + c * 16, raw);
           tmem_ld_wait();
@@ -348,11 +407,54 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           float f[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(raw[jj]);
+          if (kEpi == 1 && col0 >= p.bwd_c0) {
+            // d = mask(y) ? g (+ g2) : slope * g  with mask = (y*scale + shift > 0); sums of d and d*y
+            const uint32_t* yw = reinterpret_cast<const uint32_t*>(yq[ci]);
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq[ci]);
+            const float4* scp = reinterpret_cast<const float4*>(par_sm + c * 16);
+            const float4* shp = reinterpret_cast<const float4*>(par_sm + 256 + c * 16);
+            float yv[16];
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              const float4 sc = scp[v4], sh = shp[v4];
+              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int jj = v4 * 4 + e;
+                const uint32_t ywd = yw[jj >> 1], gwd = gw[jj >> 1];
+                const float y = (jj & 1) ? bf16_hi(ywd) : bf16_lo(ywd);
+                const float g2 = (jj & 1) ? bf16_hi(gwd) : bf16_lo(gwd);
+                yv[jj] = y;
+                const float yh = fmaf(y, scv[e], shv[e]);
+                f[jj] = yh > 0.f ? f[jj] + g2 : p.bwd_slope * f[jj];
+              }
+            }
+            if (do_stats) {
+              float m[16];
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) m[jj] = valid ? f[jj] : 0.f;
+              const float s = transpose_reduce16(m, lane);
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) m[jj] = m[jj] * yv[jj];
+              const float s2 = transpose_reduce16(m, lane);
+              if ((lane & 1) == 0) {
+                my_stats[c * 16 + stat_col] += static_cast<double>(s);
+                my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
+              }
+            }
+            if (valid && !(p.skip & 1)) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack_bf16x2(f[2 * jj], f[2 * jj + 1]);
+              st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
+            }
+            continue;
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) f[jj] += __ldg(p.bias + min(col0 + jj, p.n_out - 1));
           }
-          if (do_stats) {
+          if (do_stats && kEpi == 0) {
             float m[16];
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) m[jj] = valid ? f[jj] : 0.f;
@@ -365,7 +467,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
             }
           }
-          if (fast && col0 + 16 <= p.n_out) {
+          if (fast && col0 + 16 <= p.n_out && !(p.skip & 1)) {
             // common case: slope-type activation (identity / LeakyReLU / ReLU), 256-bit stores
             uint32_t pk[8];
 #pragma unroll
@@ -384,6 +486,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             }
           } else if (valid && col0 < p.n_out) {
             epilogue_store_generic(p, f, pix, col0);
+          }
           }
         }
       }
@@ -526,14 +629,36 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.slope2 = slope_of(a->act2);
   p.fast_store = (vec32 && !a->out_f32 && a->act <= GAP_ACT_RELU && a->act2 <= GAP_ACT_RELU) ? 1 : 0;
   GAP_CHECK_ARG(!(a->out_f32 && a->out2), "gap_conv_gemm: out2 is not supported with fp32 output");
+  const bool bwd = a->bwd_y != nullptr;
+  if (bwd) {
+    const bool ok = vec32 && !a->out_f32 && !a->out2 && a->act == GAP_ACT_NONE && !a->bias && a->bwd_c0 >= 0 &&
+                    a->bwd_c0 % 16 == 0 && a->bwd_c0 < a->n_out && (a->n_out - a->bwd_c0) % 16 == 0 &&
+                    a->bwd_y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->bwd_y) & 15) == 0 &&
+                    (!a->bwd_g2 || (a->bwd_g2_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->bwd_g2) & 15) == 0)) &&
+                    ((a->bwd_scale == nullptr) == (a->bwd_shift == nullptr));
+    if (!ok) {
+      set_error("gap_conv_gemm: the backward-fused epilogue needs a 32-byte aligned bf16 output without bias / "
+                "activation / out2, 16-aligned channel ranges and 16-byte aligned y / g2 rows");
+      return GAP_ERR_UNSUPPORTED;
+    }
+  }
+  p.bwd_y = static_cast<const __nv_bfloat16*>(a->bwd_y);
+  p.bwd_y_ld = a->bwd_y_ld;
+  p.bwd_scale = a->bwd_scale;
+  p.bwd_shift = a->bwd_shift;
+  p.bwd_g2 = static_cast<const __nv_bfloat16*>(a->bwd_g2);
+  p.bwd_g2_ld = a->bwd_g2_ld;
+  p.bwd_slope = a->bwd_slope;
+  p.bwd_c0 = a->bwd_c0;
+  p.skip = debug_get("fprop_skip", 0);
 
   const int stage_bytes = mt * kATileBytes + block_n * 128;
-  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);
   if (force_st > 0) stages = std::min(force_st, stages);
   p.num_stages = stages;
-  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes + kParamBytes;
 
   // ---- tensor maps
   const uint32_t bx_w = static_cast<uint32_t>(BW * a->in_stride);
@@ -564,12 +689,15 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBudget));
+    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   const int grid = std::min(p.total_tiles, sms);
-  conv_fprop_kernel<<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+  if (bwd)
+    conv_fprop_kernel<1><<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+  else
+    conv_fprop_kernel<0><<<grid, kFpropThreads, smem_bytes, stream>>>(p);
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

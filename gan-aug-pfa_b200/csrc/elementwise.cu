@@ -442,6 +442,24 @@ __global__ void bn_param_grads_kernel(double* __restrict__ sums, int c, float* _
   }
 }
 
+// raw = [sum d, sum d*y] from the backward-fused GEMM epilogue -> sums = [sum d, sum d*xhat]; parameter
+// gradients; raw re-zeroed for the next backward pass.
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ raw, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int c, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    const double s1 = raw[i], s2 = raw[c + i];
+    const double sx = static_cast<double>(invstd[i]) * (s2 - static_cast<double>(mean[i]) * s1);
+    sums[i] = s1;
+    sums[c + i] = sx;
+    if (dbeta) dbeta[i] += static_cast<float>(s1);
+    if (dgamma) dgamma[i] += static_cast<float>(sx);
+    raw[i] = 0.0;
+    raw[c + i] = 0.0;
+  }
+}
+
 // per-channel column sums of a bf16 [pixels][c] tensor into fp32 (bias gradients)
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long pixels, int c,
                               float* __restrict__ out) {
@@ -820,6 +838,15 @@ int gap_bn_bwd_apply(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1,
 int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* stream) {
   GAP_CHECK_ARG(sums && c > 0, "gap_bn_param_grads: bad arguments");
   bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, c, dgamma, dbeta);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_bn_bwd_finalize(double* raw, const float* mean, const float* invstd, int c, float* dgamma, float* dbeta,
+                        double* sums, void* stream) {
+  GAP_CHECK_ARG(raw && mean && invstd && sums && c > 0, "gap_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(raw, mean, invstd, c, dgamma,
+                                                                                        dbeta, sums);
   GAP_LAUNCH_CHECK();
   return 0;
 }

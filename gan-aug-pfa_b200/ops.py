@@ -83,7 +83,7 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
               n_out: int, grid_hw: tuple[int, int], *, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, act2: int = ACT_NONE,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              flops: Optional[float] = None) -> None:
+              flops: Optional[float] = None, bwd: Optional[dict] = None) -> None:
     """Launch the implicit-GEMM engine.  ``wpk`` is [n_phase, rows, taps*ctot] bf16.  ``flops`` overrides
     the algorithmic FLOP count reported to the profiler (layers that pad channels pass the true one)."""
     a = _lib.ConvGemmArgs()
@@ -142,12 +142,35 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
         a.bias = bias.data_ptr()
     else:
         a.bias = None
+    c0 = int(bwd.get("c0", 0)) if bwd is not None else 0
     if stats is not None:
-        if stats.dtype != torch.float64 or stats.numel() != 2 * n_out:
-            raise ValueError("stats must be fp64 [2*n_out]")
+        if stats.dtype != torch.float64 or stats.numel() != 2 * (n_out - c0):
+            raise ValueError("stats must be fp64 [2*(n_out - c0)]")
         a.stats = stats.data_ptr()
     else:
         a.stats = None
+    if bwd is not None:
+        # backward-fused epilogue: see gap_conv_gemm_args.bwd_* in gap_b200.h
+        y = bwd["y"]
+        yn, yh, yw, yc, yld = _nhwc_view(y)
+        if (yn, yh, yw) != (on, oh, ow) or yc != n_out - c0:
+            raise ValueError("bwd y must be [n, oh, ow, n_out - c0]")
+        a.bwd_y, a.bwd_y_ld = y.data_ptr(), yld
+        sc, sh = bwd.get("scale"), bwd.get("shift")
+        a.bwd_scale = None if sc is None else sc.data_ptr()
+        a.bwd_shift = None if sh is None else sh.data_ptr()
+        g2 = bwd.get("g2")
+        if g2 is not None:
+            gn, gh_, gw_, gc, gld = _nhwc_view(g2)
+            if (gn, gh_, gw_, gc) != (on, oh, ow, n_out - c0):
+                raise ValueError("bwd g2 must match y")
+            a.bwd_g2, a.bwd_g2_ld = g2.data_ptr(), gld
+        else:
+            a.bwd_g2, a.bwd_g2_ld = None, 0
+        a.bwd_slope = float(bwd.get("slope", 0.0))
+        a.bwd_c0 = c0
+    else:
+        a.bwd_y = None
     if flops is None:
         flops = 2.0 * n * grid_hw[0] * grid_hw[1] * geom.n_phase * n_out * geom.taps_h * geom.taps_w * ctot
     _timed("conv_fprop_kernel", flops,
@@ -401,6 +424,12 @@ def bn_bwd_apply(y, g1, g2, slope, scale, shift, mean, invstd, sums, count, dy) 
 def bn_param_grads(sums, dgamma, dbeta) -> None:
     _lib.check(_lib.lib().gap_bn_param_grads(_ptr(sums), sums.numel() // 2, _ptr(dgamma), _ptr(dbeta), _stream()),
                "gap_bn_param_grads")
+
+
+def bn_bwd_finalize(raw, mean, invstd, dgamma, dbeta, sums) -> None:
+    """raw [sum d, sum d*y] (re-zeroed) -> sums [sum d, sum d*xhat]; dgamma / dbeta accumulated (may be None)."""
+    _lib.check(_lib.lib().gap_bn_bwd_finalize(_ptr(raw), _ptr(mean), _ptr(invstd), mean.numel(), _ptr(dgamma),
+                                              _ptr(dbeta), _ptr(sums), _stream()), "gap_bn_bwd_finalize")
 
 
 def colsum_bf16(x: torch.Tensor, c: int, out: torch.Tensor) -> None:

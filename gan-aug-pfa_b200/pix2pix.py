@@ -76,7 +76,8 @@ class _BN:
     running_var: torch.Tensor = None
     nbt: torch.Tensor = None
     stats: torch.Tensor = None      # fp64 [2C] forward sums (conv epilogue)
-    sums: torch.Tensor = None       # fp64 [2C] backward sums
+    sums: torch.Tensor = None       # fp64 [2C] backward sums (raw [sum d, sum d*y] when a GEMM epilogue fills them)
+    sums2: torch.Tensor = None      # fp64 [2C] [sum d, sum d*xhat] handed to the apply pass
     scale: torch.Tensor = None
     shift: torch.Tensor = None
     mean: torch.Tensor = None
@@ -88,6 +89,7 @@ class _BN:
         self.nbt = torch.zeros((), device=dev, dtype=torch.int64)
         self.stats = torch.zeros(2 * self.c, device=dev, dtype=torch.float64)
         self.sums = torch.zeros(2 * self.c, device=dev, dtype=torch.float64)
+        self.sums2 = torch.zeros(2 * self.c, device=dev, dtype=torch.float64)
         self.scale = torch.empty(self.c, device=dev)
         self.shift = torch.empty(self.c, device=dev)
         self.mean = torch.empty(self.c, device=dev)
@@ -222,6 +224,26 @@ class _Net:
         self.repack()
 
     # -- BatchNorm helpers -----------------------------------------------------------------------
+    def _bwd_epilogue(self, bn: Optional[_BN], y: torch.Tensor, slope: float, g2=None, c0: int = 0) -> dict:
+        """Arguments of the backward-fused dgrad epilogue for the layer whose output is act(BN(y)) (bn None: the
+        layer has no BatchNorm and ``y`` is its activated output)."""
+        d = {"y": y, "slope": slope, "g2": g2, "c0": c0}
+        if bn is not None:
+            d["scale"], d["shift"] = bn.scale, bn.shift
+        return d
+
+    def _bn_backward_fused(self, bn: _BN, y, d, dy, param_grads: bool = True) -> None:
+        """BatchNorm backward when the producing dgrad epilogue already applied the activation backward and
+        accumulated [sum d, sum d*y] into bn.sums: finalize (+ parameter gradients), then one apply pass."""
+        count = y.numel() // y.shape[-1]
+        if param_grads:
+            ops.bn_bwd_finalize(bn.sums, bn.mean, bn.invstd, self.grad(bn.name + ".weight"), self.grad(bn.name + ".bias"),
+                                bn.sums2)
+            self._ready(bn.name + ".weight", bn.name + ".bias")
+        else:
+            ops.bn_bwd_finalize(bn.sums, bn.mean, bn.invstd, None, None, bn.sums2)
+        ops.bn_bwd_apply(y, d, None, 1.0, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums2, count, dy)
+
     def _bn_forward(self, bn: _BN, y: torch.Tensor, out1, act1, out2=None, act2=ACT_NONE, repeat: int = 1) -> None:
         gamma = self.param(bn.name + ".weight")
         beta = self.param(bn.name + ".bias")
@@ -407,31 +429,42 @@ class GeneratorEngine(_Net):
         ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
         self._ready(self.k_up[0] + ".weight", self.k_up[0] + ".bias")
         ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
-        # up path, outer -> inner
+        # up path, outer -> inner.  Every dgrad GEMM applies the activation backward of the layer below in its
+        # epilogue and accumulates that layer's BatchNorm-backward sums (no separate reduce pass).
         for j in range(1, L):
             bn = self.ubn[j]
             co = C[j - 1]
-            self._bn_backward(bn, self.yu[j], self.gR[j - 1][..., co:], None, 0.0, self.dyu[j])
+            if j == 1:      # gR[0] comes from the thin-layer kernel: classic reduce + apply
+                self._bn_backward(bn, self.yu[j], self.gR[j - 1][..., co:], None, 0.0, self.dyu[j])
+            else:
+                self._bn_backward_fused(bn, self.yu[j], self.gR[j - 1][..., co:], self.dyu[j])
             src = self.Rin if j == L - 1 else self.R[j]
             ci = src.shape[-1]
             ops.conv_wgrad(src, self.dyu[j], self.store.seg(self.store.g, self.k_up[j] + ".weight"), (4, 4), 2,
                            (-1, -1), 16 * co, co)
             self._ready(self.k_up[j] + ".weight")
-            dst = self.gRin if j == L - 1 else self.gR[j]
-            ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, dst, ci, S[j])
-        # innermost down conv: ReLU backward, wgrad, dgrad
-        ops.bn_bwd_apply(self.Rin, self.gRin, None, 0.0, None, None, None, None, None, 0, self.dyd[L - 1])
+            if j == L - 1:
+                # innermost: Rin = ReLU(conv) has no BatchNorm -> the epilogue writes dyd[L-1] directly
+                ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.dyd[L - 1], ci, S[j],
+                              bwd=self._bwd_epilogue(None, self.Rin, 0.0))
+            else:
+                nb = self.ubn[j + 1]     # second half of gR[j] = gradient at ReLU(BN(yu[j+1]))
+                ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.gR[j], ci, S[j], stats=nb.sums,
+                              bwd=self._bwd_epilogue(nb, self.yu[j + 1], 0.0, c0=C[j]))
         for j in range(L - 1, 0, -1):
             ops.conv_wgrad(self.dyd[j], self.A[j - 1], self.store.seg(self.store.g, self.k_down[j] + ".weight"),
                            (4, 4), 2, (-1, -1), 16 * C[j - 1], C[j - 1])
             self._ready(self.k_down[j] + ".weight")
-            ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.gA[j - 1], C[j - 1], S[j])
             jj = j - 1
+            skip = self.gR[jj][..., :C[jj]]          # gradient through the ReLU'd skip copy (models.py:208)
             if jj >= 1:
-                self._bn_backward(self.dbn[jj], self.yd[jj], self.gA[jj], self.gR[jj][..., :C[jj]], 0.2, self.dyd[jj])
+                bn = self.dbn[jj]
+                ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.gA[jj], C[jj], S[j], stats=bn.sums,
+                              bwd=self._bwd_epilogue(bn, self.yd[jj], 0.2, g2=skip))
+                self._bn_backward_fused(bn, self.yd[jj], self.gA[jj], self.dyd[jj])
             else:
-                ops.bn_bwd_apply(self.A[0], self.gA[0], self.gR[0][..., :C[0]], 0.2, None, None, None, None, None, 0,
-                                 self.dyd[0])
+                ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.dyd[0], C[0], S[j],
+                              bwd=self._bwd_epilogue(None, self.A[0], 0.2, g2=skip))
         ops.thin_conv_wgrad(self.dyd[0], self.x_nhwc, None, self.store.seg(self.store.g, self.k_down[0] + ".weight"), 64)
         self._ready(self.k_down[0] + ".weight")
 
@@ -573,15 +606,23 @@ class DiscriminatorEngine(_Net):
             ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1], self.store.seg(g, self.k_conv[last] + ".weight"))
         ops.cout1_conv_dgrad(self.dlogits, self.w_fwd[last].view(-1), self.gH[last - 1])
         for k in range(last - 1, 0, -1):
-            self._bn_backward(self.bn[k], self.y[k], self.gH[k], None, 0.2, self.dy[k], param_grads=wgrad)
+            if k == last - 1:   # gH[k] comes from the Cout=1 kernel: classic reduce + apply
+                self._bn_backward(self.bn[k], self.y[k], self.gH[k], None, 0.2, self.dy[k], param_grads=wgrad)
+            else:
+                self._bn_backward_fused(self.bn[k], self.y[k], self.gH[k], self.dy[k], param_grads=wgrad)
             s = self.stride(k)
             if wgrad:
                 ops.conv_wgrad(self.dy[k], self.H[k - 1], self.store.seg(g, self.k_conv[k] + ".weight"), (4, 4), s,
                                (-1, -1), 16 * C[k - 1], C[k - 1])
             geom = ops.geom_phase_k4s2p1() if s == 2 else ops.geom_conv_dgrad_s1(4, 1)
             grid = (self.hs[k], self.ws[k]) if s == 2 else (self.hs[k - 1], self.ws[k - 1])
-            ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.gH[k - 1], C[k - 1], grid)
-        ops.bn_bwd_apply(self.H[0], self.gH[0], None, 0.2, None, None, None, None, None, 0, self.dy[0])
+            if k - 1 >= 1:
+                nb = self.bn[k - 1]
+                ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.gH[k - 1], C[k - 1], grid, stats=nb.sums,
+                              bwd=self._bwd_epilogue(nb, self.y[k - 1], 0.2))
+            else:   # H[0] = LeakyReLU(conv + bias): the epilogue writes dy[0] directly
+                ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.dy[0], C[0], grid,
+                              bwd=self._bwd_epilogue(None, self.H[0], 0.2))
         if wgrad:
             ops.thin_conv_wgrad(self.dy[0], self._xa, self._xb, self.store.seg(g, self.k_conv[0] + ".weight"), 128,
                                 dbias=self.grad(self.k_conv[0] + ".bias"))

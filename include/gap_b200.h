@@ -95,6 +95,22 @@ typedef struct gap_conv_gemm_args {
   const float* bias; /* may be NULL */
   double* stats;     /* may be NULL; [2*n_out] */
   int out_f32;       /* 1: `out` is fp32 instead of bf16 (out2 must be NULL) */
+  /* Backward-fused epilogue (bwd_y != NULL; dgrad calls): the GEMM result g = dL/d(activation output) is turned
+   * into the gradient at the BatchNorm output before it is stored, for output channels c >= bwd_c0:
+   *     mask = (bwd_y[pix][c'] * bwd_scale[c'] + bwd_shift[c'] > 0),  c' = c - bwd_c0   (scale NULL: mask = bwd_y > 0)
+   *     d    = mask ? g + bwd_g2[pix][c'] : bwd_slope * g                       (LeakyReLU / ReLU backward, with the
+   *            U-Net skip gradient g2 that only flows through the ReLU'd copy; models.py:178,180,208)
+   *     stats[c'] += d,  stats[(n_out - bwd_c0) + c'] += d * bwd_y[pix][c']     (BatchNorm backward sums, fp64)
+   *     out[pix][c] = d
+   * Channels below bwd_c0 are stored unchanged.  Needs act = NONE, no bias / out2, a 32-byte aligned output. */
+  const void* bwd_y;
+  int64_t bwd_y_ld;
+  const float* bwd_scale;
+  const float* bwd_shift;
+  const void* bwd_g2; /* may be NULL */
+  int64_t bwd_g2_ld;
+  float bwd_slope;
+  int bwd_c0;
 } gap_conv_gemm_args;
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);
@@ -238,6 +254,11 @@ int gap_bn_bwd_apply(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1,
                      int64_t pixels, int c, const double* sums, double count, void* dy, int64_t ld_dy,
                      void* stream);
 int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* stream);
+/* After a backward-fused dgrad epilogue: raw = [sum d, sum d*y] (fp64, re-zeroed here) ->
+ * sums = [sum d, sum d*xhat] with xhat = (y - mean) * invstd, for gap_bn_bwd_apply (slope 1, no g2);
+ * dbeta += sum d, dgamma += sum d*xhat (either may be NULL). */
+int gap_bn_bwd_finalize(double* raw, const float* mean, const float* invstd, int c, float* dgamma, float* dbeta,
+                        double* sums, void* stream);
 /* bias gradient: out[c] += sum over pixels of x[pixel][c] */
 int gap_colsum_bf16(const void* x, int64_t ld, int64_t pixels, int c, float* out, void* stream);
 
