@@ -100,6 +100,22 @@ _SIGNATURES = {
     "gap_thin_conv_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _P, _P, _I, _P, _L, _I, _P, _L, _I, _P]),
     "gap_thin_conv_wgrad": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P, _P]),
     "gap_thin_convT_fwd": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P, _I, _P, _L, _P, _L, _P]),
+    "gap_im2col_k3s1p1_c3": (C.c_int, [_P, _L, _P, _I, _I, _I, _P]),
+    "gap_maxpool2x2_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "gap_maxpool2x2_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "gap_upsample_bilinear2x_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "gap_upsample_bilinear2x_bwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "gap_add_inplace_bf16": (C.c_int, [_P, _L, _P, _L, _L, _I, _P]),
+    "gap_att_add_relu_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "gap_relu_bwd": (C.c_int, [_P, _P, _P, _L, _P]),
+    "gap_att_gate_fwd": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _L, _L, _I, _P]),
+    "gap_att_gate_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
+    "gap_vec_stats": (C.c_int, [_P, _L, _P, _P]),
+    "gap_vec_bn_bwd": (C.c_int, [_P, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "gap_conv1x1_cout1_fwd": (C.c_int, [_P, _L, _P, _P, _P, _L, _I, _P]),
+    "gap_conv1x1_cout1_dgrad": (C.c_int, [_P, _P, _P, _L, _L, _I, _P]),
+    "gap_conv1x1_cout1_wgrad": (C.c_int, [_P, _P, _L, _L, _I, _P, _P, _P]),
+    "gap_seg_loss": (C.c_int, [_P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _P, _P, _F, _P, _P]),
     "gap_bn_finalize": (C.c_int, [_P, _I, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gap_bn_eval_scale_shift": (C.c_int, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "gap_bn_act": (C.c_int, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P]),

@@ -223,3 +223,94 @@ class NLayerDiscriminator(_NativeModule):
 
     def forward(self, input):
         return _DiscriminatorFn.apply(self, input, *self.parameters())
+
+
+# ================================================================================================
+# Siamese U-Net (models.py:7-145): same module structure / keys / RNG order, native execution
+# ================================================================================================
+def double_conv(in_channels, out_channels):
+    """(Conv3x3 no-bias -> BatchNorm -> ReLU) x 2 (models.py:7-15).  A plain container: SiameseUNet.forward runs it
+    through the native engine."""
+    return nn.Sequential(
+        nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1, bias=False),
+        nn.BatchNorm2d(out_channels),
+        nn.ReLU(inplace=True),
+        nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1, bias=False),
+        nn.BatchNorm2d(out_channels),
+        nn.ReLU(inplace=True),
+    )
+
+
+class AttentionGate(nn.Module):
+    """Attention gate (models.py:18-44); executed by the enclosing SiameseUNet through the native engine."""
+
+    def __init__(self, F_g, F_l, F_int):
+        super().__init__()
+        self.W_g = nn.Sequential(nn.Conv2d(F_g, F_int, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(F_int))
+        self.W_x = nn.Sequential(nn.Conv2d(F_l, F_int, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(F_int))
+        self.psi = nn.Sequential(nn.Conv2d(F_int, 1, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(1),
+                                 nn.Sigmoid())
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, g, x):  # pragma: no cover
+        raise RuntimeError("AttentionGate is executed by SiameseUNet.forward (native engine)")
+
+
+class _SiameseFn(torch.autograd.Function):
+    """One forward/backward of the whole Siamese U-Net through SiameseEngine.  The engine keeps the activations of
+    the most recent forward, so backward must follow its forward (train.py:141-143 does exactly that)."""
+
+    @staticmethod
+    def forward(ctx, module, x1, x2, *params):
+        eng = module._engine()
+        if x1.requires_grad or x2.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the input images are not provided (the reference never needs them)")
+        logits = eng.forward(x1.detach(), x2.detach())
+        ctx.module = module
+        ctx.shape = tuple(logits.shape)
+        return logits.unsqueeze(1).clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        module = ctx.module
+        eng = module._engine_obj
+        eng.zero_grad()
+        eng.dlogits.copy_(gout.reshape(ctx.shape))
+        eng.backward()
+        grads = [eng.grad(name).clone() for name, _ in module.named_parameters()]
+        return (None, None, None, *grads)
+
+
+class SiameseUNet(_NativeModule):
+    """Siamese U-Net with attention gates (models.py:47-145) executing on the native sm_100a kernels."""
+
+    def __init__(self, n_channels, n_classes):
+        super().__init__()
+        self.n_channels = n_channels
+        self.n_classes = n_classes
+        self.dconv_down1 = double_conv(n_channels, 64)
+        self.dconv_down2 = double_conv(64, 128)
+        self.dconv_down3 = double_conv(128, 256)
+        self.dconv_down4 = double_conv(256, 512)
+        self.maxpool = nn.MaxPool2d(2)
+        self.bottleneck = double_conv(512, 1024)
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.att3 = AttentionGate(F_g=2048, F_l=1024, F_int=512)
+        self.att2 = AttentionGate(F_g=512, F_l=512, F_int=256)
+        self.att1 = AttentionGate(F_g=256, F_l=256, F_int=128)
+        self.att_last = AttentionGate(F_g=128, F_l=128, F_int=64)
+        self.dconv_up3 = double_conv(2048 + 1024, 512)
+        self.dconv_up2 = double_conv(512 + 512, 256)
+        self.dconv_up1 = double_conv(256 + 256, 128)
+        self.dconv_last = double_conv(128 + 128, 64)
+        self.conv_last = nn.Conv2d(64, n_classes, 1)
+
+    def _make_engine(self, device):
+        from .siamese import SiameseEngine
+        return SiameseEngine(device, self.n_channels, self.n_classes)
+
+    def forward_encoder(self, x):  # pragma: no cover - kept for API compatibility (models.py:92-102)
+        raise RuntimeError("forward_encoder is fused into SiameseUNet.forward (native engine)")
+
+    def forward(self, x1, x2):
+        return _SiameseFn.apply(self, x1, x2, *self.parameters())

@@ -497,3 +497,99 @@ class PackPlan:
             self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         _lib.check(_lib.lib().gap_pack_weights_multi(_ptr(self._table), len(self.entries), self.total_tiles, _stream()),
                    "gap_pack_weights_multi")
+
+
+# ------------------------------------------------------------------------------------------------
+# Siamese U-Net extras (gap_b200.h "Siamese U-Net extras")
+# ------------------------------------------------------------------------------------------------
+def _px(t: torch.Tensor) -> int:
+    return t.numel() // t.shape[-1]
+
+
+def im2col_k3s1p1_c3(x: torch.Tensor, col: torch.Tensor) -> None:
+    n, h, w, _, ld = _nhwc_view(x)
+    _lib.check(_lib.lib().gap_im2col_k3s1p1_c3(_ptr(x), ld, _ptr(col), n, h, w, _stream()), "gap_im2col_k3s1p1_c3")
+
+
+def maxpool2x2_fwd(x: torch.Tensor, out: torch.Tensor) -> None:
+    n, h, w, c, ld = _nhwc_view(x)
+    _lib.check(_lib.lib().gap_maxpool2x2_fwd(_ptr(x), ld, _ptr(out), out.stride(2), n, h, w, c, _stream()),
+               "gap_maxpool2x2_fwd")
+
+
+def maxpool2x2_bwd(x: torch.Tensor, gout: torch.Tensor, gin: torch.Tensor, accumulate: bool) -> None:
+    n, h, w, c, ld = _nhwc_view(x)
+    _lib.check(_lib.lib().gap_maxpool2x2_bwd(_ptr(x), ld, _ptr(gout), gout.stride(2), _ptr(gin), gin.stride(2), n, h, w, c,
+                                             1 if accumulate else 0, _stream()), "gap_maxpool2x2_bwd")
+
+
+def upsample2x_fwd(x: torch.Tensor, out: torch.Tensor) -> None:
+    n, h, w, c, ld = _nhwc_view(x)
+    _lib.check(_lib.lib().gap_upsample_bilinear2x_fwd(_ptr(x), ld, _ptr(out), out.stride(2), n, h, w, c, _stream()),
+               "gap_upsample_bilinear2x_fwd")
+
+
+def upsample2x_bwd(gout: torch.Tensor, gin: torch.Tensor, accumulate: bool) -> None:
+    n, h, w, c, ld = _nhwc_view(gin)
+    _lib.check(_lib.lib().gap_upsample_bilinear2x_bwd(_ptr(gout), gout.stride(2), _ptr(gin), ld, n, h, w, c,
+                                                      1 if accumulate else 0, _stream()), "gap_upsample_bilinear2x_bwd")
+
+
+def add_inplace(dst: torch.Tensor, src: torch.Tensor) -> None:
+    _lib.check(_lib.lib().gap_add_inplace_bf16(_ptr(dst), dst.stride(-2), _ptr(src), src.stride(-2), _px(dst),
+                                               dst.shape[-1], _stream()), "gap_add_inplace_bf16")
+
+
+def att_add_relu_fwd(yg, scg, shg, yx, scx, shx, s) -> None:
+    _lib.check(_lib.lib().gap_att_add_relu_fwd(_ptr(yg), _ptr(scg), _ptr(shg), _ptr(yx), _ptr(scx), _ptr(shx), _ptr(s),
+                                               _px(s), s.shape[-1], _stream()), "gap_att_add_relu_fwd")
+
+
+def relu_bwd(s: torch.Tensor, gs: torch.Tensor, d: torch.Tensor) -> None:
+    _lib.check(_lib.lib().gap_relu_bwd(_ptr(s), _ptr(gs), _ptr(d), s.numel(), _stream()), "gap_relu_bwd")
+
+
+def att_gate_fwd(ypsi, scale, shift, psi, x, out) -> None:
+    _lib.check(_lib.lib().gap_att_gate_fwd(_ptr(ypsi), _ptr(scale), _ptr(shift), _ptr(psi), _ptr(x), x.stride(-2), _ptr(out),
+                                           out.stride(-2), _px(x), x.shape[-1], _stream()), "gap_att_gate_fwd")
+
+
+def att_gate_bwd(gout, x, psi, gx, accumulate: bool, dz) -> None:
+    _lib.check(_lib.lib().gap_att_gate_bwd(_ptr(gout), gout.stride(-2), _ptr(x), x.stride(-2), _ptr(psi), _ptr(gx),
+                                           gx.stride(-2), 1 if accumulate else 0, _ptr(dz), _px(x), x.shape[-1], _stream()),
+               "gap_att_gate_bwd")
+
+
+def vec_stats(y: torch.Tensor, stats: torch.Tensor) -> None:
+    _lib.check(_lib.lib().gap_vec_stats(_ptr(y), y.numel(), _ptr(stats), _stream()), "gap_vec_stats")
+
+
+def vec_bn_bwd(y, dz, scale, mean, invstd, sums, dy) -> None:
+    _lib.check(_lib.lib().gap_vec_bn_bwd(_ptr(y), _ptr(dz), y.numel(), _ptr(scale), _ptr(mean), _ptr(invstd), _ptr(sums),
+                                         _ptr(dy), _stream()), "gap_vec_bn_bwd")
+
+
+def conv1x1_cout1_fwd(x, w, bias, out) -> None:
+    _lib.check(_lib.lib().gap_conv1x1_cout1_fwd(_ptr(x), x.stride(-2), _ptr(w), _ptr(bias), _ptr(out), _px(x), x.shape[-1],
+                                                _stream()), "gap_conv1x1_cout1_fwd")
+
+
+def conv1x1_cout1_dgrad(dl, w, gx) -> None:
+    _lib.check(_lib.lib().gap_conv1x1_cout1_dgrad(_ptr(dl), _ptr(w), _ptr(gx), gx.stride(-2), _px(gx), gx.shape[-1],
+                                                  _stream()), "gap_conv1x1_cout1_dgrad")
+
+
+def conv1x1_cout1_wgrad(dl, x, dw, db) -> None:
+    _lib.check(_lib.lib().gap_conv1x1_cout1_wgrad(_ptr(dl), _ptr(x), x.stride(-2), _px(x), x.shape[-1], _ptr(dw), _ptr(db),
+                                                  _stream()), "gap_conv1x1_cout1_wgrad")
+
+
+def seg_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, w_point: float, w_dice: float, pos_weight: float,
+             smooth: float, gamma: float, focal_alpha: float, sums4: torch.Tensor, grad: Optional[torch.Tensor],
+             grad_scale: float, loss: torch.Tensor) -> None:
+    """CombinedLoss (mode 0) / FocalDiceLoss (mode 1) of train.py:82-128 with the gradient w.r.t. the logits."""
+    if logits.dtype != torch.float32 or labels.dtype != torch.int64 or logits.numel() != labels.numel():
+        raise ValueError("logits must be fp32 and labels int64 with the same number of elements")
+    _lib.check(_lib.lib().gap_seg_loss(_ptr(logits), _ptr(labels), logits.numel(), mode, w_point, w_dice, pos_weight, smooth,
+                                       gamma, focal_alpha, _ptr(sums4), _ptr(grad), grad_scale, _ptr(loss), _stream()),
+               "gap_seg_loss")

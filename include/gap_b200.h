@@ -231,6 +231,52 @@ int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_
 int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, int cw, const void* wcol, const float* bias,
                        int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Siamese U-Net extras (models.py:47-145, train.py:34-128); NHWC bf16 activations, 8-channel vectors
+ * (channels and pixel strides multiples of 8); single-channel maps (psi, final logits) are fp32 [pixels].
+ * ---------------------------------------------------------------------------------------------- */
+/* im2col of Conv2d(3 -> C, k3, s1, p1) (models.py:9 through :54): col[pix][(kh*3+kw)*3 + c], padded to 64 */
+int gap_im2col_k3s1p1_c3(const void* x, int64_t ld, void* col, int n, int h, int w, void* stream);
+/* nn.MaxPool2d(2) (models.py:58).  Backward sends the gradient to the first maximum in scan order. */
+int gap_maxpool2x2_fwd(const void* x, int64_t ldx, void* out, int64_t ldo, int n, int h, int w, int c, void* stream);
+int gap_maxpool2x2_bwd(const void* x, int64_t ldx, const void* gout, int64_t ldg, void* gin, int64_t ldi, int n, int h,
+                       int w, int c, int accumulate, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (models.py:64); h, w = INPUT size */
+int gap_upsample_bilinear2x_fwd(const void* x, int64_t ldx, void* out, int64_t ldo, int n, int h, int w, int c,
+                                void* stream);
+int gap_upsample_bilinear2x_bwd(const void* gout, int64_t ldg, void* gin, int64_t ldi, int n, int h, int w, int c,
+                                int accumulate, void* stream);
+/* dst += src: gradient accumulation for activations with several consumers (skip tensors) */
+int gap_add_inplace_bf16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t pixels, int c, void* stream);
+/* AttentionGate (models.py:18-44): s = ReLU(BN(yg) + BN(yx)) (dense [pixels][c]); d = (s > 0) ? gs : 0;
+ * psi = Sigmoid(BN(ypsi)), out = x * psi;  gate backward: gx (+)= gout * psi, dz = (sum_c gout * x) * psi * (1 - psi) */
+int gap_att_add_relu_fwd(const void* yg, const float* scale_g, const float* shift_g, const void* yx, const float* scale_x,
+                         const float* shift_x, void* s, int64_t pixels, int c, void* stream);
+int gap_relu_bwd(const void* s, const void* gs, void* d, int64_t count, void* stream);
+int gap_att_gate_fwd(const float* ypsi, const float* scale, const float* shift, float* psi, const void* x, int64_t ldx,
+                     void* out, int64_t ldo, int64_t pixels, int c, void* stream);
+int gap_att_gate_bwd(const void* gout, int64_t ldg, const void* x, int64_t ldx, const float* psi, void* gx, int64_t ldgx,
+                     int accumulate, float* dz, int64_t pixels, int c, void* stream);
+/* single-channel BatchNorm2d(1) (models.py:33): stats[0] += sum y, stats[1] += sum y^2 (then gap_bn_finalize, c = 1);
+ * backward: sums[0..1] accumulate sum dz, sum dz*xhat; dy = scale * (dz - sums[0]/n - xhat * sums[1]/n) */
+int gap_vec_stats(const float* y, int64_t n, double* stats, void* stream);
+int gap_vec_bn_bwd(const float* y, const float* dz, int64_t n, const float* scale, const float* mean, const float* invstd,
+                   double* sums, float* dy, void* stream);
+/* Conv2d(C -> 1, k1) + bias (models.py:32, :90): out[pix] = bias + x[pix] . w;  gx[pix][c] = dl[pix] * w[c];
+ * dw[c] += sum_pix dl[pix] * x[pix][c], db += sum dl.  w is the fp32 master (rounded to bf16 in the kernel). */
+int gap_conv1x1_cout1_fwd(const void* x, int64_t ldx, const float* w, const float* bias, float* out, int64_t pixels, int c,
+                          void* stream);
+int gap_conv1x1_cout1_dgrad(const float* dl, const float* w, void* gx, int64_t ldg, int64_t pixels, int c, void* stream);
+int gap_conv1x1_cout1_wgrad(const float* dl, const void* x, int64_t ldx, int64_t pixels, int c, float* dw, float* db,
+                            void* stream);
+/* Segmentation losses on fp32 logits vs int64 {0,1} labels (train.py:34-128):
+ *   mode 0 CombinedLoss  = w_point * BCEWithLogits(pos_weight) + w_dice * Dice(smooth)      (train.py:82-105)
+ *   mode 1 FocalDiceLoss = w_point * Focal(gamma, focal_alpha) + w_dice * Dice(smooth)     (train.py:108-128)
+ * loss[0] is written; grad (may be NULL) = grad_scale * d(loss)/d(logit); sums4 is a 4-double workspace. */
+int gap_seg_loss(const float* logits, const int64_t* labels, int64_t n, int mode, float w_point, float w_dice,
+                 float pos_weight, float smooth, float gamma, float focal_alpha, double* sums4, float* grad,
+                 float grad_scale, double* loss, void* stream);
+
 /* nn.BatchNorm2d training bookkeeping (models.py:179,181,231,239): statistics -> scale/shift,
  * saved mean / inv-std, running stats (momentum, unbiased var, `repeat` identical updates),
  * num_batches_tracked += repeat.  Re-zeroes `stats`. */

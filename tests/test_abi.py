@@ -9,7 +9,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def _declared_symbols():
     text = (ROOT / "include" / "gap_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(gap_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(gap_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_entry_points():
