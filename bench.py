@@ -267,18 +267,144 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+def run_secondary(args) -> None:
+    """Secondary workloads of BASELINE.json's configs 4 and 5 (single GPU or independent replicas): generator
+    inference throughput and the Siamese U-Net training step.  Same JSON schema, their own metric names."""
+    import torch.distributed as dist
+    from gan_aug_pfa_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    if args.workload == "gen_infer":
+        from gan_aug_pfa_b200.pix2pix import GeneratorEngine
+        N = 256
+        eng = GeneratorEngine(dev)
+        eng.training = True
+        warm = (torch.rand(8, 3, HW, HW, generator=gen) * 2 - 1).to(dev)
+        for _ in range(2):
+            eng.forward(warm)                      # non-trivial running statistics, as after training
+        eng.training = False
+        host = [(torch.rand(N, 3, HW, HW, generator=gen) * 2 - 1).pin_memory() for _ in range(2)]
+        devb = [h.to(dev) for h in host]
+        out_host = torch.empty(N, 3, HW, HW).pin_memory()
+
+        def step(i, e2e=False):
+            x = devb[i % 2]
+            if e2e:
+                x = stage.copy_(host[i % 2], non_blocking=True)
+            eng.forward(x)
+            if e2e:
+                out_host.copy_(eng.output_nchw(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        stage = torch.empty_like(devb[0])
+        units, metric, unit = N, "generator_inference_images_per_sec_256", "images/s"
+        gflop = 12.046041088
+        h2d, d2h = N * 3 * HW * HW * 4, N * 3 * HW * HW * 4
+        cfg = {"workload": "generator_inference_b256_256x256", "batch_per_gpu": N, "bn": "eval (running statistics)"}
+    else:
+        from gan_aug_pfa_b200.siamese import SiameseEngine
+        N, S = 4, 512
+        eng = SiameseEngine(dev)
+        from gan_aug_pfa_b200 import models as M
+        torch.manual_seed(0)
+        eng.load_state_dict({k: v.detach() for k, v in M.SiameseUNet(3, 1).state_dict().items()})
+        host = [((torch.rand(N, 3, S, S, generator=gen) * 2 - 1).pin_memory(),
+                 (torch.rand(N, 3, S, S, generator=gen) * 2 - 1).pin_memory(),
+                 (torch.rand(N, S, S, generator=gen) < 0.05).long().pin_memory()) for _ in range(2)]
+        devb = [tuple(t.to(dev) for t in b) for b in host]
+        stage = tuple(torch.empty_like(t) for t in devb[0])
+        loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
+
+        def step(i, e2e=False):
+            b = devb[i % 2]
+            if e2e:
+                for dst, src in zip(stage, host[i % 2]):
+                    dst.copy_(src, non_blocking=True)
+                b = stage
+            loss = eng.train_step(*b, kind="combined")
+            if e2e:
+                loss_host.copy_(loss, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        units, metric, unit = N, "siamese_train_pairs_per_sec_512", "pairs/s"
+        gflop = 2207.23
+        h2d, d2h = 2 * N * 3 * S * S * 4 + N * S * S * 8, 8
+        cfg = {"workload": "siamese_unet_train_b4_512x512_combined_loss", "batch_per_gpu": N, "loss": "CombinedLoss(0.5, 1:9)",
+               "optimizer": "AdamW(1.0152e-4, wd 1.118e-5)"}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    _lib.LAUNCHES = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    launches = _lib.LAUNCHES
+    ms = e0.elapsed_time(e1)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i, e2e=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    value = world * units * args.steps / (ms * 1e-3)
+    peaks = _peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfg, "clocks": clocks.summary(),
+            "e2e": {"value": world * units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": (value / world) * gflop * 1e9 / 1e12, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": (value / world) * gflop * 1e9 / (peak_tf * 1e12), "traffic": None,
+                         "note": "whole-step algorithmic conv FLOP/s (SURVEY.md §8d) over the measured sustained bf16 peak"},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pix2pix_train", choices=["pix2pix_train", "gen_infer", "siamese_train"],
+                    help="pix2pix_train = the BASELINE.json metric (default); gen_infer = generate_synthetic_data.py's "
+                         "generator forward at batch 256 (config 4); siamese_train = train.py's step at 512x512, batch 4 "
+                         "(config 5, CombinedLoss)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "pix2pix_train":
         run_ours(args)
+    else:
+        run_secondary(args)
 
 
 if __name__ == "__main__":

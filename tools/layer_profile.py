@@ -62,10 +62,27 @@ _lib._lib = Proxy()
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-tr = Pix2PixTrainer(dev)
+WORK = sys.argv[4] if len(sys.argv) > 4 else "pix2pix"
 gen = torch.Generator().manual_seed(1234)
-A = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
-B = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
+if WORK == "siamese":
+    from gan_aug_pfa_b200.siamese import SiameseEngine
+    from gan_aug_pfa_b200 import models as M
+
+    class _T:
+        def __init__(self):
+            self.e = SiameseEngine(dev)
+            self.e.load_state_dict({k: v.detach() for k, v in M.SiameseUNet(3, 1).state_dict().items()})
+
+        def train_step(self, a, b):
+            return self.e.train_step(a, b, LAB, kind="combined")
+    tr = _T()
+    A = (torch.rand(N, 3, 512, 512, generator=gen) * 2 - 1).to(dev)
+    B = (torch.rand(N, 3, 512, 512, generator=gen) * 2 - 1).to(dev)
+    LAB = (torch.rand(N, 512, 512, generator=gen) < 0.05).long().to(dev)
+else:
+    tr = Pix2PixTrainer(dev)
+    A = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
+    B = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
 for _ in range(3):
     tr.train_step(A, B)
 torch.cuda.synchronize()
