@@ -489,8 +489,15 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                            float wd, int decoupled, float bc1, float bc2_sqrt, float grad_scale) {
+                            float wd, int decoupled, float bc1, float bc2_sqrt, float grad_scale,
+                            const int* __restrict__ step_dev) {
   const long long n4 = n >> 2;
+  if (step_dev != nullptr) {
+    // step counter kept on the device (CUDA-graph replay): bias corrections computed here
+    const double st = static_cast<double>(*step_dev);
+    bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), st));
+    bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), st)));
+  }
   const float step_size = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -873,7 +880,25 @@ int gap_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, static_cast<float>(bc1),
-      static_cast<float>(sqrt(bc2)), grad_scale);
+      static_cast<float>(sqrt(bc2)), grad_scale, nullptr);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void inc_step_kernel(int* step) { *step += 1; }
+
+int gap_adam_flat_devstep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int decoupled, int* step_dev, float grad_scale, void* stream) {
+  GAP_CHECK_ARG(p && g && m && v && n > 0 && step_dev, "gap_adam_flat_devstep: bad arguments");
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15) {
+    set_error("gap_adam_flat_devstep: buffers must be 16-byte aligned");
+    return GAP_ERR_ALIGNMENT;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled,
+                                                        1.f, 1.f, grad_scale, step_dev);
   GAP_LAUNCH_CHECK();
   return 0;
 }

@@ -443,6 +443,13 @@ def adam_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step, 
                "gap_adam_flat")
 
 
+def adam_flat_devstep(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step_dev, grad_scale=1.0) -> None:
+    """Adam / AdamW with the step counter in device memory (int32 tensor), for CUDA-graph replay."""
+    _lib.check(_lib.lib().gap_adam_flat_devstep(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps,
+                                                weight_decay, 1 if decoupled else 0, _ptr(step_dev), grad_scale, _stream()),
+               "gap_adam_flat_devstep")
+
+
 def pack_weights(w: torch.Tensor, w_off: int, out: torch.Tensor, mode: int, n_phase: int, rows: int, rows_pad: int,
                  taps: tuple[int, int], c: int, c_pad: int, krow: int, strides: tuple[int, int, int, int],
                  kdim: int = 0) -> None:

@@ -46,6 +46,7 @@ class ParamStore:
         self.total = 0
         self.p = self.g = self.m = self.v = None
         self.step = 0
+        self.step_dev = None
 
     def add(self, name: str, numel: int) -> int:
         off = self.total
@@ -220,7 +221,11 @@ class _Net:
                   decoupled: bool = False, grad_scale: float = 1.0) -> None:
         s = self.store
         s.step += 1
-        ops.adam_flat(s.p, s.g, s.m, s.v, lr, betas[0], betas[1], eps, weight_decay, decoupled, s.step, grad_scale)
+        if s.step_dev is None:
+            s.step_dev = torch.full((1,), s.step - 1, device=s.p.device, dtype=torch.int32)
+        # the step counter lives on the device (incremented by the kernel) so a captured graph can be replayed
+        ops.adam_flat_devstep(s.p, s.g, s.m, s.v, lr, betas[0], betas[1], eps, weight_decay, decoupled, s.step_dev,
+                              grad_scale)
         self.repack()
 
     # -- BatchNorm helpers -----------------------------------------------------------------------
@@ -657,12 +662,37 @@ class Pix2PixTrainer:
         # data parallel: bucketed all-reduce of the flat gradient buffers; the generator's buckets are reduced
         # on a side stream while its backward pass is still running (buffer order = completion order)
         self.g_reducer = self.d_reducer = None
+        self._graph = None
         if world > 1 and allreduce is None:
             from .parallel import GradBucketReducer
             self.g_reducer = GradBucketReducer(self.G.store.g, self.G.grad_segments(), bucket_elems=bucket_elems)
             self.d_reducer = GradBucketReducer(self.D.store.g, self.D.grad_segments(), bucket_elems=1 << 30,
                                                comm_stream=self.g_reducer.comm_stream)
             self.G.grad_hook = self.g_reducer.mark_ready
+
+    def train_step_graphed(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
+        """train_step through a CUDA graph: the first call (after at least one eager step has sized every
+        buffer) captures the ~175 launches of the iteration, later calls copy the batch into the static input
+        buffers and replay.  Same results as train_step; single-GPU only."""
+        if self.world > 1:
+            return self.train_step(real_A, real_B)
+        if self._graph is None or self._g_in[0].shape != real_A.shape:
+            self._g_in = (torch.empty_like(real_A), torch.empty_like(real_B))
+            self._g_in[0].copy_(real_A)
+            self._g_in[1].copy_(real_B)
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                first = self.train_step(*self._g_in)  # this call's iteration, eagerly (also sizes every buffer)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):       # capture only: nothing executes here
+                self._g_out = self.train_step(*self._g_in)
+            return first
+        self._g_in[0].copy_(real_A, non_blocking=True)
+        self._g_in[1].copy_(real_B, non_blocking=True)
+        self._graph.replay()
+        return self._g_out
 
     def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
         """real_A / real_B: fp32 NCHW on the device.  Returns a device tensor [loss_d, loss_g] (fp64);

@@ -313,6 +313,11 @@ int gap_colsum_bf16(const void* x, int64_t ld, int64_t pixels, int c, float* out
 int gap_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int decoupled, int step, float grad_scale, void* stream);
 
+/* Same step with the step counter kept in device memory (*step_dev is incremented, then used for the bias
+ * corrections), so that a captured CUDA graph of the whole iteration can be replayed. */
+int gap_adam_flat_devstep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int decoupled, int* step_dev, float grad_scale, void* stream);
+
 /* fp32 master weights (arbitrary strides) -> bf16 K-major GEMM operand; modes in elementwise.cu. */
 int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows, int rows_pad, int taps_h,
                      int taps_w, int c, int c_pad, int krow, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,

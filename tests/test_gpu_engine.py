@@ -164,3 +164,25 @@ def test_full_batch_step_is_finite_and_reproducible_in_loss():
         del tr
         torch.cuda.empty_cache()
     assert torch.allclose(vals[0], vals[1], rtol=1e-3)
+
+
+def test_graphed_train_step_matches_eager():
+    """Pix2PixTrainer.train_step_graphed (CUDA-graph replay, device-side Adam step counter) == train_step."""
+    from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(9)
+    batches = [(torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1, torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1)
+               for _ in range(4)]
+    res = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        tr = Pix2PixTrainer(dev, num_downs=5)
+        seq = []
+        for a, b in batches:
+            fn = tr.train_step_graphed if graphed else tr.train_step
+            seq.append(fn(a.to(dev), b.to(dev)).cpu().clone())
+        res.append(torch.stack(seq))
+        if graphed:
+            assert int(tr.G.store.step_dev) == len(batches)
+    # fp32 atomics make the two runs differ in the last bits only
+    assert torch.allclose(res[0], res[1], rtol=2e-3, atol=2e-4), (res[0], res[1])
