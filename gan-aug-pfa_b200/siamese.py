@@ -185,9 +185,12 @@ class SiameseEngine(_Net):
 
     # -- layers --------------------------------------------------------------------------------------
     def _conv_bn_relu(self, x: torch.Tensor, key: str, out: torch.Tensor, pass_id: int, gx: Optional[torch.Tensor],
-                      gout: torch.Tensor, gx_accumulate: bool = False) -> None:
+                      gout: torch.Tensor, gx_accumulate: bool = False, gout_premasked: bool = False,
+                      below: Optional[dict] = None) -> dict:
         """out = ReLU(BN(conv3x3(x))) (models.py:9-14).  gout: gradient buffer of `out`; gx: gradient buffer of `x`
-        (None: the network input)."""
+        (None: the network input).  gout_premasked: the consumer's dgrad epilogue already applied this layer's ReLU
+        backward and accumulated its BatchNorm sums (bn.sums holds [sum d, sum d*y]).  below: the record of the
+        conv-BN-ReLU layer that produced `x`; when given, this layer's dgrad does the same for it."""
         co, ci, k = self.conv_meta[key]
         bn = self.bns[key[:-1] + str(int(key[-1]) + 1)]
         n, h, w, _ = out.shape
@@ -204,7 +207,12 @@ class SiameseEngine(_Net):
 
         def backward() -> None:
             dy = self._scratch("dy", (n, h, w, co))
-            self._bn_bwd(bn, sv, y, gout, 0.0, dy)
+            if gout_premasked:
+                ops.bn_bwd_finalize(bn.sums, sv.mean, sv.invstd, self.grad(bn.name + ".weight"),
+                                    self.grad(bn.name + ".bias"), bn.sums2)
+                ops.bn_bwd_apply(y, gout, None, 1.0, sv.scale, sv.shift, sv.mean, sv.invstd, bn.sums2, n * h * w, dy)
+            else:
+                self._bn_bwd(bn, sv, y, gout, 0.0, dy)
             wseg = self.store.seg(self.store.g, key + ".weight")
             if ci == 3:
                 ops.conv_wgrad(dy, x, wseg, (1, 1), 1, (0, 0), 64, 0, flops=2.0 * n * h * w * co * 27)
@@ -216,18 +224,24 @@ class SiameseEngine(_Net):
                 t = self._scratch("gx", (n, h, w, ci))
                 ops.conv_gemm([dy], self.w_dg[key], ops.geom_conv_dgrad_s1(3, 1), t, ci, (h, w))
                 ops.add_inplace(gx, t)
+            elif below is not None:
+                b = below
+                ops.conv_gemm([dy], self.w_dg[key], ops.geom_conv_dgrad_s1(3, 1), gx, ci, (h, w), stats=b["bn"].sums,
+                              bwd={"y": b["y"], "scale": b["sv"].scale, "shift": b["sv"].shift, "slope": 0.0})
             else:
                 ops.conv_gemm([dy], self.w_dg[key], ops.geom_conv_dgrad_s1(3, 1), gx, ci, (h, w))
 
         self._tape.append(backward)
+        return {"bn": bn, "sv": sv, "y": y}
 
     def _double_conv(self, x, name: str, out, pass_id: int, gx, gout, gx_accumulate: bool = False) -> None:
         co = self.conv_meta[name + ".0"][0]
         n, h, w, _ = out.shape
         mid = self._scratch(f"mid.{name}.{pass_id}", (n, h, w, co))
         gmid = self._scratch(f"gmid.{name}.{pass_id}", (n, h, w, co))
-        self._conv_bn_relu(x, name + ".0", mid, pass_id, gx, gmid, gx_accumulate)
-        self._conv_bn_relu(mid, name + ".3", out, pass_id, gmid, gout)
+        # the second conv's dgrad epilogue applies the first layer's ReLU backward and BatchNorm-backward sums
+        rec = self._conv_bn_relu(x, name + ".0", mid, pass_id, gx, gmid, gx_accumulate, gout_premasked=True)
+        self._conv_bn_relu(mid, name + ".3", out, pass_id, gmid, gout, below=rec)
 
     def _conv1x1_bn(self, x: torch.Tensor, key: str, gx: torch.Tensor) -> Tuple[torch.Tensor, _Saved]:
         """y = conv1x1(x) + bias with BatchNorm statistics (AttentionGate W_g / W_x, models.py:21-29).  The gradient
