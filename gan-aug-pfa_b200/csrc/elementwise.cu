@@ -279,32 +279,46 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, long long ld_
                               __nv_bfloat16* __restrict__ o2, long long ld2, int act2) {
   const int cv = c >> 3;
   const long long total = pixels * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c8 = static_cast<int>(i - pix * cv) << 3;
-    const uint4 raw = *reinterpret_cast<const uint4*>(y + pix * ld_y + c8);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    float v[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread (the kernel is HBM-latency bound otherwise)
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    uint4 raw[U];
+    long long pixv[U];
+    int c8v[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[2 * j] = bf16_lo(w[j]);
-      v[2 * j + 1] = bf16_hi(w[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      pixv[u] = i / cv;
+      c8v[u] = static_cast<int>(i - pixv[u] * cv) << 3;
+      if (i < total) raw[u] = __ldg(reinterpret_cast<const uint4*>(y + pixv[u] * ld_y + c8v[u]));
     }
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c8), s1 = *reinterpret_cast<const float4*>(scale + c8 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c8), h1 = *reinterpret_cast<const float4*>(shift + c8 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-    uint32_t pk[4];
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= total) break;
+      const long long pix = pixv[u];
+      const int c8 = c8v[u];
+      const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act1), act_fwd(v[2 * j + 1], act1));
-    *reinterpret_cast<uint4*>(o1 + pix * ld1 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    if (o2) {
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] = bf16_lo(w[j]);
+        v[2 * j + 1] = bf16_hi(w[j]);
+      }
+      const float4 s0 = *reinterpret_cast<const float4*>(scale + c8), s1 = *reinterpret_cast<const float4*>(scale + c8 + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(shift + c8), h1 = *reinterpret_cast<const float4*>(shift + c8 + 4);
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act2), act_fwd(v[2 * j + 1], act2));
-      *reinterpret_cast<uint4*>(o2 + pix * ld2 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act1), act_fwd(v[2 * j + 1], act1));
+      *reinterpret_cast<uint4*>(o1 + pix * ld1 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (o2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act2), act_fwd(v[2 * j + 1], act2));
+        *reinterpret_cast<uint4*>(o2 + pix * ld2 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
     }
   }
 }
@@ -347,64 +361,94 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
     v[2 * j + 1] = bf16_hi(w[j]);
   }
 }
+__device__ __forceinline__ void unpack_u4(const uint4& raw, float (&v)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = bf16_lo(w[j]);
+    v[2 * j + 1] = bf16_hi(w[j]);
+  }
+}
 __device__ __forceinline__ void loadf8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 template <bool APPLY>
-__global__ void bn_bwd_kernel(const BnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
   const int cv = a.c >> 3;
   const bool ident = a.scale == nullptr;
   extern __shared__ float sm_red[];  // [blockDim.y][cv*8][2] for the reduce pass
   for (int cg = threadIdx.x; cg < cv; cg += blockDim.x) {
     const int c8 = cg << 3;
-    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
-    if (!ident) {
-      loadf8(a.scale + c8, sc);
-      loadf8(a.shift + c8, sh);
-      loadf8(a.mean + c8, mu);
-      loadf8(a.invstd + c8, is);
+    // per-channel constants, folded so that few registers stay live:
+    //   mask:   y*sc + sh > 0
+    //   apply:  dy = sc*(d - m1 - xhat*m2) = sc*d + ca*y + cb,  ca = -sc*m2*invstd, cb = -sc*m1 - ca*mean
+    //   reduce: sums of d and d*y (converted to sum d*xhat = invstd*(sum d*y - mean*sum d) at the end)
+    float sc[8], sh[8], ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = ident ? 1.f : a.scale[c8 + j];
+      sh[j] = ident ? 0.f : a.shift[c8 + j];
+      ca[j] = 0.f;
+      cb[j] = 0.f;
     }
     if (APPLY && !ident) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        m1[j] = static_cast<float>(a.sums[c8 + j] * a.inv_count);
-        m2[j] = static_cast<float>(a.sums[a.c + c8 + j] * a.inv_count);
+        const float m1 = static_cast<float>(a.sums[c8 + j] * a.inv_count);
+        const float m2 = static_cast<float>(a.sums[a.c + c8 + j] * a.inv_count);
+        ca[j] = -sc[j] * m2 * a.invstd[c8 + j];
+        cb[j] = -sc[j] * m1 - ca[j] * a.mean[c8 + j];
       }
     }
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long pix = blockIdx.x * (long long)blockDim.y + threadIdx.y; pix < a.pixels;
-         pix += (long long)gridDim.x * blockDim.y) {
-      float y[8], g1[8], g2[8];
-      load8(a.y + pix * a.ld_y + c8, y);
-      load8(a.g1 + pix * a.ld_g1 + c8, g1);
-      if (a.g2) load8(a.g2 + pix * a.ld_g2 + c8, g2);
-      float d[8], xh[8];
+    constexpr int U = 4;   // pixels in flight per thread: loads of all U issued before any use
+    const long long pstride = (long long)gridDim.x * blockDim.y;
+    for (long long pix0 = blockIdx.x * (long long)blockDim.y + threadIdx.y; pix0 < a.pixels; pix0 += U * pstride) {
+      uint4 yr[U], g1r[U], g2r[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float yh = ident ? y[j] : fmaf(y[j], sc[j], sh[j]);
-        const float gp = a.g2 ? g1[j] + g2[j] : g1[j];
-        d[j] = yh > 0.f ? gp : a.slope * g1[j];
-        xh[j] = ident ? 0.f : (y[j] - mu[j]) * is[j];
-      }
-      if (APPLY) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float o0 = d[2 * j], o1 = d[2 * j + 1];
-          if (!ident) {
-            o0 = sc[2 * j] * (o0 - m1[2 * j] - xh[2 * j] * m2[2 * j]);
-            o1 = sc[2 * j + 1] * (o1 - m1[2 * j + 1] - xh[2 * j + 1] * m2[2 * j + 1]);
-          }
-          pk[j] = pack_bf16x2(o0, o1);
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * pstride;
+        if (pix < a.pixels) {
+          yr[u] = __ldg(reinterpret_cast<const uint4*>(a.y + pix * a.ld_y + c8));
+          g1r[u] = __ldg(reinterpret_cast<const uint4*>(a.g1 + pix * a.ld_g1 + c8));
+          if (a.g2) g2r[u] = __ldg(reinterpret_cast<const uint4*>(a.g2 + pix * a.ld_g2 + c8));
         }
-        *reinterpret_cast<uint4*>(a.dy + pix * a.ld_dy + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      } else {
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * pstride;
+        if (pix >= a.pixels) break;
+        float y[8], g1[8], g2[8];
+        unpack_u4(yr[u], y);
+        unpack_u4(g1r[u], g1);
+        if (a.g2) unpack_u4(g2r[u], g2);
+        float d[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          s1[j] += d[j];
-          s2[j] += d[j] * xh[j];
+          const float yh = fmaf(y[j], sc[j], sh[j]);
+          const float gp = a.g2 ? g1[j] + g2[j] : g1[j];
+          d[j] = yh > 0.f ? gp : a.slope * g1[j];
+        }
+        if (APPLY) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float o0 = d[2 * j], o1 = d[2 * j + 1];
+            if (!ident) {
+              o0 = fmaf(sc[2 * j], o0, fmaf(ca[2 * j], y[2 * j], cb[2 * j]));
+              o1 = fmaf(sc[2 * j + 1], o1, fmaf(ca[2 * j + 1], y[2 * j + 1], cb[2 * j + 1]));
+            }
+            pk[j] = pack_bf16x2(o0, o1);
+          }
+          *reinterpret_cast<uint4*>(a.dy + pix * a.ld_dy + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += d[j];
+            s2[j] += d[j] * y[j];
+          }
         }
       }
     }
@@ -412,8 +456,10 @@ __global__ void bn_bwd_kernel(const BnBwdArgs a) {
       float* slot = sm_red + (static_cast<size_t>(threadIdx.y) * cv * 8 + c8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        // sum d*xhat = invstd * (sum d*y - mean * sum d)
+        const float mu = ident ? 0.f : a.mean[c8 + j], is = ident ? 0.f : a.invstd[c8 + j];
         slot[2 * j] = s1[j];
-        slot[2 * j + 1] = s2[j];
+        slot[2 * j + 1] = is * (s2[j] - mu * s1[j]);
       }
     }
   }
