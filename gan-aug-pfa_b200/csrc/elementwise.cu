@@ -643,7 +643,8 @@ __global__ void pack_weights_kernel(const PackArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const gap_pack_entry* __restrict__ table,
                                                                  int n_entries) {
-  __shared__ float tile[32][33];
+  // One CTA = one 64 x 64 (row, channel) tile of one (phase, tap) slice of one table entry.
+  __shared__ float tile[64][65];
   __shared__ int s_entry;
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     int lo = 0, hi = n_entries - 1;   // last entry whose tile_begin <= blockIdx.x
@@ -676,27 +677,78 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const gap_pack_
   const float* __restrict__ w = a.w + kh * a.s_kh + kw * a.s_kw;
   __nv_bfloat16* __restrict__ out = static_cast<__nv_bfloat16*>(a.out) +
                                     static_cast<long long>(ph) * a.rows_pad * a.krow + tap * a.c_pad;
-  const int r0 = tr * 32, c0 = tc * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r0 = tr * 64, c0 = tc * 64;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int tx16 = tid & 15, ty16 = tid >> 4;     // 16 x 16 thread layout: 4 elements along the fast axis each
+  const bool out_vec = (a.krow % 4 == 0) && (a.c_pad % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 7) == 0);
   if (a.s_r == 1 && a.s_c != 1) {
-    // master is contiguous along rows: transpose through shared memory
+    // master contiguous along rows: read float4 along r, transpose through shared memory, write along c
+    const bool in_vec = (a.s_c % 4 == 0) && (a.s_kh % 4 == 0) && (a.s_kw % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.w) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i, r = r0 + tx;
-      tile[ty + 8 * i][tx] = (r < a.rows && c < a.c) ? w[r + c * a.s_c] : 0.f;
+      const int c = c0 + ty16 + 16 * i, r = r0 + tx16 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < a.c) {
+        const float* src = w + r + static_cast<long long>(c) * a.s_c;
+        if (in_vec && r + 3 < a.rows) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          if (r < a.rows) v.x = src[0];
+          if (r + 1 < a.rows) v.y = src[1];
+          if (r + 2 < a.rows) v.z = src[2];
+          if (r + 3 < a.rows) v.w = src[3];
+        }
+      }
+      tile[ty16 + 16 * i][tx16 * 4 + 0] = v.x;
+      tile[ty16 + 16 * i][tx16 * 4 + 1] = v.y;
+      tile[ty16 + 16 * i][tx16 * 4 + 2] = v.z;
+      tile[ty16 + 16 * i][tx16 * 4 + 3] = v.w;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty + 8 * i, c = c0 + tx;
-      if (r < a.rows && c < a.c) out[static_cast<long long>(r) * a.krow + c] = __float2bfloat16(tile[tx][ty + 8 * i]);
+      const int r = r0 + ty16 + 16 * i, c = c0 + tx16 * 4;
+      if (r >= a.rows || c >= a.c) continue;
+      __nv_bfloat16* dst = out + static_cast<long long>(r) * a.krow + c;
+      const float v0 = tile[tx16 * 4 + 0][ty16 + 16 * i], v1 = tile[tx16 * 4 + 1][ty16 + 16 * i];
+      const float v2 = tile[tx16 * 4 + 2][ty16 + 16 * i], v3 = tile[tx16 * 4 + 3][ty16 + 16 * i];
+      if (out_vec && c + 3 < a.c) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+      } else {
+        dst[0] = __float2bfloat16(v0);
+        if (c + 1 < a.c) dst[1] = __float2bfloat16(v1);
+        if (c + 2 < a.c) dst[2] = __float2bfloat16(v2);
+        if (c + 3 < a.c) dst[3] = __float2bfloat16(v3);
+      }
     }
   } else {
+    const bool in_vec = (a.s_c == 1) && (a.s_r % 4 == 0) && (a.s_kh % 4 == 0) && (a.s_kw % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.w) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty + 8 * i, c = c0 + tx;
-      if (r < a.rows && c < a.c)
-        out[static_cast<long long>(r) * a.krow + c] = __float2bfloat16(w[r * a.s_r + c * a.s_c]);
+      const int r = r0 + ty16 + 16 * i, c = c0 + tx16 * 4;
+      if (r >= a.rows || c >= a.c) continue;
+      const float* src = w + static_cast<long long>(r) * a.s_r + static_cast<long long>(c) * a.s_c;
+      float v0, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      if (in_vec && c + 3 < a.c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+        v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+      } else {
+        v0 = src[0];
+        if (c + 1 < a.c) v1 = src[a.s_c];
+        if (c + 2 < a.c) v2 = src[2 * a.s_c];
+        if (c + 3 < a.c) v3 = src[3 * a.s_c];
+      }
+      __nv_bfloat16* dst = out + static_cast<long long>(r) * a.krow + c;
+      if (out_vec && c + 3 < a.c) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+      } else {
+        dst[0] = __float2bfloat16(v0);
+        if (c + 1 < a.c) dst[1] = __float2bfloat16(v1);
+        if (c + 2 < a.c) dst[2] = __float2bfloat16(v2);
+        if (c + 3 < a.c) dst[3] = __float2bfloat16(v3);
+      }
     }
   }
 }

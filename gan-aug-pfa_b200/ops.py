@@ -486,7 +486,7 @@ class PackPlan:
         e.out = out.data_ptr() + 2 * out_off
         e.mode, e.n_phase, e.rows, e.rows_pad = mode, n_phase, rows, rows_pad
         e.taps_h, e.taps_w, e.c, e.c_pad, e.krow = taps[0], taps[1], c, c_pad, krow
-        e.tiles_r, e.tiles_c = (rows + 31) // 32, (c + 31) // 32
+        e.tiles_r, e.tiles_c = (rows + 63) // 64, (c + 63) // 64
         e.tile_begin = self.total_tiles
         e.s_r, e.s_c, e.s_kh, e.s_kw = strides
         self.total_tiles += n_phase * taps[0] * taps[1] * e.tiles_r * e.tiles_c

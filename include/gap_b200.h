@@ -324,8 +324,8 @@ int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows,
                      int kdim, void* stream);
 
 /* All operands of a network in one launch.  `table` lives in DEVICE memory; the host fills tile_begin
- * (exclusive prefix sum of n_phase*taps_h*taps_w*tiles_r*tiles_c), tiles_r = ceil(rows/32),
- * tiles_c = ceil(c/32).  Same element mapping as gap_pack_weights modes 0-2, except that padding
+ * (exclusive prefix sum of n_phase*taps_h*taps_w*tiles_r*tiles_c), tiles_r = ceil(rows/64),
+ * tiles_c = ceil(c/64).  Same element mapping as gap_pack_weights modes 0-2, except that padding
  * elements (c >= C, rows >= R, k >= taps*c_pad) are not written: zero the operand buffers once. */
 typedef struct gap_pack_entry {
   const float* w;
