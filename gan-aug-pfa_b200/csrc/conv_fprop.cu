@@ -74,6 +74,16 @@ struct alignas(64) FpropParams {
   float bwd_slope;
   int bwd_c0;
   int skip;  // bring-up ablation: 1 no global stores, 2 no y / g2 loads, 4 no statistics
+  // Halo mode: the taps of one kernel column that differ only by whole input rows (th = g + in_stride*i) share ONE
+  // A tile of BH + halo_taps - 1 rows; tap i reads it through a descriptor shifted by i*BW rows (BW % 8 == 0, so the
+  // shift is a whole number of 1024-byte swizzle atoms).  Cuts the A-operand TMA traffic of small-N layers.
+  int halo;            // 0 / 1
+  int halo_taps;       // taps per group (taps_h / in_stride)
+  int halo_groups;     // in_stride
+  int a_tile_bytes;    // bytes of one A tile in shared memory (16 KiB, or the halo tile rounded up to 1 KiB)
+  int a_load_bytes;    // bytes one A TMA load delivers
+  int b_per_stage;     // B tiles per pipeline stage (1, or halo_taps)
+  int chunks_tot;      // 64-channel chunks over both sources
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -180,8 +190,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int a_bytes = p.mt * kATileBytes;
-  const int stage_bytes = a_bytes + p.block_n * 128;
+  const int a_bytes = p.mt * p.a_tile_bytes;
+  const int stage_bytes = a_bytes + p.b_per_stage * p.block_n * 128;
   const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
   // barrier slots (8 bytes each): full[0..7], empty[8..15], tfull[16..17], tempty[18..19]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -244,6 +254,34 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
         const int n1 = m1.tn * BNI;
         const uint32_t tx_bytes = static_cast<uint32_t>(p.block_n * 128 + (has1 ? 2 : 1) * kATileBytes);
         const int b_row = wc.n_tile * p.block_n;
+        if (p.halo) {
+          const uint32_t txh = static_cast<uint32_t>(p.halo_taps * p.block_n * 128 + (has1 ? 2 : 1) * p.a_load_bytes);
+          for (int t_w = 0; t_w < p.taps_w; ++t_w) {
+            for (int g = 0; g < p.halo_groups; ++g) {
+              int cc = 0;
+              for (int s = 0; s < 2; ++s) {
+                for (int c = 0; c < p.src_chunks[s]; ++c, ++cc) {
+                  mbar_wait(empty_bar(stage), phase ^ 1u);
+                  mbar_expect_tx(full_bar(stage), txh);
+                  const uint32_t a_dst = smem_base + stage * stage_bytes;
+                  tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + g, n0);
+                  if (has1)
+                    tma_load_4d(a_dst + p.a_tile_bytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + g, n1);
+                  for (int i = 0; i < p.halo_taps; ++i) {
+                    const int t_h = g + p.halo_groups * i;
+                    tma_load_3d(a_dst + a_bytes + i * p.block_n * 128, &p.tmB, full_bar(stage),
+                                ((t_h * p.taps_w + t_w) * p.chunks_tot + cc) * kBlockK, b_row, wc.phase);
+                  }
+                  if (++stage == p.num_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                  }
+                }
+              }
+            }
+          }
+          continue;
+        }
         int kcol = 0;
         for (int t_h = 0; t_h < p.taps_h; ++t_h) {
           for (int t_w = 0; t_w < p.taps_w; ++t_w) {
@@ -285,12 +323,26 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
           const uint32_t b_addr = a_addr + a_bytes;
-          for (int j = 0; j < mt_eff; ++j) {
+          if (p.halo) {
+            const uint32_t row_shift = static_cast<uint32_t>(128 << p.log_bw);   // one input row of the tile = BW pixels
+            for (int j = 0; j < mt_eff; ++j) {
+              for (int i = 0; i < p.halo_taps; ++i) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t adesc = make_sw128_desc(a_addr + j * kATileBytes + k * 32, 16, 1024);
-              const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t adesc = make_sw128_desc(a_addr + j * p.a_tile_bytes + i * row_shift + k * 32, 16, 1024);
+                  const uint64_t bdesc = make_sw128_desc(b_addr + i * p.block_n * 128 + k * 32, 16, 1024);
+                  umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | i | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          } else {
+            for (int j = 0; j < mt_eff; ++j) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t adesc = make_sw128_desc(a_addr + j * kATileBytes + k * 32, 16, 1024);
+                const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+                umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(empty_bar(stage));
@@ -554,8 +606,30 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   FpropParams p;
   memset(&p, 0, sizeof(p));
   // ---- M tile shape
-  const int log_bw = std::min(7, ilog2_ceil(a->gw));
-  const int log_bh = std::min(7 - log_bw, ilog2_ceil(a->gh));
+  int log_bw = std::min(7, ilog2_ceil(a->gw));
+  int log_bh = std::min(7 - log_bw, ilog2_ceil(a->gh));
+  // Halo mode (see FpropParams): needs a tile inside one image whose width is a multiple of 8 pixels and at least
+  // two taps that differ by whole input rows; the N tile must be small enough for halo_taps B tiles per stage
+  // (checked below, after block_n is known).
+  const int halo_taps = a->taps_h / a->in_stride;
+  bool halo = debug_get("fprop_halo", 1) != 0 && halo_taps >= 2 && a->taps_h % a->in_stride == 0;
+  if (halo) {
+    if (a->gw >= 16 && a->gh >= 8) {
+      log_bw = 4;
+      log_bh = 3;
+    } else if (a->gw >= 8 && a->gh >= 16) {
+      log_bw = 3;
+      log_bh = 4;
+    } else {
+      halo = false;
+    }
+  }
+  const int n_pad_h = (a->n_out + 15) / 16 * 16;
+  if (halo && std::min(n_pad_h, 256) * halo_taps > 256) {
+    halo = false;     // would need more than 32 KiB of B tiles per stage: these layers are B-traffic bound anyway
+    log_bw = std::min(7, ilog2_ceil(a->gw));
+    log_bh = std::min(7 - log_bw, ilog2_ceil(a->gh));
+  }
   const int BW = 1 << log_bw, BH = 1 << log_bh, BNI = kBlockM / (BW * BH);
   p.log_bw = log_bw;
   p.log_bh = log_bh;
@@ -595,6 +669,15 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.src_chunks[0] = a->src_c[0] / 64;
   p.src_chunks[1] = a->src_c[1] / 64;
   p.k_iters = a->taps_h * a->taps_w * (ctot / 64);
+  p.chunks_tot = ctot / 64;
+  const int halo_rows = BH + halo_taps - 1;
+  p.halo = halo ? 1 : 0;
+  p.halo_taps = halo ? halo_taps : 1;
+  p.halo_groups = halo ? a->in_stride : 1;
+  p.a_load_bytes = halo ? halo_rows * BW * 128 : kATileBytes;
+  p.a_tile_bytes = halo ? (p.a_load_bytes + 1023) / 1024 * 1024 : kATileBytes;
+  p.b_per_stage = halo ? halo_taps : 1;
+  if (halo) p.k_iters = a->taps_w * a->in_stride * (ctot / 64);
   p.n_img = a->n;
   p.gh = a->gh;
   p.gw = a->gw;
@@ -652,7 +735,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.bwd_c0 = a->bwd_c0;
   p.skip = debug_get("fprop_skip", 0);
 
-  const int stage_bytes = mt * kATileBytes + block_n * 128;
+  const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * block_n * 128;
   int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);
@@ -662,7 +745,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
 
   // ---- tensor maps
   const uint32_t bx_w = static_cast<uint32_t>(BW * a->in_stride);
-  const uint32_t bx_h = static_cast<uint32_t>(BH * a->in_stride);
+  const uint32_t bx_h = static_cast<uint32_t>((halo ? halo_rows : BH) * a->in_stride);
   if (bx_w > 256 || bx_h > 256) {
     set_error("gap_conv_gemm: TMA box %ux%u exceeds 256", bx_w, bx_h);
     return GAP_ERR_UNSUPPORTED;
