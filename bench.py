@@ -263,8 +263,15 @@ def run_ours(args) -> None:
     roofline = None
     if dom is not None:
         ach = kern[dom]["tflops"]
+        traffic = None
+        tpath = ROOT / "profiles" / "r1_roofline_traffic.json"
+        if tpath.exists():
+            traffic = json.loads(tpath.read_text()).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None,
+                    "frac": ach / peak_tf, "traffic": traffic,
+                    "traffic_source": "ncu dram__bytes_read+write per launch, averaged over the step's launches "
+                                      "(profiles/r1_step_metrics_ncu.csv)" if traffic else None,
+                    "algorithmic_flop_per_launch": agg[dom][0] / max(1, agg[dom][2]),
                     "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
                     "per_kernel": kern,
                     "step_frac_of_peak": (value / world) * GFLOP_PER_IMG * 1e9 / (peak_tf * 1e12)}
