@@ -603,6 +603,7 @@ struct ThinConvTParams {
   long long ld_bf;
   float* out_f32;
   long long ld_f;
+  uint8_t* out_u8;   // [n][2ih][2iw][3]: uint8((v*0.5 + 0.5) * 255), the image generate_synthetic_data.py:69-88 saves
   int tiles_x, tiles_y;
   long long total_tiles;
 };
@@ -717,6 +718,13 @@ __global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTPara
       const long long o = (img * oh + y) * ow + x;
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o * p.ld_f) = make_float4(v[0], v[1], v[2], 0.f);
       if (p.out_bf) *reinterpret_cast<uint2*>(p.out_bf + o * p.ld_bf) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
+      if (p.out_u8) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float u = fminf(fmaxf((v[j] * 0.5f + 0.5f) * 255.f, 0.f), 255.f);
+          p.out_u8[o * 3 + j] = static_cast<uint8_t>(u);   // truncation, like torchvision's to_pil_image (mul(255).byte())
+        }
+      }
     }
   }
 }
@@ -753,6 +761,15 @@ __global__ void bce_logits_const_f32_kernel(const float* __restrict__ x, long lo
       atomicAdd(loss_acc, static_cast<double>(v));
       if (dbias) atomicAdd(dbias, gg);
     }
+  }
+}
+
+// uint8 HWC image -> normalised NHWC bf16 with 4 channel slots: (x/255 - 0.5)/0.5 (dataset.py:155-159 on the device)
+__global__ void u8_hwc_to_nhwc_bf16_kernel(const uint8_t* __restrict__ x, bf16* __restrict__ out, long long ld,
+                                           long long pixels) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+    const float a = x[i * 3] * (2.f / 255.f) - 1.f, b = x[i * 3 + 1] * (2.f / 255.f) - 1.f, c = x[i * 3 + 2] * (2.f / 255.f) - 1.f;
+    *reinterpret_cast<uint2*>(out + i * ld) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, 0.f));
   }
 }
 
@@ -975,9 +992,9 @@ int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_
 }
 
 int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, int cw, const void* wcol, const float* bias,
-                       int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, void* stream) {
+                       int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, uint8_t* out_u8, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GAP_CHECK_ARG(wide && wcol && (out_bf16 || out_f32) && n > 0 && ih > 0 && iw > 0, "gap_thin_convT_fwd: bad arguments");
+  GAP_CHECK_ARG(wide && wcol && (out_bf16 || out_f32 || out_u8) && n > 0 && ih > 0 && iw > 0, "gap_thin_convT_fwd: bad arguments");
   GAP_CHECK_ARG(act == GAP_ACT_NONE || act == GAP_ACT_TANH, "gap_thin_convT_fwd: activation must be none or Tanh");
   if ((cw != 64 && cw != 128) || ld_w % 8 || (out_bf16 && ld_bf % 4) || (out_f32 && ld_f % 4) ||
       (reinterpret_cast<uintptr_t>(wide) & 15) || (reinterpret_cast<uintptr_t>(wcol) & 15) ||
@@ -999,6 +1016,7 @@ int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, in
   p.ld_bf = ld_bf;
   p.out_f32 = out_f32;
   p.ld_f = ld_f;
+  p.out_u8 = out_u8;
   p.tiles_x = (iw + 15) / 16;
   p.tiles_y = (ih + 7) / 8;
   p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
@@ -1010,6 +1028,15 @@ int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, in
   }
   const int grid = static_cast<int>(std::min<long long>(p.total_tiles, static_cast<long long>(debug_get("thin_convT_ctas_per_sm", cw == 64 ? 3 : 2)) * sm_count()));
   thin_convT_fwd_kernel<<<grid, 256, smem, st>>>(p);
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_u8_hwc_to_nhwc_bf16(const uint8_t* x, void* out, int64_t out_ld, int64_t pixels, void* stream) {
+  GAP_CHECK_ARG(x && out && pixels > 0 && out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+                "gap_u8_hwc_to_nhwc_bf16: bad arguments");
+  const int blocks = static_cast<int>(std::min<int64_t>((pixels + 255) / 256, 148 * 16));
+  u8_hwc_to_nhwc_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<bf16*>(out), out_ld, pixels);
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

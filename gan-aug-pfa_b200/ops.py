@@ -368,8 +368,17 @@ def thin_conv_wgrad(wide: torch.Tensor, s0: torch.Tensor, s1: Optional[torch.Ten
                                               _ptr(dbias), _stream()), "gap_thin_conv_wgrad")
 
 
+def u8_hwc_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
+    """uint8 [n,h,w,3] -> normalised NHWC bf16 with 4 channel slots (dataset.py:155-159 on the device)."""
+    if x.dtype != torch.uint8 or x.shape[-1] != 3 or not x.is_contiguous() or not x.is_cuda:
+        raise ValueError("expected a contiguous CUDA uint8 [n,h,w,3] tensor")
+    _lib.check(_lib.lib().gap_u8_hwc_to_nhwc_bf16(_ptr(x), _ptr(out), out.stride(2), x.numel() // 3, _stream()),
+               "gap_u8_hwc_to_nhwc_bf16")
+
+
 def thin_convT_fwd(wide: torch.Tensor, wcol: torch.Tensor, bias: Optional[torch.Tensor], act: int,
-                   out_bf16: Optional[torch.Tensor], out_f32: Optional[torch.Tensor]) -> None:
+                   out_bf16: Optional[torch.Tensor], out_f32: Optional[torch.Tensor],
+                   out_u8: Optional[torch.Tensor] = None) -> None:
     """ConvTranspose2d(cw -> 3, k4, s2, p1) (+bias, Tanh) into 4-slot NHWC outputs; wcol bf16 [48 = tap*3+co, cw]."""
     n, ih, iw, cw, ldw = _nhwc_view(wide)
     if wcol.dtype != torch.bfloat16 or tuple(wcol.shape) != (48, cw) or not wcol.is_contiguous():
@@ -379,7 +388,7 @@ def thin_convT_fwd(wide: torch.Tensor, wcol: torch.Tensor, bias: Optional[torch.
             raise ValueError("output must be [n, 2ih, 2iw, >=4]")
     _lib.check(_lib.lib().gap_thin_convT_fwd(_ptr(wide), ldw, n, ih, iw, cw, _ptr(wcol), _ptr(bias), act, _ptr(out_bf16),
                                              0 if out_bf16 is None else out_bf16.stride(2), _ptr(out_f32),
-                                             0 if out_f32 is None else out_f32.stride(2), _stream()),
+                                             0 if out_f32 is None else out_f32.stride(2), _ptr(out_u8), _stream()),
                "gap_thin_convT_fwd")
 
 

@@ -390,16 +390,25 @@ class GeneratorEngine(_Net):
         self._n = (n, h, w)
 
     # -- forward --------------------------------------------------------------------------------
-    def forward(self, x_nchw: torch.Tensor, bn_repeat: int = 1) -> torch.Tensor:
-        """x: fp32 NCHW on the device.  Returns fake as fp32 NHWC [n,h,w,4] (channel 3 is padding);
-        the bf16 copy is self.fake_bf.  bn_repeat=2 folds the reference's second identical forward."""
-        n, _, h, w = x_nchw.shape
+    def forward(self, x_nchw: torch.Tensor, bn_repeat: int = 1, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: fp32 NCHW on the device, or uint8 NHWC [n,h,w,3] (normalised on the device like dataset.py:155-159).
+        Returns fake as fp32 NHWC [n,h,w,4] (channel 3 is padding); the bf16 copy is self.fake_bf.  bn_repeat=2
+        folds the reference's second identical forward.  out_u8 (uint8 [n,h,w,3]) additionally receives the image
+        generate_synthetic_data.py:69-88 saves, written by the last layer's epilogue."""
+        u8_in = x_nchw.dtype == torch.uint8
+        if u8_in:
+            n, h, w, _ = x_nchw.shape
+        else:
+            n, _, h, w = x_nchw.shape
         self._alloc(n, h, w)
         L, C, S = self.L, self.C, self.S
         g_s2 = ops.geom_conv_fwd(4, 2, 1)
         g_1x1 = ops.geom_conv_fwd(1, 1, 0)
         g_ph = ops.geom_phase_k4s2p1()
-        ops.nchw_to_nhwc_bf16(x_nchw, self.x_nhwc)
+        if u8_in:
+            ops.u8_hwc_to_nhwc_bf16(x_nchw, self.x_nhwc)
+        else:
+            ops.nchw_to_nhwc_bf16(x_nchw, self.x_nhwc)
         ops.thin_conv_fwd(self.x_nhwc, None, self.w_d_thin, None, self.A[0], ACT_LRELU, self.R[0][..., :C[0]], ACT_RELU)
         for j in range(1, L - 1):
             bn = self.dbn[j]
@@ -412,7 +421,8 @@ class GeneratorEngine(_Net):
             bn = self.ubn[j]
             ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats if self.training else None)
             self._bn_forward(bn, self.yu[j], self.R[j - 1][..., C[j - 1]:], ACT_RELU, repeat=bn_repeat)
-        ops.thin_convT_fwd(self.R[0], self.w_u_T2, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32)
+        ops.thin_convT_fwd(self.R[0], self.w_u_T2, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32,
+                           out_u8)
         return self.fake_f32
 
     def output_nchw(self) -> torch.Tensor:

@@ -229,7 +229,12 @@ int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_
  * conv (models.py:223).  wide: NHWC bf16 [n, ih, iw, cw]; wcol: bf16 [48 = (kh*4+kw)*3 + co][cw]; outputs
  * [n, 2ih, 2iw, 4 slots] in bf16 and / or fp32 (slot 3 is written as zero); act = GAP_ACT_NONE or GAP_ACT_TANH. */
 int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, int cw, const void* wcol, const float* bias,
-                       int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, void* stream);
+                       int act, void* out_bf16, int64_t ld_bf, float* out_f32, int64_t ld_f, uint8_t* out_u8, void* stream);
+/* SURVEY.md §8(f) ranks 1-2 (the I/O either side of the generator): out_u8 above, if not NULL, receives the image
+ * generate_synthetic_data.py:69-88 writes to PNG — uint8 [n][2ih][2iw][3] = byte((v*0.5 + 0.5) * 255) — straight from
+ * the last layer's epilogue; gap_u8_hwc_to_nhwc_bf16 is dataset.py's ToTensor + Normalize(0.5, 0.5) (dataset.py:155-159)
+ * on the device: uint8 HWC [pixels][3] -> NHWC bf16 with 4 channel slots, x*(2/255) - 1. */
+int gap_u8_hwc_to_nhwc_bf16(const uint8_t* x, void* out, int64_t out_ld, int64_t pixels, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Siamese U-Net extras (models.py:47-145, train.py:34-128); NHWC bf16 activations, 8-channel vectors

@@ -173,3 +173,29 @@ def test_thin_convT_fwd(n, ih, iw, cw, bias, act):
     assert rel(o32.cpu()[..., :3], nhwc(ref)) < 1e-4
     assert rel(obf.cpu().float()[..., :3], nhwc(ref)) < 4e-3
     assert float(o32.cpu()[..., 3].abs().max()) == 0.0
+
+
+def test_uint8_image_input_and_output_paths():
+    """uint8 HWC -> normalised NHWC bf16 (dataset.py:155-159) and the generator's uint8 image
+    output (generate_synthetic_data.py:69-88: x*0.5+0.5 -> to_pil_image = mul(255).byte())."""
+    g = torch.Generator().manual_seed(8)
+    img = torch.randint(0, 256, (2, 12, 10, 3), generator=g, dtype=torch.uint8)
+    out = torch.full((2, 12, 10, 4), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.u8_hwc_to_nhwc_bf16(img.to(DEV), out)
+    ref = (img.float() / 255 - 0.5) / 0.5
+    assert rel(out.cpu().float()[..., :3], ref) < 4e-3
+    assert float(out.cpu().float()[..., 3].abs().max()) == 0.0
+    # last ConvT layer with the uint8 epilogue
+    n, ih, iw, cw = 2, 8, 16, 64
+    x = torch.randn(n, cw, ih, iw, generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn(cw, 3, 4, 4, generator=g) / (4 * cw) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(3, generator=g)
+    y = torch.tanh(F.conv_transpose2d(x, wt, b, stride=2, padding=1))
+    w2 = wt.permute(2, 3, 1, 0).reshape(48, cw).to(torch.bfloat16).contiguous()
+    o32 = torch.empty(n, 2 * ih, 2 * iw, 4, device=DEV)
+    ou8 = torch.zeros(n, 2 * ih, 2 * iw, 3, device=DEV, dtype=torch.uint8)
+    ops.thin_convT_fwd(nhwc(x).to(torch.bfloat16).to(DEV), w2.to(DEV), b.to(DEV), ops.ACT_TANH, None, o32, ou8)
+    want = ((o32.cpu()[..., :3] * 0.5 + 0.5) * 255).clamp(0, 255).to(torch.uint8)      # same fp32 values, same truncation
+    assert torch.equal(ou8.cpu(), want)
+    ref_u8 = ((nhwc(y) * 0.5 + 0.5) * 255).to(torch.uint8).int()
+    assert int((ou8.cpu().int() - ref_u8).abs().max()) <= 1                               # vs the fp32 reference: +-1 level
