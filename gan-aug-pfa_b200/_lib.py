@@ -45,6 +45,7 @@ class ConvGemmArgs(C.Structure):
         ("bwd_scale", C.c_void_p), ("bwd_shift", C.c_void_p),
         ("bwd_g2", C.c_void_p), ("bwd_g2_ld", C.c_int64),
         ("bwd_slope", C.c_float), ("bwd_c0", C.c_int),
+        ("scale", C.c_void_p),
     ]
 
 

@@ -51,6 +51,7 @@ struct alignas(64) FpropParams {
   long long out2_ld;
   int act2;
   const float* bias;
+  const float* scale;   // per-channel multiplier applied before the bias (eval-mode BatchNorm folded into the epilogue)
   double* stats;
   int num_stages;
   uint32_t idesc;
@@ -502,6 +503,10 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             }
             continue;
           }
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) f[jj] *= __ldg(p.scale + min(col0 + jj, p.n_out - 1));
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) f[jj] += __ldg(p.bias + min(col0 + jj, p.n_out - 1));
@@ -700,6 +705,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.out2_ld = a->out2_ld;
   p.act2 = a->act2;
   p.bias = a->bias;
+  p.scale = a->scale;
   p.stats = a->stats;
   p.idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
   const bool vec32 =
@@ -714,7 +720,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   GAP_CHECK_ARG(!(a->out_f32 && a->out2), "gap_conv_gemm: out2 is not supported with fp32 output");
   const bool bwd = a->bwd_y != nullptr;
   if (bwd) {
-    const bool ok = vec32 && !a->out_f32 && !a->out2 && a->act == GAP_ACT_NONE && !a->bias && a->bwd_c0 >= 0 &&
+    const bool ok = vec32 && !a->out_f32 && !a->out2 && a->act == GAP_ACT_NONE && !a->bias && !a->scale && a->bwd_c0 >= 0 &&
                     a->bwd_c0 % 16 == 0 && a->bwd_c0 < a->n_out && (a->n_out - a->bwd_c0) % 16 == 0 &&
                     a->bwd_y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->bwd_y) & 15) == 0 &&
                     (!a->bwd_g2 || (a->bwd_g2_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->bwd_g2) & 15) == 0)) &&

@@ -83,7 +83,7 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
               n_out: int, grid_hw: tuple[int, int], *, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, act2: int = ACT_NONE,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              flops: Optional[float] = None, bwd: Optional[dict] = None) -> None:
+              flops: Optional[float] = None, bwd: Optional[dict] = None, scale: Optional[torch.Tensor] = None) -> None:
     """Launch the implicit-GEMM engine.  ``wpk`` is [n_phase, rows, taps*ctot] bf16.  ``flops`` overrides
     the algorithmic FLOP count reported to the profiler (layers that pad channels pass the true one)."""
     a = _lib.ConvGemmArgs()
@@ -143,6 +143,12 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
     else:
         a.bias = None
     c0 = int(bwd.get("c0", 0)) if bwd is not None else 0
+    if scale is not None:
+        if scale.dtype != torch.float32 or scale.numel() < n_out:
+            raise ValueError("scale must be fp32 with >= n_out elements")
+        a.scale = scale.data_ptr()
+    else:
+        a.scale = None
     if stats is not None:
         if stats.dtype != torch.float64 or stats.numel() != 2 * (n_out - c0):
             raise ValueError("stats must be fp64 [2*(n_out - c0)]")

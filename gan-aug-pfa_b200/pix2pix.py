@@ -260,6 +260,11 @@ class _Net:
             ops.bn_eval_scale_shift(gamma, beta, bn.running_mean, bn.running_var, BN_EPS, bn.scale, bn.shift)
         ops.bn_act(y, bn.scale, bn.shift, out1, act1, out2, act2)
 
+    def _bn_eval(self, bn: _BN) -> None:
+        """eval-mode BatchNorm as (scale, shift) from the running statistics (generate_synthetic_data.py:55)."""
+        ops.bn_eval_scale_shift(self.param(bn.name + ".weight"), self.param(bn.name + ".bias"), bn.running_mean,
+                                bn.running_var, BN_EPS, bn.scale, bn.shift)
+
     def _bn_backward(self, bn: _BN, y, g1, g2, slope: float, dy, param_grads: bool = True) -> None:
         count = y.numel() // y.shape[-1]
         ops.bn_bwd_reduce(y, g1, g2, slope, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums)
@@ -412,14 +417,23 @@ class GeneratorEngine(_Net):
         ops.thin_conv_fwd(self.x_nhwc, None, self.w_d_thin, None, self.A[0], ACT_LRELU, self.R[0][..., :C[0]], ACT_RELU)
         for j in range(1, L - 1):
             bn = self.dbn[j]
-            ops.conv_gemm([self.A[j - 1]], self.w_d_fwd[j], g_s2, self.yd[j], C[j], S[j],
-                          stats=bn.stats if self.training else None)
+            if not self.training:      # eval: BatchNorm folds into the conv epilogue (scale, shift), no extra pass
+                self._bn_eval(bn)
+                ops.conv_gemm([self.A[j - 1]], self.w_d_fwd[j], g_s2, self.A[j], C[j], S[j], act=ACT_LRELU,
+                              out2=self.R[j][..., :C[j]], act2=ACT_RELU, scale=bn.scale, bias=bn.shift)
+                continue
+            ops.conv_gemm([self.A[j - 1]], self.w_d_fwd[j], g_s2, self.yd[j], C[j], S[j], stats=bn.stats)
             self._bn_forward(bn, self.yd[j], self.A[j], ACT_LRELU, self.R[j][..., :C[j]], ACT_RELU, bn_repeat)
         ops.conv_gemm([self.A[L - 2]], self.w_d_fwd[L - 1], g_s2, self.Rin, C[L - 1], S[L - 1], act=ACT_RELU)
         for j in range(L - 1, 0, -1):
             src = self.Rin if j == L - 1 else self.R[j]
             bn = self.ubn[j]
-            ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats if self.training else None)
+            if not self.training:
+                self._bn_eval(bn)
+                ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.R[j - 1][..., C[j - 1]:], C[j - 1], S[j], act=ACT_RELU,
+                              scale=bn.scale, bias=bn.shift)
+                continue
+            ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats)
             self._bn_forward(bn, self.yu[j], self.R[j - 1][..., C[j - 1]:], ACT_RELU, repeat=bn_repeat)
         ops.thin_convT_fwd(self.R[0], self.w_u_T2, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32,
                            out_u8)

@@ -111,6 +111,10 @@ typedef struct gap_conv_gemm_args {
   int64_t bwd_g2_ld;
   float bwd_slope;
   int bwd_c0;
+  /* Optional per-channel multiplier applied to the accumulator before the bias: v = acc*scale[co] + bias[co].
+   * Eval-mode BatchNorm (generate_synthetic_data.py:55, train.py:151, evaluate.py:146) folds into the conv this way
+   * (scale = gamma/sqrt(running_var+eps), bias = beta - running_mean*scale), so no normalisation pass runs. */
+  const float* scale;
 } gap_conv_gemm_args;
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);
