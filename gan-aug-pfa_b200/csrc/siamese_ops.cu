@@ -246,6 +246,36 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ gout, long long l
   }
 }
 
+// nn.Dropout(p) (models.py:198) in place on a bf16 [pixels][c] tensor (channel slice allowed): x = keep ? x/(1-p) : 0,
+// keep decided by a counter-based hash of (seed, offset + element index), so forward and backward regenerate the
+// same mask without storing it (the backward applies the same kernel to the gradient).
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return static_cast<uint32_t>((z ^ (z >> 31)) >> 32);
+}
+__global__ void dropout_kernel(bf16* __restrict__ x, long long ld, long long pixels, int c, float p_drop, float scale,
+                               unsigned long long seed, unsigned long long offset) {
+  const int cv = c >> 3;
+  const long long total = pixels * cv;
+  const uint32_t thresh = static_cast<uint32_t>(fminf(p_drop, 0.999999f) * 4294967296.0f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c8 = static_cast<int>(i - pix * cv) << 3;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + pix * ld + c8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint64_t idx = static_cast<uint64_t>(pix) * c + c8 + j;
+      const bool keep = mix32(seed * 0xD1342543DE82EF95ull + offset + idx) >= thresh;
+      v[j] = keep ? v[j] * scale : 0.f;
+    }
+    *reinterpret_cast<uint4*>(x + pix * ld + c8) = pack8(v);
+  }
+}
+
 // dst += src  (bf16, 8 channels per thread; gradient accumulation for activations with several consumers)
 __global__ void add_inplace_kernel(bf16* __restrict__ dst, long long ldd, const bf16* __restrict__ src, long long lds,
                                    long long pixels, int c) {
@@ -607,6 +637,13 @@ int gap_upsample_bilinear2x_bwd(const void* gout, int64_t ldg, void* gin, int64_
   const long long total = static_cast<long long>(n) * h * w * (c / 8);
   upsample2x_bwd_kernel<<<grid_of(total, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(gout), ldg, static_cast<bf16*>(gin), ldi, n, h, w, c, accumulate);
+  SI_LAUNCH_OK();
+}
+
+int gap_dropout_bf16(void* x, int64_t ld, int64_t pixels, int c, float p_drop, uint64_t seed, uint64_t offset, void* stream) {
+  GAP_CHECK_ARG(x && pixels > 0 && c % 8 == 0 && ld % 8 == 0 && p_drop >= 0.f && p_drop < 1.f, "gap_dropout_bf16: bad arguments");
+  dropout_kernel<<<grid_of(pixels * (c / 8), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(x), ld, pixels, c, p_drop, 1.f / (1.f - p_drop), seed, offset);
   SI_LAUNCH_OK();
 }
 

@@ -133,9 +133,8 @@ class UNetGenerator(_NativeModule):
         super().__init__()
         if norm_layer is not nn.BatchNorm2d:
             raise NotImplementedError("only norm_layer=nn.BatchNorm2d (the reference default) is implemented natively")
-        if use_dropout:
-            raise NotImplementedError("use_dropout=True is not implemented natively (the reference never enables it)")
         self._cfg = (input_nc, output_nc, num_downs, ngf)
+        self._use_dropout = bool(use_dropout)
         blk = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=None, norm_layer=norm_layer,
                                       innermost=True)
         for _ in range(num_downs - 5):
@@ -149,7 +148,7 @@ class UNetGenerator(_NativeModule):
 
     def _make_engine(self, device):
         i, o, n, f = self._cfg
-        return GeneratorEngine(device, i, o, n, f, init=False)
+        return GeneratorEngine(device, i, o, n, f, init=False, use_dropout=self._use_dropout)
 
     def forward(self, input):
         return _GeneratorFn.apply(self, input, *self.parameters())

@@ -557,6 +557,12 @@ def upsample2x_bwd(gout: torch.Tensor, gin: torch.Tensor, accumulate: bool) -> N
                                                       1 if accumulate else 0, _stream()), "gap_upsample_bilinear2x_bwd")
 
 
+def dropout_(x: torch.Tensor, p_drop: float, seed: int, offset: int) -> None:
+    """In-place nn.Dropout(p) with a regenerable mask (same (seed, offset) -> same mask; used on the gradient too)."""
+    _lib.check(_lib.lib().gap_dropout_bf16(_ptr(x), x.stride(-2), _px(x), x.shape[-1], p_drop, seed & (2**64 - 1),
+                                           offset & (2**64 - 1), _stream()), "gap_dropout_bf16")
+
+
 def add_inplace(dst: torch.Tensor, src: torch.Tensor) -> None:
     _lib.check(_lib.lib().gap_add_inplace_bf16(_ptr(dst), dst.stride(-2), _ptr(src), src.stride(-2), _px(dst),
                                                dst.shape[-1], _stream()), "gap_add_inplace_bf16")

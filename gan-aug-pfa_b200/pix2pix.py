@@ -286,8 +286,14 @@ class GeneratorEngine(_Net):
                      "dyu", "dyd")
 
     def __init__(self, device, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64,
-                 init: bool = True) -> None:
+                 init: bool = True, use_dropout: bool = False, dropout_seed: int = 0) -> None:
         super().__init__(device)
+        # nn.Dropout(0.5) after the up-norm of the num_downs-5 blocks at ngf*8 (models.py:156-157,197-198); their up
+        # outputs are yu[j] for j = L-2 ... L-1-(num_downs-5)
+        self.use_dropout = use_dropout
+        self.dropout_seed = dropout_seed
+        self.dropout_calls = 0          # forward counter: every forward draws fresh masks
+        self._drop_off: Dict[int, int] = {}
         if input_nc != 3 or output_nc != 3:
             raise NotImplementedError("the native generator supports input_nc = output_nc = 3")
         if ngf % 64 != 0 or num_downs < 5:
@@ -435,9 +441,19 @@ class GeneratorEngine(_Net):
                 continue
             ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats)
             self._bn_forward(bn, self.yu[j], self.R[j - 1][..., C[j - 1]:], ACT_RELU, repeat=bn_repeat)
+            if self._dropout_layer(j):
+                # ReLU(Dropout(v)) = Dropout(ReLU(v)): the mask multiplies the slot the parent block reads
+                slot = self.R[j - 1][..., C[j - 1]:]
+                self._drop_off[j] = (self.dropout_calls << 40) + (j << 34)
+                ops.dropout_(slot, 0.5, self.dropout_seed, self._drop_off[j])
         ops.thin_convT_fwd(self.R[0], self.w_u_T2, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32,
                            out_u8)
+        self.dropout_calls += 1
         return self.fake_f32
+
+    def _dropout_layer(self, j: int) -> bool:
+        """True if the block whose up-conv output is yu[j] ends in nn.Dropout(0.5) (training mode only)."""
+        return self.use_dropout and self.training and (self.L - 1 - (self.L - 5)) <= j <= self.L - 2
 
     def output_nchw(self) -> torch.Tensor:
         n, h, w = self._n
@@ -463,7 +479,9 @@ class GeneratorEngine(_Net):
         for j in range(1, L):
             bn = self.ubn[j]
             co = C[j - 1]
-            if j == 1:      # gR[0] comes from the thin-layer kernel: classic reduce + apply
+            if self._dropout_layer(j):
+                ops.dropout_(self.gR[j - 1][..., co:], 0.5, self.dropout_seed, self._drop_off[j])   # same mask as forward
+            if j == 1 or self._dropout_layer(j):      # gR[0] comes from the thin-layer kernel: classic reduce + apply
                 self._bn_backward(bn, self.yu[j], self.gR[j - 1][..., co:], None, 0.0, self.dyu[j])
             else:
                 self._bn_backward_fused(bn, self.yu[j], self.gR[j - 1][..., co:], self.dyu[j])
@@ -476,6 +494,9 @@ class GeneratorEngine(_Net):
                 # innermost: Rin = ReLU(conv) has no BatchNorm -> the epilogue writes dyd[L-1] directly
                 ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.dyd[L - 1], ci, S[j],
                               bwd=self._bwd_epilogue(None, self.Rin, 0.0))
+            elif self._dropout_layer(j + 1):
+                # the dropout mask has to hit the gradient before the ReLU / BatchNorm backward: plain dgrad here
+                ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.gR[j], ci, S[j])
             else:
                 nb = self.ubn[j + 1]     # second half of gR[j] = gradient at ReLU(BN(yu[j+1]))
                 ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.gR[j], ci, S[j], stats=nb.sums,
@@ -673,10 +694,10 @@ class Pix2PixTrainer:
 
     def __init__(self, device, lr_g: float = 1e-4, lr_d: float = 1e-4, beta1: float = 0.5, num_downs: int = 7,
                  ngf: int = 64, ndf: int = 64, n_layers: int = 3, allreduce=None, world: int = 1,
-                 bucket_elems: int = 8 << 20) -> None:
+                 bucket_elems: int = 8 << 20, use_dropout: bool = False) -> None:
         self.dev = torch.device(device)
         # construction order G then D fixes the seeded weights (train_gan.py:138-139)
-        self.G = GeneratorEngine(self.dev, 3, 3, num_downs, ngf)
+        self.G = GeneratorEngine(self.dev, 3, 3, num_downs, ngf, use_dropout=use_dropout)
         self.D = DiscriminatorEngine(self.dev, 6, ndf, n_layers)
         self.lr_g, self.lr_d, self.betas = lr_g, lr_d, (beta1, 0.999)
         self.loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float64)  # d_real, d_fake, g_gan, l1
@@ -698,7 +719,7 @@ class Pix2PixTrainer:
         """train_step through a CUDA graph: the first call (after at least one eager step has sized every
         buffer) captures the ~175 launches of the iteration, later calls copy the batch into the static input
         buffers and replay.  Same results as train_step; single-GPU only."""
-        if self.world > 1:
+        if self.world > 1 or self.G.use_dropout:      # dropout draws host-numbered masks per forward: no replay
             return self.train_step(real_A, real_B)
         if self._graph is None or self._g_in[0].shape != real_A.shape:
             self._g_in = (torch.empty_like(real_A), torch.empty_like(real_B))
@@ -731,7 +752,8 @@ class Pix2PixTrainer:
         ops.nchw_to_nhwc_bf16(real_B, self.b_nhwc)
         # ---- D step (train_gan.py:55-63)
         D.zero_grad()
-        G.forward(real_A, bn_repeat=2)                     # :56 and :65 (identical forward, done once)
+        # :56 and :65 are the same forward (done once, BatchNorm buffers updated twice) unless dropout draws new masks
+        G.forward(real_A, bn_repeat=1 if G.use_dropout else 2)
         a_nhwc = G.x_nhwc
         logits = D.forward(a_nhwc, self.b_nhwc)            # :57
         cnt = logits.numel()
@@ -749,6 +771,8 @@ class Pix2PixTrainer:
         D.adam_step(self.lr_d, self.betas, grad_scale=1.0 / self.world)   # :63
         # ---- G step (train_gan.py:64-71)
         G.zero_grad()
+        if G.use_dropout:
+            G.forward(real_A, bn_repeat=1)                 # :65 with fresh dropout masks
         logits = D.forward(a_nhwc, G.fake_bf)              # :66 (updated D)
         ops.bce_logits_const_f32(logits, 1.0, 1.0 / cnt, D.dlogits, self.loss_acc[2:3])   # :67
         dfake = D.backward(wgrad=False, input_grad=True)

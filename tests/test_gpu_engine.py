@@ -186,3 +186,50 @@ def test_graphed_train_step_matches_eager():
             assert int(tr.G.store.step_dev) == len(batches)
     # fp32 atomics make the two runs differ in the last bits only
     assert torch.allclose(res[0], res[1], rtol=2e-3, atol=2e-4), (res[0], res[1])
+
+
+def test_dropout_kernel_mask_is_regenerable_and_fair():
+    """gap_dropout_bf16 (nn.Dropout(0.5), models.py:197-198): x -> {0, 2x}, same (seed, offset) -> same mask (that is how
+    the backward pass re-applies it to the gradient), keep probability 0.5."""
+    x = (torch.rand(4, 8, 8, 512, device=DEV) + 0.5).to(torch.bfloat16)
+    a, b, c = x.clone(), x.clone(), x.clone()
+    ops.dropout_(a, 0.5, 7, 1 << 40)
+    ops.dropout_(b, 0.5, 7, 1 << 40)
+    ops.dropout_(c, 0.5, 7, 2 << 40)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    kept = a != 0
+    assert abs(float(kept.float().mean()) - 0.5) < 0.01
+    assert torch.equal(a[kept].float(), (2 * x[kept].float()).to(torch.bfloat16).float())
+    half = x[..., 256:].clone()
+    wide = x.clone()
+    ops.dropout_(wide[..., 256:], 0.5, 3, 0)          # channel slice of a wider buffer
+    assert torch.equal(wide[..., :256], x[..., :256]) and not torch.equal(wide[..., 256:], half)
+
+
+def test_generator_with_dropout_trains_and_evaluates():
+    """UNetGenerator(use_dropout=True): the two ngf*8 blocks end in Dropout(0.5) (models.py:156-157).  Mask parity with
+    torch's RNG is not possible, so: eval mode equals the no-dropout network, training forwards differ between calls
+    (fresh masks), and the full GAN iteration (second generator forward NOT elided) runs with finite losses."""
+    gen = torch.Generator().manual_seed(3)
+    A = (torch.rand(2, 3, 256, 256, generator=gen) * 2 - 1).to(DEV)
+    B = (torch.rand(2, 3, 256, 256, generator=gen) * 2 - 1).to(DEV)
+    torch.manual_seed(0)
+    t_plain = Pix2PixTrainer(DEV)
+    torch.manual_seed(0)
+    t_drop = Pix2PixTrainer(DEV, use_dropout=True)
+    for t in (t_plain, t_drop):
+        t.G.training = False
+        t.G.forward(A)
+    assert torch.equal(t_plain.G.fake_f32, t_drop.G.fake_f32)
+    t_drop.G.training = True
+    t_drop.G.forward(A)
+    f1 = t_drop.G.fake_f32.clone()
+    t_drop.G.forward(A)
+    assert not torch.equal(f1, t_drop.G.fake_f32)
+    nbt0 = int(t_drop.G.state_dict()["model.model.1.model.2.num_batches_tracked"])
+    losses = t_drop.train_step(A, B).cpu()
+    assert torch.isfinite(losses).all()
+    # two real generator forwards per iteration -> BatchNorm buffers advance by 2, as in the reference
+    assert int(t_drop.G.state_dict()["model.model.1.model.2.num_batches_tracked"]) == nbt0 + 2
+    g = t_drop.G.store.g
+    assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
