@@ -196,7 +196,17 @@ class SiameseEngine(_Net):
         n, h, w, _ = out.shape
         y = self._scratch(f"y.{key}.{pass_id}", (n, h, w, co))
         sv = self._sv(bn.name, pass_id, co)
-        stats = bn.stats if self.training else None
+        if not self.training:
+            # eval (train.py:151, evaluate.py:146): BatchNorm folds into the conv epilogue; nothing is kept for backward
+            self._bn_stats(bn, sv, n * h * w)
+            if ci == 3:
+                ops.conv_gemm([x], self.w_fwd[key], ops.geom_conv_fwd(1, 1, 0), out, co, (h, w), act=ACT_RELU,
+                              scale=sv.scale, bias=sv.shift, flops=2.0 * n * h * w * co * 27)
+            else:
+                ops.conv_gemm([x], self.w_fwd[key], ops.geom_conv_fwd(3, 1, 1), out, co, (h, w), act=ACT_RELU,
+                              scale=sv.scale, bias=sv.shift)
+            return {"bn": bn, "sv": sv, "y": y}
+        stats = bn.stats
         if ci == 3:
             ops.conv_gemm([x], self.w_fwd[key], ops.geom_conv_fwd(1, 1, 0), y, co, (h, w), stats=stats,
                           flops=2.0 * n * h * w * co * 27)

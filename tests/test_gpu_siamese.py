@@ -164,6 +164,10 @@ def test_siamese_forward_and_losses_match_reference_golden():
         out_e = m(gold["x1"].to(DEV), gold["x2"].to(DEV))
     assert torch.isfinite(out_e).all()
     assert int(m.state_dict()["dconv_down1.1.num_batches_tracked"]) == 2
+    sd_cpu = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref_e = O.siamese_forward(sd_cpu, gold["x1"], gold["x2"], False, None)
+    assert rel(out_e.cpu(), ref_e) < 0.15            # eval path: BatchNorm folded into the conv epilogues
 
 
 def test_siamese_gradients_and_train_steps_match_oracle():
