@@ -122,6 +122,7 @@ class _GeneratorFn(torch.autograd.Function):
         eng.zero_grad()
         ops.tanh_bwd(gout.contiguous().float(), eng.fake_f32, eng.dpre)
         eng.backward()
+        eng._join_wgrad()
         grads = [eng.grad(name).clone() for name, _ in module.named_parameters()]
         return (None, None, *grads)
 
@@ -185,6 +186,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         if wgrad:
             ops.sum_f32(eng.dlogits, eng.grad(eng.k_conv[-1] + ".bias"))
         eng.backward(wgrad=wgrad, input_grad=ctx.x_grad, input_grad_a=ctx.x_grad)
+        eng._join_wgrad()
         gx = None
         if ctx.x_grad:
             gx = torch.empty(n, 6, h, w, device=gout.device)

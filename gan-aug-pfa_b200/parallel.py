@@ -61,10 +61,12 @@ class GradBucketReducer:
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream(flat.device) if self.cuda else None)
         self.launched_before_finish = 0          # statistics of the last step (tests / logging)
         self._pending: List[int] = []
+        self._streams: List[set] = []
         self._next = 0
 
     def begin(self) -> None:
         self._pending = [len(names) for _, _, names in self.buckets]
+        self._streams = [set() for _ in self.buckets]
         self._next = 0
         self.launched_before_finish = 0
 
@@ -72,19 +74,24 @@ class GradBucketReducer:
         begin, end, _ = self.buckets[b]
         view = self.flat[begin:end]
         if self.cuda:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.flat.device))
-            self.comm_stream.wait_event(ev)
+            # wait for the compute stream and for every side stream that produced a segment of this bucket
+            for st in {torch.cuda.current_stream(self.flat.device)} | (self._streams[b] if self._streams else set()):
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, op=dist.ReduceOp.SUM)
         else:
             dist.all_reduce(view, op=dist.ReduceOp.SUM)
 
-    def mark_ready(self, name: str) -> None:
+    def mark_ready(self, name: str, stream=None) -> None:
+        """``stream``: the (side) stream the segment's last kernel was enqueued on, if not the current one."""
         b = self.bucket_of.get(name)
         if b is None:
             raise KeyError(f"unknown gradient segment {name!r}")
         self._pending[b] -= 1
+        if stream is not None:
+            self._streams[b].add(stream)
         # buckets are launched in order on every rank (NCCL collectives must be issued in the same order)
         while self._next < len(self.buckets) and self._pending[self._next] <= 0:
             self._launch(self._next)

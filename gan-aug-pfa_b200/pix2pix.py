@@ -110,10 +110,35 @@ class _Net:
         self.training = True
         self.grad_hook = None     # callable(segment name) fired when a gradient segment is final (data-parallel buckets)
 
-    def _ready(self, *keys: str) -> None:
+    def _ready(self, *keys: str, side: bool = False) -> None:
         if self.grad_hook is not None:
+            st = self._wgrad_stream if (side and self._wgrad_used) else None
             for k in keys:
-                self.grad_hook(k)
+                self.grad_hook(k, st)
+
+    # Weight gradients are off the critical path of a backward pass (only the optimizer needs them), so they are
+    # enqueued on a side stream: the block scheduler fills the SMs that the dgrad chain leaves idle (small deep layers,
+    # tail waves of the persistent GEMMs) with wgrad CTAs.  Joined before anything they read is overwritten.
+    overlap_wgrad = True
+    _wgrad_stream = None
+    _wgrad_used = False
+
+    def _fork_wgrad(self, fn) -> None:
+        if not self.overlap_wgrad:
+            fn()
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(self.dev)
+        self._wgrad_stream.wait_stream(cur)          # everything enqueued so far (the operands) is visible
+        with torch.cuda.stream(self._wgrad_stream):
+            fn()
+        self._wgrad_used = True
+
+    def _join_wgrad(self) -> None:
+        if self._wgrad_used:
+            torch.cuda.current_stream(self.dev).wait_stream(self._wgrad_stream)
+            self._wgrad_used = False
 
     def grad_segments(self) -> List[Tuple[str, int, int]]:
         """(name, offset, numel) of every gradient segment in flat-buffer (= backward-completion) order."""
@@ -193,6 +218,7 @@ class _Net:
         raise NotImplementedError
 
     def zero_grad(self) -> None:
+        self._join_wgrad()
         self.store.g.zero_()
 
     # -- in-flight activation sets (autograd path: several forwards may precede one backward) --------
@@ -219,6 +245,7 @@ class _Net:
 
     def adam_step(self, lr: float, betas=(0.5, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                   decoupled: bool = False, grad_scale: float = 1.0) -> None:
+        self._join_wgrad()
         s = self.store
         s.step += 1
         if s.step_dev is None:
@@ -406,6 +433,7 @@ class GeneratorEngine(_Net):
         Returns fake as fp32 NHWC [n,h,w,4] (channel 3 is padding); the bf16 copy is self.fake_bf.  bn_repeat=2
         folds the reference's second identical forward.  out_u8 (uint8 [n,h,w,3]) additionally receives the image
         generate_synthetic_data.py:69-88 saves, written by the last layer's epilogue."""
+        self._join_wgrad()
         u8_in = x_nchw.dtype == torch.uint8
         if u8_in:
             n, h, w, _ = x_nchw.shape
@@ -469,10 +497,15 @@ class GeneratorEngine(_Net):
         g_s2 = ops.geom_conv_fwd(4, 2, 1)
         g_1x1 = ops.geom_conv_fwd(1, 1, 0)
         g_ph = ops.geom_phase_k4s2p1()
-        # outermost up-conv (GEMM + col2im form)
-        ops.thin_conv_wgrad(self.R[0], self.dpre, None, self.store.seg(self.store.g, self.k_up[0] + ".weight"), 64)
-        ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
-        self._ready(self.k_up[0] + ".weight", self.k_up[0] + ".bias")
+        self._join_wgrad()
+        gseg = lambda key: self.store.seg(self.store.g, key)
+        # outermost up-conv
+
+        def _w0():
+            ops.thin_conv_wgrad(self.R[0], self.dpre, None, gseg(self.k_up[0] + ".weight"), 64)
+            ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
+        self._fork_wgrad(_w0)
+        self._ready(self.k_up[0] + ".weight", self.k_up[0] + ".bias", side=True)
         ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
         # up path, outer -> inner.  Every dgrad GEMM applies the activation backward of the layer below in its
         # epilogue and accumulates that layer's BatchNorm-backward sums (no separate reduce pass).
@@ -487,9 +520,9 @@ class GeneratorEngine(_Net):
                 self._bn_backward_fused(bn, self.yu[j], self.gR[j - 1][..., co:], self.dyu[j])
             src = self.Rin if j == L - 1 else self.R[j]
             ci = src.shape[-1]
-            ops.conv_wgrad(src, self.dyu[j], self.store.seg(self.store.g, self.k_up[j] + ".weight"), (4, 4), 2,
-                           (-1, -1), 16 * co, co)
-            self._ready(self.k_up[j] + ".weight")
+            self._fork_wgrad(lambda src=src, j=j, co=co: ops.conv_wgrad(
+                src, self.dyu[j], gseg(self.k_up[j] + ".weight"), (4, 4), 2, (-1, -1), 16 * co, co))
+            self._ready(self.k_up[j] + ".weight", side=True)
             if j == L - 1:
                 # innermost: Rin = ReLU(conv) has no BatchNorm -> the epilogue writes dyd[L-1] directly
                 ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.dyd[L - 1], ci, S[j],
@@ -502,9 +535,9 @@ class GeneratorEngine(_Net):
                 ops.conv_gemm([self.dyu[j]], self.w_u_dg[j], g_s2, self.gR[j], ci, S[j], stats=nb.sums,
                               bwd=self._bwd_epilogue(nb, self.yu[j + 1], 0.0, c0=C[j]))
         for j in range(L - 1, 0, -1):
-            ops.conv_wgrad(self.dyd[j], self.A[j - 1], self.store.seg(self.store.g, self.k_down[j] + ".weight"),
-                           (4, 4), 2, (-1, -1), 16 * C[j - 1], C[j - 1])
-            self._ready(self.k_down[j] + ".weight")
+            self._fork_wgrad(lambda j=j: ops.conv_wgrad(
+                self.dyd[j], self.A[j - 1], gseg(self.k_down[j] + ".weight"), (4, 4), 2, (-1, -1), 16 * C[j - 1], C[j - 1]))
+            self._ready(self.k_down[j] + ".weight", side=True)
             jj = j - 1
             skip = self.gR[jj][..., :C[jj]]          # gradient through the ReLU'd skip copy (models.py:208)
             if jj >= 1:
@@ -515,8 +548,8 @@ class GeneratorEngine(_Net):
             else:
                 ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.dyd[0], C[0], S[j],
                               bwd=self._bwd_epilogue(None, self.A[0], 0.2, g2=skip))
-        ops.thin_conv_wgrad(self.dyd[0], self.x_nhwc, None, self.store.seg(self.store.g, self.k_down[0] + ".weight"), 64)
-        self._ready(self.k_down[0] + ".weight")
+        self._fork_wgrad(lambda: ops.thin_conv_wgrad(self.dyd[0], self.x_nhwc, None, gseg(self.k_down[0] + ".weight"), 64))
+        self._ready(self.k_down[0] + ".weight", side=True)
 
 
 # ================================================================================================
@@ -631,6 +664,7 @@ class DiscriminatorEngine(_Net):
         """xa, xb: NHWC bf16 [n,h,w,>=3] (the two halves of torch.cat((A, B), 1), train_gan.py:57,59,66).
         Returns fp32 logits [n,h',w',1]."""
         n, h, w, _ = xa.shape
+        self._join_wgrad()
         self._alloc(n, h, w)
         C = self.C
         self._xa, self._xb = xa, xb
@@ -652,8 +686,10 @@ class DiscriminatorEngine(_Net):
         C = self.C
         last = self.n_conv - 1
         g = self.store.g
+        self._join_wgrad()
         if wgrad:
-            ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1], self.store.seg(g, self.k_conv[last] + ".weight"))
+            self._fork_wgrad(lambda: ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1],
+                                                          self.store.seg(g, self.k_conv[last] + ".weight")))
         ops.cout1_conv_dgrad(self.dlogits, self.w_fwd[last].view(-1), self.gH[last - 1])
         for k in range(last - 1, 0, -1):
             if k == last - 1:   # gH[k] comes from the Cout=1 kernel: classic reduce + apply
@@ -662,8 +698,9 @@ class DiscriminatorEngine(_Net):
                 self._bn_backward_fused(self.bn[k], self.y[k], self.gH[k], self.dy[k], param_grads=wgrad)
             s = self.stride(k)
             if wgrad:
-                ops.conv_wgrad(self.dy[k], self.H[k - 1], self.store.seg(g, self.k_conv[k] + ".weight"), (4, 4), s,
-                               (-1, -1), 16 * C[k - 1], C[k - 1])
+                self._fork_wgrad(lambda k=k, s=s: ops.conv_wgrad(
+                    self.dy[k], self.H[k - 1], self.store.seg(g, self.k_conv[k] + ".weight"), (4, 4), s, (-1, -1),
+                    16 * C[k - 1], C[k - 1]))
             geom = ops.geom_phase_k4s2p1() if s == 2 else ops.geom_conv_dgrad_s1(4, 1)
             grid = (self.hs[k], self.ws[k]) if s == 2 else (self.hs[k - 1], self.ws[k - 1])
             if k - 1 >= 1:
@@ -674,8 +711,9 @@ class DiscriminatorEngine(_Net):
                 ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.dy[0], C[0], grid,
                               bwd=self._bwd_epilogue(None, self.H[0], 0.2))
         if wgrad:
-            ops.thin_conv_wgrad(self.dy[0], self._xa, self._xb, self.store.seg(g, self.k_conv[0] + ".weight"), 128,
-                                dbias=self.grad(self.k_conv[0] + ".bias"))
+            self._fork_wgrad(lambda: ops.thin_conv_wgrad(self.dy[0], self._xa, self._xb,
+                                                         self.store.seg(g, self.k_conv[0] + ".weight"), 128,
+                                                         dbias=self.grad(self.k_conv[0] + ".bias")))
         if input_grad:
             ops.thin_convT_fwd(self.dy[0], self.w_T2, None, ACT_NONE, None, self.dfake)
             if input_grad_a:
@@ -763,6 +801,7 @@ class Pix2PixTrainer:
         logits = D.forward(a_nhwc, G.fake_bf)              # :59
         ops.bce_logits_const_f32(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2], d_bias_last)   # :60,61
         D.backward(wgrad=True, input_grad=False)           # :62
+        D._join_wgrad()
         if self.d_reducer is not None:
             self.d_reducer.begin()
             self.d_reducer.finish()
@@ -782,6 +821,7 @@ class Pix2PixTrainer:
             self.g_reducer.begin()
         G.backward()
         if self.g_reducer is not None:
+            G._join_wgrad()
             self.g_reducer.finish()
         elif self.allreduce is not None:
             self.allreduce(G.store.g)
