@@ -79,6 +79,18 @@ def geom_phase_k4s2p1() -> Geometry:
     return Geometry(4, 2, 2, 1, (-1, 0), (-1, 0), 2)
 
 
+_SPLITK_WS: dict = {}
+
+
+def _splitk_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-filled fp32 scratch for split-K launches (gap_conv_gemm_args.splitk_ws); the kernels leave it zeroed."""
+    ws = _SPLITK_WS.get(device)
+    if ws is None:
+        ws = torch.zeros(8 << 20, device=device, dtype=torch.float32)      # 32 MiB: n*oh*ow*n_out <= 8 Mi elements
+        _SPLITK_WS[device] = ws
+    return ws
+
+
 def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, out: torch.Tensor,
               n_out: int, grid_hw: tuple[int, int], *, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, act2: int = ACT_NONE,
@@ -177,6 +189,8 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
         a.bwd_c0 = c0
     else:
         a.bwd_y = None
+    ws = _splitk_workspace(out.device)
+    a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     if flops is None:
         flops = 2.0 * n * grid_hw[0] * grid_hw[1] * geom.n_phase * n_out * geom.taps_h * geom.taps_w * ctot
     _timed("conv_fprop_kernel", flops,

@@ -115,6 +115,11 @@ typedef struct gap_conv_gemm_args {
    * Eval-mode BatchNorm (generate_synthetic_data.py:55, train.py:151, evaluate.py:146) folds into the conv this way
    * (scale = gamma/sqrt(running_var+eps), bias = beta - running_mean*scale), so no normalisation pass runs. */
   const float* scale;
+  /* Optional split-K workspace (device, fp32, ZERO-filled, >= n*oh*ow*n_out*4 bytes): layers with too few output
+   * tiles for the GPU (deep U-Net levels, small batches) split the K loop over CTAs, accumulate partial tiles here and
+   * finish with a small epilogue kernel that leaves the workspace zeroed again.  NULL disables split-K. */
+  void* splitk_ws;
+  size_t splitk_ws_bytes;
 } gap_conv_gemm_args;
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);

@@ -139,6 +139,14 @@ if __name__ == "__main__":
         print("=== forced mt", mt)
         _lib.debug_set("fprop_mt", mt)
         allok &= run_all()
+    _lib.debug_set("fprop_mt", 0)
+    for sp in (3, 7):
+        print("=== forced split-K", sp)
+        _lib.debug_set("fprop_splits", sp)
+        _lib.debug_set("fprop_halo", 0)
+        allok &= run_all()
+    _lib.debug_set("fprop_splits", 0)
+    _lib.debug_set("fprop_halo", 1)
     print("ALL OK" if allok else "SOME FAILED", f"({time.time()-t0:.1f}s)", flush=True)
     if allok:
         for mt in (1, 2):
