@@ -773,11 +773,13 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     }
   }
   // Split-K for layers with too few output tiles (see FpropParams): keep a wide N tile and cut K instead.
+  // Measured (tools/sweep_splitk.py): only the M = 256 layers gain (38 -> 27 us), M >= 1024 lose to the finish pass and
+  // the fp32 atomics make results run-to-run non-deterministic, so it is OFF unless gap_debug_set("fprop_splitk", 1).
   int splits = 1;
   const int k_iters_full = a->taps_h * a->taps_w * ((a->src_c[0] + a->src_c[1]) / 64);
   const long long ws_need = static_cast<long long>(a->n) * a->oh * a->ow * a->n_out * 4;
   if (!halo && force_bn == 0 && a->splitk_ws != nullptr && static_cast<long long>(a->splitk_ws_bytes) >= ws_need &&
-      a->n_out % 4 == 0 && debug_get("fprop_splitk", 1) != 0) {
+      a->n_out % 4 == 0 && debug_get("fprop_splitk", 0) != 0) {
     int bn_wide = ((n_pad + (n_pad + 255) / 256 - 1) / ((n_pad + 255) / 256) + 15) / 16 * 16;
     const int nt_wide = (n_pad + bn_wide - 1) / bn_wide;
     const int items = m_tiles * nt_wide;
