@@ -23,7 +23,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kEpiWarps = 8;   // two warps per TMEM lane quarter: one warp per scheduler is latency-bound in the epilogue
-constexpr int kFpropThreads = 64 + 32 * kEpiWarps;
+constexpr int kProducer2Warp = 2 + kEpiWarps;   // second TMA producer warp (takes the odd pipeline iterations)
+constexpr int kFpropThreads = 64 + 32 * kEpiWarps + 32;
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
 constexpr int kTmemCols = 512;
@@ -244,9 +245,14 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   const int BNI = kBlockM >> (p.log_bw + p.log_bh);
   const int n_taps = p.taps_h * p.taps_w;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0 || warp == kProducer2Warp) {
+    // ------------------------------------------------------------------ TMA producers
+    // Two single-lane producers split the pipeline iterations even / odd: one lane needs ~280 cycles of fixed work per
+    // iteration (mbarrier try_wait + expect_tx + address arithmetic, measured) plus ~50 per TMA, which is the bound for
+    // small tiles (N <= 64, or the deep layers with 128 iterations of tiny MMAs).
     if (elect_one()) {
+      const uint32_t my_par = warp == 0 ? 0u : 1u;
+      uint32_t it = 0;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -270,12 +276,14 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             const int t_h = tap / p.taps_w, t_w = tap - t_h * p.taps_w;
             const int s = cc >= p.src_chunks[0] ? 1 : 0;
             const int c = cc - (s ? p.src_chunks[0] : 0);
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), tx_bytes);
-            const uint32_t a_dst = smem_base + stage * stage_bytes;
-            tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
-            if (has1) tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
-            tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kk * kBlockK, b_row, wc.phase);
+            if ((it++ & 1u) == my_par) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
+              if (has1) tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
+              tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kk * kBlockK, b_row, wc.phase);
+            }
             if (++stage == p.num_stages) {
               stage = 0;
               phase ^= 1u;
@@ -290,16 +298,18 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               int cc = 0;
               for (int s = 0; s < 2; ++s) {
                 for (int c = 0; c < p.src_chunks[s]; ++c, ++cc) {
-                  mbar_wait(empty_bar(stage), phase ^ 1u);
-                  mbar_expect_tx(full_bar(stage), txh);
-                  const uint32_t a_dst = smem_base + stage * stage_bytes;
-                  tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + g, n0);
-                  if (has1)
-                    tma_load_4d(a_dst + p.a_tile_bytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + g, n1);
-                  for (int i = 0; i < p.halo_taps; ++i) {
-                    const int t_h = g + p.halo_groups * i;
-                    tma_load_3d(a_dst + a_bytes + i * p.block_n * 128, &p.tmB, full_bar(stage),
-                                ((t_h * p.taps_w + t_w) * p.chunks_tot + cc) * kBlockK, b_row, wc.phase);
+                  if ((it++ & 1u) == my_par) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), txh);
+                    const uint32_t a_dst = smem_base + stage * stage_bytes;
+                    tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + g, n0);
+                    if (has1)
+                      tma_load_4d(a_dst + p.a_tile_bytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + g, n1);
+                    for (int i = 0; i < p.halo_taps; ++i) {
+                      const int t_h = g + p.halo_groups * i;
+                      tma_load_3d(a_dst + a_bytes + i * p.block_n * 128, &p.tmB, full_bar(stage),
+                                  ((t_h * p.taps_w + t_w) * p.chunks_tot + cc) * kBlockK, b_row, wc.phase);
+                    }
                   }
                   if (++stage == p.num_stages) {
                     stage = 0;
@@ -316,13 +326,15 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           for (int t_w = 0; t_w < p.taps_w; ++t_w) {
             for (int s = 0; s < 2; ++s) {
               for (int c = 0; c < p.src_chunks[s]; ++c) {
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), tx_bytes);
-                const uint32_t a_dst = smem_base + stage * stage_bytes;
-                tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
-                if (has1)
-                  tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
-                tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kcol, b_row, wc.phase);
+                if ((it++ & 1u) == my_par) {
+                  mbar_wait(empty_bar(stage), phase ^ 1u);
+                  mbar_expect_tx(full_bar(stage), tx_bytes);
+                  const uint32_t a_dst = smem_base + stage * stage_bytes;
+                  tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
+                  if (has1)
+                    tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
+                  tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kcol, b_row, wc.phase);
+                }
                 kcol += kBlockK;
                 if (++stage == p.num_stages) {
                   stage = 0;
