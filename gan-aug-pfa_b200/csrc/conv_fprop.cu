@@ -16,6 +16,7 @@
 // ConvTranspose2d dgrad (a strided gather) — see gap_b200.h.
 #include "common.h"
 #include "ptx.cuh"
+#include "mma_sync.cuh"
 
 namespace gap {
 
@@ -31,6 +32,7 @@ constexpr int kTmemCols = 512;
 constexpr int kStatsBytes = 4 * 256 * 2 * 8;  // per-epilogue-warp fp64 partial sums
 constexpr int kBarrierBytes = 256;
 constexpr int kParamBytes = 2 * 256 * 4;  // per-N-tile scale / shift of the backward-fused epilogue
+constexpr int kColStageBytes = kEpiWarps * 1024;  // per-epilogue-warp 32x16 bf16 tile for the column sums
 constexpr int kSmemBudget = 227 * 1024;
 
 struct alignas(64) FpropParams {
@@ -174,6 +176,59 @@ __device__ __forceinline__ float transpose_reduce16(const float (&v)[16], uint32
   return w1;
 }
 
+// Column sums of one 32-row x 16-column chunk on the warp MMA.  The chunk lives one row per lane as eight packed
+// bf16 pairs (`a`, and `b` for the second factor; kSame: b == a).  The rows are staged in a 1 KiB smem tile
+// (16-byte halves XOR-swizzled by bit 2 of the row so the 128-bit stores and the ldmatrix rows are conflict-free),
+// read back transposed as MMA fragments, and reduced by   ones(16x32) * A   and   diag(B^T * A):
+//   sum1[c] = sum_r a[r][c]          sum2[c] = sum_r a[r][c] * b[r][c]
+// Products of bf16 pairs are exact in the fp32 accumulators.  Holder lanes l = 4m + (m >> 1), m = 0..7, receive
+// out = {sum1[m], sum1[m+8], sum2[m], sum2[m+8]}; the other lanes receive unrelated values.
+// Replaces two 31-shuffle transpose reductions (~140 instructions per chunk) by ~25.
+template <bool kSame>
+__device__ __forceinline__ void warp_colstats16(const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t stage,
+                                                uint32_t lane, float (&out)[4]) {
+  const uint32_t wr = stage + lane * 32u;
+  const uint32_t wsw = ((lane >> 2) & 1u) << 4;
+  const uint32_t mi = lane >> 3, rr = lane & 7u;
+  const uint32_t row0 = (mi & 1u) * 8u + rr;  // + 16 for the second k block (bit 2 of the row is unchanged)
+  const uint32_t rd = stage + row0 * 32u + ((((mi >> 1) & 1u) << 4) ^ (((row0 >> 2) & 1u) << 4));
+  uint32_t qa[2][4], qb[2][4];
+  __syncwarp();  // the previous chunk's fragment loads are done
+  st_shared_v4(wr + wsw, a[0], a[1], a[2], a[3]);
+  st_shared_v4(wr + (16u ^ wsw), a[4], a[5], a[6], a[7]);
+  __syncwarp();
+  ldmatrix_x4_trans(qa[0], rd);
+  ldmatrix_x4_trans(qa[1], rd + 512u);
+  if (!kSame) {
+    __syncwarp();
+    st_shared_v4(wr + wsw, b[0], b[1], b[2], b[3]);
+    st_shared_v4(wr + (16u ^ wsw), b[4], b[5], b[6], b[7]);
+    __syncwarp();
+    ldmatrix_x4_trans(qb[0], rd);
+    ldmatrix_x4_trans(qb[1], rd + 512u);
+  }
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    // fragments of the transposed loads: [0] rows 0-7 / cols 0-7, [1] rows 8-15 / cols 0-7, [2] rows 0-7 / cols 8-15,
+    // [3] rows 8-15 / cols 8-15  ->  B fragments {[0],[1]} (cols 0-7), {[2],[3]} (cols 8-15); A = tile^T = {[0],[2],[1],[3]}
+    const uint32_t(&fa)[4] = qa[kb];
+    const uint32_t(&fb)[4] = kSame ? qa[kb] : qb[kb];
+    const uint32_t at[4] = {fb[0], fb[2], fb[1], fb[3]};
+    mma_bf16_16816(s0, ones, fa[0], fa[1]);
+    mma_bf16_16816(s1, ones, fa[2], fa[3]);
+    mma_bf16_16816(q0, at, fa[0], fa[1]);
+    mma_bf16_16816(q1, at, fa[2], fa[3]);
+  }
+  const int sel = (lane >> 2) & 1;
+  out[0] = sel ? s0[1] : s0[0];
+  out[1] = sel ? s1[1] : s1[0];
+  out[2] = sel ? q0[1] : q0[0];
+  out[3] = sel ? q1[3] : q1[2];
+}
+
 // Cold path of the epilogue: partial column chunks, unaligned outputs, fp32 output, Tanh / Sigmoid.
 // Kept out of line so the hot loop stays small (the inlined version was instruction-cache bound).
 __device__ __noinline__ void epilogue_store_generic(const FpropParams& p, const float (&f)[16], long long pix,
@@ -211,6 +266,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 20);
   double* stats_sm = reinterpret_cast<double*>(bar_gen + kBarrierBytes);
   float* par_sm = reinterpret_cast<float*>(bar_gen + kBarrierBytes + kStatsBytes);  // [2][256] scale | shift
+  const uint32_t colstage_base = bar_base + kBarrierBytes + kStatsBytes + kParamBytes;  // [kEpiWarps][1 KiB]
 
   // Warp index broadcast from lane 0: the role dispatch and the producer / MMA loops are then
   // warp-uniform for the compiler, so TMA / MMA operands stay in uniform registers (a per-lane
@@ -414,7 +470,9 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     int cur_ntile = -1;
     double* my_stats = stats_sm + q * 512;  // [256 sum][256 sumsq]
     const bool do_stats = p.stats != nullptr && !(p.skip & 4) && kEpi != 2;
-    const int stat_col = ((lane >> 1) & 15);
+    const uint32_t colstage = colstage_base + static_cast<uint32_t>(warp - 2) * 1024u;
+    const bool stat_holder = (lane >> 3) == (lane & 3u);  // lanes 4m + (m >> 1): columns m and m + 8 of a chunk
+    const int stat_col = static_cast<int>(lane >> 2);
 
     auto flush_stats = [&](int n_tile) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -535,25 +593,24 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
                 f[jj] = yh > 0.f ? f[jj] + g2 : p.bwd_slope * f[jj];
               }
             }
+            uint32_t pk[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) pk[jj] = valid ? pack_bf16x2(f[2 * jj], f[2 * jj + 1]) : 0u;
             if (do_stats) {
-              float m[16];
+              // sums of d and d*y over the 32 rows, from the bf16 values that are stored / were loaded
+              uint32_t yk[8];
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) m[jj] = valid ? f[jj] : 0.f;
-              const float s = transpose_reduce16(m, lane);
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) m[jj] = m[jj] * yv[jj];
-              const float s2 = transpose_reduce16(m, lane);
-              if ((lane & 1) == 0) {
-                my_stats[c * 16 + stat_col] += static_cast<double>(s);
-                my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
+              for (int jj = 0; jj < 8; ++jj) yk[jj] = yw[jj];
+              float cs[4];
+              warp_colstats16<false>(pk, yk, colstage, lane, cs);
+              if (stat_holder) {
+                my_stats[c * 16 + stat_col] += static_cast<double>(cs[0]);
+                my_stats[c * 16 + stat_col + 8] += static_cast<double>(cs[1]);
+                my_stats[256 + c * 16 + stat_col] += static_cast<double>(cs[2]);
+                my_stats[256 + c * 16 + stat_col + 8] += static_cast<double>(cs[3]);
               }
             }
-            if (valid && !(p.skip & 1)) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack_bf16x2(f[2 * jj], f[2 * jj + 1]);
-              st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
-            }
+            if (valid && !(p.skip & 1)) st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
             continue;
           }
           if (p.scale != nullptr) {
@@ -565,16 +622,17 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             for (int jj = 0; jj < 16; ++jj) f[jj] += __ldg(p.bias + min(col0 + jj, p.n_out - 1));
           }
           if (do_stats && kEpi == 0) {
-            float m[16];
+            // BatchNorm batch statistics (sum, sum of squares) of the bf16-rounded pre-activation values
+            uint32_t pr[8];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) m[jj] = valid ? f[jj] : 0.f;
-            const float s = transpose_reduce16(m, lane);
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) m[jj] = m[jj] * m[jj];
-            const float s2 = transpose_reduce16(m, lane);
-            if ((lane & 1) == 0) {
-              my_stats[c * 16 + stat_col] += static_cast<double>(s);
-              my_stats[256 + c * 16 + stat_col] += static_cast<double>(s2);
+            for (int jj = 0; jj < 8; ++jj) pr[jj] = valid ? pack_bf16x2(f[2 * jj], f[2 * jj + 1]) : 0u;
+            float cs[4];
+            warp_colstats16<true>(pr, pr, colstage, lane, cs);
+            if (stat_holder) {
+              my_stats[c * 16 + stat_col] += static_cast<double>(cs[0]);
+              my_stats[c * 16 + stat_col + 8] += static_cast<double>(cs[1]);
+              my_stats[256 + c * 16 + stat_col] += static_cast<double>(cs[2]);
+              my_stats[256 + c * 16 + stat_col + 8] += static_cast<double>(cs[3]);
             }
           }
           if (fast && col0 + 16 <= p.n_out && !(p.skip & 1)) {
@@ -775,14 +833,34 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   int block_n = ((n_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
   const int sms = sm_count();
   const int force_bn = debug_get("fprop_block_n", 0);
+  int model_mt = 0;
   if (force_bn > 0) {
     block_n = force_bn;
     n_tiles = (n_pad + block_n - 1) / block_n;
-  } else {
-    while (m_tiles * n_tiles < sms && block_n >= 64 && block_n % 32 == 0) {
-      block_n /= 2;
-      n_tiles = (n_pad + block_n - 1) / block_n;
+  } else if (!halo && m_tiles * n_tiles < 2 * sms) {
+    // Under-filled launch (the 8x8 .. 1x1 bottleneck layers): every CTA runs one or two latency-bound K loops, so
+    // pick the N tile and the M tiles per item by a per-iteration cost model fitted to tools/sweep_deep.py:
+    // cycles per pipeline iteration ~ max(130 + 280 per A tile + 80 per 64 B rows, MMA time 2*mt*bn + 100), times
+    // the number of waves.  (The old rule halved block_n until every SM had an item: up to 2x slower.)
+    const int wide = block_n;
+    long long best = -1;
+    for (int bn_c : {wide, 128, 64}) {
+      if (bn_c > wide || (bn_c != wide && wide % bn_c != 0)) continue;
+      for (int mt_c = 1; mt_c <= 2; ++mt_c) {
+        if (mt_c == 2 && m_tiles_pp < 2) continue;
+        const long long items =
+            static_cast<long long>((m_tiles_pp + mt_c - 1) / mt_c) * a->n_phase * ((n_pad + bn_c - 1) / bn_c);
+        const long long waves = (items + sms - 1) / sms;
+        const long long it_cost = std::max(130 + 280 * mt_c + 80 * bn_c / 64, 2 * mt_c * bn_c + 100);
+        const long long cost = waves * it_cost;
+        if (best < 0 || cost < best) {
+          best = cost;
+          block_n = bn_c;
+          model_mt = mt_c;
+        }
+      }
     }
+    n_tiles = (n_pad + block_n - 1) / block_n;
   }
   // Split-K for layers with too few output tiles (see FpropParams): keep a wide N tile and cut K instead.
   // Measured (tools/sweep_splitk.py): only the M = 256 layers gain (38 -> 27 us), M >= 1024 lose to the finish pass and
@@ -812,6 +890,10 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   // Two M tiles per work item share each B tile (halves the weight traffic from L2) when there is
   // still at least ~2 waves of work items left.
   int mt = (m_tiles_pp >= 2 && (m_tiles / 2) * n_tiles >= 2 * sms) ? 2 : 1;
+  // With a 256-wide N tile two M tiles fill all 512 TMEM columns, so the epilogue cannot overlap the next item's
+  // main loop: that only pays for long K loops (tools/sweep_mt.py: mt = 1 is 5-17 % faster below 128 iterations).
+  if (mt == 2 && 2 * block_n > kAccStride && k_iters_full < 128) mt = 1;
+  if (model_mt > 0) mt = model_mt;
   const int force_mt = debug_get("fprop_mt", 0);
   if (force_mt > 0) mt = std::min(force_mt, 2);
   p.mt = mt;
@@ -895,12 +977,12 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.skip = debug_get("fprop_skip", 0);
 
   const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * block_n * 128;
-  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes - kColStageBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);
   if (force_st > 0) stages = std::min(force_st, stages);
   p.num_stages = stages;
-  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes + kParamBytes;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes + kParamBytes + kColStageBytes;
 
   // ---- tensor maps
   const uint32_t bx_w = static_cast<uint32_t>(BW * a->in_stride);

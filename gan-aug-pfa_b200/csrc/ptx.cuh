@@ -218,6 +218,10 @@ __device__ __forceinline__ void st_global_32B(void* dst, const uint32_t (&v)[8],
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // fp32 vector reduction into global memory (no return value): 4 consecutive floats, 16-byte aligned.
 __device__ __forceinline__ void red_add_v4_f32(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -64,12 +64,14 @@ def test_conv(n, cin, cout, h, k, s, p, bias=False, act=ops.ACT_NONE, stats=Fals
     ref = F.conv2d(x.float(), w.to(torch.bfloat16).float(), b, stride=s, padding=p)
     ok = True
     if stats:
-        rs = ref.double().sum((0, 2, 3))
-        rq = (ref.double() ** 2).sum((0, 2, 3))
+        rb = ref.to(torch.bfloat16).double()   # the statistics are those of the bf16-rounded tensor
+        rs = rb.sum((0, 2, 3))
+        rq = (rb ** 2).sum((0, 2, 3))
         e1 = ((st[:cout] - rs).abs().max() / rs.abs().max().clamp_min(1e-9)).item()
         e2 = ((st[cout:] - rq).abs().max() / rq.abs().max()).item()
-        print(f"     stats rel err sum={e1:.3e} sumsq={e2:.3e}")
-        ok &= e1 < 1e-3 and e2 < 1e-3
+        sok = e1 < 3e-3 and e2 < 3e-3
+        print(f"{'OK  ' if sok else 'FAIL'} stats rel err sum={e1:.3e} sumsq={e2:.3e}")
+        ok &= sok
     if act == ops.ACT_LRELU:
         ref = F.leaky_relu(ref, 0.2)
     elif act == ops.ACT_TANH:
