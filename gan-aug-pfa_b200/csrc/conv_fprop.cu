@@ -231,8 +231,12 @@ __device__ __forceinline__ void warp_colstats16(const uint32_t (&a)[8], const ui
 
 // Cold path of the epilogue: partial column chunks, unaligned outputs, fp32 output, Tanh / Sigmoid.
 // Kept out of line so the hot loop stays small (the inlined version was instruction-cache bound).
-__device__ __noinline__ void epilogue_store_generic(const FpropParams& p, const float (&f)[16], long long pix,
-                                                    int col0) {
+// The 16 values travel in registers (four float4 arguments): passing the array by reference made the compiler
+// spill it to local memory on EVERY chunk of the hot path (4 STL.128 per chunk, as many L1 wavefronts as the
+// backward epilogue's global loads -- ncu, profiles/r1_ncu_bwd_epilogue.md).
+__device__ __noinline__ void epilogue_store_generic(const FpropParams& p, float4 v0, float4 v1, float4 v2, float4 v3,
+                                                    long long pix, int col0) {
+  const float f[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
     for (int j = 0; j < 16; ++j)
@@ -653,7 +657,9 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               st_global_32B(p.out2 + pix * p.out2_ld + col0, pk, true);
             }
           } else if (valid && col0 < p.n_out) {
-            epilogue_store_generic(p, f, pix, col0);
+            epilogue_store_generic(p, make_float4(f[0], f[1], f[2], f[3]), make_float4(f[4], f[5], f[6], f[7]),
+                                   make_float4(f[8], f[9], f[10], f[11]), make_float4(f[12], f[13], f[14], f[15]), pix,
+                                   col0);
           }
           }
         }
