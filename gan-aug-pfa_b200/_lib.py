@@ -127,6 +127,11 @@ _SIGNATURES = {
     "gap_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _P, _P, _P, _L, _I, _P, _D, _P, _L, _P]),
     "gap_bn_param_grads": (C.c_int, [_P, _I, _P, _P, _P]),
     "gap_bn_bwd_finalize": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P]),
+    # y ld d ld scale shift mean invstd pixels c raw count dgamma dbeta ticket dy ld stream
+    "gap_bn_bwd_apply_raw": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _P, _D, _P, _P, _P, _P, _L, _P]),
+    # stats count gamma beta eps momentum repeat rm rv nbt scale shift mean invstd ticket y ld pixels c o1 ld1 a1 o2 ld2 a2 stream
+    "gap_bn_train_act": (C.c_int, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _L,
+                                   _I, _P, _L, _I, _P]),
     "gap_colsum_bf16": (C.c_int, [_P, _L, _L, _I, _P, _P]),
     "gap_adam_flat": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _F, _P]),
     "gap_adam_flat_devstep": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),

@@ -120,12 +120,15 @@ struct MTile {
 
 __device__ __forceinline__ WorkCoord decode_work(const FpropParams& p, int t) {
   WorkCoord c;
+  // N tile fastest, then the output-parity phase, then the M tile: the four phases of an M tile read the same input
+  // window, so they run on neighbouring CTAs at the same time and share it in L2 (phase-major order re-read the
+  // input from DRAM once per phase: 534 MB instead of 335 MB on the 128->64 dgrad, ncu dram__bytes_read).
   c.n_tile = t % p.n_tiles;
   t /= p.n_tiles;
-  c.sm = t % p.sm_tiles;
-  t /= p.sm_tiles;
   c.phase = t % p.n_phase;
-  c.split = t / p.n_phase;
+  t /= p.n_phase;
+  c.sm = t % p.sm_tiles;
+  c.split = t / p.sm_tiles;
   c.ph = c.phase >> 1;
   c.pw = c.phase & 1;
   return c;
@@ -518,6 +521,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
         __syncwarp();
         cur_ntile = wc.n_tile;
       }
+      // (Tried: prefetch.global.L2 of the next work item's y / g2 rows here.  5 % SLOWER: the loads wait on the L1
+      // data pipe, which the tensor-core operand reads and TMA writes keep ~70 % busy, not on DRAM.)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int n_chunks = p.block_n >> 4;
@@ -584,7 +589,11 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             float yv[16];
 #pragma unroll
             for (int v4 = 0; v4 < 4; ++v4) {
-              const float4 sc = scp[v4], sh = shp[v4];
+              float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bwd_scale != nullptr) {   // no BatchNorm below: the mask is just y > 0, skip the smem reads
+                sc = scp[v4];
+                sh = shp[v4];
+              }
               const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {

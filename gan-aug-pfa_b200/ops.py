@@ -461,6 +461,27 @@ def bn_bwd_finalize(raw, mean, invstd, dgamma, dbeta, sums) -> None:
                                               _ptr(dbeta), _ptr(sums), _stream()), "gap_bn_bwd_finalize")
 
 
+def bn_bwd_apply_raw(y, d, scale, shift, mean, invstd, raw, count, dgamma, dbeta, ticket, dy) -> None:
+    """bn_bwd_finalize + bn_bwd_apply in one launch (raw sums re-zeroed by the kernel's last block)."""
+    pixels, c, ld = _rows_ld(y)
+    _lib.check(_lib.lib().gap_bn_bwd_apply_raw(_ptr(y), ld, _ptr(d), d.stride(-2), _ptr(scale), _ptr(shift), _ptr(mean),
+                                               _ptr(invstd), pixels, c, _ptr(raw), float(count), _ptr(dgamma),
+                                               _ptr(dbeta), _ptr(ticket), _ptr(dy), dy.stride(-2), _stream()),
+               "gap_bn_bwd_apply_raw")
+
+
+def bn_train_act(stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, nbt, scale, shift,
+                 save_mean, save_invstd, ticket, y, out1, act1, out2=None, act2: int = ACT_NONE) -> None:
+    """Training-mode BatchNorm forward in one launch (= bn_finalize + bn_act)."""
+    pixels, c, ld = _rows_ld(y)
+    _lib.check(_lib.lib().gap_bn_train_act(_ptr(stats), float(count), _ptr(gamma), _ptr(beta), eps, momentum, repeat,
+                                           _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(scale), _ptr(shift),
+                                           _ptr(save_mean), _ptr(save_invstd), _ptr(ticket), _ptr(y), ld, pixels, c,
+                                           _ptr(out1), out1.stride(-2), act1, _ptr(out2),
+                                           0 if out2 is None else out2.stride(-2), act2, _stream()),
+               "gap_bn_train_act")
+
+
 def colsum_bf16(x: torch.Tensor, c: int, out: torch.Tensor) -> None:
     pixels = x.numel() // x.shape[-1]
     _lib.check(_lib.lib().gap_colsum_bf16(_ptr(x), x.stride(-2), pixels, c, _ptr(out), _stream()), "gap_colsum_bf16")

@@ -81,6 +81,9 @@ if WORK == "siamese":
     LAB = (torch.rand(N, 512, 512, generator=gen) < 0.05).long().to(dev)
 else:
     tr = Pix2PixTrainer(dev)
+    import os
+    if os.environ.get("GAP_NO_OVERLAP"):      # serialise the wgrad side stream: clean per-kernel times
+        tr.G.overlap_wgrad = tr.D.overlap_wgrad = False
     A = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
     B = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
 for _ in range(3):
