@@ -18,7 +18,8 @@
 
 namespace gap {
 
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 224;   // warps: 0 TMA, 1 MMA, 2..5 epilogue, 6 second TMA lane
+constexpr int kWgProducer2Warp = 6;
 constexpr int kWgBlockK = 64;             // pixels per K tile
 constexpr int kWgBoxBytes = 64 * 64 * 2;  // one 64ch x 64px TMA box
 constexpr int kWgMaxStages = 6;
@@ -37,6 +38,7 @@ struct alignas(64) WgradParams {
   int mt;  // 128-row M tiles per CTA (1 or 2): they share every N-operand box
   int num_stages, tmem_cols;
   uint32_t idesc;
+  int dual;   // two TMA producer lanes share each stage (see the producer loop)
   float* out;
   long long ld_m, ld_tap;
   long long* trace;  // bring-up: clock64 samples of CTA 0 ([0..255] producer, [256..511] mma, [512..] epilogue)
@@ -86,7 +88,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     tma_prefetch_desc(&p.tmM);
     tma_prefetch_desc(&p.tmN);
     for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), p.dual ? 2 : 1);   // with two producer lanes both post their bytes
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(done_bar, 1);
@@ -107,26 +109,38 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int m_boxes = (p.skip & 8) ? 0 : min(2 * p.mt, (p.m_c - m_base + 63) / 64);
   const int n_boxes = (p.skip & 4) ? 0 : min(p.block_n / 64, (p.n_c - n_tile * p.block_n + 63) / 64);
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
+  if (warp == 0 || warp == kWgProducer2Warp) {
+    // ------------------------------------------------------------------ TMA producers
+    // Two lanes (one per warp) share every stage: issuing one stage costs a single lane ~280 cycles + ~50 per TMA (up
+    // to 8 boxes here), more than the 512 MMA cycles a 128 x 256 stage lasts.  Lane 0 issues the M boxes and the first
+    // taps, lane 1 the remaining taps; each posts its own byte count on the stage's barrier (2 arrivals).
+    // (Alternating whole stages between the lanes was slower on the 3-stage configurations: two stages' boxes then
+    // interleave in the TMA queue and both complete late.)
+    // Measured (tools/sweep_wgrad.py, wgrad_dual=0/1 in one process): +15 % on the 128 x (4 taps x 64) stage of the
+    // 64->128 layers, neutral elsewhere.
+    const bool second = warp == kWgProducer2Warp;
+    if ((!second || p.dual) && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = static_cast<uint32_t>((m_boxes + ntap * n_boxes) * kWgBoxBytes);
+      const int t_split = !p.dual ? ntap : (ntap > 1 ? ntap / 2 : 0);   // lane 0: taps [0, t_split), lane 1: the rest
+      const int t_lo = second ? t_split : 0, t_hi = second ? ntap : t_split;
+      const int my_m = second ? 0 : m_boxes;
+      const uint32_t tx = static_cast<uint32_t>((my_m + (t_hi - t_lo) * n_boxes) * kWgBoxBytes);
       int tw = pt0 % p.tiles_w;
       int th = (pt0 / p.tiles_w) % p.tiles_h;
       int tn = pt0 / (p.tiles_w * p.tiles_h);
-      const int t_h0 = tap0 / p.taps_w, t_w0 = tap0 - t_h0 * p.taps_w;
+      const int tap_lo = tap0 + t_lo;
+      const int t_h0 = tap_lo / p.taps_w, t_w0 = tap_lo - t_h0 * p.taps_w;
       for (int pt = pt0; pt < pt1; ++pt) {
         const int gx0 = tw * BW, gy0 = th * BH, n0 = tn * BNI;
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (tracing && pt - pt0 < 128) p.trace[2 * (pt - pt0)] = clock64();
+        if (tracing && !second && pt - pt0 < 128) p.trace[2 * (pt - pt0)] = clock64();
         mbar_expect_tx(full_bar(stage), tx);
         const uint32_t a_dst = smem_base + stage * stage_bytes;
-        for (int b = 0; b < m_boxes; ++b)
+        for (int b = 0; b < my_m; ++b)
           tma_load_4d(a_dst + b * kWgBoxBytes, &p.tmM, full_bar(stage), m_base + b * 64, gx0, gy0, n0);
         int t_h = t_h0, t_w = t_w0;
-        for (int t_i = 0; t_i < ntap; ++t_i) {
+        for (int t_i = t_lo; t_i < t_hi; ++t_i) {
           const uint32_t b_dst = a_dst + a_bytes + t_i * b_tap_bytes;
           for (int b = 0; b < n_boxes; ++b)
             tma_load_4d(b_dst + b * kWgBoxBytes, &p.tmN, full_bar(stage), n_tile * p.block_n + b * 64,
@@ -136,7 +150,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
             ++t_h;
           }
         }
-        if (tracing && pt - pt0 < 128) p.trace[2 * (pt - pt0) + 1] = clock64();
+        if (tracing && !second && pt - pt0 < 128) p.trace[2 * (pt - pt0) + 1] = clock64();
         if (++tw == p.tiles_w) {
           tw = 0;
           if (++th == p.tiles_h) {
@@ -329,6 +343,11 @@ extern "C" int gap_conv_wgrad(const gap_wgrad_args* a, void* stream_v) {
   if (force_sp > 0) splits = std::min(force_sp, p.pix_tiles);
   p.splits = splits;
   p.idesc = make_idesc_bf16(128, block_n, 1, 1);
+  p.dual = 1;
+  {
+    const int force_dual = debug_get("wgrad_dual", -1);
+    if (force_dual >= 0) p.dual = force_dual ? 1 : 0;
+  }
   p.out = a->out;
   p.ld_m = a->ld_m;
   p.ld_tap = a->ld_tap;

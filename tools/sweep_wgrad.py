@@ -30,6 +30,7 @@ for name, n, mc, nc, gh, k, s, p in SHAPES:
     for v in variants:
         for kk in ("wgrad_mt", "wgrad_tpc", "wgrad_splits", "wgrad_acc_cols", "wgrad_block_n"):
             _lib.debug_set(kk, int(v.get(kk, 0)) if kk != "wgrad_acc_cols" else int(v.get(kk, 512)))
+        _lib.debug_set("wgrad_dual", int(v.get("wgrad_dual", -1)))
         try:
             us, tf = bench(n, mc, nc, gh, k, s, p, 0, iters=10, convT=False)
             line += f" | {us:7.1f} us {tf:6.0f} TF"
