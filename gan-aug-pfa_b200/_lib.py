@@ -120,6 +120,7 @@ _SIGNATURES = {
     "gap_conv1x1_cout1_dgrad": (C.c_int, [_P, _P, _P, _L, _L, _I, _P]),
     "gap_conv1x1_cout1_wgrad": (C.c_int, [_P, _P, _L, _L, _I, _P, _P, _P]),
     "gap_seg_loss": (C.c_int, [_P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _P, _P, _F, _P, _P]),
+    "gap_seg_confusion": (C.c_int, [_P, _P, _I, _I, _L, _P, _P]),
     "gap_bn_finalize": (C.c_int, [_P, _I, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gap_bn_eval_scale_shift": (C.c_int, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "gap_bn_act": (C.c_int, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P]),

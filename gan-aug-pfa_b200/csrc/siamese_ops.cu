@@ -3,6 +3,8 @@
 // align_corners=True, the attention gate's elementwise pieces, 1x1 convolutions to a single channel
 // (psi, conv_last) and the Dice / Focal / BCE loss family.  All of them are HBM-bound elementwise or
 // reduction kernels: 16-byte vector accesses along the channel axis, warp-shuffle reductions, fp32 math.
+#include <algorithm>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -590,6 +592,41 @@ using namespace gap;
     return 0;                     \
   } while (0)
 
+// evaluate.py:34-64 (calculate_metrics) on the device: preds = sigmoid(logits) > 0.5 against {0,1} labels, one
+// [TP, FP, FN, TN] count row per sample (the reference loops over samples and moves every map to the CPU first).
+// gridDim.y = samples; counts are accumulated (+=) so a caller can sum over batches.
+__global__ void seg_confusion_kernel(const float* __restrict__ logits, const long long* __restrict__ lab_i64,
+                                     const float* __restrict__ lab_f32, long long hw,
+                                     unsigned long long* __restrict__ counts) {
+  const long long base = static_cast<long long>(blockIdx.y) * hw;
+  unsigned int c[4] = {0u, 0u, 0u, 0u};
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hw;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = logits[base + i];
+    // the reference thresholds the fp32 sigmoid, not the logit: logits in (0, ~6e-8] round to exactly 0.5 -> negative
+    const bool pred = 1.f / (1.f + expf(-x)) > 0.5f;
+    const bool tgt = lab_i64 ? lab_i64[base + i] != 0 : lab_f32[base + i] != 0.f;
+    if (pred && tgt) ++c[0];
+    else if (pred && !tgt) ++c[1];
+    else if (!pred && tgt) ++c[2];
+    else ++c[3];
+  }
+  __shared__ unsigned int red[4][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned int v = c[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long tot = 0;
+    for (int w2 = 0; w2 < static_cast<int>(blockDim.x >> 5); ++w2) tot += red[threadIdx.x][w2];
+    if (tot) atomicAdd(counts + blockIdx.y * 4 + threadIdx.x, tot);
+  }
+}
+
 extern "C" {
 
 int gap_im2col_k3s1p1_c3(const void* x, int64_t ld, void* col, int n, int h, int w, void* stream) {
@@ -751,6 +788,17 @@ int gap_seg_loss(const float* logits, const int64_t* labels, int64_t n, int mode
   seg_loss_reduce_kernel<<<grid_of(n, 256, 148 * 4), 256, 0, st>>>(a);
   GAP_CUDA(cudaGetLastError());
   seg_loss_grad_kernel<<<grid_of(n, 256, 148 * 8), 256, 0, st>>>(a);
+  SI_LAUNCH_OK();
+}
+
+int gap_seg_confusion(const float* logits, const void* labels, int labels_are_i64, int n, int64_t hw, int64_t* counts,
+                      void* stream) {
+  GAP_CHECK_ARG(logits && labels && counts && n > 0 && hw > 0, "gap_seg_confusion: bad arguments");
+  const int bx = static_cast<int>(std::min<long long>((hw + 255) / 256, 148 * 4 / std::max(1, std::min(n, 16)) + 1));
+  dim3 grid(bx, n);
+  seg_confusion_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels_are_i64 ? static_cast<const long long*>(labels) : nullptr,
+      labels_are_i64 ? nullptr : static_cast<const float*>(labels), hw, reinterpret_cast<unsigned long long*>(counts));
   SI_LAUNCH_OK();
 }
 

@@ -656,3 +656,19 @@ def seg_loss(logits: torch.Tensor, labels: torch.Tensor, mode: int, w_point: flo
     _lib.check(_lib.lib().gap_seg_loss(_ptr(logits), _ptr(labels), logits.numel(), mode, w_point, w_dice, pos_weight, smooth,
                                        gamma, focal_alpha, _ptr(sums4), _ptr(grad), grad_scale, _ptr(loss), _stream()),
                "gap_seg_loss")
+
+
+def seg_confusion(logits: torch.Tensor, labels: torch.Tensor, counts: torch.Tensor) -> None:
+    """counts[n, 4] (int64, accumulated) += per-sample [TP, FP, FN, TN] of sigmoid(logits) > 0.5 vs {0,1} labels
+    (evaluate.py:34-46).  logits fp32 [n, ...]; labels int64 or fp32 with the same number of elements."""
+    n = logits.shape[0]
+    if logits.dtype != torch.float32 or not logits.is_contiguous() or not labels.is_contiguous():
+        raise ValueError("logits must be contiguous fp32, labels contiguous")
+    if labels.dtype not in (torch.int64, torch.float32) or labels.numel() != logits.numel():
+        raise ValueError("labels must be int64 or fp32 with as many elements as logits")
+    if counts.dtype != torch.int64 or tuple(counts.shape) != (n, 4) or not counts.is_contiguous():
+        raise ValueError("counts must be a contiguous int64 [n, 4] tensor")
+    if not (logits.is_cuda and labels.is_cuda and counts.is_cuda):
+        raise ValueError("seg_confusion needs CUDA tensors (there is no CPU path)")
+    _lib.check(_lib.lib().gap_seg_confusion(_ptr(logits), _ptr(labels), 1 if labels.dtype == torch.int64 else 0, n,
+                                            logits.numel() // n, _ptr(counts), _stream()), "gap_seg_confusion")

@@ -295,6 +295,12 @@ int gap_seg_loss(const float* logits, const int64_t* labels, int64_t n, int mode
                  float pos_weight, float smooth, float gamma, float focal_alpha, double* sums4, float* grad,
                  float grad_scale, double* loss, void* stream);
 
+/* evaluate.py:34-64 calculate_metrics, device side: per-sample counts[n][4] += [TP, FP, FN, TN] of
+ * (sigmoid(logits) > 0.5) against {0,1} labels (int64 when labels_are_i64, else fp32); logits are [n][hw] fp32.
+ * The caller zeroes counts once and may accumulate several batches; the ratios are formed on the host. */
+int gap_seg_confusion(const float* logits, const void* labels, int labels_are_i64, int n, int64_t hw, int64_t* counts,
+                      void* stream);
+
 /* nn.BatchNorm2d training bookkeeping (models.py:179,181,231,239): statistics -> scale/shift,
  * saved mean / inv-std, running stats (momentum, unbiased var, `repeat` identical updates),
  * num_batches_tracked += repeat.  Re-zeroes `stats`. */

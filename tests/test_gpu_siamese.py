@@ -240,3 +240,50 @@ def test_native_train_step_combined_and_focal_dice():
     fd = float(eng.train_step(x1, x2, lab, kind="focal_dice", beta=0.6701, gamma=1.7929, focal_alpha=0.6032,
                               smooth=1.96e-6).cpu())
     assert 0.0 < fd < 1.0
+
+
+def _ref_calculate_metrics(preds, targets, smooth=1e-6):
+    """evaluate.py:34-64 restated (the file itself imports matplotlib at module scope)."""
+    preds = (preds > 0.5).float().view(-1)
+    targets = targets.view(-1)
+    tp = (preds * targets).sum()
+    fp = ((1 - targets) * preds).sum()
+    fn = (targets * (1 - preds)).sum()
+    tn = ((1 - targets) * (1 - preds)).sum()
+    precision = (tp + smooth) / (tp + fp + smooth)
+    recall = (tp + smooth) / (tp + fn + smooth)
+    f1 = (2 * precision * recall + smooth) / (precision + recall + smooth)
+    union = preds.sum() + targets.sum() - tp
+    return {"accuracy": ((tp + tn + smooth) / (tp + tn + fp + fn + smooth)).item(), "precision": precision.item(),
+            "recall": recall.item(), "f1": f1.item(), "iou": ((tp + smooth) / (union + smooth)).item()}, (tp, fp, fn, tn)
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 7, 5), (3, 64, 64), (4, 512, 512)])
+def test_confusion_counts_and_metrics_match_calculate_metrics(n, h, w):
+    """gap_seg_confusion + metrics.py == calculate_metrics (evaluate.py:34-64): integer counts bit-exact, ratios equal
+    (same fp32 formulas); empty-positive / all-positive samples and logits at the sigmoid rounding edge included."""
+    from gan_aug_pfa_b200 import metrics
+    g = torch.Generator().manual_seed(n * h + w)
+    logits = torch.randn(n, 1, h, w, generator=g) * 3
+    labels = (torch.rand(n, h, w, generator=g) < 0.1).long()
+    labels[0] = 0                                   # a sample without positives
+    if n > 1:
+        labels[1] = 1                               # and one with only positives
+    flat = logits.view(-1)
+    flat[:6] = torch.tensor([0.0, 1e-9, 5e-8, 2e-7, -1e-9, -0.0])   # sigmoid rounds to exactly 0.5 for the tiny ones
+    counts = metrics.confusion_counts(logits.to(DEV), labels.to(DEV)).cpu()
+    per_sample = metrics.batch_metrics(logits.to(DEV), labels.to(DEV))
+    for k in range(n):
+        ref, (tp, fp, fn, tn) = _ref_calculate_metrics(torch.sigmoid(logits[k:k + 1]), labels[k:k + 1].float())
+        assert counts[k].tolist() == [int(tp), int(fp), int(fn), int(tn)]
+        for key in metrics.METRIC_KEYS:
+            assert per_sample[k][key] == pytest.approx(ref[key], rel=1e-6, abs=1e-9)
+    # accumulation over batches and fp32 labels
+    acc = torch.zeros(n, 4, device=DEV, dtype=torch.int64)
+    metrics.confusion_counts(logits.to(DEV), labels.to(DEV), acc)
+    metrics.confusion_counts(logits.to(DEV), labels.float().to(DEV), acc)
+    assert torch.equal(acc.cpu(), 2 * counts)
+    whole = metrics.calculate_metrics(logits.to(DEV), labels.to(DEV))
+    ref_whole, _ = _ref_calculate_metrics(torch.sigmoid(logits), labels.float())
+    for key in metrics.METRIC_KEYS:
+        assert whole[key] == pytest.approx(ref_whole[key], rel=1e-6, abs=1e-9)
