@@ -165,8 +165,13 @@ def run_ours(args) -> None:
     N = BATCH_PER_GPU
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 2
-    host = [(torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory(),
-             torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory()) for _ in range(n_batches)]
+    if args.inputs == "u8":     # raw uint8 images; ToTensor + JointNormalize run on the device
+        host = [(torch.randint(0, 256, (N, HW, HW, 3), generator=gen, dtype=torch.uint8).pin_memory(),
+                 torch.randint(0, 256, (N, HW, HW, 3), generator=gen, dtype=torch.uint8).pin_memory())
+                for _ in range(n_batches)]
+    else:                       # fp32 NCHW in [-1, 1]: what the reference's DataLoader hands to train_gan.py:53-54
+        host = [(torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory(),
+                 torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory()) for _ in range(n_batches)]
     devb = [(a.to(dev), b.to(dev)) for a, b in host]
 
     def barrier():
@@ -283,10 +288,10 @@ def run_ours(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "pix2pix_gan_train_b64_256x256", "batch_per_gpu": N, "image": f"{HW}x{HW}x3",
-                       "parallelism": f"dp{world}", "cuda_graph": world == 1, "l2": "per-step working set (several GB of activations) >> 126 MB L2; "
+                       "parallelism": f"dp{world}", "cuda_graph": world == 1, "inputs": args.inputs, "l2": "per-step working set (several GB of activations) >> 126 MB L2; "
                        "two alternating input batches", "algorithmic_gflop_per_image": GFLOP_PER_IMG},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N * 3 * HW * HW * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]),
                     "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": roofline,
@@ -459,6 +464,9 @@ def main() -> None:
                     help="pix2pix_train = the BASELINE.json metric (default); gen_infer = generate_synthetic_data.py's "
                          "generator forward at batch 256 (config 4); siamese_train = train.py's step at 512x512, batch 4 "
                          "(config 5, CombinedLoss)")
+    ap.add_argument("--inputs", default="f32", choices=["f32", "u8"],
+                    help="pix2pix_train only: host batches as fp32 NCHW in [-1,1] (the reference DataLoader's output, "
+                         "default) or raw uint8 HWC images normalised on the device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

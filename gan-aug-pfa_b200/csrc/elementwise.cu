@@ -159,18 +159,24 @@ __global__ void col2im_k4s2p1_kernel(const __nv_bfloat16* __restrict__ col, long
 // fake: fp32 NHWC (ld_f), real: fp32 NCHW (the caller's tensor), dfake_d: fp32 NHWC (ld_d, may be
 // NULL), dpre: bf16 NHWC (ld_p).  loss_acc[0] accumulates the raw L1 sum in fp64.
 // ------------------------------------------------------------------------------------------------
+// REAL_U8: `real` is the raw uint8 HWC image [pixel][c]; it is normalised like the dataset does in fp32
+// ((x / 255) * 2 - 1, dataset.py:28-29,155-159), so the loss sees exactly the reference's real_B without an fp32 copy.
+template <bool REAL_U8>
 __global__ void gen_out_bwd_kernel(const float* __restrict__ fake, long long ld_f,
-                                   const float* __restrict__ real, long long hw,
+                                   const void* __restrict__ real_v, long long hw,
                                    const float* __restrict__ dfake_d, long long ld_d, float l1_scale,
                                    __nv_bfloat16* __restrict__ dpre, long long ld_p, long long pixels, int c,
                                    double* __restrict__ loss_acc) {
+  const float* real = static_cast<const float*>(real_v);
+  const unsigned char* real_u8 = static_cast<const unsigned char*>(real_v);
   float part = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels;
        i += (long long)gridDim.x * blockDim.x) {
     const long long img = i / hw, pix = i - img * hw;
     for (int ch = 0; ch < c; ++ch) {
       const float f = fake[i * ld_f + ch];
-      const float r = real[(img * c + ch) * hw + pix];
+      const float r = REAL_U8 ? (static_cast<float>(real_u8[i * c + ch]) / 255.f) * 2.f - 1.f
+                              : real[(img * c + ch) * hw + pix];
       const float d = f - r;
       part += fabsf(d);
       float g = l1_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
@@ -975,9 +981,20 @@ int gap_gen_out_bwd(const float* fake, int64_t ld_f, const float* real_nchw, int
                     double* loss_acc, void* stream) {
   GAP_CHECK_ARG(fake && real_nchw && dpre && loss_acc && pixels > 0 && c > 0 && hw > 0 && pixels % hw == 0,
                 "gap_gen_out_bwd: bad arguments");
-  gen_out_bwd_kernel<<<grid_for(pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  gen_out_bwd_kernel<false><<<grid_for(pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       fake, ld_f, real_nchw, hw, dfake_d, ld_d, l1_scale, static_cast<__nv_bfloat16*>(dpre), ld_p, pixels, c,
       loss_acc);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_gen_out_bwd_u8(const float* fake, int64_t ld_f, const uint8_t* real_hwc, int64_t hw, const float* dfake_d,
+                       int64_t ld_d, float l1_scale, void* dpre, int64_t ld_p, int64_t pixels, int c,
+                       double* loss_acc, void* stream) {
+  GAP_CHECK_ARG(fake && real_hwc && dpre && loss_acc && pixels > 0 && c > 0 && hw > 0 && pixels % hw == 0,
+                "gap_gen_out_bwd_u8: bad arguments");
+  gen_out_bwd_kernel<true><<<grid_for(pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fake, ld_f, real_hwc, hw, dfake_d, ld_d, l1_scale, static_cast<__nv_bfloat16*>(dpre), ld_p, pixels, c, loss_acc);
   GAP_LAUNCH_CHECK();
   return 0;
 }

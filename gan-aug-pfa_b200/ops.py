@@ -274,13 +274,20 @@ def col2im_k4s2p1(col: torch.Tensor, ctot: int, c0: int, cn: int, bias: Optional
         n, hi, wi, _stream()), "gap_col2im_k4s2p1")
 
 
-def gen_out_bwd(fake_f32: torch.Tensor, real_nchw: torch.Tensor, dfake_d: Optional[torch.Tensor], l1_scale: float,
+def gen_out_bwd(fake_f32: torch.Tensor, real: torch.Tensor, dfake_d: Optional[torch.Tensor], l1_scale: float,
                 dpre: torch.Tensor, loss_acc: torch.Tensor) -> None:
+    """L1 * lambda + Tanh backward.  ``real`` is real_B either as fp32 NCHW (what the reference's DataLoader yields) or
+    as the raw uint8 [n, h, w, 3] image (normalised in the kernel like dataset.py does)."""
     n, h, w, _ = fake_f32.shape
-    c = real_nchw.shape[1]
-    _lib.check(_lib.lib().gap_gen_out_bwd(_ptr(fake_f32), fake_f32.stride(2), _ptr(real_nchw), h * w, _ptr(dfake_d),
-                                          0 if dfake_d is None else dfake_d.stride(2), l1_scale, _ptr(dpre),
-                                          dpre.stride(2), n * h * w, c, _ptr(loss_acc), _stream()), "gap_gen_out_bwd")
+    if real.dtype == torch.uint8:
+        if tuple(real.shape) != (n, h, w, 3) or not real.is_contiguous():
+            raise ValueError("uint8 real_B must be contiguous [n, h, w, 3]")
+        fn, name, c = _lib.lib().gap_gen_out_bwd_u8, "gap_gen_out_bwd_u8", 3
+    else:
+        fn, name, c = _lib.lib().gap_gen_out_bwd, "gap_gen_out_bwd", real.shape[1]
+    _lib.check(fn(_ptr(fake_f32), fake_f32.stride(2), _ptr(real), h * w, _ptr(dfake_d),
+                  0 if dfake_d is None else dfake_d.stride(2), l1_scale, _ptr(dpre), dpre.stride(2), n * h * w, c,
+                  _ptr(loss_acc), _stream()), name)
 
 
 def bce_logits_const(logits: torch.Tensor, target: float, grad_scale: float, dlogits: Optional[torch.Tensor],

@@ -802,16 +802,27 @@ class Pix2PixTrainer:
         return self._g_out
 
     def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
-        """real_A / real_B: fp32 NCHW on the device.  Returns a device tensor [loss_d, loss_g] (fp64);
-        no host synchronisation happens here."""
+        """real_A / real_B: fp32 NCHW in [-1, 1] on the device (what the reference's DataLoader yields), or BOTH as raw
+        uint8 [n, h, w, 3] images: the ToTensor + JointNormalize of dataset.py:28-29,155-159 then runs on the device
+        inside the first kernels (4x less host->device traffic).  Returns a device tensor [loss_d, loss_g] (fp64); no
+        host synchronisation happens here."""
         G, D = self.G, self.D
-        n, _, h, w = real_A.shape
+        u8 = real_A.dtype == torch.uint8
+        if u8 != (real_B.dtype == torch.uint8):
+            raise ValueError("real_A and real_B must both be fp32 NCHW or both uint8 NHWC")
+        if u8:
+            n, h, w, _ = real_A.shape
+        else:
+            n, _, h, w = real_A.shape
         if self.a_nhwc is None or self.a_nhwc.shape[:3] != (n, h, w):
             self.a_nhwc = torch.zeros(n, h, w, 4, device=self.dev, dtype=torch.bfloat16)
             self.b_nhwc = torch.zeros_like(self.a_nhwc)
         G.training = D.training = True
         self.loss_acc.zero_()
-        ops.nchw_to_nhwc_bf16(real_B, self.b_nhwc)
+        if u8:
+            ops.u8_hwc_to_nhwc_bf16(real_B, self.b_nhwc)
+        else:
+            ops.nchw_to_nhwc_bf16(real_B, self.b_nhwc)
         # ---- D step (train_gan.py:55-63)
         D.zero_grad()
         # :56 and :65 are the same forward (done once, BatchNorm buffers updated twice) unless dropout draws new masks

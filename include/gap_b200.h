@@ -182,6 +182,11 @@ int gap_col2im_k4s2p1(const void* col, int64_t ldc, int ctot, int c0, int cn, co
 int gap_gen_out_bwd(const float* fake, int64_t ld_f, const float* real_nchw, int64_t hw, const float* dfake_d,
                     int64_t ld_d, float l1_scale, void* dpre, int64_t ld_p, int64_t pixels, int c,
                     double* loss_acc, void* stream);
+/* Same with real_B as the raw uint8 HWC image [pixel][c], normalised in the kernel exactly like the dataset does
+ * ((x/255)*2-1 in fp32, dataset.py:28-29,155-159): the device-side input pipeline of the training loop. */
+int gap_gen_out_bwd_u8(const float* fake, int64_t ld_f, const uint8_t* real_hwc, int64_t hw, const float* dfake_d,
+                       int64_t ld_d, float l1_scale, void* dpre, int64_t ld_p, int64_t pixels, int c,
+                       double* loss_acc, void* stream);
 
 /* BCEWithLogitsLoss against ones / zeros (train_gan.py:42,58,60,67): loss_acc += sum l(x, t);
  * dlogits[i*ld_d] = grad_scale * (sigmoid(x) - t) in bf16 (dlogits may be NULL). */

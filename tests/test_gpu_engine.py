@@ -211,6 +211,28 @@ def test_fused_batchnorm_launches_give_the_same_training_steps():
         assert torch.allclose(res[1], res[k + 1], rtol=2e-2, atol=2e-3)   # three GAN steps amplify last-bit differences
 
 
+def test_train_step_accepts_raw_uint8_images():
+    """Device-side input pipeline: uint8 [n,h,w,3] pairs give the same iteration as their
+    ToTensor + JointNormalize fp32 NCHW form (dataset.py:28-29,155-159), eagerly and through the CUDA graph."""
+    from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(12)
+    a8 = torch.randint(0, 256, (2, 64, 64, 3), generator=gen, dtype=torch.uint8)
+    b8 = torch.randint(0, 256, (2, 64, 64, 3), generator=gen, dtype=torch.uint8)
+    to_f32 = lambda u: ((u.float() / 255.0) * 2.0 - 1.0).permute(0, 3, 1, 2).contiguous()
+    res = []
+    for mode in ("f32", "u8", "u8_graph"):
+        torch.manual_seed(0)
+        tr = Pix2PixTrainer(dev, num_downs=5)
+        fn = tr.train_step_graphed if mode == "u8_graph" else tr.train_step
+        args = (to_f32(a8).to(dev), to_f32(b8).to(dev)) if mode == "f32" else (a8.to(dev), b8.to(dev))
+        res.append(torch.stack([fn(*args).cpu().clone() for _ in range(3)]))
+    assert torch.allclose(res[0], res[1], rtol=2e-3, atol=2e-4), (res[0], res[1])
+    assert torch.allclose(res[1], res[2], rtol=2e-3, atol=2e-4), (res[1], res[2])
+    with pytest.raises(ValueError):
+        tr.train_step(a8.to(dev), to_f32(b8).to(dev))
+
+
 def test_dropout_kernel_mask_is_regenerable_and_fair():
     """gap_dropout_bf16 (nn.Dropout(0.5), models.py:197-198): x -> {0, 2x}, same (seed, offset) -> same mask (that is how
     the backward pass re-applies it to the gradient), keep probability 0.5."""
