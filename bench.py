@@ -55,7 +55,40 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self) -> bool:
+        """In-process NVML sampling every 10 ms (the same counters nvidia-smi prints; one nvidia-smi invocation takes
+        longer than a whole default timed region).  Returns False when NVML is unavailable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:        # NVML ignores CUDA_VISIBLE_DEVICES: find the device torch calls `index` by its UUID
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = [str(sm), str(mx), str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0), "", "", "", ""]
+                for mask, col in bits:
+                    row[col] = "Active" if rs & mask else "Not Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+        return True
+
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
@@ -82,8 +115,9 @@ class ClockSampler:
         mx = max((float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = sorted(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit())
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def _cpu_baseline(seconds_budget: float = 20.0) -> dict:
