@@ -452,26 +452,34 @@ class GeneratorEngine(_Net):
         self._n = (n, h, w)
 
     # -- forward --------------------------------------------------------------------------------
-    def forward(self, x_nchw: torch.Tensor, bn_repeat: int = 1, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x: fp32 NCHW on the device, or uint8 NHWC [n,h,w,3] (normalised on the device like dataset.py:155-159).
-        Returns fake as fp32 NHWC [n,h,w,4] (channel 3 is padding); the bf16 copy is self.fake_bf.  bn_repeat=2
-        folds the reference's second identical forward.  out_u8 (uint8 [n,h,w,3]) additionally receives the image
-        generate_synthetic_data.py:69-88 saves, written by the last layer's epilogue."""
-        self._join_wgrad()
+    def prepare_input(self, x_nchw: torch.Tensor) -> torch.Tensor:
+        """Size the buffers for x and convert it into self.x_nhwc (NHWC bf16, 4 channel slots); returns that tensor."""
         u8_in = x_nchw.dtype == torch.uint8
         if u8_in:
             n, h, w, _ = x_nchw.shape
         else:
             n, _, h, w = x_nchw.shape
         self._alloc(n, h, w)
-        L, C, S = self.L, self.C, self.S
-        g_s2 = ops.geom_conv_fwd(4, 2, 1)
-        g_1x1 = ops.geom_conv_fwd(1, 1, 0)
-        g_ph = ops.geom_phase_k4s2p1()
         if u8_in:
             ops.u8_hwc_to_nhwc_bf16(x_nchw, self.x_nhwc)
         else:
             ops.nchw_to_nhwc_bf16(x_nchw, self.x_nhwc)
+        return self.x_nhwc
+
+    def forward(self, x_nchw: torch.Tensor, bn_repeat: int = 1, out_u8: Optional[torch.Tensor] = None,
+                x_ready: bool = False) -> torch.Tensor:
+        """x: fp32 NCHW on the device, or uint8 NHWC [n,h,w,3] (normalised on the device like dataset.py:155-159).
+        Returns fake as fp32 NHWC [n,h,w,4] (channel 3 is padding); the bf16 copy is self.fake_bf.  bn_repeat=2
+        folds the reference's second identical forward.  out_u8 (uint8 [n,h,w,3]) additionally receives the image
+        generate_synthetic_data.py:69-88 saves, written by the last layer's epilogue.  x_ready: prepare_input(x) has
+        already run (the trainer converts the input before it forks the generator onto its own stream)."""
+        self._join_wgrad()
+        if not x_ready:
+            self.prepare_input(x_nchw)
+        L, C, S = self.L, self.C, self.S
+        g_s2 = ops.geom_conv_fwd(4, 2, 1)
+        g_1x1 = ops.geom_conv_fwd(1, 1, 0)
+        g_ph = ops.geom_phase_k4s2p1()
         ops.thin_conv_fwd(self.x_nhwc, None, self.w_d_thin, None, self.A[0], ACT_LRELU, self.R[0][..., :C[0]], ACT_RELU)
         for j in range(1, L - 1):
             bn = self.dbn[j]
@@ -754,6 +762,8 @@ class Pix2PixTrainer:
     """train_gan_one_epoch's loop body (train_gan.py:52-74) on one GPU; `world` > 1 adds the
     data-parallel gradient all-reduce (see parallel.py)."""
 
+    overlap_g_fwd = True     # generator forward on its own stream while D processes the real pair (see train_step)
+
     def __init__(self, device, lr_g: float = 1e-4, lr_d: float = 1e-4, beta1: float = 0.5, num_downs: int = 7,
                  ngf: int = 64, ndf: int = 64, n_layers: int = 3, allreduce=None, world: int = 1,
                  bucket_elems: int = 8 << 20, use_dropout: bool = False) -> None:
@@ -770,6 +780,7 @@ class Pix2PixTrainer:
         # on a side stream while its backward pass is still running (buffer order = completion order)
         self.g_reducer = self.d_reducer = None
         self._graph = None
+        self._g_stream = None
         if world > 1 and allreduce is None:
             from .parallel import GradBucketReducer
             self.g_reducer = GradBucketReducer(self.G.store.g, self.G.grad_segments(), bucket_elems=bucket_elems)
@@ -826,13 +837,27 @@ class Pix2PixTrainer:
         # ---- D step (train_gan.py:55-63)
         D.zero_grad()
         # :56 and :65 are the same forward (done once, BatchNorm buffers updated twice) unless dropout draws new masks
-        G.forward(real_A, bn_repeat=1 if G.use_dropout else 2)
-        a_nhwc = G.x_nhwc
+        a_nhwc = G.prepare_input(real_A)
+        cur = torch.cuda.current_stream(self.dev)
+        fork = self.overlap_g_fwd
+        if fork:
+            # The discriminator's pass over the REAL pair (:57-58 and its backward) does not depend on the generator:
+            # run the generator forward on its own stream meanwhile, so its under-filled 8x8 .. 1x1 bottleneck layers
+            # share the GPU with the discriminator's large layers.  Joined before D sees fake_B.
+            if self._g_stream is None:
+                self._g_stream = torch.cuda.Stream(self.dev)
+            self._g_stream.wait_stream(cur)
+            with torch.cuda.stream(self._g_stream):
+                G.forward(real_A, bn_repeat=1 if G.use_dropout else 2, x_ready=True)
+        else:
+            G.forward(real_A, bn_repeat=1 if G.use_dropout else 2, x_ready=True)
         logits = D.forward(a_nhwc, self.b_nhwc)            # :57
         cnt = logits.numel()
         d_bias_last = D.grad(D.k_conv[-1] + ".bias")
         ops.bce_logits_const_f32(logits, 1.0, 0.5 / cnt, D.dlogits, self.loss_acc[0:1], d_bias_last)   # :58,61
         D.backward(wgrad=True, input_grad=False)
+        if fork:
+            cur.wait_stream(self._g_stream)
         logits = D.forward(a_nhwc, G.fake_bf)              # :59
         ops.bce_logits_const_f32(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2], d_bias_last)   # :60,61
         D.backward(wgrad=True, input_grad=False)           # :62

@@ -34,8 +34,11 @@ for combo in itertools.product((True, False), repeat=len(attrs)):
     torch.manual_seed(0)
     tr = Pix2PixTrainer(dev)
     for a, v in zip(attrs, combo):
-        setattr(tr.G, a, v)
-        setattr(tr.D, a, v)
+        if hasattr(tr, a):
+            setattr(tr, a, v)
+        else:
+            setattr(tr.G, a, v)
+            setattr(tr.D, a, v)
     trainers[combo] = tr
 for rnd in range(2):
     for combo, tr in trainers.items():
