@@ -77,6 +77,7 @@ struct alignas(64) FpropParams {
   long long bwd_g2_ld;
   float bwd_slope;
   int bwd_c0;
+  int bwd_ld32;   // y / g2 rows allow 256-bit loads
   int skip;  // bring-up ablation: 1 no global stores, 2 no y / g2 loads, 4 no statistics
   // Halo mode: the taps of one kernel column that differ only by whole input rows (th = g + in_stride*i) share ONE
   // A tile of BH + halo_taps - 1 rows; tap i reads it through a descriptor shifted by i*BW rows (BW % 8 == 0, so the
@@ -549,13 +550,21 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               yq[i][0] = yq[i][1] = gq[i][0] = gq[i][1] = make_uint4(0, 0, 0, 0);
               const int colp = wc.n_tile * p.block_n + (cg + 2 * i) * 16;
               if (valid && cg + 2 * i < n_chunks && colp >= p.bwd_c0 && colp < p.n_out && !(p.skip & 2)) {
-                const uint4* yp = reinterpret_cast<const uint4*>(p.bwd_y + pix * p.bwd_y_ld + (colp - p.bwd_c0));
-                yq[i][0] = __ldg(yp);
-                yq[i][1] = __ldg(yp + 1);
+                const __nv_bfloat16* yp = p.bwd_y + pix * p.bwd_y_ld + (colp - p.bwd_c0);
+                if (p.bwd_ld32) {
+                  ld_global_nc_32B(yp, yq[i][0], yq[i][1]);
+                } else {
+                  yq[i][0] = __ldg(reinterpret_cast<const uint4*>(yp));
+                  yq[i][1] = __ldg(reinterpret_cast<const uint4*>(yp) + 1);
+                }
                 if (p.bwd_g2 != nullptr) {
-                  const uint4* gp = reinterpret_cast<const uint4*>(p.bwd_g2 + pix * p.bwd_g2_ld + (colp - p.bwd_c0));
-                  gq[i][0] = __ldg(gp);
-                  gq[i][1] = __ldg(gp + 1);
+                  const __nv_bfloat16* gp = p.bwd_g2 + pix * p.bwd_g2_ld + (colp - p.bwd_c0);
+                  if (p.bwd_ld32) {
+                    ld_global_nc_32B(gp, gq[i][0], gq[i][1]);
+                  } else {
+                    gq[i][0] = __ldg(reinterpret_cast<const uint4*>(gp));
+                    gq[i][1] = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
+                  }
                 }
               }
             }
@@ -989,6 +998,12 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.bwd_g2_ld = a->bwd_g2_ld;
   p.bwd_slope = a->bwd_slope;
   p.bwd_c0 = a->bwd_c0;
+  // 256-bit y / g2 loads when every chunk start is 32-byte aligned
+  p.bwd_ld32 = (bwd && a->bwd_y_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(a->bwd_y) & 31) == 0 &&
+                (!a->bwd_g2 || (a->bwd_g2_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(a->bwd_g2) & 31) == 0)) &&
+                debug_get("fprop_ld32", 1) != 0)
+                   ? 1
+                   : 0;
   p.skip = debug_get("fprop_skip", 0);
 
   const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * block_n * 128;

@@ -218,6 +218,13 @@ __device__ __forceinline__ void st_global_32B(void* dst, const uint32_t (&v)[8],
   }
 }
 
+// 256-bit read-only global load (32-byte aligned): one L1 request per lane instead of two 128-bit ones.
+__device__ __forceinline__ void ld_global_nc_32B(const void* src, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(src));
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }

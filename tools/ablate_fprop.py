@@ -37,11 +37,12 @@ w2 = torch.randn(1, 128, 16 * 64, **bf)
 out2 = torch.empty(N, 64, 64, 128, **bf)
 st = torch.zeros(256, device=dev, dtype=torch.float64)
 fl2 = 2.0 * N * 64 * 64 * 128 * 16 * 64
-for skip in (0, 8, 0, 8, 2, 7):
+for skip, ld32 in ((0, 1), (0, 0), (0, 1), (0, 0), (2, 1), (7, 1)):
     _lib.debug_set("fprop_skip", skip)
+    _lib.debug_set("fprop_ld32", ld32)
     t0 = timeit(lambda: ops.conv_gemm([dy], w, geom, out, 64, (64, 64)))
     t1 = timeit(lambda: ops.conv_gemm([dy], w, geom, out, 64, (64, 64), bwd=dict(y=y, slope=0.2)))
     t2 = timeit(lambda: ops.conv_gemm([dy], w, geom, out, 64, (64, 64), bwd=dict(y=y, slope=0.2, g2=g2)))
     t3 = timeit(lambda: ops.conv_gemm([x], w2, ops.geom_conv_fwd(4, 2, 1), out2, 128, (64, 64), stats=st))
-    print(f"skip {skip}: dgrad 128->64 ph4 plain {t0:6.1f} us ({fl/t0/1e6:5.0f} TF) | +bwd act {t1:6.1f} | +bwd act+g2 {t2:6.1f} |"
+    print(f"skip {skip} ld32 {ld32}: dgrad 128->64 ph4 plain {t0:6.1f} us ({fl/t0/1e6:5.0f} TF) | +bwd act {t1:6.1f} | +bwd act+g2 {t2:6.1f} |"
           f" fwd 64->128 s2 stats {t3:6.1f} us ({fl2/t3/1e6:5.0f} TF)", flush=True)
