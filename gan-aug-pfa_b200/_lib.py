@@ -137,6 +137,7 @@ _SIGNATURES = {
     "gap_colsum_bf16": (C.c_int, [_P, _L, _L, _I, _P, _P]),
     "gap_adam_flat": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _F, _P]),
     "gap_adam_flat_devstep": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
+    "gap_gan_losses": (C.c_int, [_P, _D, _D, _D, _P, _P]),
     "gap_pack_weights": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _I, _P]),
     "gap_pack_weights_multi": (C.c_int, [_P, _I, _I, _P]),
 }

@@ -1171,6 +1171,16 @@ int gap_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float
   return 0;
 }
 
+// train_gan.py:61,68-69 from the four loss sums of one iteration (fp64): acc = [sum BCE(D(real),1), sum BCE(D(fake),0),
+// sum BCE(D(fake),1), sum |fake - real|] -> out = [loss_D, loss_G]; acc is re-zeroed for the next iteration.
+__global__ void gan_losses_kernel(double* acc, double inv_cnt, double l1_weight_over_numel, double* out) {
+  if (threadIdx.x == 0) {
+    out[0] = 0.5 * (acc[0] + acc[1]) * inv_cnt;
+    out[1] = acc[2] * inv_cnt + l1_weight_over_numel * acc[3];
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+  }
+}
+
 __global__ void inc_step_kernel(int* step) { *step += 1; }
 
 int gap_adam_flat_devstep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
@@ -1185,6 +1195,13 @@ int gap_adam_flat_devstep(float* p, const float* g, float* m, float* v, int64_t 
   inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
   adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled,
                                                         1.f, 1.f, grad_scale, step_dev);
+  GAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int gap_gan_losses(double* acc4, double count, double l1_weight, double numel, double* out2, void* stream) {
+  GAP_CHECK_ARG(acc4 && out2 && count > 0 && numel > 0, "gap_gan_losses: bad arguments");
+  gan_losses_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(acc4, 1.0 / count, l1_weight / numel, out2);
   GAP_LAUNCH_CHECK();
   return 0;
 }

@@ -290,6 +290,14 @@ def gen_out_bwd(fake_f32: torch.Tensor, real: torch.Tensor, dfake_d: Optional[to
                   _ptr(loss_acc), _stream()), name)
 
 
+def gan_losses(acc4: torch.Tensor, count: int, l1_weight: float, numel: int, out2: torch.Tensor) -> None:
+    """[loss_D, loss_G] of train_gan.py:61,68-69 from the iteration's four fp64 loss sums (re-zeroed)."""
+    if acc4.dtype != torch.float64 or out2.dtype != torch.float64 or acc4.numel() < 4 or out2.numel() < 2:
+        raise ValueError("acc4 / out2 must be fp64 with 4 / 2 elements")
+    _lib.check(_lib.lib().gap_gan_losses(_ptr(acc4), float(count), float(l1_weight), float(numel), _ptr(out2), _stream()),
+               "gap_gan_losses")
+
+
 def bce_logits_const(logits: torch.Tensor, target: float, grad_scale: float, dlogits: Optional[torch.Tensor],
                      loss_acc: torch.Tensor) -> None:
     _lib.check(_lib.lib().gap_bce_logits_const(_ptr(logits), logits.numel(), target, grad_scale, _ptr(dlogits),

@@ -772,7 +772,8 @@ class Pix2PixTrainer:
         self.G = GeneratorEngine(self.dev, 3, 3, num_downs, ngf, use_dropout=use_dropout)
         self.D = DiscriminatorEngine(self.dev, 6, ndf, n_layers)
         self.lr_g, self.lr_d, self.betas = lr_g, lr_d, (beta1, 0.999)
-        self.loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float64)  # d_real, d_fake, g_gan, l1
+        self.loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float64)  # d_real, d_fake, g_gan, l1 (re-zeroed by
+        self.loss_out = torch.zeros(2, device=self.dev, dtype=torch.float64)  # gap_gan_losses at the end of each step)
         self.allreduce = allreduce
         self.world = world
         self.a_nhwc = None
@@ -829,7 +830,6 @@ class Pix2PixTrainer:
             self.a_nhwc = torch.zeros(n, h, w, 4, device=self.dev, dtype=torch.bfloat16)
             self.b_nhwc = torch.zeros_like(self.a_nhwc)
         G.training = D.training = True
-        self.loss_acc.zero_()
         if u8:
             ops.u8_hwc_to_nhwc_bf16(real_B, self.b_nhwc)
         else:
@@ -886,7 +886,5 @@ class Pix2PixTrainer:
         elif self.allreduce is not None:
             self.allreduce(G.store.g)
         G.adam_step(self.lr_g, self.betas, grad_scale=1.0 / self.world)   # :71
-        la = self.loss_acc
-        loss_d = 0.5 * (la[0] + la[1]) / cnt
-        loss_g = la[2] / cnt + LAMBDA_L1 * la[3] / numel
-        return torch.stack([loss_d, loss_g])
+        ops.gan_losses(self.loss_acc, cnt, LAMBDA_L1, numel, self.loss_out)      # :61, :68-69
+        return self.loss_out.clone()     # (callers may keep the result across steps)

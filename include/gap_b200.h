@@ -362,6 +362,12 @@ int gap_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float
 int gap_adam_flat_devstep(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int decoupled, int* step_dev, float grad_scale, void* stream);
 
+/* loss_D = (loss_D_real + loss_D_fake) * 0.5 and loss_G = loss_G_GAN + lambda * loss_G_L1 (train_gan.py:61,68-69)
+ * from the four fp64 sums the loss kernels accumulated: acc4 = [sum BCE(D(real),1), sum BCE(D(fake),0),
+ * sum BCE(D(fake'),1), sum |fake-real|], count = logits per pass, numel = elements of fake.  out2 = [loss_D, loss_G];
+ * acc4 is re-zeroed. */
+int gap_gan_losses(double* acc4, double count, double l1_weight, double numel, double* out2, void* stream);
+
 /* fp32 master weights (arbitrary strides) -> bf16 K-major GEMM operand; modes in elementwise.cu. */
 int gap_pack_weights(const float* w, void* out, int mode, int n_phase, int rows, int rows_pad, int taps_h,
                      int taps_w, int c, int c_pad, int krow, int64_t s_r, int64_t s_c, int64_t s_kh, int64_t s_kw,

@@ -44,7 +44,8 @@ def _worker(rank, world, port, q):
         local = flat.clone()
         allreduce = make_allreduce(world, bucket_elems=1000)     # several buckets, ragged tail
         allreduce(flat)
-        q.put((rank, local, flat))
+        # numpy arrays travel by value: a torch tensor in an mp.Queue is a shared-memory handle that dies with the sender
+        q.put((rank, local.numpy(), flat.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -61,6 +62,7 @@ def test_bucketed_allreduce_world2_matches_sum_of_replica_grads():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [(r, torch.from_numpy(a), torch.from_numpy(b)) for r, a, b in res]
     total = res[0][1] + res[1][1]
     for _, _, reduced in res:
         assert torch.allclose(reduced, total, rtol=1e-6, atol=1e-9)
@@ -118,7 +120,7 @@ def _reducer_worker(rank, world, port, q):
             red.mark_ready(name)
             launched.append(red.launched_before_finish)
         red.finish()
-        q.put((rank, local, flat, launched, len(red.buckets)))
+        q.put((rank, local.numpy(), flat.numpy(), launched, len(red.buckets)))
     finally:
         dist.destroy_process_group()
 
@@ -135,6 +137,7 @@ def test_grad_bucket_reducer_world2_overlapped_protocol():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [(r, torch.from_numpy(a), torch.from_numpy(b), l, n) for r, a, b, l, n in res]
     total = res[0][1] + res[1][1]
     for _, _, reduced, launched, n_buckets in res:
         assert torch.allclose(reduced, total, rtol=1e-6, atol=1e-9)      # every element reduced exactly once
