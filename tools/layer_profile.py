@@ -84,6 +84,7 @@ else:
     import os
     if os.environ.get("GAP_NO_OVERLAP"):      # serialise the wgrad side stream: clean per-kernel times
         tr.G.overlap_wgrad = tr.D.overlap_wgrad = False
+        tr.overlap_g_fwd = False
     A = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
     B = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
 for _ in range(3):
