@@ -144,42 +144,6 @@ __device__ __forceinline__ MTile decode_mtile(const FpropParams& p, int mi) {
   return m;
 }
 
-// Sum the 16 per-row values of v across the 32 lanes of the warp.  On return lane l holds in its
-// return value the full column sum of column ((l>>1) & 15) ... precisely: column index
-// 8*b4 + 4*b3 + 2*b2 + b1 where b_i are bits of the lane id (lanes differing in bit 0 agree).
-__device__ __forceinline__ float transpose_reduce16(const float (&v)[16], uint32_t lane) {
-  float w8[8];
-  const bool b4 = lane & 16;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float mine = b4 ? v[8 + j] : v[j];
-    float other = b4 ? v[j] : v[8 + j];
-    w8[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
-  }
-  float w4[4];
-  const bool b3 = lane & 8;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float mine = b3 ? w8[4 + j] : w8[j];
-    float other = b3 ? w8[j] : w8[4 + j];
-    w4[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
-  }
-  float w2[2];
-  const bool b2 = lane & 4;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    float mine = b2 ? w4[2 + j] : w4[j];
-    float other = b2 ? w4[j] : w4[2 + j];
-    w2[j] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
-  }
-  const bool b1 = lane & 2;
-  float mine = b1 ? w2[1] : w2[0];
-  float other = b1 ? w2[0] : w2[1];
-  float w1 = mine + __shfl_xor_sync(0xffffffffu, other, 2);
-  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-  return w1;
-}
-
 // Column sums of one 32-row x 16-column chunk on the warp MMA.  The chunk lives one row per lane as eight packed
 // bf16 pairs (`a`, and `b` for the second factor; kSame: b == a).  The rows are staged in a 1 KiB smem tile
 // (16-byte halves XOR-swizzled by bit 2 of the row so the 128-bit stores and the ldmatrix rows are conflict-free),

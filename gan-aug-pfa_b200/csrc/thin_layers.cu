@@ -287,9 +287,10 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams 
 
   // asynchronous (cp.async) load of the input patch of one tile into a patch buffer
   auto issue_patch = [&](long long tile, int buf) {
-    const int tx = static_cast<int>(tile % p.tiles_x);
-    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
-    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int t32 = static_cast<int>(tile), tpi = p.tiles_x * p.tiles_y;   // 32-bit: 64-bit division is ~10 % of the kernel
+    const int img32 = t32 / tpi, rem32 = t32 - img32 * tpi;
+    const int ty = rem32 / p.tiles_x, tx = rem32 - ty * p.tiles_x;
+    const long long img = img32;
     const int oy0 = ty * 8, ox0 = tx * 16;
     const bf16* s0i = p.s0 + img * p.h * p.w_in * p.ld0;
     const bf16* s1i = CT == 8 ? p.s1 + img * p.h * p.w_in * p.ld1 : p.s0;
@@ -310,9 +311,10 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams 
   if (static_cast<long long>(blockIdx.x) < p.total_tiles) issue_patch(blockIdx.x, 0);
   int buf = 0;
   for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
-    const int tx = static_cast<int>(tile % p.tiles_x);
-    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
-    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int t32 = static_cast<int>(tile), tpi = p.tiles_x * p.tiles_y;   // 32-bit: 64-bit division is ~10 % of the kernel
+    const int img32 = t32 / tpi, rem32 = t32 - img32 * tpi;
+    const int ty = rem32 / p.tiles_x, tx = rem32 - ty * p.tiles_x;
+    const long long img = img32;
     const int oy0 = ty * 8, ox0 = tx * 16;
     const uint32_t* patch = patch_buf + buf * PATCH_WORDS;
     const long long next = tile + gridDim.x;
@@ -469,9 +471,10 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradPar
   const int nthr = blockDim.x;
 
   auto issue_tile = [&](long long tile, int buf) {
-    const int tx = static_cast<int>(tile % p.tiles_x);
-    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
-    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+    const int t32 = static_cast<int>(tile), tpi = p.tiles_x * p.tiles_y;   // 32-bit: 64-bit division is ~10 % of the kernel
+    const int img32 = t32 / tpi, rem32 = t32 - img32 * tpi;
+    const int ty = rem32 / p.tiles_x, tx = rem32 - ty * p.tiles_x;
+    const long long img = img32;
     const int oy0 = ty * 8, ox0 = tx * 16;
     const bf16* s0i = p.s0 + img * p.h * p.w_in * p.ld0;
     const bf16* s1i = CT == 8 ? p.s1 + img * p.h * p.w_in * p.ld1 : p.s0;
@@ -591,9 +594,13 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradPar
 // source pixels + 1 ring) is multiplied by wcol[48 = tap*3 + co][cw] into col[halo pixel][48] (fp32, shared
 // memory) with warp MMAs, then every output pixel of the 16 x 32 output tile sums its 4 taps (col2im inside
 // the CTA; the ring makes the tile self-contained), adds the bias, applies Tanh and is written once.
-// dynamic smem: wide_s[192][cw+8] (bf16) | w_s[48][cw+8] (bf16) | col_s[192][COLS] (fp32)
+// The halo tile arrives by TMA (one 4-D box per 64 channels, out-of-range pixels zero-filled): the per-thread
+// cp.async loop it replaces was 40 % of the kernel's instructions (ncu source page), on an issue-bound kernel.
+// dynamic smem (1 KiB aligned): wide_s[cw/64][192 rows][128 B] (bf16, 128B-swizzled TMA tiles) | w_s[48][cw+8] (bf16) |
+//                               col_s[192][COLS] (fp32) | mbarrier
 // ------------------------------------------------------------------------------------------------
 struct ThinConvTParams {
+  CUtensorMap tm_wide;   // [n][ih][iw][cw] bf16, box 64 ch x 18 x 10 x 1, 128B swizzle, OOB = zero (the halo ring)
   const bf16* wide;
   long long ld_w;
   const bf16* wcol;
@@ -608,20 +615,43 @@ struct ThinConvTParams {
   long long total_tiles;
 };
 
-constexpr int kColStride = 52;  // fp32 per col_s row (48 used)
+constexpr int kColStride = 50;  // fp32 per col_s row (48 used); 50 = 18 mod 32 keeps the col2im reads of 16 neighbouring halo pixels in distinct banks
 
-__global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTParams p) {
-  extern __shared__ __align__(16) uint8_t dsm[];
+constexpr int kWideBoxRows = 180;               // 10 x 18 halo pixels per box
+constexpr int kWideTileBytes = 192 * 128;       // one 64-channel tile: 192 MMA rows (180 loaded, 12 kept zero)
+
+// tanh through one exp and one fast division: absolute error ~1e-7 (the output is an image in [-1, 1]; the libdevice
+// tanhf it replaces cost 12 % of the kernel's instructions).
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.f * x);              // inf for large x -> 1, 0 for very negative x -> -1
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+__global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const __grid_constant__ ThinConvTParams p) {
+  extern __shared__ uint8_t dsm_raw[];
+  const uint32_t wide_a = (smem_u32(dsm_raw) + 1023u) & ~1023u;
+  uint8_t* dsm = dsm_raw + (wide_a - smem_u32(dsm_raw));
   const int wstride = p.cw + 8;
-  bf16* wide_s = reinterpret_cast<bf16*>(dsm);
-  bf16* w_s = wide_s + 192 * wstride;
+  const int nbox = p.cw >> 6;
+  bf16* w_s = reinterpret_cast<bf16*>(dsm + nbox * kWideTileBytes);
   float* col_s = reinterpret_cast<float*>(w_s + 48 * wstride);
+  const uint32_t bar = smem_u32(col_s + 192 * kColStride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int vshift = p.cw == 64 ? 3 : 4;
   const int oh = 2 * p.ih, ow = 2 * p.iw;
   const int mg = warp >> 1, nh = warp & 1;   // warp = 3 m-tiles (48 halo pixels) x 3 n-tiles (24 columns)
 
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tm_wide);
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  // MMA rows 180..191 of every tile are never written by the TMA box: keep them zero
+  for (int idx = tid; idx < nbox * 12 * 8; idx += 256) {
+    const int b = idx / 96, r = (idx % 96) >> 3, seg = idx & 7;
+    *reinterpret_cast<uint4*>(dsm + b * kWideTileBytes + (kWideBoxRows + r) * 128 + seg * 16) = make_uint4(0, 0, 0, 0);
+  }
   for (int idx = tid; idx < (48 << vshift); idx += 256) {
     const int r = idx >> vshift, seg = idx & ((1 << vshift) - 1);
     *reinterpret_cast<uint4*>(w_s + r * wstride + seg * 8) = ldg128(p.wcol + static_cast<long long>(r) * p.cw + seg * 8);
@@ -632,30 +662,30 @@ __global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTPara
     bias3[1] = __ldg(p.bias + 1);
     bias3[2] = __ldg(p.bias + 2);
   }
-  const uint32_t wide_a = smem_u32(wide_s), w_a = smem_u32(w_s);
+  const uint32_t w_a = smem_u32(w_s);
   const int kchunks = p.cw >> 4;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  uint32_t phase = 0;
 
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int tx = static_cast<int>(tile % p.tiles_x);
-    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
-    const long long img = tile / (static_cast<long long>(p.tiles_x) * p.tiles_y);
+  // tid 0 issues the halo-tile load of `tile`; it runs one tile ahead: the next load is issued as soon as the MMA
+  // phase has finished reading wide_s and overlaps the col2im phase (which only reads col_s)
+  auto issue_load = [&](int tile) {
+    const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    mbar_expect_tx(bar, static_cast<uint32_t>(nbox * kWideBoxRows * 128));
+    for (int b = 0; b < nbox; ++b)
+      tma_load_4d(wide_a + b * kWideTileBytes, &p.tm_wide, bar, b * 64, tx * 16 - 1, ty * 8 - 1, img);
+  };
+  const int total = static_cast<int>(p.total_tiles);
+  __syncthreads();  // w_s, the zero rows and the barrier are set up
+  if (tid == 0 && static_cast<int>(blockIdx.x) < total) issue_load(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
     const int i0 = ty * 8, j0 = tx * 16;
-    __syncthreads();  // previous tile finished with wide_s / col_s; w_s loaded
-    {
-      const bf16* wi = p.wide + img * p.ih * p.iw * p.ld_w;
-      const int ldw = static_cast<int>(p.ld_w);
-      for (int idx = tid; idx < (192 << vshift); idx += 256) {
-        const int pix = idx >> vshift, seg = idx & ((1 << vshift) - 1);
-        const int r = pix / 18, c = pix - r * 18;
-        const int gy = i0 - 1 + r, gx = j0 - 1 + c;
-        const bool ok = pix < 180 && static_cast<unsigned>(gy) < static_cast<unsigned>(p.ih) &&
-                        static_cast<unsigned>(gx) < static_cast<unsigned>(p.iw);
-        cp_async16(wide_a + (pix * wstride + seg * 8) * 2, wi + (ok ? (gy * p.iw + gx) * ldw + seg * 8 : 0), ok ? 16 : 0);
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    mbar_wait(bar, phase);
+    phase ^= 1u;
     // ---- col = wide_s (192 x cw) * wcol^T (cw x 48)
     float acc[3][3][4];
 #pragma unroll
@@ -667,8 +697,12 @@ __global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTPara
     for (int kc = 0; kc < kchunks; ++kc) {
       uint32_t a[3][4], b[4], b4, b5;
 #pragma unroll
-      for (int mi = 0; mi < 3; ++mi)
-        ldmatrix_x4(a[mi], wide_a + (((mg * 3 + mi) * 16 + (lane & 15)) * wstride + kc * 16 + (lane >> 4) * 8) * 2);
+      for (int mi = 0; mi < 3; ++mi) {
+        // 128B-swizzled tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+        const int row = (mg * 3 + mi) * 16 + (lane & 15);
+        const int chunk = ((kc & 3) << 1) + (lane >> 4);
+        ldmatrix_x4(a[mi], wide_a + (kc >> 2) * kWideTileBytes + row * 128 + ((chunk ^ (row & 7)) << 4));
+      }
       ldb_16x16(b, w_a + ((nh * 24) * wstride + kc * 16) * 2, wstride * 2, lane);
       ldmatrix_x2(b4, b5, w_a + ((nh * 24 + 16 + (lane & 7)) * wstride + kc * 16 + ((lane >> 3) & 1) * 8) * 2);
 #pragma unroll
@@ -688,7 +722,8 @@ __global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTPara
         *reinterpret_cast<float2*>(col_s + (px0 + 8) * kColStride + col) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
       }
     }
-    __syncthreads();
+    __syncthreads();   // col_s complete; nobody reads wide_s any more
+    if (tid == 0 && tile + static_cast<int>(gridDim.x) < total) issue_load(tile + gridDim.x);
     // ---- col2im inside the tile: output (yl, xl) sums its 2 x 2 taps
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -711,11 +746,11 @@ __global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTPara
         }
       }
       if (p.act == GAP_ACT_TANH) {
-        v[0] = tanhf(v[0]);
-        v[1] = tanhf(v[1]);
-        v[2] = tanhf(v[2]);
+        v[0] = tanh_fast(v[0]);
+        v[1] = tanh_fast(v[1]);
+        v[2] = tanh_fast(v[2]);
       }
-      const long long o = (img * oh + y) * ow + x;
+      const long long o = (static_cast<long long>(img) * oh + y) * ow + x;
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o * p.ld_f) = make_float4(v[0], v[1], v[2], 0.f);
       if (p.out_bf) *reinterpret_cast<uint2*>(p.out_bf + o * p.ld_bf) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
       if (p.out_u8) {
@@ -726,6 +761,7 @@ __global__ void __launch_bounds__(256) thin_convT_fwd_kernel(const ThinConvTPara
         }
       }
     }
+    __syncthreads();   // col_s is free for the next tile
   }
 }
 
@@ -914,6 +950,7 @@ int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t l
   p.tiles_x = (p.ow + 15) / 16;
   p.tiles_y = (p.oh + 7) / 8;
   p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  GAP_CHECK_ARG(p.total_tiles < (1ll << 31), "gap_thin_conv_fwd: too many tiles");
   p.skip = debug_get("thin_skip", 0);
   const int ct = src1 ? 8 : 4;
   const size_t smem = 2 * 18 * 34 * ct * 2 + static_cast<size_t>(cw) * (16 * ct + 8) * 2 + 128 * static_cast<size_t>(cw + 8) * 2;
@@ -968,6 +1005,7 @@ int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_
   p.tiles_x = (p.ow + 15) / 16;
   p.tiles_y = (p.oh + 7) / 8;
   p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  GAP_CHECK_ARG(p.total_tiles < (1ll << 31), "gap_thin_conv_wgrad: too many tiles");
   const int ct = src1 ? 8 : 4;
   const size_t smem = 2 * 18 * 34 * ct * 2 + 2 * 128 * static_cast<size_t>(cw + 8) * 2;
   const int threads = 128 * (cw / 64);
@@ -1020,7 +1058,18 @@ int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, in
   p.tiles_x = (iw + 15) / 16;
   p.tiles_y = (ih + 7) / 8;
   p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
-  const size_t smem = (192 + 48) * static_cast<size_t>(cw + 8) * 2 + 192 * kColStride * 4;
+  GAP_CHECK_ARG(p.total_tiles < (1ll << 31), "gap_thin_convT_fwd: too many tiles");
+  {
+    const uint64_t ld_b = static_cast<uint64_t>(ld_w) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(cw), static_cast<uint64_t>(iw), static_cast<uint64_t>(ih),
+                        static_cast<uint64_t>(n)};
+    uint64_t strides[3] = {ld_b, ld_b * iw, ld_b * iw * ih};
+    uint32_t box[4] = {64, 18, 10, 1};
+    int rc = encode_tmap_bf16(&p.tm_wide, wide, 4, dims, strides, box, nullptr, true);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + static_cast<size_t>(cw / 64) * kWideTileBytes + 48 * static_cast<size_t>(cw + 8) * 2 +
+                      192 * kColStride * 4 + 16;
   static bool set = false;
   if (!set) {
     GAP_CUDA(cudaFuncSetAttribute(thin_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

@@ -32,6 +32,22 @@ bias = torch.randn(64, device=dev)
 o64 = torch.empty(N, 128, 128, 64, **bf)
 o64b = torch.empty(N, 128, 128, 64, **bf)
 o128 = torch.empty(N, 128, 128, 128, **bf)
+wide128 = torch.randn(N, 128, 128, 128, **bf)
+wide64 = torch.randn(N, 128, 128, 64, **bf)
+wcol128 = torch.randn(48, 128, **bf)
+wcol64 = torch.randn(48, 64, **bf)
+b3 = torch.randn(3, device=dev)
+fake_bf = torch.zeros(N, 256, 256, 4, **bf)
+fake_f32 = torch.zeros(N, 256, 256, 4, device=dev)
+dw8 = torch.zeros(64, 96, device=dev)
+dw4 = torch.zeros(64, 48, device=dev)
+db = torch.zeros(64, device=dev)
+t4 = timeit(lambda: ops.thin_convT_fwd(wide128, wcol128, b3, ops.ACT_TANH, fake_bf, fake_f32))
+t5 = timeit(lambda: ops.thin_convT_fwd(wide64, wcol64, None, ops.ACT_NONE, fake_bf, None))
+t6 = timeit(lambda: ops.thin_conv_wgrad(o64, xa, xb, dw8, 96, db))
+t7 = timeit(lambda: ops.thin_conv_wgrad(o64, xa, None, dw4, 48, None))
+print(f"G.last fwd (convT 128->3, tanh, bf16+f32 out) {t4:.1f} us | D.0 input grad (convT 64->3, bf16 out) {t5:.1f} us | "
+      f"D.0 wgrad {t6:.1f} us | G.0 wgrad {t7:.1f} us", flush=True)
 for cps in [int(a) for a in sys.argv[1:]] or [0]:
     _lib.debug_set("thin_skip", cps)
     t1 = timeit(lambda: ops.thin_conv_fwd(xa, xb, w8, bias, o64, ops.ACT_LRELU))

@@ -34,6 +34,16 @@ def label_of(name, args):
         mr = a.m_rows if a.m_rows > 0 else a.m_c
         fl = 2.0 * a.n * a.gh * a.gw * mr * a.n_c * a.taps_h * a.taps_w
         return f"wgrad n{a.n} m{a.m_c} n{a.n_c} grid{a.gh}x{a.gw} taps{a.taps_h}x{a.taps_w} s{a.stride}", fl
+    def _i(v):
+        return int(getattr(v, "value", v) or 0)
+    if name == "gap_bn_bwd_apply":     # y ld g1 ld g2 ld slope scale shift mean invstd pixels c ...
+        px, c = _i(args[11]), _i(args[12])
+        nb = 3 if args[4] is not None and getattr(args[4], "value", args[4]) else 2
+        return f"bn_bwd_apply px{px} c{c} tensors{nb + 1}", -float(px * c * 2 * (nb + 1))
+    if name == "gap_bn_act":           # y ld scale shift pixels c o1 ld1 a1 o2 ...
+        px, c = _i(args[4]), _i(args[5])
+        no = 2 if args[9] is not None and getattr(args[9], "value", args[9]) else 1
+        return f"bn_act px{px} c{c} outs{no}", -float(px * c * 2 * (1 + no))
     return name[4:], 0.0
 
 
@@ -123,12 +133,12 @@ for lab, v in agg.items():
     d[2] += v[2] / STEPS
 print("--- by kind")
 for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][1]):
-    tf = f"{v[2] / v[1] / 1e6:7.1f} TF/s" if v[2] else ""
+    tf = (f"{v[2] / v[1] / 1e6:7.1f} TF/s" if v[2] > 0 else f"{-v[2] / v[1] / 1e3:7.0f} GB/s") if v[2] else ""
     print(f"{v[1]:9.1f} us {100 * v[1] / tot:5.1f}% x{v[0]:4.0f}  {k} {tf}")
 print("--- by shape")
 for lab, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     us = v[1] / STEPS
     if us < MIN_US:
         continue
-    tf = f"{v[2] / v[1] / 1e6:7.1f} TF/s" if v[2] else ""
+    tf = (f"{v[2] / v[1] / 1e6:7.1f} TF/s" if v[2] > 0 else f"{-v[2] / v[1] / 1e3:7.0f} GB/s") if v[2] else ""
     print(f"{us:9.1f} us {100 * us / tot:5.1f}% x{v[0] / STEPS:4.0f}  {lab} {tf}")
