@@ -242,9 +242,12 @@ __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restric
 // generator's last ConvTranspose2d (models.py:184).  The input patch of an 8 x 16 output tile is staged in
 // shared memory once and the im2col matrix only ever exists as MMA fragments.
 // CTA = 128 output pixels; warp = 2 output rows (2 x m16) x 64 output channels.
-// dynamic smem: patch[2][18][34][CT] (double-buffered with cp.async) | ws[cw][16*CT + 8] | out_s[128][cw + 8]
+// The output tile leaves through TMA stores from a 128B-swizzled smem tile (ragged tiles are clipped by the unit):
+// the per-thread copy-out loop it replaces was ~19 % of the kernel's instructions (ncu source page).
+// dynamic smem (1 KiB aligned): out_s[cw/64][128][128 B] | patch[2][18][34][CT] (cp.async double buffer) | ws[cw][16*CT + 8]
 // ------------------------------------------------------------------------------------------------
 struct ThinFwdParams {
+  CUtensorMap tm_out[2];   // out1 / out2 as [n][oh][ow][cw] bf16: box 64 ch x 16 x 8 x 1, 128B swizzle (TMA store)
   const bf16* s0;
   long long ld0;
   const bf16* s1;
@@ -264,16 +267,17 @@ struct ThinFwdParams {
 };
 
 template <int CT>
-__global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams p) {
+__global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __grid_constant__ ThinFwdParams p) {
   constexpr int K = 16 * CT;
   constexpr int WSTRIDE = K + 8;      // bf16 elements per weight row in smem
   constexpr int PW = CT / 2;          // 32-bit words per patch pixel
-  extern __shared__ __align__(16) uint8_t dsm[];
+  extern __shared__ uint8_t dsm_raw[];
+  const uint32_t out_a = (smem_u32(dsm_raw) + 1023u) & ~1023u;             // out_s: cw/64 swizzled tiles of 16 KiB
+  uint8_t* dsm = dsm_raw + (out_a - smem_u32(dsm_raw));
   constexpr int PATCH_WORDS = 18 * 34 * PW;
-  uint32_t* patch_buf = reinterpret_cast<uint32_t*>(dsm);                  // [2][18][34][PW]
-  bf16* ws = reinterpret_cast<bf16*>(dsm + 2 * PATCH_WORDS * 4);
-  bf16* out_s = ws + static_cast<size_t>(p.cw) * WSTRIDE;
-  const int ostride = p.cw + 8;
+  const int out_bytes = (p.cw >> 6) * 16384;
+  uint32_t* patch_buf = reinterpret_cast<uint32_t*>(dsm + out_bytes);      // [2][18][34][PW]
+  bf16* ws = reinterpret_cast<bf16*>(dsm + out_bytes + 2 * PATCH_WORDS * 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int mp = warp & 3, nh = warp >> 2;
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams 
     } else {
       cp_async_wait<0>();
     }
+    if (tid == 0) tma_store_wait_read();   // the previous tile's TMA stores have read out_s
     __syncthreads();  // this tile's patch has landed for every thread; out_s of the previous tile is free; ws loaded
 
     float acc[2][8][4];
@@ -388,14 +393,19 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams 
       bf16* outp = pass == 0 ? p.out1 : p.out2;
       if (outp == nullptr) break;
       const float slope = pass == 0 ? p.slope1 : p.slope2;
-      const int ldo = static_cast<int>(pass == 0 ? p.ldo1 : p.ldo2);
       const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
       const bool ident = slope == 1.f;
-      if (pass == 1) __syncthreads();
+      if (pass == 1) {
+        if (tid == 0) tma_store_wait_read();
+        __syncthreads();
+      }
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        bf16* row0 = out_s + ((2 * mp + m) * 16 + g) * ostride + nh * 64 + 2 * t;
-        bf16* row1 = row0 + 8 * ostride;
+        // 128B-swizzled [128 pixels][64 ch] tile per channel half: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+        // (g = r & 7 here, so the eight rows of a warp store hit eight different chunks: conflict-free)
+        const int r0 = (2 * mp + m) * 16 + g;
+        const uint32_t row0 = out_a + nh * 16384 + r0 * 128 + 4 * t;
+        const uint32_t row1 = row0 + 8 * 128;      // row r0 + 8: same r & 7
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           // act(v) = max(v, slope*v) for slope in [0,1], applied to the packed bf16 pair
@@ -405,23 +415,21 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const ThinFwdParams 
             lo = __hmax2(lo, __hmul2(lo, slope2));
             hi = __hmax2(hi, __hmul2(hi, slope2));
           }
-          *reinterpret_cast<__nv_bfloat162*>(row0 + nt * 8) = lo;
-          *reinterpret_cast<__nv_bfloat162*>(row1 + nt * 8) = hi;
+          const uint32_t sw = static_cast<uint32_t>((nt ^ g) << 4);
+          st_shared_b32(row0 + sw, *reinterpret_cast<const uint32_t*>(&lo));
+          st_shared_b32(row1 + sw, *reinterpret_cast<const uint32_t*>(&hi));
         }
       }
+      fence_proxy_async_smem();
       __syncthreads();
-      // 128 pixels x (cw/8) 16-byte vectors; cw/8 is 8 or 16
-      const int vshift = p.cw == 64 ? 3 : 4;
-      bf16* out_img = outp + img * p.oh * p.ow * ldo;
-      for (int idx = tid; idx < (128 << vshift); idx += nthr) {
-        const int px = idx >> vshift, seg = idx & ((1 << vshift) - 1);
-        const int oy = oy0 + (px >> 4), ox = ox0 + (px & 15);
-        if (oy < p.oh && ox < p.ow && !(p.skip & 2))
-          *reinterpret_cast<uint4*>(out_img + (oy * p.ow + ox) * ldo + seg * 8) =
-              *reinterpret_cast<const uint4*>(out_s + px * ostride + seg * 8);
+      if (tid == 0 && !(p.skip & 2)) {
+        for (int b = 0; b < (p.cw >> 6); ++b)
+          tma_store_4d(&p.tm_out[pass], out_a + b * 16384, b * 64, ox0, oy0, static_cast<int>(img));
+        tma_store_commit();
       }
     }
   }
+  if (tid == 0) tma_store_wait_all();
 }
 
 
@@ -953,7 +961,20 @@ int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t l
   GAP_CHECK_ARG(p.total_tiles < (1ll << 31), "gap_thin_conv_fwd: too many tiles");
   p.skip = debug_get("thin_skip", 0);
   const int ct = src1 ? 8 : 4;
-  const size_t smem = 2 * 18 * 34 * ct * 2 + static_cast<size_t>(cw) * (16 * ct + 8) * 2 + 128 * static_cast<size_t>(cw + 8) * 2;
+  for (int o = 0; o < 2; ++o) {
+    const void* base = o == 0 ? out1 : out2;
+    const int64_t ldo = o == 0 ? ldo1 : ldo2;
+    if (base == nullptr) continue;
+    const uint64_t ld_b = static_cast<uint64_t>(ldo) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(cw), static_cast<uint64_t>(p.ow), static_cast<uint64_t>(p.oh),
+                        static_cast<uint64_t>(n)};
+    uint64_t strides[3] = {ld_b, ld_b * p.ow, ld_b * p.ow * p.oh};
+    uint32_t box[4] = {64, 16, 8, 1};
+    int rc = encode_tmap_bf16(&p.tm_out[o], base, 4, dims, strides, box, nullptr, true);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + static_cast<size_t>(cw / 64) * 16384 + 2 * 18 * 34 * ct * 2 +
+                      static_cast<size_t>(cw) * (16 * ct + 8) * 2;
   const int threads = 128 * (cw / 64);
   const int grid = static_cast<int>(std::min<long long>(p.total_tiles, static_cast<long long>(debug_get("thin_ctas_per_sm", 4)) * sm_count()));
   if (ct == 8) {
