@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __grid_constan
 // dynamic smem: patch[2][18][34][CT] | wide_s[2][128][cw + 8]   (bf16, cp.async double buffers)
 // ------------------------------------------------------------------------------------------------
 struct ThinWgradParams {
+  CUtensorMap tm_wide;   // [n][oh][ow][cw] bf16: box 64 ch x 16 x 8 x 1, 128B swizzle, ragged tiles zero-filled
   const bf16* wide;
   long long ld_w;
   const bf16* s0;
@@ -465,18 +466,28 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
 }
 
 template <int CT>
-__global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradParams p) {
+__global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const __grid_constant__ ThinWgradParams p) {
   constexpr int PW = CT / 2;
   constexpr int PATCH_WORDS = 18 * 34 * PW;
   constexpr int NT = CT / 2;             // n-tiles (8 columns) per kernel row: 4 taps * CT / 8
-  extern __shared__ __align__(16) uint8_t dsm[];
-  uint32_t* patch_buf = reinterpret_cast<uint32_t*>(dsm);
-  bf16* wide_buf = reinterpret_cast<bf16*>(dsm + 2 * PATCH_WORDS * 4);
-  const int wstride = p.cw + 8;
+  // dynamic smem (1 KiB aligned): wide[2][cw/64][128 px][128 B] (TMA, 128B swizzle) | patch[2][18][34][CT] | 2 mbarriers
+  extern __shared__ uint8_t dsm_raw[];
+  const uint32_t wide_base = (smem_u32(dsm_raw) + 1023u) & ~1023u;
+  uint8_t* dsm = dsm_raw + (wide_base - smem_u32(dsm_raw));
+  const int wide_bytes = (p.cw >> 6) * 16384;          // one buffer
+  uint32_t* patch_buf = reinterpret_cast<uint32_t*>(dsm + 2 * wide_bytes);
+  const uint32_t bar0 = smem_u32(patch_buf + 2 * PATCH_WORDS);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int kh = warp & 3, mh = warp >> 2;
   const int nthr = blockDim.x;
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tm_wide);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
 
   auto issue_tile = [&](long long tile, int buf) {
     const int t32 = static_cast<int>(tile), tpi = p.tiles_x * p.tiles_y;   // 32-bit: 64-bit division is ~10 % of the kernel
@@ -497,15 +508,13 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradPar
       cp_async8(dst0 + idx * PW * 4, s0i + pix * ld0, ok ? 8 : 0);
       if (CT == 8) cp_async8(dst0 + idx * PW * 4 + 8, s1i + pix * ld1, ok ? 8 : 0);
     }
-    const bf16* wi = p.wide + img * p.oh * p.ow * p.ld_w;
-    const int ldw = static_cast<int>(p.ld_w);
-    const uint32_t wdst = smem_u32(wide_buf + buf * 128 * wstride);
-    const int vshift = p.cw == 64 ? 3 : 4;
-    for (int idx = tid; idx < (128 << vshift); idx += nthr) {
-      const int px = idx >> vshift, seg = idx & ((1 << vshift) - 1);
-      const int oy = oy0 + (px >> 4), ox = ox0 + (px & 15);
-      const bool ok = oy < p.oh && ox < p.ow;
-      cp_async16(wdst + (px * wstride + seg * 8) * 2, wi + (ok ? (oy * p.ow + ox) * ldw + seg * 8 : 0), ok ? 16 : 0);
+    // the wide tile (dY / X at the coarse resolution) comes by TMA: the per-thread cp.async loop was 16 % of the
+    // kernel's instructions; pixels outside the image are zero-filled by the unit
+    if (tid == 0) {
+      const uint32_t bar = bar0 + 8 * buf;
+      mbar_expect_tx(bar, static_cast<uint32_t>(wide_bytes));
+      for (int b = 0; b < (p.cw >> 6); ++b)
+        tma_load_4d(wide_base + buf * wide_bytes + b * 16384, &p.tm_wide, bar, b * 64, ox0, oy0, img32);
     }
     cp_async_commit();
   };
@@ -525,6 +534,7 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradPar
 
   if (static_cast<long long>(blockIdx.x) < p.total_tiles) issue_tile(blockIdx.x, 0);
   int buf = 0;
+  uint32_t wphase[2] = {0u, 0u};
   for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
     const long long next = tile + gridDim.x;
     __syncthreads();  // everyone finished reading buffer buf^1 (previous tile)
@@ -534,9 +544,11 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradPar
     } else {
       cp_async_wait<0>();
     }
+    mbar_wait(bar0 + 8 * buf, wphase[buf]);
+    wphase[buf] ^= 1u;
     __syncthreads();
     const uint32_t patch_a = smem_u32(patch_buf + buf * PATCH_WORDS);
-    const uint32_t wide_a = smem_u32(wide_buf + buf * 128 * wstride);
+    const uint32_t wide_a = wide_base + buf * wide_bytes + mh * 16384;
 #pragma unroll 2
     for (int r = 0; r < 8; ++r) {     // k-step: output row r of the tile, 16 pixels
       // A (m = channels, k = pixels): wide_s[px][cw] read transposed
@@ -544,8 +556,8 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const ThinWgradPar
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
         const int px = r * 16 + (lane & 7) + ((lane >> 4) << 3);
-        const int col = mh * 64 + mi * 16 + ((lane >> 3) & 1) * 8;
-        ldmatrix_x4_trans(a[mi], wide_a + (px * wstride + col) * 2);
+        const int chunk = mi * 2 + ((lane >> 3) & 1);          // 16-byte chunk of the 64-channel row (128B swizzle)
+        ldmatrix_x4_trans(a[mi], wide_a + px * 128 + ((chunk ^ (px & 7)) << 4));
       }
       // B (k = pixels, n = (tap, slot)): patch pixels (2r + kh, 2*ox + kw) are the rows
 #pragma unroll
@@ -1028,7 +1040,16 @@ int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_
   p.total_tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
   GAP_CHECK_ARG(p.total_tiles < (1ll << 31), "gap_thin_conv_wgrad: too many tiles");
   const int ct = src1 ? 8 : 4;
-  const size_t smem = 2 * 18 * 34 * ct * 2 + 2 * 128 * static_cast<size_t>(cw + 8) * 2;
+  {
+    const uint64_t ld_b = static_cast<uint64_t>(ld_w) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(cw), static_cast<uint64_t>(p.ow), static_cast<uint64_t>(p.oh),
+                        static_cast<uint64_t>(n)};
+    uint64_t strides[3] = {ld_b, ld_b * p.ow, ld_b * p.ow * p.oh};
+    uint32_t box[4] = {64, 16, 8, 1};
+    int rc = encode_tmap_bf16(&p.tm_wide, wide, 4, dims, strides, box, nullptr, true);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + 2 * static_cast<size_t>(cw / 64) * 16384 + 2 * 18 * 34 * ct * 2 + 16;
   const int threads = 128 * (cw / 64);
   const int grid = static_cast<int>(std::min<long long>(p.total_tiles, static_cast<long long>(debug_get("thin_wgrad_ctas_per_sm", 3)) * sm_count()));
   if (ct == 8) {
