@@ -114,9 +114,23 @@ __device__ __forceinline__ float gather_dlogit(const float* __restrict__ dlog, l
 // CTA = 128 input pixels; warp = one 64-channel range, its 8 B fragments held in registers.
 // dynamic smem: wT[c][24] | us[128][24] | out_s[8][16][72]   (bf16)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cout1_dgrad_kernel(const float* __restrict__ dlog, int ih, int iw, int oh, int ow,
+// BWD: the copy-out also applies the activation backward of the layer below (d = (y*scale+shift > 0) ? g : slope*g,
+// the LeakyReLU after BatchNorm, models.py:239-240) and accumulates that layer's BatchNorm-backward sums
+// [sum d | sum d*y] (of the stored bf16 d) -- the same contract as the tcgen05 dgrad epilogue, so the separate
+// reduce pass over y and g disappears.  Needs c <= 512 (one 64-channel range per warp).
+struct Cout1Bwd {
+  const bf16* y;
+  long long ld_y;
+  const float* scale;
+  const float* shift;
+  float slope;
+  double* sums;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __restrict__ dlog, int ih, int iw, int oh, int ow,
                                                           int pad, long long npix, const bf16* __restrict__ w, int c,
-                                                          bf16* __restrict__ gx, long long ld_gx) {
+                                                          bf16* __restrict__ gx, long long ld_gx, const Cout1Bwd b) {
   extern __shared__ __align__(16) uint8_t dsm[];
   bf16* wT = reinterpret_cast<bf16*>(dsm);
   bf16* us = wT + static_cast<size_t>(c) * 24;
@@ -129,6 +143,17 @@ __global__ void __launch_bounds__(256) cout1_dgrad_kernel(const float* __restric
   }
   const uint32_t us_a = smem_u32(us);
   bf16* my_out = out_s + warp * 16 * 72;
+  // BWD: this lane always copies out the same 8 channels (warp's 64-channel range, segment lane & 7)
+  float bsc[8], bsh[8], s1[8], s2[8];
+  if (BWD) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = warp * 64 + (lane & 7) * 8 + j;
+      bsc[j] = ch < c ? __ldg(b.scale + ch) : 0.f;
+      bsh[j] = ch < c ? __ldg(b.shift + ch) : 0.f;
+      s1[j] = s2[j] = 0.f;
+    }
+  }
   for (long long tile = blockIdx.x; tile * 128 < npix; tile += gridDim.x) {
     __syncthreads();  // wT ready (first pass) / previous tile's us consumed
 #pragma unroll
@@ -147,6 +172,18 @@ __global__ void __launch_bounds__(256) cout1_dgrad_kernel(const float* __restric
         bfr[nt][1] = *reinterpret_cast<const uint32_t*>(row + 2 * t + 8);
       }
       for (int mt = 0; mt < 8; ++mt) {
+        // BWD: request this 16-pixel slab's y values before the MMAs (they are independent of them): the copy-out
+        // below was latency-bound on these loads
+        uint4 yq[4];
+        if (BWD) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int idx = lane + i * 32, r = idx >> 3, seg = idx & 7;
+            const long long pix = tile * 128 + mt * 16 + r;
+            yq[i] = pix < npix ? __ldg(reinterpret_cast<const uint4*>(b.y + pix * b.ld_y + n0 + seg * 8))
+                               : make_uint4(0, 0, 0, 0);
+          }
+        }
         uint32_t a[4];
         lda_16x16(a, us_a + mt * 16 * 48, 48, lane);
 #pragma unroll
@@ -161,10 +198,56 @@ __global__ void __launch_bounds__(256) cout1_dgrad_kernel(const float* __restric
         for (int i = 0; i < 4; ++i) {
           const int idx = lane + i * 32, r = idx >> 3, seg = idx & 7;
           const long long pix = tile * 128 + mt * 16 + r;
-          if (pix < npix)
-            *reinterpret_cast<uint4*>(gx + pix * ld_gx + n0 + seg * 8) = *reinterpret_cast<const uint4*>(my_out + r * 72 + seg * 8);
+          if (pix < npix) {
+            uint4 v = *reinterpret_cast<const uint4*>(my_out + r * 72 + seg * 8);
+            if (BWD) {
+              const uint4 yv = yq[i];
+              const uint32_t gw[4] = {v.x, v.y, v.z, v.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int j2 = 0; j2 < 4; ++j2) {
+                float d[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j = 2 * j2 + e;
+                  const float gj = e ? bf16_hi(gw[j2]) : bf16_lo(gw[j2]);
+                  const float yj = e ? bf16_hi(yw[j2]) : bf16_lo(yw[j2]);
+                  d[e] = fmaf(yj, bsc[j], bsh[j]) > 0.f ? gj : b.slope * gj;
+                }
+                pk[j2] = pack_bf16x2(d[0], d[1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {      // sums of the stored (bf16-rounded) values
+                  const int j = 2 * j2 + e;
+                  const float dj = e ? bf16_hi(pk[j2]) : bf16_lo(pk[j2]);
+                  const float yj = e ? bf16_hi(yw[j2]) : bf16_lo(yw[j2]);
+                  s1[j] += dj;
+                  s2[j] = fmaf(dj, yj, s2[j]);
+                }
+              }
+              v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            *reinterpret_cast<uint4*>(gx + pix * ld_gx + n0 + seg * 8) = v;
+          }
         }
         __syncwarp();
+      }
+    }
+  }
+  if (BWD) {
+    // lanes l, l+8, l+16, l+24 hold the same channels
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+    }
+    if (lane < 8 && warp * 64 < c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = warp * 64 + lane * 8 + j;
+        atomicAdd(b.sums + ch, static_cast<double>(s1[j]));
+        atomicAdd(b.sums + c + ch, static_cast<double>(s2[j]));
       }
     }
   }
@@ -876,31 +959,56 @@ int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c
   return 0;
 }
 
-int gap_cout1_conv_dgrad(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
-                         int64_t ld_gx, int ih, int iw, void* stream) {
+static int cout1_dgrad_launch(const char* who, const float* dlogits, int n, int oh, int ow, const void* w, int ksize,
+                              int pad, int c, void* gx, int64_t ld_gx, int ih, int iw, const Cout1Bwd* bwd, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GAP_CHECK_ARG(dlogits && w && gx && n > 0 && oh > 0 && ow > 0 && ih > 0 && iw > 0, "gap_cout1_conv_dgrad: bad arguments");
+  if (!(dlogits && w && gx && n > 0 && oh > 0 && ow > 0 && ih > 0 && iw > 0)) {
+    set_error("%s: bad arguments", who);
+    return GAP_ERR_BAD_ARG;
+  }
   if (ksize != 4 || c % 64 != 0 || c <= 0 || ld_gx % 8 != 0 || (reinterpret_cast<uintptr_t>(gx) & 15)) {
-    set_error("gap_cout1_conv_dgrad: needs ksize 4, channels %% 64 == 0 and 16-byte aligned rows");
+    set_error("%s: needs ksize 4, channels %% 64 == 0 and 16-byte aligned rows", who);
     return GAP_ERR_UNSUPPORTED;
   }
   const long long npix = static_cast<long long>(n) * ih * iw;
   const size_t smem = (static_cast<size_t>(c) * 24 + 128 * 24 + 8 * 16 * 72) * sizeof(bf16);
   if (smem > 200 * 1024) {
-    set_error("gap_cout1_conv_dgrad: %d channels do not fit shared memory", c);
+    set_error("%s: %d channels do not fit shared memory", who, c);
     return GAP_ERR_UNSUPPORTED;
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    GAP_CUDA(cudaFuncSetAttribute(cout1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
+  static size_t attr[2] = {0, 0};
+  const int v = bwd ? 1 : 0;
+  if (smem > attr[v]) {
+    if (bwd)
+      GAP_CUDA(cudaFuncSetAttribute(cout1_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    else
+      GAP_CUDA(cudaFuncSetAttribute(cout1_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr[v] = smem;
   }
   const int tiles = static_cast<int>((npix + 127) / 128);
-  cout1_dgrad_kernel<<<std::min(tiles, 2 * sm_count()), 256, smem, st>>>(dlogits, ih, iw, oh, ow, pad, npix,
-                                                                         static_cast<const bf16*>(w), c,
-                                                                         static_cast<bf16*>(gx), ld_gx);
+  const int grid = std::min(tiles, 2 * sm_count());
+  if (bwd)
+    cout1_dgrad_kernel<true><<<grid, 256, smem, st>>>(dlogits, ih, iw, oh, ow, pad, npix, static_cast<const bf16*>(w), c,
+                                                       static_cast<bf16*>(gx), ld_gx, *bwd);
+  else
+    cout1_dgrad_kernel<false><<<grid, 256, smem, st>>>(dlogits, ih, iw, oh, ow, pad, npix, static_cast<const bf16*>(w), c,
+                                                        static_cast<bf16*>(gx), ld_gx, Cout1Bwd{});
   GAP_CUDA(cudaGetLastError());
   return 0;
+}
+
+int gap_cout1_conv_dgrad(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
+                         int64_t ld_gx, int ih, int iw, void* stream) {
+  return cout1_dgrad_launch("gap_cout1_conv_dgrad", dlogits, n, oh, ow, w, ksize, pad, c, gx, ld_gx, ih, iw, nullptr, stream);
+}
+
+int gap_cout1_conv_dgrad_bwd(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
+                             int64_t ld_gx, int ih, int iw, const void* y, int64_t ld_y, const float* scale,
+                             const float* shift, float slope, double* sums, void* stream) {
+  GAP_CHECK_ARG(y && scale && shift && sums && c <= 512 && ld_y % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "gap_cout1_conv_dgrad_bwd: needs y / scale / shift / sums, c <= 512 and 16-byte aligned y rows");
+  const Cout1Bwd b{static_cast<const bf16*>(y), ld_y, scale, shift, slope, sums};
+  return cout1_dgrad_launch("gap_cout1_conv_dgrad_bwd", dlogits, n, oh, ow, w, ksize, pad, c, gx, ld_gx, ih, iw, &b, stream);
 }
 
 int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void* x, int64_t ld_x, int ih, int iw, int c,

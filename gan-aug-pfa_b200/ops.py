@@ -334,13 +334,26 @@ def cout1_conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
                                              _ptr(logits), _stream()), "gap_cout1_conv_fwd")
 
 
-def cout1_conv_dgrad(dlogits: torch.Tensor, w: torch.Tensor, gx: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:
+def cout1_conv_dgrad(dlogits: torch.Tensor, w: torch.Tensor, gx: torch.Tensor, ksize: int = 4, pad: int = 1,
+                     bwd: Optional[dict] = None) -> None:
+    """Input gradient of Conv2d(C -> 1, k4, s1).  ``bwd`` = dict(y, scale, shift, slope, sums) fuses the activation
+    backward of the layer below and its BatchNorm-backward sums into the kernel (see gap_cout1_conv_dgrad_bwd)."""
     n, ih, iw, c, ld = _nhwc_view(gx)
     oh, ow = ih + 2 * pad - ksize + 1, iw + 2 * pad - ksize + 1
     if dlogits.dtype != torch.float32 or dlogits.numel() != n * oh * ow:
         raise ValueError("dlogits must be fp32 [n, oh, ow]")
-    _lib.check(_lib.lib().gap_cout1_conv_dgrad(_ptr(dlogits), n, oh, ow, _ptr(w), ksize, pad, c, _ptr(gx), ld, ih, iw,
-                                               _stream()), "gap_cout1_conv_dgrad")
+    if bwd is None:
+        _lib.check(_lib.lib().gap_cout1_conv_dgrad(_ptr(dlogits), n, oh, ow, _ptr(w), ksize, pad, c, _ptr(gx), ld, ih, iw,
+                                                   _stream()), "gap_cout1_conv_dgrad")
+        return
+    y = bwd["y"]
+    yn, yh, yw, yc, yld = _nhwc_view(y)
+    if (yn, yh, yw, yc) != (n, ih, iw, c) or bwd["sums"].dtype != torch.float64 or bwd["sums"].numel() != 2 * c:
+        raise ValueError("bwd y must match gx and sums must be fp64 [2c]")
+    _lib.check(_lib.lib().gap_cout1_conv_dgrad_bwd(_ptr(dlogits), n, oh, ow, _ptr(w), ksize, pad, c, _ptr(gx), ld, ih, iw,
+                                                   _ptr(y), yld, _ptr(bwd["scale"]), _ptr(bwd["shift"]),
+                                                   float(bwd.get("slope", 0.0)), _ptr(bwd["sums"]), _stream()),
+               "gap_cout1_conv_dgrad_bwd")
 
 
 def cout1_conv_wgrad(dlogits: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:

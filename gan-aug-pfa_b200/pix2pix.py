@@ -722,12 +722,12 @@ class DiscriminatorEngine(_Net):
         if wgrad:
             self._fork_wgrad(lambda: ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1],
                                                           self.store.seg(g, self.k_conv[last] + ".weight")))
-        ops.cout1_conv_dgrad(self.dlogits, self.w_fwd[last].view(-1), self.gH[last - 1])
+        # the Cout = 1 dgrad kernel applies the LeakyReLU backward of the last BatchNorm layer and accumulates its sums
+        lb = self.bn[last - 1]
+        ops.cout1_conv_dgrad(self.dlogits, self.w_fwd[last].view(-1), self.gH[last - 1],
+                             bwd=dict(y=self.y[last - 1], scale=lb.scale, shift=lb.shift, slope=0.2, sums=lb.sums))
         for k in range(last - 1, 0, -1):
-            if k == last - 1:   # gH[k] comes from the Cout=1 kernel: classic reduce + apply
-                self._bn_backward(self.bn[k], self.y[k], self.gH[k], None, 0.2, self.dy[k], param_grads=wgrad)
-            else:
-                self._bn_backward_fused(self.bn[k], self.y[k], self.gH[k], self.dy[k], param_grads=wgrad)
+            self._bn_backward_fused(self.bn[k], self.y[k], self.gH[k], self.dy[k], param_grads=wgrad)
             s = self.stride(k)
             if wgrad:
                 self._fork_wgrad(lambda k=k, s=s: ops.conv_wgrad(

@@ -213,6 +213,12 @@ int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c
                        int ksize, int pad, float* z_ws, float* logits, void* stream);
 int gap_cout1_conv_dgrad(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
                          int64_t ld_gx, int ih, int iw, void* stream);
+/* The same dgrad with the activation backward of the layer below and its BatchNorm-backward sums fused into the
+ * copy-out: gx = (y*scale+shift > 0) ? g : slope*g;  sums[0..c) += sum gx, sums[c..2c) += sum gx*y (fp64, of the stored
+ * bf16 values) -- the contract of gap_conv_gemm's bwd_* epilogue, finished by gap_bn_bwd_finalize + gap_bn_bwd_apply. */
+int gap_cout1_conv_dgrad_bwd(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
+                             int64_t ld_gx, int ih, int iw, const void* y, int64_t ld_y, const float* scale,
+                             const float* shift, float slope, double* sums, void* stream);
 int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void* x, int64_t ld_x, int ih, int iw, int c,
                          int ksize, int pad, float* dw, void* stream);
 

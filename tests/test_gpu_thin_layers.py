@@ -50,6 +50,32 @@ def test_cout1_conv_forward_and_gradients(n, c, h):
     assert rel(dw.cpu().view(4, 4, c), 2 * wr.grad[0].permute(1, 2, 0)) < 6e-3
 
 
+def test_cout1_conv_dgrad_with_fused_activation_backward_and_bn_sums():
+    """gap_cout1_conv_dgrad_bwd == gap_cout1_conv_dgrad followed by the LeakyReLU-after-BatchNorm mask and the
+    [sum d, sum d*y] reduction (bit-exact on the stored tensor: both round g to bf16 before masking)."""
+    g = torch.Generator().manual_seed(21)
+    n, c, h, slope = 3, 512, 9, 0.2
+    w = (torch.randn(1, c, 4, 4, generator=g) / 64).to(torch.bfloat16)
+    wd = w.permute(0, 2, 3, 1).reshape(-1).contiguous().to(DEV)
+    dl = (torch.randn(n, h - 1, h - 1, generator=g) * 0.05).to(DEV)
+    y = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16).to(DEV)
+    scale = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(c, generator=g) * 0.3).to(DEV)
+    gx = torch.empty(n, h, h, c, device=DEV, dtype=torch.bfloat16)
+    ops.cout1_conv_dgrad(dl, wd, gx)
+    yh = y.float() * scale + shift
+    d_ref = torch.where(yh > 0, gx.float(), (slope * gx.float())).to(torch.bfloat16)
+    out = torch.full_like(gx, float("nan"))
+    sums = torch.zeros(2 * c, device=DEV, dtype=torch.float64)
+    ops.cout1_conv_dgrad(dl, wd, out, bwd=dict(y=y, scale=scale, shift=shift, slope=slope, sums=sums))
+    assert torch.equal(out, d_ref)
+    dd = d_ref.double()
+    s1, s2 = dd.sum((0, 1, 2)), (dd * y.double()).sum((0, 1, 2))
+    denom = (dd ** 2).sum((0, 1, 2)).sqrt().max()
+    assert float((sums[:c] - s1).abs().max() / denom) < 1e-5
+    assert float((sums[c:] - s2).abs().max() / denom) < 1e-5
+
+
 def test_cout1_conv_channel_slice_input():
     """x may be a channel slice of a wider NHWC buffer (pixel stride > channels)."""
     g = torch.Generator().manual_seed(3)
