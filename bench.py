@@ -220,11 +220,35 @@ def run_ours(args) -> None:
             return float(t.item())
         return ms
 
-    # single GPU: the iteration's ~175 launches are replayed from one CUDA graph (same kernels, no launch gaps)
-    step_fn = tr.train_step_graphed if world == 1 else tr.train_step
-    # ---- device-resident timing
+    # Single GPU: the iteration's ~175 launches can be replayed from one CUDA graph (same kernels, no launch gaps) or
+    # launched eagerly (three streams; the host enqueues a step faster than the GPU runs it).  Which is faster depends
+    # on the host: calibrate both during warm-up (untimed, interleaved so clock drift cancels) and keep the faster.
+    step_fn, use_graph = tr.train_step, False
     for i in range(args.warmup):
         step_fn(*devb[i % n_batches])
+    if world == 1 and args.step_mode != "eager":
+        use_graph = True
+        if args.step_mode == "auto":
+            def block(fn, n=5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for i in range(n):
+                    fn(*devb[i % n_batches])
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b)
+            block(tr.train_step_graphed, 3)                      # capture + first replays
+            t_e = t_g = 0.0
+            for _ in range(3):
+                t_e += block(tr.train_step)
+                t_g += block(tr.train_step_graphed)
+            use_graph = t_g < t_e
+        if use_graph:
+            step_fn = tr.train_step_graphed
+            for i in range(3):
+                step_fn(*devb[i % n_batches])
+    # ---- device-resident timing
     barrier()
     _lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -236,7 +260,7 @@ def run_ours(args) -> None:
         e1.record()
         barrier()
     launches = _lib.LAUNCHES
-    if world == 1:
+    if use_graph:
         # graph replays do not pass through the Python launchers: count the launches of one eager iteration
         _lib.LAUNCHES = 0
         tr.train_step(*devb[0])
@@ -281,13 +305,19 @@ def run_ours(args) -> None:
     e2e_value = world * N * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel roofline: time every GEMM launch of a few steps with CUDA events
+    # (side streams serialised for these steps: with the generator forward / the wgrads overlapping other kernels a
+    # launch's event-to-event time would include the work it shares the GPU with)
     prof_steps = min(2, args.steps)
+    saved = (tr.overlap_g_fwd, tr.G.overlap_wgrad, tr.D.overlap_wgrad)
+    tr.overlap_g_fwd = tr.G.overlap_wgrad = tr.D.overlap_wgrad = False
+    tr.train_step(*devb[0])
     ops.PROFILE = []
     for i in range(prof_steps):
         tr.train_step(*devb[i % n_batches])
     torch.cuda.synchronize()
     prof = ops.PROFILE
     ops.PROFILE = None
+    tr.overlap_g_fwd, tr.G.overlap_wgrad, tr.D.overlap_wgrad = saved
     agg: dict = {}
     for name, flops, ev0, ev1 in prof:
         d = agg.setdefault(name, [0.0, 0.0, 0])
@@ -322,7 +352,7 @@ def run_ours(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "pix2pix_gan_train_b64_256x256", "batch_per_gpu": N, "image": f"{HW}x{HW}x3",
-                       "parallelism": f"dp{world}", "cuda_graph": world == 1, "inputs": args.inputs, "l2": "per-step working set (several GB of activations) >> 126 MB L2; "
+                       "parallelism": f"dp{world}", "cuda_graph": use_graph, "inputs": args.inputs, "l2": "per-step working set (several GB of activations) >> 126 MB L2; "
                        "two alternating input batches", "algorithmic_gflop_per_image": GFLOP_PER_IMG},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]),
@@ -498,6 +528,9 @@ def main() -> None:
                     help="pix2pix_train = the BASELINE.json metric (default); gen_infer = generate_synthetic_data.py's "
                          "generator forward at batch 256 (config 4); siamese_train = train.py's step at 512x512, batch 4 "
                          "(config 5, CombinedLoss)")
+    ap.add_argument("--step-mode", default="auto", choices=["auto", "graph", "eager"],
+                    help="single-GPU pix2pix_train: CUDA-graph replay, eager launches, or (default) whichever measures "
+                         "faster in an untimed calibration after the warm-up")
     ap.add_argument("--inputs", default="f32", choices=["f32", "u8"],
                     help="pix2pix_train only: host batches as fp32 NCHW in [-1,1] (the reference DataLoader's output, "
                          "default) or raw uint8 HWC images normalised on the device")

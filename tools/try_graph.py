@@ -1,4 +1,4 @@
-"""Eager vs CUDA-graph replay, wgrad side-stream overlap on/off (run under gpurun)."""
+"""Eager vs CUDA-graph replay of the training step, interleaved blocks (thermal drift cancels) (run under gpurun)."""
 import sys
 from pathlib import Path
 import torch
@@ -12,9 +12,7 @@ A = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
 B = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
 
 
-def timeit(fn, iters=15):
-    for _ in range(4):
-        fn()
+def timeit(fn, iters=20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -25,12 +23,14 @@ def timeit(fn, iters=15):
     return e0.elapsed_time(e1) / iters
 
 
-for overlap in (True, False):
-    torch.manual_seed(0)
-    tr = Pix2PixTrainer(dev)
-    tr.G.overlap_wgrad = tr.D.overlap_wgrad = overlap
-    t_e = timeit(lambda: tr.train_step(A, B))
-    t_g = timeit(lambda: tr.train_step_graphed(A, B))
-    t_e2 = timeit(lambda: tr.train_step(A, B))
-    print(f"overlap_wgrad={overlap}: eager {t_e:.3f} ms  graph {t_g:.3f} ms  eager again {t_e2:.3f} ms", flush=True)
-    del tr
+torch.manual_seed(0)
+tr = Pix2PixTrainer(dev)
+for _ in range(5):
+    tr.train_step(A, B)
+    tr.train_step_graphed(A, B)
+te, tg = [], []
+for rnd in range(6):
+    te.append(timeit(lambda: tr.train_step(A, B)))
+    tg.append(timeit(lambda: tr.train_step_graphed(A, B)))
+print("eager:", " ".join(f"{t:.3f}" for t in te), f"  mean {sum(te) / len(te):.3f} ms")
+print("graph:", " ".join(f"{t:.3f}" for t in tg), f"  mean {sum(tg) / len(tg):.3f} ms")
