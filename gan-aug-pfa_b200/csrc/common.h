@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <utility>
+#include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -20,6 +22,27 @@ int debug_get(const char* key, int dflt);
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
                      bool swizzle128);
+
+// Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_wait / pdl_trigger): the kernel's prologue
+// (barrier init, TMEM allocation, descriptor prefetch, launch latency) overlaps the tail of the previous kernel in the
+// stream.  Only for kernels that call pdl_wait() before their first global-memory access.
+// MEASURED (tools/ab_knob.py pdl 0 1, ABBA-ordered blocks of the eager training step): 8.47 ms without, 8.66 ms with
+// the attribute -- early-scheduled dependents disturb the balance between the three streams of the step -- so it is
+// OFF unless gap_debug_set("pdl", 1).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = debug_get("pdl", 0) != 0 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 #define GAP_CHECK_ARG(cond, ...)      \
   do {                                \

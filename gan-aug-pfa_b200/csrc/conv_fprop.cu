@@ -268,6 +268,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // the next kernel's CTAs may be scheduled as SMs drain; they block in their own pdl_wait()
+  pdl_wait();      // everything above overlapped the previous kernel; its results are visible from here on
 
   const int BW = 1 << p.log_bw, BH = 1 << p.log_bh;
   const int BNI = kBlockM >> (p.log_bw + p.log_bh);
@@ -1015,7 +1017,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   }
   const int grid = std::min(p.total_tiles, sms);
   if (splits > 1) {
-    conv_fprop_kernel<2><<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+    GAP_CUDA(launch_pdl(conv_fprop_kernel<2>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
     GAP_CUDA(cudaGetLastError());
     const long long pixels = static_cast<long long>(a->n) * a->oh * a->ow;
     const int n8 = (a->n_out + 7) / 8;
@@ -1031,9 +1033,9 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     return 0;
   }
   if (bwd)
-    conv_fprop_kernel<1><<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+    GAP_CUDA(launch_pdl(conv_fprop_kernel<1>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
   else
-    conv_fprop_kernel<0><<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+    GAP_CUDA(launch_pdl(conv_fprop_kernel<0>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

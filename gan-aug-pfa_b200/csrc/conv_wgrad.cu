@@ -102,6 +102,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();      // the prologue above overlapped the previous kernel in the stream
 
   const int BW = 1 << p.log_bw, BH = 1 << p.log_bh;
   const int BNI = kWgBlockK >> (p.log_bw + p.log_bh);
@@ -400,7 +402,7 @@ extern "C" int gap_conv_wgrad(const gap_wgrad_args* a, void* stream_v) {
     attr_set = true;
   }
   const int grid = base * splits;
-  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(p);
+  GAP_CUDA(launch_pdl(conv_wgrad_kernel, dim3(grid), dim3(kWgThreads), smem_bytes, stream, p));
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

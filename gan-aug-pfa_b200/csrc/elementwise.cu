@@ -238,6 +238,8 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, int c, double cou
                                    float* __restrict__ running_var, long long* __restrict__ nbt,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c) {
     const double mean = stats[i] / count;
@@ -283,6 +285,8 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, long long ld_
                               const float* __restrict__ shift, long long pixels, int c,
                               __nv_bfloat16* __restrict__ o1, long long ld1, int act1,
                               __nv_bfloat16* __restrict__ o2, long long ld2, int act2) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = c >> 3;
   const long long total = pixels * cv;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -493,6 +497,8 @@ __device__ __forceinline__ void loadf8(const float* p, float (&v)[8]) {
 
 template <bool APPLY, bool RAW>
 __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = a.c >> 3;
   const bool ident = a.scale == nullptr;
   extern __shared__ float sm_red[];  // [blockDim.y][cv*8][2] for the reduce pass
@@ -634,6 +640,8 @@ __global__ void bn_param_grads_kernel(double* __restrict__ sums, int c, float* _
 __global__ void bn_bwd_finalize_kernel(double* __restrict__ raw, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, int c, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c) {
     const double s1 = raw[i], s2 = raw[c + i];
@@ -1012,9 +1020,9 @@ int gap_bn_finalize(double* stats, int c, double count, const float* gamma, cons
                     float momentum, int repeat, float* running_mean, float* running_var, int64_t* nbt,
                     float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
   GAP_CHECK_ARG(stats && scale && shift && c > 0 && count > 0, "gap_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, c, count, gamma, beta, eps, momentum, repeat, running_mean, running_var,
-      reinterpret_cast<long long*>(nbt), scale, shift, save_mean, save_invstd);
+  GAP_CUDA(launch_pdl(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), stats, c,
+                      count, gamma, beta, eps, momentum, repeat, running_mean, running_var,
+                      reinterpret_cast<long long*>(nbt), scale, shift, save_mean, save_invstd));
   GAP_LAUNCH_CHECK();
   return 0;
 }
@@ -1036,9 +1044,10 @@ int gap_bn_act(const void* y, int64_t ld_y, const float* scale, const float* shi
     set_error("gap_bn_act: pixel strides must be multiples of 8");
     return GAP_ERR_ALIGNMENT;
   }
-  bn_act_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, pixels, c, static_cast<__nv_bfloat16*>(out1), ld1,
-      act1, static_cast<__nv_bfloat16*>(out2), ld2, act2);
+  GAP_CUDA(launch_pdl(bn_act_kernel, dim3(grid_for(pixels * (c / 8), 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                      static_cast<const __nv_bfloat16*>(y), static_cast<long long>(ld_y), scale, shift,
+                      static_cast<long long>(pixels), c, static_cast<__nv_bfloat16*>(out1), static_cast<long long>(ld1),
+                      act1, static_cast<__nv_bfloat16*>(out2), static_cast<long long>(ld2), act2));
   GAP_LAUNCH_CHECK();
   return 0;
 }
@@ -1072,9 +1081,9 @@ static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
   const long long slabs = (a.pixels + by - 1) / by;
   const int grid = static_cast<int>(slabs < 148 * 8 ? (slabs < 1 ? 1 : slabs) : 148 * 8);
   if (apply && a.raw_mode) {
-    bn_bwd_kernel<true, true><<<grid, block, 0, st>>>(a);
+    GAP_CUDA(launch_pdl(bn_bwd_kernel<true, true>, dim3(grid), block, 0, st, a));
   } else if (apply) {
-    bn_bwd_kernel<true, false><<<grid, block, 0, st>>>(a);
+    GAP_CUDA(launch_pdl(bn_bwd_kernel<true, false>, dim3(grid), block, 0, st, a));
   } else {
     const size_t smem = static_cast<size_t>(by) * a.c * 2 * sizeof(float);
     if (smem > 48 * 1024) {
@@ -1084,7 +1093,7 @@ static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
         set = true;
       }
     }
-    bn_bwd_kernel<false, false><<<grid, block, smem, st>>>(a);
+    GAP_CUDA(launch_pdl(bn_bwd_kernel<false, false>, dim3(grid), block, smem, st, a));
   }
   GAP_CUDA(cudaGetLastError());
   return 0;
@@ -1138,8 +1147,8 @@ int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* s
 int gap_bn_bwd_finalize(double* raw, const float* mean, const float* invstd, int c, float* dgamma, float* dbeta,
                         double* sums, void* stream) {
   GAP_CHECK_ARG(raw && mean && invstd && sums && c > 0, "gap_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(raw, mean, invstd, c, dgamma,
-                                                                                        dbeta, sums);
+  GAP_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), raw,
+                      mean, invstd, c, dgamma, dbeta, sums));
   GAP_LAUNCH_CHECK();
   return 0;
 }

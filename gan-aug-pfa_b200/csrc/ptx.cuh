@@ -239,6 +239,13 @@ __device__ __forceinline__ void ld_global_nc_32B(const void* src, uint4& lo, uin
                : "l"(src));
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; it must not touch global memory before pdl_wait() (which
+// returns once the predecessor grid has completed and flushed).  pdl_trigger() lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has issued it.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }

@@ -1,10 +1,13 @@
-"""Eager vs CUDA-graph replay of the training step, interleaved blocks (thermal drift cancels) (run under gpurun)."""
+"""Interleaved A/B of a gap_debug_set knob on the eager training step: python tools/ab_knob.py knob v0 v1 [rounds]"""
 import sys
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from gan_aug_pfa_b200 import _lib  # noqa: E402
 from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer  # noqa: E402
 
+knob, v0, v1 = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+rounds = int(sys.argv[4]) if len(sys.argv) > 4 else 6
 dev = torch.device("cuda:0")
 N = 64
 gen = torch.Generator().manual_seed(1234)
@@ -27,14 +30,11 @@ torch.manual_seed(0)
 tr = Pix2PixTrainer(dev)
 for _ in range(5):
     tr.train_step(A, B)
-    tr.train_step_graphed(A, B)
-te, tg = [], []
-for rnd in range(6):
-    if rnd % 2 == 0:      # ABBA order: drift cancels
-        te.append(timeit(lambda: tr.train_step(A, B)))
-        tg.append(timeit(lambda: tr.train_step_graphed(A, B)))
-    else:
-        tg.append(timeit(lambda: tr.train_step_graphed(A, B)))
-        te.append(timeit(lambda: tr.train_step(A, B)))
-print("eager:", " ".join(f"{t:.3f}" for t in te), f"  mean {sum(te) / len(te):.3f} ms")
-print("graph:", " ".join(f"{t:.3f}" for t in tg), f"  mean {sum(tg) / len(tg):.3f} ms")
+t = {v0: [], v1: []}
+for rnd in range(rounds):
+    for v in ((v0, v1) if rnd % 2 == 0 else (v1, v0)):      # ABBA order: drift cancels
+        _lib.debug_set(knob, v)
+        tr.train_step(A, B)
+        t[v].append(timeit(lambda: tr.train_step(A, B)))
+for v in (v0, v1):
+    print(f"{knob}={v}:", " ".join(f"{x:.3f}" for x in t[v]), f"  mean {sum(t[v]) / len(t[v]):.3f} ms")
