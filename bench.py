@@ -240,9 +240,13 @@ def run_ours(args) -> None:
                 return a.elapsed_time(b)
             block(tr.train_step_graphed, 3)                      # capture + first replays
             t_e = t_g = 0.0
-            for _ in range(3):
-                t_e += block(tr.train_step)
-                t_g += block(tr.train_step_graphed)
+            for r in range(4):                                   # ABBA order: clock drift cancels
+                if r % 2 == 0:
+                    t_e += block(tr.train_step)
+                    t_g += block(tr.train_step_graphed)
+                else:
+                    t_g += block(tr.train_step_graphed)
+                    t_e += block(tr.train_step)
             use_graph = t_g < t_e
         if use_graph:
             step_fn = tr.train_step_graphed

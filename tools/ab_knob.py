@@ -1,4 +1,5 @@
-"""Interleaved A/B of a gap_debug_set knob on the eager training step: python tools/ab_knob.py knob v0 v1 [rounds]"""
+"""Interleaved (ABBA) A/B on the eager training step of a gap_debug_set knob, or of a trainer / engine attribute when the
+name starts with "tr." (e.g. tr.overlap_g_fwd, tr.G.overlap_wgrad): python tools/ab_knob.py knob v0 v1 [rounds]"""
 import sys
 from pathlib import Path
 import torch
@@ -33,7 +34,14 @@ for _ in range(5):
 t = {v0: [], v1: []}
 for rnd in range(rounds):
     for v in ((v0, v1) if rnd % 2 == 0 else (v1, v0)):      # ABBA order: drift cancels
-        _lib.debug_set(knob, v)
+        if knob.startswith("tr."):
+            obj = tr
+            parts = knob.split(".")[1:]
+            for a in parts[:-1]:
+                obj = getattr(obj, a)
+            setattr(obj, parts[-1], bool(v))
+        else:
+            _lib.debug_set(knob, v)
         tr.train_step(A, B)
         t[v].append(timeit(lambda: tr.train_step(A, B)))
 for v in (v0, v1):
