@@ -1054,7 +1054,7 @@ int gap_bn_act(const void* y, int64_t ld_y, const float* scale, const float* shi
     return GAP_ERR_ALIGNMENT;
   }
   // 4 vectors per thread and sweep (U in the kernel)
-  GAP_CUDA(launch_pdl(bn_act_kernel, dim3(grid_even(pixels * (c / 8), 256 * 4, 148 * 16)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+  GAP_CUDA(launch_pdl(bn_act_kernel, dim3(grid_even(pixels * (c / 8), 256 * 4, 148 * debug_get("bn_act_bps", 4))), dim3(256), 0, static_cast<cudaStream_t>(stream),
                       static_cast<const __nv_bfloat16*>(y), static_cast<long long>(ld_y), scale, shift,
                       static_cast<long long>(pixels), c, static_cast<__nv_bfloat16*>(out1), static_cast<long long>(ld1),
                       act1, static_cast<__nv_bfloat16*>(out2), static_cast<long long>(ld2), act2));
@@ -1089,7 +1089,7 @@ static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
   if (by < 1) by = 1;
   dim3 block(bx, by);
   const long long slabs = (a.pixels + by - 1) / by;
-  const int grid = grid_even(slabs, 4, 148 * 8);   // 4 pixel slabs per block and sweep (U in the kernel)
+  const int grid = grid_even(slabs, 4, 148 * debug_get("bn_bwd_bps", 2));   // 4 pixel slabs per block and sweep (U in the kernel); resident blocks only
   if (apply && a.raw_mode) {
     GAP_CUDA(launch_pdl(bn_bwd_kernel<true, true>, dim3(grid), block, 0, st, a));
   } else if (apply) {
