@@ -52,6 +52,30 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
   }
 }
 
+// 3 channels into 4-slot pixels (the image inputs of both networks), 4 pixels per thread: three 16-byte plane loads and
+// one 32-byte store instead of 12 scalar loads and 12 two-byte stores (the scalar version ran at 2 TB/s).
+__global__ void nchw3_f32_to_nhwc4_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long hw4,
+                                               long long total4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw4, q = i - img * hw4;
+    const float4* base = reinterpret_cast<const float4*>(x) + img * 3 * hw4 + q;
+    const float4 r = __ldg(base), g = __ldg(base + hw4), b = __ldg(base + 2 * hw4);
+    uint4 lo, hi;
+    lo.x = pack_bf16x2(r.x, g.x);
+    lo.y = pack_bf16x2(b.x, 0.f);
+    lo.z = pack_bf16x2(r.y, g.y);
+    lo.w = pack_bf16x2(b.y, 0.f);
+    hi.x = pack_bf16x2(r.z, g.z);
+    hi.y = pack_bf16x2(b.z, 0.f);
+    hi.z = pack_bf16x2(r.w, g.w);
+    hi.w = pack_bf16x2(b.w, 0.f);
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = lo;
+    o[1] = hi;
+  }
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ x, float* __restrict__ out, int n, int c,
                                         long long hw, long long ld, int c_total, int c_off) {
@@ -926,6 +950,15 @@ int gap_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, int h, in
                               void* stream) {
   GAP_CHECK_ARG(x && out && n > 0 && c > 0 && c <= out_ld, "gap_nchw_f32_to_nhwc_bf16: bad arguments");
   const long long hw = static_cast<long long>(h) * w;
+  if (c == 3 && out_ld == 4 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // (slot 3 is written as zero, which is what the 4-slot image layout holds there anyway)
+    const long long total4 = n * hw / 4;
+    nchw3_f32_to_nhwc4_bf16_kernel<<<grid_even(total4, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<__nv_bfloat16*>(out), hw / 4, total4);
+    GAP_LAUNCH_CHECK();
+    return 0;
+  }
   nchw_f32_to_nhwc_bf16_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(out), n, c, hw, out_ld);
   GAP_LAUNCH_CHECK();

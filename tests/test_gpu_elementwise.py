@@ -273,3 +273,16 @@ def test_pack_plan_matches_single_tensor_pack():
     torch.cuda.synchronize()
     for a, b in zip(outs, refs):
         assert torch.equal(a.cpu().float(), b.cpu().float())
+
+
+@pytest.mark.parametrize("n,h,w,slots", [(2, 8, 12, 4), (1, 5, 7, 4), (3, 16, 16, 8)])
+def test_nchw_f32_to_nhwc_bf16_image_layouts(n, h, w, slots):
+    """fp32 NCHW images -> NHWC bf16 channel slots: the vectorised 3-into-4 path (h*w % 4 == 0), its scalar fallback
+    (odd sizes) and a wider pixel stride; unused slots stay zero."""
+    g = torch.Generator().manual_seed(n * h + w)
+    x = torch.rand(n, 3, h, w, generator=g) * 2 - 1
+    out = torch.zeros(n, h, w, slots, device=DEV, dtype=torch.bfloat16)
+    ops.nchw_to_nhwc_bf16(x.to(DEV), out)
+    ref = torch.zeros(n, h, w, slots, dtype=torch.bfloat16)
+    ref[..., :3] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(out.cpu(), ref)
