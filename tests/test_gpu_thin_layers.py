@@ -131,6 +131,8 @@ def _pack_thin(w, groups):
     (2, 32, 64, 64, 1, False, True),      # generator first conv: LeakyReLU + ReLU outputs (models.py:177,178,208)
     (3, 48, 32, 64, 2, True, False),      # discriminator first conv on cat(A, B) (models.py:223)
     (2, 20, 36, 128, 1, False, False),    # generator last ConvT seen from its dgrad; partial tiles
+    (1, 8, 8, 64, 1, False, True),        # image smaller than one tile: the TMA store box exceeds the tensor
+    (2, 4, 12, 64, 2, True, False),
     (1, 256, 256, 64, 2, True, False),
 ])
 def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
@@ -155,6 +157,7 @@ def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
     (2, 32, 64, 64, 1, False),       # generator first conv wgrad
     (3, 48, 32, 64, 2, True),        # discriminator first conv wgrad + bias grad
     (2, 20, 36, 128, 1, False),      # generator last ConvT wgrad (wide = its input); partial tiles
+    (1, 8, 8, 64, 1, False),         # image smaller than one tile (TMA box exceeds the tensor)
     (5, 64, 64, 64, 2, True),
 ])
 def test_thin_conv_wgrad(n, h, w, cw, groups, bias):
@@ -182,6 +185,8 @@ def test_thin_conv_wgrad(n, h, w, cw, groups, bias):
     (2, 16, 32, 128, True, "tanh"),     # generator last layer (models.py:184,186)
     (3, 24, 16, 64, False, "none"),     # discriminator first conv, input gradient
     (2, 10, 18, 64, True, "tanh"),      # partial tiles
+    (1, 4, 4, 128, True, "tanh"),       # input smaller than one halo tile (TMA box exceeds the tensor)
+    (2, 2, 6, 64, False, "none"),
 ])
 def test_thin_convT_fwd(n, ih, iw, cw, bias, act):
     g = torch.Generator().manual_seed(ih + cw)
