@@ -142,13 +142,15 @@ def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
     b = torch.randn(cw, generator=g) if bias else None
     ref = F.conv2d(torch.cat(xs, 1), wt, b, stride=2, padding=1)
     srcs = [_slots(x).to(DEV) for x in xs]
-    wide = torch.full((n, h // 2, w // 2, 2 * cw), float("nan"), device=DEV, dtype=torch.bfloat16)
+    guard = torch.full((n + 2, h // 2, w // 2, 2 * cw), float("nan"), device=DEV, dtype=torch.bfloat16)
+    wide = guard[1:-1]                                     # guard images before and after (TMA stores must clip)
     out1 = wide[..., :cw]                                  # a channel slot of a wider buffer
     out2 = torch.full((n, h // 2, w // 2, cw), float("nan"), device=DEV, dtype=torch.bfloat16) if two_out else None
     ops.thin_conv_fwd(srcs[0], srcs[1] if groups == 2 else None, _pack_thin(wt, groups).to(DEV),
                       b.to(DEV) if bias else None, out1, ops.ACT_LRELU, out2, ops.ACT_RELU)
     assert rel(out1.cpu().float(), nhwc(F.leaky_relu(ref, 0.2))) < 4e-3
     assert torch.isnan(wide[..., cw:].float()).all()       # the neighbouring slot is untouched
+    assert torch.isnan(guard[0].float()).all() and torch.isnan(guard[-1].float()).all()
     if two_out:
         assert rel(out2.cpu().float(), nhwc(F.relu(ref))) < 4e-3
 
