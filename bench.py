@@ -49,11 +49,51 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
+    _CHILD = r'''
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+uuid, idx = sys.argv[1], int(sys.argv[2])
+try:
+    h = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+while True:
+    try:
+        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1000.0, rs,
+          flush=True)
+    time.sleep(0.004)
+'''
+
     def __init__(self, index: int) -> None:
+        """Starts an NVML sampler in a child process right away (it needs ~1 s to come up and, unlike a thread, does not
+        compete with the launching thread for the GIL); `with sampler:` marks the window whose samples are kept."""
         self.index = index
         self.rows: list[list[str]] = []
         self._stop = threading.Event()
         self._t = None
+        self._t0 = self._t1 = 0.0
+        self._child = None
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+            self._child = subprocess.Popen([sys.executable, "-c", self._CHILD, uuid, str(index)], stdout=subprocess.PIPE,
+                                           stderr=subprocess.DEVNULL, text=True)
+            import atexit
+            atexit.register(self._kill_child)      # never leave the sampler behind, whatever happens to the run
+        except Exception:
+            self._child = None
+
+    def _kill_child(self) -> None:
+        c = self._child
+        if c is not None and c.poll() is None:
+            try:
+                c.kill()
+            except Exception:
+                pass
 
     def _run_nvml(self) -> bool:
         """In-process NVML sampling every 10 ms (the same counters nvidia-smi prints; one nvidia-smi invocation takes
@@ -100,13 +140,35 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
+        self._t0 = time.time()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
 
     def __exit__(self, *a):
+        self._t1 = time.time()
         self._stop.set()
         self._t.join(timeout=6)
+        if self._child is not None:
+            try:
+                self._child.terminate()
+                out, _ = self._child.communicate(timeout=5)
+            except Exception:
+                out = ""
+            rows = []
+            for line in out.splitlines():
+                f = line.split()
+                if len(f) != 5:
+                    continue
+                try:
+                    ts, sm, mx, pw, rs = float(f[0]), f[1], f[2], f[3], int(f[4])
+                except ValueError:
+                    continue
+                if self._t0 <= ts <= self._t1:
+                    act = lambda m: "Active" if rs & m else "Not Active"
+                    rows.append([sm, mx, pw, act(0x8), act(0x40), act(0x20), act(0x4)])
+            if len(rows) > len(self.rows):      # the child saw more of the window than the in-process thread
+                self.rows = rows
 
     def summary(self) -> dict:
         if not self.rows:
@@ -194,6 +256,7 @@ def run_ours(args) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    clock_sampler = ClockSampler(local)       # the child process needs a moment to come up: start it before the warm-up
     torch.manual_seed(0)
     tr = Pix2PixTrainer(dev, world=world)     # world > 1: bucketed NCCL all-reduce overlapped with the backward pass
     N = BATCH_PER_GPU
@@ -256,7 +319,7 @@ def run_ours(args) -> None:
     barrier()
     _lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with clock_sampler as clocks:
         barrier()
         e0.record()
         for i in range(args.steps):
@@ -382,6 +445,7 @@ def run_secondary(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    clock_sampler = ClockSampler(local)       # started early: the sampling child needs a moment to come up
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -483,7 +547,7 @@ def run_secondary(args) -> None:
     barrier()
     _lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with clock_sampler as clocks:
         barrier()
         e0.record()
         for i in range(args.steps):
