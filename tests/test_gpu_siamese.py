@@ -242,20 +242,7 @@ def test_native_train_step_combined_and_focal_dice():
     assert 0.0 < fd < 1.0
 
 
-def _ref_calculate_metrics(preds, targets, smooth=1e-6):
-    """evaluate.py:34-64 restated (the file itself imports matplotlib at module scope)."""
-    preds = (preds > 0.5).float().view(-1)
-    targets = targets.view(-1)
-    tp = (preds * targets).sum()
-    fp = ((1 - targets) * preds).sum()
-    fn = (targets * (1 - preds)).sum()
-    tn = ((1 - targets) * (1 - preds)).sum()
-    precision = (tp + smooth) / (tp + fp + smooth)
-    recall = (tp + smooth) / (tp + fn + smooth)
-    f1 = (2 * precision * recall + smooth) / (precision + recall + smooth)
-    union = preds.sum() + targets.sum() - tp
-    return {"accuracy": ((tp + tn + smooth) / (tp + tn + fp + fn + smooth)).item(), "precision": precision.item(),
-            "recall": recall.item(), "f1": f1.item(), "iou": ((tp + smooth) / (union + smooth)).item()}, (tp, fp, fn, tn)
+_ref_calculate_metrics = O.calculate_metrics      # evaluate.py:34-64 restated in the oracle
 
 
 @pytest.mark.parametrize("n,h,w", [(1, 7, 5), (3, 64, 64), (4, 512, 512)])

@@ -5,23 +5,10 @@ import pytest
 import torch
 
 from gan_aug_pfa_b200 import metrics
+from oracle import pix2pix_oracle as O
 
 
-def _calculate_metrics(preds, targets, smooth=1e-6):
-    """evaluate.py:34-64 restated (the file imports matplotlib at module scope, so it is not imported here)."""
-    preds = (preds > 0.5).float().view(-1)
-    targets = targets.view(-1)
-    tp = (preds * targets).sum()
-    fp = ((1 - targets) * preds).sum()
-    fn = (targets * (1 - preds)).sum()
-    tn = ((1 - targets) * (1 - preds)).sum()
-    precision = (tp + smooth) / (tp + fp + smooth)
-    recall = (tp + smooth) / (tp + fn + smooth)
-    f1 = (2 * precision * recall + smooth) / (precision + recall + smooth)
-    union = preds.sum() + targets.sum() - tp
-    out = {"accuracy": (tp + tn + smooth) / (tp + tn + fp + fn + smooth), "precision": precision, "recall": recall,
-           "f1": f1, "iou": (tp + smooth) / (union + smooth)}
-    return {k: v.item() for k, v in out.items()}, (int(tp), int(fp), int(fn), int(tn))
+_calculate_metrics = O.calculate_metrics
 
 
 @pytest.mark.parametrize("seed,p_pos,p_pred", [(0, 0.05, 0.07), (1, 0.5, 0.5), (2, 0.0, 0.1), (3, 0.2, 0.0), (4, 1.0, 1.0)])

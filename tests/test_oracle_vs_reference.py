@@ -128,3 +128,22 @@ def test_siamese_forward_and_losses(ref_models):
     assert abs(float(tr.CombinedLoss()(ref, lab)) - float(O.combined_loss(ref, lab))) < 1e-6
     fd = tr.FocalDiceLoss(beta=0.67, focal_gamma=1.79, focal_alpha=0.6, dice_smooth=1.96e-6)
     assert abs(float(fd(ref, lab)) - float(O.focal_dice_loss(ref, lab, 0.67, 1.79, 0.6, 1.96e-6))) < 1e-6
+
+
+def test_calculate_metrics_restatement_matches_the_reference_function():
+    """O.calculate_metrics == evaluate.py's own calculate_metrics.  Only that function is executed (extracted from the
+    file's AST): importing evaluate.py would create directories under /Users/... and needs matplotlib."""
+    import ast
+    tree = ast.parse((REF / "evaluate.py").read_text())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "calculate_metrics")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), str(REF / "evaluate.py"), "exec"), ns)
+    g = torch.Generator().manual_seed(0)
+    for p_pos, p_pred in ((0.05, 0.07), (0.5, 0.5), (0.0, 0.2), (0.3, 0.0), (1.0, 1.0)):
+        targets = (torch.rand(1, 48, 48, generator=g) < p_pos).float()
+        probs = torch.sigmoid(torch.randn(1, 1, 48, 48, generator=g) + (2.0 if p_pred >= 1.0 else -2.0 + 4 * p_pred))
+        ref = ns["calculate_metrics"](probs, targets)
+        got, _ = O.calculate_metrics(probs, targets)
+        assert set(got) == set(ref)
+        for k in ref:
+            assert got[k] == pytest.approx(ref[k], rel=1e-7, abs=1e-12), k
