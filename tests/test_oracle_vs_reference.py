@@ -147,3 +147,19 @@ def test_calculate_metrics_restatement_matches_the_reference_function():
         assert set(got) == set(ref)
         for k in ref:
             assert got[k] == pytest.approx(ref[k], rel=1e-7, abs=1e-12), k
+
+
+def test_uint8_normalisation_matches_the_reference_transforms():
+    """The device-side input pipeline (gap_u8_hwc_to_nhwc_bf16, gap_gen_out_bwd_u8) assumes
+    JointNormalize(JointToTensor(img)) == (uint8 / 255) * 2 - 1 in fp32, HWC -> CHW: check that against the reference's
+    own transform classes on a PIL image (dataset.py:21-36,155-159)."""
+    import numpy as np
+    from PIL import Image
+    ds = _load("dataset")
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (24, 40, 3), generator=g, dtype=torch.uint8)
+    img = Image.fromarray(u8.numpy(), mode="RGB")
+    sample = {"image1": img, "image2": img, "label": None}
+    sample = ds.JointNormalize()(ds.JointToTensor()(sample))
+    mine = ((u8.float() / 255.0) * 2.0 - 1.0).permute(2, 0, 1)
+    assert torch.equal(sample["image1"], mine) and torch.equal(sample["image2"], mine)
