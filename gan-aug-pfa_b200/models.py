@@ -64,15 +64,39 @@ class UnetSkipConnectionBlock(nn.Module):
 
 
 class _NativeModule(nn.Module):
-    """Shared engine management: lazily builds the native engine on the parameters' CUDA device,
-    aliases the BatchNorm buffers, and refreshes the engine's master weights when a Parameter changed."""
+    """Shared engine management.  The first CUDA forward builds the native engine and re-homes the module's state in
+    it: every Parameter whose GEMM-native master layout is a dense permutation of the torch layout becomes a strided
+    VIEW of the engine's flat fp32 master buffer (same shape, same values, `state_dict()` unchanged), so
+    `torch.optim.*.step()` updates the masters in place and the only per-step synchronisation left is the one-launch
+    bf16 operand re-pack; the BatchNorm buffers are aliased the other way round (the engine updates the module's
+    tensors).  The three zero-padded thin-layer weights stay ordinary Parameters and are copied (three tiny launches).
+
+    Staleness is detected through `Parameter._version` (bumped by every in-place op, i.e. by optimizers and
+    `load_state_dict`).  Writes through `p.data` do not bump it: call `module.sync()` after such edits."""
 
     _engine_obj = None
     _engine_key = None
     _versions = None
+    _copied = ()
 
     def _make_engine(self, device):
         raise NotImplementedError
+
+    def _adopt_parameters(self, eng) -> None:
+        copied = []
+        with torch.no_grad():
+            for name, q in self.named_parameters():
+                view = eng.param(name)
+                view.copy_(q)
+                if view.is_non_overlapping_and_dense():
+                    q.data = view              # same Parameter object (optimizers keep working), engine-owned storage
+                else:
+                    copied.append((name, q))
+        object.__setattr__(self, "_copied", tuple(copied))
+
+    def sync(self) -> None:
+        """Force the engine to re-read the parameters (needed only after edits through `.data`)."""
+        object.__setattr__(self, "_versions", None)
 
     def _engine(self):
         p = next(self.parameters())
@@ -80,38 +104,56 @@ class _NativeModule(nn.Module):
             raise RuntimeError(f"{type(self).__name__}: the native kernels need CUDA tensors; there is no CPU "
                                "fallback (move the module with .to('cuda'))")
         key = (p.device, tuple(id(b) for b in self.buffers()))
-        if self._engine_obj is None or self._engine_key != key:
+        eng = self._engine_obj
+        if eng is not None and self._engine_key == key:
+            # a .to() / .float() / manual re-assignment replaced parameter storage: adopt again
+            for name, q in self.named_parameters():
+                if q.data_ptr() != eng.param(name).data_ptr() and not any(q is c for _, c in self._copied):
+                    eng = None
+                    break
+        if eng is None or self._engine_key != key:
             eng = self._make_engine(p.device)
             sd = dict(self.named_buffers())
             for prefix, bn in eng.bns.items():          # alias: running stats are updated in place
                 bn.running_mean = sd[prefix + ".running_mean"]
                 bn.running_var = sd[prefix + ".running_var"]
                 bn.nbt = sd[prefix + ".num_batches_tracked"]
+            self._adopt_parameters(eng)
             object.__setattr__(self, "_engine_obj", eng)
             object.__setattr__(self, "_engine_key", key)
             object.__setattr__(self, "_versions", None)
-        eng = self._engine_obj
         versions = tuple(q._version for q in self.parameters())
         if versions != self._versions:
             with torch.no_grad():
-                for name, q in self.named_parameters():
+                for name, q in self._copied:
                     eng.param(name).copy_(q)
             eng.repack()
             object.__setattr__(self, "_versions", versions)
         eng.training = self.training
         return eng
 
+    def _grads_for_autograd(self, eng, names):
+        """Parameter gradients for autograd: ONE copy of the flat gradient buffer, handed out as strided views with the
+        parameters' own strides (so AccumulateGrad adopts them without another copy, and later backward passes, which
+        overwrite the engine's buffer, cannot disturb `p.grad`)."""
+        eng._join_wgrad()
+        flat = eng.store.g.clone()
+        return [eng.view(flat, name) for name in names]
+
 
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, *params):
+    def forward(ctx, module, x, grad_mode, *params):
         eng = module._engine()
         if x.requires_grad:
             raise NotImplementedError("gradient w.r.t. the generator input is not provided (the reference never needs it)")
         eng.forward(x.detach().contiguous().float())
         out = eng.output_nchw()
         ctx.module = module
-        ctx.snap = eng.detach_buffers() if any(p.requires_grad for p in params) else None
+        # under no_grad / for frozen parameters nothing is kept: the next forward reuses the activation buffers
+        # (grad_mode is sampled by the caller: inside Function.forward autograd is always off)
+        need = grad_mode and any(p.requires_grad for p in params)
+        ctx.snap = eng.detach_buffers() if need else None
         return out
 
     @staticmethod
@@ -122,9 +164,8 @@ class _GeneratorFn(torch.autograd.Function):
         eng.zero_grad()
         ops.tanh_bwd(gout.contiguous().float(), eng.fake_f32, eng.dpre)
         eng.backward()
-        eng._join_wgrad()
-        grads = [eng.grad(name).clone() for name, _ in module.named_parameters()]
-        return (None, None, *grads)
+        grads = module._grads_for_autograd(eng, [name for name, _ in module.named_parameters()])
+        return (None, None, None, *grads)
 
 
 class UNetGenerator(_NativeModule):
@@ -152,12 +193,12 @@ class UNetGenerator(_NativeModule):
         return GeneratorEngine(device, i, o, n, f, init=False, use_dropout=self._use_dropout)
 
     def forward(self, input):
-        return _GeneratorFn.apply(self, input, *self.parameters())
+        return _GeneratorFn.apply(self, input, torch.is_grad_enabled(), *self.parameters())
 
 
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, *params):
+    def forward(ctx, module, x, grad_mode, *params):
         eng = module._engine()
         n, c, h, w = x.shape
         xd = x.detach().contiguous().float()
@@ -169,7 +210,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         out = logits.permute(0, 3, 1, 2).clone()
         ctx.module = module
         ctx.shape = (n, h, w)
-        need = x.requires_grad or any(p.requires_grad for p in params)
+        need = grad_mode and (x.requires_grad or any(p.requires_grad for p in params))
         ctx.snap = eng.detach_buffers() if need else None
         ctx.x_grad = x.requires_grad
         return out
@@ -192,8 +233,9 @@ class _DiscriminatorFn(torch.autograd.Function):
             gx = torch.empty(n, 6, h, w, device=gout.device)
             ops.nhwc_to_nchw_f32(eng.dreal, gx, 3, 6, 0)
             ops.nhwc_to_nchw_f32(eng.dfake, gx, 3, 6, 3)
-        grads = [eng.grad(name).clone() if wgrad else None for name, _ in module.named_parameters()]
-        return (None, gx, *grads)
+        names = [name for name, _ in module.named_parameters()]
+        grads = module._grads_for_autograd(eng, names) if wgrad else [None] * len(names)
+        return (None, gx, None, *grads)
 
 
 class NLayerDiscriminator(_NativeModule):
@@ -223,7 +265,7 @@ class NLayerDiscriminator(_NativeModule):
         return DiscriminatorEngine(device, i, d, n, init=False)
 
     def forward(self, input):
-        return _DiscriminatorFn.apply(self, input, *self.parameters())
+        return _DiscriminatorFn.apply(self, input, torch.is_grad_enabled(), *self.parameters())
 
 
 # ================================================================================================
@@ -278,7 +320,7 @@ class _SiameseFn(torch.autograd.Function):
         eng.zero_grad()
         eng.dlogits.copy_(gout.reshape(ctx.shape))
         eng.backward()
-        grads = [eng.grad(name).clone() for name, _ in module.named_parameters()]
+        grads = module._grads_for_autograd(eng, [name for name, _ in module.named_parameters()])
         return (None, None, None, *grads)
 
 
