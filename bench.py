@@ -6,9 +6,9 @@ images/sec at 256^2").
 
 ours:       one process per GPU (torchrun for N > 1), batch 64 per GPU, 256x256 synthetic RGB pairs,
             bf16 tensor-core kernels from libgap_b200.so; prints ONE JSON line on rank 0.
-reference:  the CPU restatement of the reference's train_gan_one_epoch iteration (oracle/, a port of
-            train_gan.py:52-74 + models.py; the reference itself is pure Python and cannot travel to
-            the GPU box), timed on the host cores on a bounded sample of the same workload.
+reference:  the reference's own CPU implementation of the path — its unmodified models.py + train_gan.train_gan_one_epoch,
+            byte-compiled into oracle/_ref by oracle/stage_ref.py — timed on this box's host cores with every host
+            thread, same config (batch 64 per step), metric and unit.
 """
 from __future__ import annotations
 
@@ -182,71 +182,205 @@ while True:
                 "samples": len(self.rows), "power_w": pw[len(pw) // 2] if pw else None}
 
 
-def _cpu_baseline(seconds_budget: float = 20.0) -> dict:
-    """Oracle port of one train_gan_one_epoch iteration (batch 1, 256^2, fp32) on the host cores."""
-    from oracle import pix2pix_oracle as O
-    from gan_aug_pfa_b200 import spec as MI
-    torch.manual_seed(0)
-    sd_g, sd_d = MI.default_state_dicts()
-    og = O.AdamState(sd_g, O.param_names(sd_g), 1e-4, (0.5, 0.999))
-    od = O.AdamState(sd_d, O.param_names(sd_d), 1e-4, (0.5, 0.999))
-    gen = torch.Generator().manual_seed(1234)
-    A = torch.rand(1, 3, HW, HW, generator=gen) * 2 - 1
-    B = torch.rand(1, 3, HW, HW, generator=gen) * 2 - 1
-    O.gan_train_step(sd_g, sd_d, og, od, A, B)      # warm-up
+def _host_threads() -> int:
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _gan_config(world: int) -> dict:
+    """The workload description shared by both arms (the driver compares these)."""
+    return {"workload": "pix2pix_gan_train_b64_256x256", "batch_per_gpu": BATCH_PER_GPU, "image": f"{HW}x{HW}x3",
+            "parallelism": f"dp{world}", "algorithmic_gflop_per_image": GFLOP_PER_IMG,
+            "l2": "no flush needed: the per-step working set (several GB of activations) >> 126 MB L2, and two input "
+                  "batches alternate"}
+
+
+class ReferenceGanLoop:
+    """The reference's OWN iteration: `train_gan.train_gan_one_epoch` (train_gan.py:46-75) over its own
+    `models.UNetGenerator` / `NLayerDiscriminator` with `optim.Adam(1e-4, (0.5, 0.999))` (train_gan.py:138-141), loaded
+    from oracle/_ref (the unmodified reference, byte-compiled by oracle/stage_ref.py).  mode "fp32" = the reference as
+    it is; "bf16_cl" = the same loop under torch.autocast(bfloat16) with channels_last modules and inputs (the best
+    the existing library kernels offer).  `models` swaps in another implementation of the models.py surface (the
+    drop-in modules).  Falls back to the oracle port (kind "port") when oracle/_ref is not staged."""
+
+    def __init__(self, device, batch: int, mode: str = "fp32", models=None, tag: str = "ref") -> None:
+        from oracle import ref_loader
+        self.dev = torch.device(device)
+        self.mode = mode
+        self.batch = batch
+        g = torch.Generator().manual_seed(1234)
+        self.batches = []
+        for _ in range(2):
+            a = (torch.rand(batch, 3, HW, HW, generator=g) * 2 - 1).to(self.dev)
+            b = (torch.rand(batch, 3, HW, HW, generator=g) * 2 - 1).to(self.dev)
+            if mode == "bf16_cl":
+                a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+            self.batches.append({"image1": a, "image2": b})
+        torch.manual_seed(0)
+        if ref_loader.available():
+            self.kind = "reference"
+            ns = ref_loader.load(models=models, tag=tag)
+            ns.train_gan.DEVICE = self.dev          # configuration constant of the script (train_gan.py:25)
+            self.ns = ns
+            self.gen = ns.train_gan.UNetGenerator(input_nc=3, output_nc=3).to(self.dev)
+            self.disc = ns.train_gan.NLayerDiscriminator(input_nc=6).to(self.dev)
+            if mode == "bf16_cl":
+                self.gen = self.gen.to(memory_format=torch.channels_last)
+                self.disc = self.disc.to(memory_format=torch.channels_last)
+            self.opt_g = torch.optim.Adam(self.gen.parameters(), lr=1e-4, betas=(0.5, 0.999))
+            self.opt_d = torch.optim.Adam(self.disc.parameters(), lr=1e-4, betas=(0.5, 0.999))
+        else:
+            if models is not None or mode != "fp32":
+                raise FileNotFoundError("oracle/_ref is not staged")
+            from oracle import pix2pix_oracle as O
+            from gan_aug_pfa_b200 import spec as MI
+            self.kind = "port"
+            self.O = O
+            sd_g, sd_d = MI.default_state_dicts()
+            self.sd = tuple({k: v.to(self.dev) for k, v in sd.items()} for sd in (sd_g, sd_d))
+            self.opt = (O.AdamState(self.sd[0], O.param_names(self.sd[0]), 1e-4, (0.5, 0.999)),
+                        O.AdamState(self.sd[1], O.param_names(self.sd[1]), 1e-4, (0.5, 0.999)))
+
+    def step(self, i: int):
+        batch = self.batches[i % 2]
+        if self.kind == "port":
+            return self.O.gan_train_step(self.sd[0], self.sd[1], self.opt[0], self.opt[1], batch["image1"], batch["image2"])[:2]
+        if self.mode == "bf16_cl":
+            with torch.autocast(self.dev.type, dtype=torch.bfloat16):
+                return self.ns.train_gan.train_gan_one_epoch(self.gen, self.disc, [batch], self.opt_g, self.opt_d)
+        return self.ns.train_gan.train_gan_one_epoch(self.gen, self.disc, [batch], self.opt_g, self.opt_d)
+
+
+def _time_cpu_loop(loop: ReferenceGanLoop, steps: int, warmup: int, budget_s: float):
+    """Runs `warmup` untimed and up to `steps` timed iterations; stops early when the projected total exceeds
+    `budget_s` (each iteration is a full batch of the workload: ~7 TFLOP of fp32 on the host cores).  Returns
+    (images/s, seconds per step, steps executed)."""
+    t_w = time.perf_counter()
+    for i in range(warmup):
+        loop.step(i)
+    per = (time.perf_counter() - t_w) / max(1, warmup)
+    n_run = steps if warmup == 0 else max(1, min(steps, int(budget_s / max(per, 1e-9))))
     t0 = time.perf_counter()
-    it = 0
-    while True:
-        O.gan_train_step(sd_g, sd_d, og, od, A, B)
-        it += 1
-        el = time.perf_counter() - t0
-        if el > seconds_budget or it >= 40:
+    done = 0
+    for i in range(n_run):
+        loop.step(i)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
             break
-    return {"value": it / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{it} iterations of batch 1 at 256x256 fp32 (oracle port of train_gan.py:52-74), "
-                      f"{el:.1f} s on {os.cpu_count()} host cpus"}
+    el = time.perf_counter() - t0
+    return done * loop.batch / el, el / done, done
+
+
+def _cpu_baseline(budget_s: float = 25.0) -> dict:
+    """The CPU arm on a bounded sample: the unmodified reference loop (oracle/_ref) at the workload's own batch (64),
+    fp32, every host thread: one untimed iteration, then as many timed ones as fit in ~25 s."""
+    threads = _host_threads()
+    torch.set_num_threads(threads)
+    loop = ReferenceGanLoop("cpu", BATCH_PER_GPU, "fp32", tag="cpubase")
+    val, per, done = _time_cpu_loop(loop, steps=8, warmup=1, budget_s=budget_s)
+    return {"value": val, "unit": UNIT, "cores": threads, "kind": loop.kind,
+            "sample": f"{done} iteration(s) of train_gan_one_epoch at batch {BATCH_PER_GPU}, 256x256, fp32 after 1 warm-up "
+                      f"({per:.1f} s each) on {threads} host threads"}
 
 
 def run_reference(args) -> None:
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: its unmodified models.py +
+    train_gan.train_gan_one_epoch) on this box's host cores, same config / metric / unit as our arm.  Each step is one
+    full batch-64 iteration; when K of them would not fit in ~4 minutes, fewer are executed and `steps_executed` says
+    how many (the rate is per executed step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pix2pix_oracle as O
-    from gan_aug_pfa_b200 import spec as MI
-    torch.manual_seed(0)
-    sd_g, sd_d = MI.default_state_dicts()
-    og = O.AdamState(sd_g, O.param_names(sd_g), 1e-4, (0.5, 0.999))
-    od = O.AdamState(sd_d, O.param_names(sd_d), 1e-4, (0.5, 0.999))
-    sample_batch = 2
-    gen = torch.Generator().manual_seed(1234)
-    A = torch.rand(sample_batch, 3, HW, HW, generator=gen) * 2 - 1
-    B = torch.rand(sample_batch, 3, HW, HW, generator=gen) * 2 - 1
-    for _ in range(max(1, min(args.warmup, 2))):
-        O.gan_train_step(sd_g, sd_d, og, od, A, B)
-    steps = args.steps
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.gan_train_step(sd_g, sd_d, og, od, A, B)
-    el = time.perf_counter() - t0
-    val = steps * sample_batch / el
+    threads = _host_threads()
+    torch.set_num_threads(threads)
+    loop = ReferenceGanLoop("cpu", BATCH_PER_GPU, "fp32", tag="cpuarm")
+    val, per, done = _time_cpu_loop(loop, steps=args.steps, warmup=max(1, min(args.warmup, 1)), budget_s=200.0)
+    sample = (f"{done} of {args.steps} steps executed, each one train_gan_one_epoch iteration at batch {BATCH_PER_GPU}, "
+              f"256x256, fp32, {threads} host threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pix2pix_gan_train_b64_256x256", "sample_batch_per_step": sample_batch,
-                   "note": "CPU oracle port of train_gan_one_epoch; each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{steps} steps of batch {sample_batch} at 256x256 fp32"},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "steps_executed": done, "warmup": args.warmup, "ms_per_step": 1e3 * per, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _gan_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": loop.kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args) -> None:
-    import torch.distributed as dist
-    from gan_aug_pfa_b200 import _lib, ops
-    from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
+def _gpu_loop_rate(loop: ReferenceGanLoop, steps: int, warmup: int) -> float:
+    for i in range(warmup):
+        loop.step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loop.step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return steps * loop.batch / (e0.elapsed_time(e1) * 1e-3)
 
+
+def _library_baseline(dev) -> dict:
+    """SURVEY.md §8(d) / BASELINE.md §2: the existing Blackwell library kernels on this very GPU — the unmodified
+    reference loop with DEVICE=cuda (torch eager -> cuDNN 9 / ATen), batch 64, (a) as it is (fp32 tensors; torch's
+    default lets cuDNN use TF32 for convolutions) and (b) under bf16 autocast with channels_last."""
+    out = {"unit": UNIT, "batch": BATCH_PER_GPU,
+           "what": "oracle/_ref train_gan_one_epoch + reference models on cuda via torch eager (cuDNN), "
+                   "cudnn.benchmark on, 3 warm-up + 5 timed iterations, CUDA events"}
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ("fp32", "bf16_cl"):
+            key = "fp32" if mode == "fp32" else "bf16_autocast_channels_last"
+            try:
+                loop = ReferenceGanLoop(dev, BATCH_PER_GPU, mode, tag="lib_" + mode)
+                out[key] = _gpu_loop_rate(loop, steps=5, warmup=3)
+                del loop
+            except Exception as e:      # a missing staged reference must not kill the bench line
+                out[key] = None
+                out[key + "_error"] = f"{type(e).__name__}: {e}"[:200]
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = prev
+    return out
+
+
+def _dropin_leg(dev) -> dict:
+    """The path the unchanged scripts take: the reference's real train_gan_one_epoch (oracle/_ref) driving the drop-in
+    gan_aug_pfa_b200.models modules through torch autograd and torch.optim.Adam, batch 64."""
+    from gan_aug_pfa_b200 import models as M
+    try:
+        loop = ReferenceGanLoop(dev, BATCH_PER_GPU, "fp32", models=M, tag="dropin")
+        val = _gpu_loop_rate(loop, steps=5, warmup=3)
+        del loop
+        torch.cuda.empty_cache()
+        return {"value": val, "unit": UNIT, "what": "oracle/_ref train_gan.train_gan_one_epoch on the drop-in modules "
+                "(torch autograd + torch.optim.Adam around the native engine; the reference's second generator forward "
+                "and its discarded D weight gradients are executed, 105.2 GFLOP/image)"}
+    except Exception as e:
+        return {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
+
+
+def _roofline_dict(ach_tf: float, peaks: dict, **extra) -> dict:
+    """Tensor-bound roofline entry.  `frac` is quoted against the BURST peak (MEASURED_PEAKS.json bf16_tflops): the
+    timed regions here last a fraction of a second at ~1.75-1.8 GHz, the conditions the burst figure was measured
+    under; `frac_sustained` divides by the seconds-long sustained figure (median 1357 MHz) for comparison."""
+    burst = peaks["bf16_tflops"]
+    sus = peaks.get("bf16_tflops_sustained", burst)
+    d = {"bound": "tensor", "achieved": ach_tf, "peak": burst, "unit": "TFLOP/s", "frac": ach_tf / burst,
+         "peak_sustained": sus, "frac_sustained": ach_tf / sus,
+         "peak_source": f"{peaks['_source']} MEASURED_PEAKS.json: bf16_tflops (burst) for frac, bf16_tflops_sustained for "
+                        "frac_sustained"}
+    d.update(extra)
+    return d
+
+
+def _setup_dist():
+    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -254,11 +388,35 @@ def run_ours(args) -> None:
         raise RuntimeError("bench.py needs a CUDA device: the gap_* kernels have no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    return dist, world, rank, local, dev
+
+
+def _barrier(dist, world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(dist, world, dev, *vals):
+    if world > 1:
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+    return list(vals)
+
+
+def run_ours(args) -> None:
+    from gan_aug_pfa_b200 import _lib, ops, parallel
+    from gan_aug_pfa_b200.io import PairPrefetcher
+    from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
+
+    dist, world, rank, local, dev = _setup_dist()
     clock_sampler = ClockSampler(local)       # the child process needs a moment to come up: start it before the warm-up
     torch.manual_seed(0)
-    tr = Pix2PixTrainer(dev, world=world)     # world > 1: bucketed NCCL all-reduce overlapped with the backward pass
+    tr = Pix2PixTrainer(dev, world=world)     # world > 1: bucketed NCCL all-reduce overlapped with the backward pass;
+    #                                           replicas are broadcast from rank 0 at construction
     N = BATCH_PER_GPU
     gen = torch.Generator().manual_seed(1234 + rank)
     n_batches = 2
@@ -271,19 +429,7 @@ def run_ours(args) -> None:
                  torch.rand(N, 3, HW, HW, generator=gen).mul_(2).sub_(1).pin_memory()) for _ in range(n_batches)]
     devb = [(a.to(dev), b.to(dev)) for a, b in host]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    # Single GPU: the iteration's ~175 launches can be replayed from one CUDA graph (same kernels, no launch gaps) or
+    # Single GPU: the iteration's launches can be replayed from one CUDA graph (same kernels, no launch gaps) or
     # launched eagerly (three streams; the host enqueues a step faster than the GPU runs it).  Which is faster depends
     # on the host: calibrate both during warm-up (untimed, interleaved so clock drift cancels) and keep the faster.
     step_fn, use_graph = tr.train_step, False
@@ -316,60 +462,52 @@ def run_ours(args) -> None:
             for i in range(3):
                 step_fn(*devb[i % n_batches])
     # ---- device-resident timing
-    barrier()
+    _barrier(dist, world)
     _lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with clock_sampler as clocks:
-        barrier()
+        _barrier(dist, world)
         e0.record()
         for i in range(args.steps):
             losses = step_fn(*devb[i % n_batches])
         e1.record()
-        barrier()
+        _barrier(dist, world)
     launches = _lib.LAUNCHES
     if use_graph:
         # graph replays do not pass through the Python launchers: count the launches of one eager iteration
         _lib.LAUNCHES = 0
         tr.train_step(*devb[0])
         launches = _lib.LAUNCHES * args.steps
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    (ms,) = _max_over_ranks(dist, world, dev, e0.elapsed_time(e1))
     value = world * N * args.steps / (ms * 1e-3)
     loss_host = losses.cpu().tolist()
 
-    # ---- end to end: pinned host inputs, H2D inside the timed region (prefetched on a copy stream into two staging
-    # buffers while the previous iteration computes), losses read back to the host every step
-    stage = [(torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])) for _ in range(2)]
-    loss_pinned = torch.empty(2, dtype=torch.float64).pin_memory()
+    # ---- end to end through the public API: pinned host batches -> PairPrefetcher (H2D on a copy stream into two
+    # staging buffers while the previous iteration computes) -> train_step -> the step's losses copied back to pinned
+    # host memory EVERY step; the host waits for step i-1's losses while step i is already enqueued (a one-step lag:
+    # the reference's `.item()` per step, train_gan.py:72-74, without draining the GPU between iterations).
+    pre = PairPrefetcher(dev, [host[i % n_batches] for i in range(args.steps)])
+    loss_pinned = [torch.empty(2, dtype=torch.float64).pin_memory() for _ in range(2)]
+    ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
     cur = torch.cuda.current_stream()
-    copy_s = torch.cuda.Stream(dev)
-    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_used = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def prefetch(i):
-        k = i % 2
-        with torch.cuda.stream(copy_s):
-            if i >= 2:
-                copy_s.wait_event(ev_used[k])            # iteration i-2 has consumed this staging buffer
-            stage[k][0].copy_(host[i % n_batches][0], non_blocking=True)
-            stage[k][1].copy_(host[i % n_batches][1], non_blocking=True)
-            ev_copied[k].record(copy_s)
-
-    barrier()
+    seen = []
+    _barrier(dist, world)
     e0.record()
-    copy_s.wait_stream(cur)
-    prefetch(0)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            prefetch(i + 1)
-        cur.wait_event(ev_copied[i % 2])
-        out = step_fn(*stage[i % 2])
-        ev_used[i % 2].record(cur)
-        loss_pinned.copy_(out, non_blocking=True)
-        cur.synchronize()                                # the caller reads the step's losses (train_gan.py:72-74)
+    for i, (a, b) in enumerate(pre):
+        out = step_fn(a, b)
+        pre.release()                                    # the staging buffers of this batch may be refilled
+        loss_pinned[i % 2].copy_(out, non_blocking=True)
+        ev_loss[i % 2].record(cur)
+        if i >= 1:
+            ev_loss[(i - 1) % 2].synchronize()
+            seen.append(loss_pinned[(i - 1) % 2].tolist())
+    ev_loss[(args.steps - 1) % 2].synchronize()
+    seen.append(loss_pinned[(args.steps - 1) % 2].tolist())
     e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    _barrier(dist, world)
+    (ms_e2e,) = _max_over_ranks(dist, world, dev, e0.elapsed_time(e1))
     e2e_value = world * N * args.steps / (ms_e2e * 1e-3)
+    assert len(seen) == args.steps
 
     # ---- per-kernel roofline: time every GEMM launch of a few steps with CUDA events
     # (side streams serialised for these steps: with the generator forward / the wgrads overlapping other kernels a
@@ -392,66 +530,74 @@ def run_ours(args) -> None:
         d[1] += ev0.elapsed_time(ev1) * 1e-3
         d[2] += 1
     peaks = _peaks()
-    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     kern = {k: {"tflops": v[0] / v[1] / 1e12 if v[1] > 0 else 0.0, "seconds_per_step": v[1] / prof_steps,
                 "launches_per_step": v[2] // prof_steps} for k, v in agg.items()}
     dom = max(agg.items(), key=lambda kv: kv[1][1])[0] if agg else None
     roofline = None
     if dom is not None:
-        ach = kern[dom]["tflops"]
         traffic = None
-        tpath = ROOT / "profiles" / "r1_roofline_traffic.json"
-        if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get(dom, {}).get("dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": traffic,
-                    "traffic_source": "ncu dram__bytes_read+write per launch, averaged over the step's launches "
-                                      "(profiles/r1_step_metrics_ncu.csv)" if traffic else None,
-                    "algorithmic_flop_per_launch": agg[dom][0] / max(1, agg[dom][2]),
-                    "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                    "per_kernel": kern,
-                    "step_frac_of_peak": (value / world) * GFLOP_PER_IMG * 1e9 / (peak_tf * 1e12)}
+        for tname in ("r2_roofline_traffic.json", "r1_roofline_traffic.json"):
+            tpath = ROOT / "profiles" / tname
+            if tpath.exists():
+                traffic = json.loads(tpath.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+                break
+        step_tf = (value / world) * GFLOP_PER_IMG * 1e9 / 1e12
+        roofline = _roofline_dict(
+            kern[dom]["tflops"], peaks, kernel=dom, traffic=traffic,
+            traffic_source=f"ncu dram__bytes_read+write per launch, averaged over the step's launches (profiles/{tname})"
+            if traffic else None,
+            algorithmic_flop_per_launch=agg[dom][0] / max(1, agg[dom][2]), per_kernel=kern,
+            step_tflops=step_tf, step_frac_of_peak=step_tf / peaks["bf16_tflops"],
+            step_frac_of_sustained=step_tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+
+    # ---- data-parallel correctness signal + the other BASELINE configs, every rank takes part
+    replica_diff = parallel.replica_param_max_abs_diff([tr.G, tr.D]) if world > 1 else None
+    del tr, devb, pre
+    torch.cuda.empty_cache()
+    secondary = {}
+    if args.secondary:
+        for wl in ("gen_infer", "siamese_train"):
+            secondary[wl] = measure_secondary(wl, steps=max(3, min(args.steps, 8)), warmup=3, dist=dist, world=world,
+                                              rank=rank, dev=dev)
+            torch.cuda.empty_cache()
 
     if rank == 0:
-        cpu = _cpu_baseline() if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "pix2pix_gan_train_b64_256x256", "batch_per_gpu": N, "image": f"{HW}x{HW}x3",
-                       "parallelism": f"dp{world}", "cuda_graph": use_graph, "inputs": args.inputs, "l2": "per-step working set (several GB of activations) >> 126 MB L2; "
-                       "two alternating input batches", "algorithmic_gflop_per_image": GFLOP_PER_IMG},
+            "config": _gan_config(world), "cuda_graph": use_graph,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]),
-                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps, "inputs": args.inputs,
+                    "how": "PairPrefetcher (pinned host -> device staging on a copy stream) + train_step + losses to "
+                           "pinned host memory every step, read by the host with a one-step lag"},
             "gpu_launches": launches,
             "roofline": roofline,
             "final_losses": {"loss_d": loss_host[0], "loss_g": loss_host[1]},
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if replica_diff is not None:
+            line["replica_param_max_abs_diff"] = replica_diff
+        if secondary:
+            line["secondary"] = secondary
+        if world == 1 and args.baselines:
+            line["dropin"] = _dropin_leg(dev)
+            line["library_baseline"] = _library_baseline(dev)
+            line["cpu_baseline"] = _cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def run_secondary(args) -> None:
-    """Secondary workloads of BASELINE.json's configs 4 and 5 (single GPU or independent replicas): generator
-    inference throughput and the Siamese U-Net training step.  Same JSON schema, their own metric names."""
-    import torch.distributed as dist
+def measure_secondary(workload: str, steps: int, warmup: int, dist, world: int, rank: int, dev) -> dict:
+    """BASELINE.json configs 4 and 5 with the same timing rules as the main leg: generator inference (batch 256, eval
+    BatchNorm; independent replicas, no collective) and the Siamese U-Net training step at 512x512 (batch 4 per GPU,
+    CombinedLoss; data parallel with the gradient all-reduce overlapped with the backward pass when world > 1)."""
     from gan_aug_pfa_b200 import _lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    clock_sampler = ClockSampler(local)       # started early: the sampling child needs a moment to come up
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     gen = torch.Generator().manual_seed(1234 + rank)
-    if args.workload == "gen_infer":
+    if workload == "gen_infer":
         from gan_aug_pfa_b200.pix2pix import GeneratorEngine
         N = 256
         eng = GeneratorEngine(dev)
@@ -500,20 +646,26 @@ def run_secondary(args) -> None:
                 d2h_s.wait_event(ev_done[k])
                 out_host[k].copy_(out_u8[k], non_blocking=True)
                 ev_out[k].record(d2h_s)
-            if i == args.steps - 1:
+            if i == steps - 1:
                 d2h_s.synchronize()                     # every image of the timed region has reached the host
                 cur.wait_stream(d2h_s)
         units, metric, unit = N, "generator_inference_images_per_sec_256", "images/s"
         gflop = 12.046041088
         h2d, d2h = N * 3 * HW * HW, N * 3 * HW * HW          # uint8 images both ways
-        cfg = {"workload": "generator_inference_b256_256x256", "batch_per_gpu": N, "bn": "eval (running statistics)"}
+        cfg = {"workload": "generator_inference_b256_256x256", "batch_per_gpu": N, "bn": "eval (running statistics)",
+               "parallelism": f"replicas x{world}"}
+        extra = {}
     else:
+        from gan_aug_pfa_b200 import models as M
+        from gan_aug_pfa_b200 import parallel
         from gan_aug_pfa_b200.siamese import SiameseEngine
         N, S = 4, 512
         eng = SiameseEngine(dev)
-        from gan_aug_pfa_b200 import models as M
         torch.manual_seed(0)
         eng.load_state_dict({k: v.detach() for k, v in M.SiameseUNet(3, 1).state_dict().items()})
+        if world > 1:
+            parallel.broadcast_replica_state([eng])
+            eng.reducer = parallel.TailReducer(eng.store.g)
         host = [((torch.rand(N, 3, S, S, generator=gen) * 2 - 1).pin_memory(),
                  (torch.rand(N, 3, S, S, generator=gen) * 2 - 1).pin_memory(),
                  (torch.rand(N, S, S, generator=gen) < 0.05).long().pin_memory()) for _ in range(2)]
@@ -527,7 +679,7 @@ def run_secondary(args) -> None:
                 for dst, src in zip(stage, host[i % 2]):
                     dst.copy_(src, non_blocking=True)
                 b = stage
-            loss = eng.train_step(*b, kind="combined")
+            loss = eng.train_step(*b, kind="combined", grad_scale=1.0 / world)
             if e2e:
                 loss_host.copy_(loss, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -535,54 +687,59 @@ def run_secondary(args) -> None:
         gflop = 2207.23
         h2d, d2h = 2 * N * 3 * S * S * 4 + N * S * S * 8, 8
         cfg = {"workload": "siamese_unet_train_b4_512x512_combined_loss", "batch_per_gpu": N, "loss": "CombinedLoss(0.5, 1:9)",
-               "optimizer": "AdamW(1.0152e-4, wd 1.118e-5)"}
+               "optimizer": "AdamW(1.0152e-4, wd 1.118e-5)",
+               "parallelism": f"dp{world}" + (" (NCCL gradient all-reduce overlapped with the backward pass)" if world > 1 else "")}
+        extra = {}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
-    barrier()
+    _barrier(dist, world)
     _lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with clock_sampler as clocks:
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            step(i)
-        e1.record()
-        barrier()
+    _barrier(dist, world)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    _barrier(dist, world)
     launches = _lib.LAUNCHES
     ms = e0.elapsed_time(e1)
-    barrier()
+    _barrier(dist, world)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i, e2e=True)
     e1.record()
-    barrier()
+    _barrier(dist, world)
     ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-    value = world * units * args.steps / (ms * 1e-3)
+    ms, ms_e2e = _max_over_ranks(dist, world, dev, ms, ms_e2e)
+    if workload == "siamese_train" and world > 1:
+        from gan_aug_pfa_b200 import parallel
+        extra["replica_param_max_abs_diff"] = parallel.replica_param_max_abs_diff([eng])
+    value = world * units * steps / (ms * 1e-3)
     peaks = _peaks()
-    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    tf = (value / world) * gflop * 1e9 / 1e12
+    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic", "config": cfg,
+           "e2e": {"value": world * units * steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps},
+           "gpu_launches": launches,
+           "roofline": _roofline_dict(tf, peaks, traffic=None,
+                                      note="whole-step algorithmic conv FLOP/s (SURVEY.md §8d) per GPU")}
+    out.update(extra)
+    return out
+
+
+def run_secondary(args) -> None:
+    dist, world, rank, local, dev = _setup_dist()
+    clock_sampler = ClockSampler(local)
+    with clock_sampler as clocks:
+        out = measure_secondary(args.workload, args.steps, args.warmup, dist, world, rank, dev)
+    out["clocks"] = clocks.summary()
     if rank == 0:
-        print(json.dumps({
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": cfg, "clocks": clocks.summary(),
-            "e2e": {"value": world * units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "achieved": (value / world) * gflop * 1e9 / 1e12, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": (value / world) * gflop * 1e9 / (peak_tf * 1e12), "traffic": None,
-                         "note": "whole-step algorithmic conv FLOP/s (SURVEY.md §8d) over the measured sustained bf16 peak"},
-        }), flush=True)
+        print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -593,15 +750,20 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pix2pix_train", choices=["pix2pix_train", "gen_infer", "siamese_train"],
-                    help="pix2pix_train = the BASELINE.json metric (default); gen_infer = generate_synthetic_data.py's "
-                         "generator forward at batch 256 (config 4); siamese_train = train.py's step at 512x512, batch 4 "
-                         "(config 5, CombinedLoss)")
+                    help="pix2pix_train = the BASELINE.json metric (default; its JSON line also carries quick `secondary` "
+                         "legs for the other two); gen_infer = generate_synthetic_data.py's generator forward at batch 256 "
+                         "(config 4); siamese_train = train.py's step at 512x512, batch 4 per GPU (config 5, CombinedLoss)")
     ap.add_argument("--step-mode", default="auto", choices=["auto", "graph", "eager"],
                     help="single-GPU pix2pix_train: CUDA-graph replay, eager launches, or (default) whichever measures "
                          "faster in an untimed calibration after the warm-up")
-    ap.add_argument("--inputs", default="f32", choices=["f32", "u8"],
-                    help="pix2pix_train only: host batches as fp32 NCHW in [-1,1] (the reference DataLoader's output, "
-                         "default) or raw uint8 HWC images normalised on the device")
+    ap.add_argument("--inputs", default="u8", choices=["f32", "u8"],
+                    help="pix2pix_train: host batches as raw uint8 HWC images normalised on the device (default: what an "
+                         "image pipeline holds before dataset.py's ToTensor / JointNormalize) or as fp32 NCHW in [-1,1] "
+                         "(the reference DataLoader's output, 4x the H2D bytes)")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the quick generator-inference / Siamese legs appended to the pix2pix_train line")
+    ap.add_argument("--no-baselines", dest="baselines", action="store_false",
+                    help="skip the drop-in, cuDNN library and CPU baseline legs (single GPU only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -172,5 +172,9 @@ def check(rc: int, what: str = "gap call") -> None:
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")
 
 
+DEBUG_KNOBS: dict = {}      # what was set through debug_set (the launchers consult it, e.g. for the split-K workspace)
+
+
 def debug_set(key: str, value: int) -> None:
+    DEBUG_KNOBS[key] = int(value)
     lib().gap_debug_set(key.encode(), int(value))

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -36,7 +37,11 @@ static std::map<std::string, int>& dbg_map() {
   static std::map<std::string, int> m;
   return m;
 }
+// Knobs exist for bring-up A/B runs only.  Until gap_debug_set is called for the first time (i.e. always, in
+// production) a lookup is one relaxed atomic load: no mutex, no string map on the launch path.
+static std::atomic<int> g_dbg_any{0};
 int debug_get(const char* key, int dflt) {
+  if (g_dbg_any.load(std::memory_order_relaxed) == 0) return dflt;
   std::lock_guard<std::mutex> lk(g_dbg_mu);
   auto it = dbg_map().find(key);
   return it == dbg_map().end() ? dflt : it->second;
@@ -116,6 +121,7 @@ int gap_sm_count(void) { return gap::sm_count(); }
 int gap_debug_set(const char* key, int value) {
   std::lock_guard<std::mutex> lk(gap::g_dbg_mu);
   gap::dbg_map()[key] = value;
+  gap::g_dbg_any.store(1, std::memory_order_relaxed);
   return 0;
 }
 }

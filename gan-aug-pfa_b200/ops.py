@@ -33,6 +33,8 @@ def _timed(name: str, flops: float, fn) -> None:
 
 
 def _stream() -> C.c_void_p:
+    """The current stream of the CURRENT device: the engines pin the current device to their own for the duration of
+    every entry point (pix2pix._on_device), so this is the stream of the tensors being launched on."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -83,11 +85,14 @@ _SPLITK_WS: dict = {}
 
 
 def _splitk_workspace(device: torch.device) -> torch.Tensor:
-    """Zero-filled fp32 scratch for split-K launches (gap_conv_gemm_args.splitk_ws); the kernels leave it zeroed."""
-    ws = _SPLITK_WS.get(device)
+    """Zero-filled fp32 scratch for split-K launches (gap_conv_gemm_args.splitk_ws); the kernels leave it zeroed.
+    One per (device, stream): the trainer runs conv_gemm concurrently on several streams, and two split-K launches
+    must never accumulate into the same buffer."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _SPLITK_WS.get(key)
     if ws is None:
         ws = torch.zeros(8 << 20, device=device, dtype=torch.float32)      # 32 MiB: n*oh*ow*n_out <= 8 Mi elements
-        _SPLITK_WS[device] = ws
+        _SPLITK_WS[key] = ws
     return ws
 
 
@@ -189,8 +194,11 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
         a.bwd_c0 = c0
     else:
         a.bwd_y = None
-    ws = _splitk_workspace(out.device)
-    a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
+    if _lib.DEBUG_KNOBS.get("fprop_splitk", 0) or _lib.DEBUG_KNOBS.get("fprop_splits", 0):
+        ws = _splitk_workspace(out.device)      # split-K is an opt-in experiment (off by default, see conv_fprop.cu)
+        a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
+    else:
+        a.splitk_ws, a.splitk_ws_bytes = None, 0
     if flops is None:
         flops = 2.0 * n * grid_hw[0] * grid_hw[1] * geom.n_phase * n_out * geom.taps_h * geom.taps_w * ctot
     _timed("conv_fprop_kernel", flops,

@@ -104,3 +104,86 @@ class GradBucketReducer:
             self._next += 1
         if self.cuda:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+
+
+class TailReducer:
+    """Overlapped SUM all-reduce for a flat gradient buffer laid out in FORWARD (module) order, as the Siamese
+    engine's is: its backward pass finalises the buffer from the tail towards the head, so "everything from offset
+    X on is final" is a watermark that only moves down.  :meth:`ready_from` reduces [X, previous watermark) on the
+    communication stream once at least ``min_elems`` elements have accumulated; :meth:`finish` reduces what is left
+    and makes the compute stream wait.  Every rank calls ready_from with the same sequence of offsets (they run the
+    same network), so the collectives are issued in the same order everywhere."""
+
+    def __init__(self, flat: torch.Tensor, min_elems: int = 4 << 20,
+                 comm_stream: Optional["torch.cuda.Stream"] = None) -> None:
+        self.flat = flat
+        self.min_elems = min_elems
+        self.cuda = flat.is_cuda
+        self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream(flat.device) if self.cuda else None)
+        self.hi = flat.numel()
+        self.launched: List[Tuple[int, int]] = []      # (begin, end) of the reductions of the last step
+
+    def begin(self) -> None:
+        self.hi = self.flat.numel()
+        self.launched = []
+
+    def _launch(self, lo: int) -> None:
+        view = self.flat[lo:self.hi]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.flat.device))
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM)
+        self.launched.append((lo, self.hi))
+        self.hi = lo
+
+    def ready_from(self, offset: int) -> None:
+        if offset < 0 or offset > self.hi:
+            raise ValueError(f"watermark {offset} must move down from {self.hi}")
+        if self.hi - offset >= self.min_elems:
+            self._launch(offset)
+
+    def finish(self) -> None:
+        if self.hi > 0:
+            self._launch(0)
+        if self.cuda:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+
+
+def broadcast_replica_state(nets, src: int = 0) -> None:
+    """Make every replica start from rank ``src``'s model: parameters, Adam moments / step and BatchNorm buffers of the
+    given engines are broadcast, then the bf16 operands are re-packed (what DistributedDataParallel does at construction).
+    No-op without an initialised process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for net in nets:
+        st = net.store
+        for buf in (st.p, st.m, st.v):
+            dist.broadcast(buf, src)
+        step = torch.tensor([st.step], device=st.p.device, dtype=torch.int64)
+        dist.broadcast(step, src)
+        st.step = int(step.item())
+        if st.step_dev is not None:
+            st.step_dev.fill_(st.step)
+        for bn in net.bns.values():
+            dist.broadcast(bn.running_mean, src)
+            dist.broadcast(bn.running_var, src)
+            dist.broadcast(bn.nbt, src)
+        net.repack()
+
+
+def replica_param_max_abs_diff(nets) -> float:
+    """max over parameters of (max over ranks - min over ranks): 0.0 when the replicas hold bit-identical models, which
+    the data-parallel step guarantees (identical all-reduced gradients into a deterministic optimizer)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0.0
+    worst = 0.0
+    for net in nets:
+        hi, lo = net.store.p.clone(), net.store.p.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        worst = max(worst, float((hi - lo).abs().max().item()))
+    return worst

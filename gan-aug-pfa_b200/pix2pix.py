@@ -20,6 +20,7 @@ are not computed.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -36,6 +37,19 @@ LAMBDA_L1 = 100.0  # train_gan.py:33
 
 def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
+
+
+def _on_device(fn):
+    """Entry points run with the engine's device current: the library launches on the thread's current device and the
+    launchers pass that device's current stream, so an engine built on cuda:1 must not launch while cuda:0 is current."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        idx = self.dev.index
+        if idx is None or torch.cuda.current_device() == idx:
+            return fn(self, *a, **k)
+        with torch.cuda.device(idx):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 class ParamStore:
@@ -114,6 +128,7 @@ class _Net:
         self.key_order: List[str] = []
         self.training = True
         self.grad_hook = None     # callable(segment name) fired when a gradient segment is final (data-parallel buckets)
+        self.alloc_gen = 0        # bumped whenever _alloc (re)allocates the activation set: captured graphs go stale
 
     def _ready(self, *keys: str, side: bool = False) -> None:
         if self.grad_hook is not None:
@@ -206,6 +221,7 @@ class _Net:
                             "num_batches_tracked": bn.nbt}[leaf]
         return out
 
+    @_on_device
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         mine = self.state_dict()
         missing = [k for k in mine if k not in sd]
@@ -228,6 +244,7 @@ class _Net:
     def repack(self) -> None:
         raise NotImplementedError
 
+    @_on_device
     def zero_grad(self) -> None:
         self._join_wgrad()
         self.store.g.zero_()
@@ -254,13 +271,15 @@ class _Net:
             else:
                 setattr(self, a, v)
 
+    @_on_device
     def adam_step(self, lr: float, betas=(0.5, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                   decoupled: bool = False, grad_scale: float = 1.0) -> None:
         self._join_wgrad()
         s = self.store
-        s.step += 1
         if s.step_dev is None:
-            s.step_dev = torch.full((1,), s.step - 1, device=s.p.device, dtype=torch.int32)
+            s.step_dev = torch.full((1,), s.step, device=s.p.device, dtype=torch.int32)
+        if not torch.cuda.is_current_stream_capturing():     # a capture executes nothing: replays bump the host copy
+            s.step += 1
         # the step counter lives on the device (incremented by the kernel) so a captured graph can be replayed
         ops.adam_flat_devstep(s.p, s.g, s.m, s.v, lr, betas[0], betas[1], eps, weight_decay, decoupled, s.step_dev,
                               grad_scale)
@@ -450,8 +469,10 @@ class GeneratorEngine(_Net):
         self.dyu = [None] + [torch.empty_like(self.yu[j]) for j in range(1, L)]
         self.dyd = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L)]
         self._n = (n, h, w)
+        self.alloc_gen += 1
 
     # -- forward --------------------------------------------------------------------------------
+    @_on_device
     def prepare_input(self, x_nchw: torch.Tensor) -> torch.Tensor:
         """Size the buffers for x and convert it into self.x_nhwc (NHWC bf16, 4 channel slots); returns that tensor."""
         u8_in = x_nchw.dtype == torch.uint8
@@ -466,6 +487,7 @@ class GeneratorEngine(_Net):
             ops.nchw_to_nhwc_bf16(x_nchw, self.x_nhwc)
         return self.x_nhwc
 
+    @_on_device
     def forward(self, x_nchw: torch.Tensor, bn_repeat: int = 1, out_u8: Optional[torch.Tensor] = None,
                 x_ready: bool = False) -> torch.Tensor:
         """x: fp32 NCHW on the device, or uint8 NHWC [n,h,w,3] (normalised on the device like dataset.py:155-159).
@@ -515,6 +537,7 @@ class GeneratorEngine(_Net):
         """True if the block whose up-conv output is yu[j] ends in nn.Dropout(0.5) (training mode only)."""
         return self.use_dropout and self.training and (self.L - 1 - (self.L - 5)) <= j <= self.L - 2
 
+    @_on_device
     def output_nchw(self) -> torch.Tensor:
         n, h, w = self._n
         out = torch.empty(n, 3, h, w, device=self.dev)
@@ -522,6 +545,7 @@ class GeneratorEngine(_Net):
         return out
 
     # -- backward -------------------------------------------------------------------------------
+    @_on_device
     def backward(self) -> None:
         """Consumes self.dpre (gradient w.r.t. the pre-Tanh output, bf16 NHWC) and accumulates every
         parameter gradient into the flat gradient buffer."""
@@ -691,7 +715,9 @@ class DiscriminatorEngine(_Net):
         self.dy = [torch.empty_like(t) for t in self.H]
         self.dfake = torch.zeros(n, h, w, 4, device=self.dev)
         self._n = (n, h, w)
+        self.alloc_gen += 1
 
+    @_on_device
     def forward(self, xa: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
         """xa, xb: NHWC bf16 [n,h,w,>=3] (the two halves of torch.cat((A, B), 1), train_gan.py:57,59,66).
         Returns fp32 logits [n,h',w',1]."""
@@ -711,6 +737,7 @@ class DiscriminatorEngine(_Net):
                            self.logits)
         return self.logits
 
+    @_on_device
     def backward(self, wgrad: bool, input_grad: bool, input_grad_a: bool = False) -> Optional[torch.Tensor]:
         """Consumes self.dlogits (fp32 [n, h', w']).  wgrad=False skips every parameter gradient (the G step);
         input_grad=True returns d(loss)/d(xb) as fp32 NHWC.  The last conv's bias gradient (sum of dlogits) is
@@ -735,13 +762,16 @@ class DiscriminatorEngine(_Net):
                     16 * C[k - 1], C[k - 1]))
             geom = ops.geom_phase_k4s2p1() if s == 2 else ops.geom_conv_dgrad_s1(4, 1)
             grid = (self.hs[k], self.ws[k]) if s == 2 else (self.hs[k - 1], self.ws[k - 1])
+            # algorithmic FLOPs of a dgrad = those of the layer's forward (the stride-1 dgrad runs its GEMM over the
+            # 32x32 input grid with zero-padded borders: 6.6 % more MMA work than the 31x31 forward, not counted)
+            fl = 2.0 * self.dy[k].shape[0] * self.hs[k] * self.ws[k] * C[k] * C[k - 1] * 16
             if k - 1 >= 1:
                 nb = self.bn[k - 1]
                 ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.gH[k - 1], C[k - 1], grid, stats=nb.sums,
-                              bwd=self._bwd_epilogue(nb, self.y[k - 1], 0.2))
+                              bwd=self._bwd_epilogue(nb, self.y[k - 1], 0.2), flops=fl)
             else:   # H[0] = LeakyReLU(conv + bias): the epilogue writes dy[0] directly
                 ops.conv_gemm([self.dy[k]], self.w_dg[k], geom, self.dy[0], C[0], grid,
-                              bwd=self._bwd_epilogue(None, self.H[0], 0.2))
+                              bwd=self._bwd_epilogue(None, self.H[0], 0.2), flops=fl)
         if wgrad:
             self._fork_wgrad(lambda: ops.thin_conv_wgrad(self.dy[0], self._xa, self._xb,
                                                          self.store.seg(g, self.k_conv[0] + ".weight"), 128,
@@ -781,6 +811,7 @@ class Pix2PixTrainer:
         # on a side stream while its backward pass is still running (buffer order = completion order)
         self.g_reducer = self.d_reducer = None
         self._graph = None
+        self._graph_sig = None
         self._g_stream = None
         if world > 1 and allreduce is None:
             from .parallel import GradBucketReducer
@@ -788,14 +819,30 @@ class Pix2PixTrainer:
             self.d_reducer = GradBucketReducer(self.D.store.g, self.D.grad_segments(), bucket_elems=1 << 30,
                                                comm_stream=self.g_reducer.comm_stream)
             self.G.grad_hook = self.g_reducer.mark_ready
+        if world > 1:
+            self.sync_replicas()
 
+    def sync_replicas(self, src: int = 0) -> None:
+        """Data parallel: every replica adopts rank `src`'s parameters, Adam state and BatchNorm buffers (like
+        DistributedDataParallel at construction).  Call again after loading a checkpoint on one rank only."""
+        from .parallel import broadcast_replica_state
+        broadcast_replica_state([self.G, self.D], src)
+
+    def _graph_key(self, real_A: torch.Tensor) -> tuple:
+        """Everything a captured iteration bakes in: input shape / dtype, the activation sets (raw device pointers and
+        TMA tensor maps of the engines' buffers) and the optimizer hyper-parameters (kernel arguments)."""
+        return (tuple(real_A.shape), real_A.dtype, self.G.alloc_gen, self.D.alloc_gen, self.lr_g, self.lr_d, self.betas)
+
+    @_on_device
     def train_step_graphed(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
-        """train_step through a CUDA graph: the first call (after at least one eager step has sized every
-        buffer) captures the ~175 launches of the iteration, later calls copy the batch into the static input
-        buffers and replay.  Same results as train_step; single-GPU only."""
+        """train_step through a CUDA graph: the first call (and any call after the input shape, the engines' activation
+        buffers or lr / betas changed — e.g. an eager train_step at another batch size re-allocated them) runs the
+        iteration eagerly and captures its launches; later calls copy the batch into the static input buffers and
+        replay.  Same results as train_step (a fresh tensor per call); single-GPU only."""
         if self.world > 1 or self.G.use_dropout:      # dropout draws host-numbered masks per forward: no replay
             return self.train_step(real_A, real_B)
-        if self._graph is None or self._g_in[0].shape != real_A.shape:
+        if self._graph is None or self._graph_sig != self._graph_key(real_A):
+            self._graph = None
             self._g_in = (torch.empty_like(real_A), torch.empty_like(real_B))
             self._g_in[0].copy_(real_A)
             self._g_in[1].copy_(real_B)
@@ -804,15 +851,19 @@ class Pix2PixTrainer:
             with torch.cuda.stream(side):
                 first = self.train_step(*self._g_in)  # this call's iteration, eagerly (also sizes every buffer)
             torch.cuda.current_stream(self.dev).wait_stream(side)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):       # capture only: nothing executes here
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):             # capture only: nothing executes here
                 self._g_out = self.train_step(*self._g_in)
+            self._graph, self._graph_sig = graph, self._graph_key(real_A)
             return first
         self._g_in[0].copy_(real_A, non_blocking=True)
         self._g_in[1].copy_(real_B, non_blocking=True)
         self._graph.replay()
-        return self._g_out
+        self.G.store.step += 1                        # host mirrors of the device-side Adam step counters
+        self.D.store.step += 1
+        return self._g_out.clone()
 
+    @_on_device
     def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
         """real_A / real_B: fp32 NCHW in [-1, 1] on the device (what the reference's DataLoader yields), or BOTH as raw
         uint8 [n, h, w, 3] images: the ToTensor + JointNormalize of dataset.py:28-29,155-159 then runs on the device

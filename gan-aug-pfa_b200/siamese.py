@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 from .ops import ACT_NONE, ACT_RELU
-from .pix2pix import BN_EPS, BN_MOMENTUM, _BN, _Net
+from .pix2pix import BN_EPS, BN_MOMENTUM, _BN, _Net, _on_device
 
 ENC = (("dconv_down1", 64), ("dconv_down2", 128), ("dconv_down3", 256), ("dconv_down4", 512), ("bottleneck", 1024))
 DEC = (("att3", "dconv_up3", 2048, 1024, 512), ("att2", "dconv_up2", 512, 512, 256), ("att1", "dconv_up1", 256, 256, 128),
@@ -75,6 +75,9 @@ class SiameseEngine(_Net):
         self._plan = None
         self._n = None
         self._tape: List[Callable[[], None]] = []
+        self._marks: Dict[int, int] = {}     # tape index -> flat-buffer offset from which every gradient is final once
+        #                                      that entry has run (the backward pass finalises the buffer tail first)
+        self.reducer = None                  # parallel.TailReducer when data parallel (see train_step)
 
     # -- registration ------------------------------------------------------------------------------
     def _reg_convk(self, key: str, cout: int, cin: int, k: int, bias: bool) -> None:
@@ -317,11 +320,13 @@ class SiameseEngine(_Net):
         self._tape.append(backward)
 
     # -- forward ---------------------------------------------------------------------------------------
+    @_on_device
     def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
         """x1, x2: fp32 NCHW on the device.  Returns fp32 logits [n, h, w] (n_classes = 1)."""
         n, _, h, w = x1.shape
         self._alloc(n, h, w)
         self._tape = []
+        self._marks = {}
         for p, x in enumerate((x1, x2)):
             ops.nchw_to_nhwc_bf16(x.contiguous().float(), self.x_in[p])
             ops.im2col_k3s1p1_c3(self.x_in[p], self.col[p])
@@ -329,6 +334,8 @@ class SiameseEngine(_Net):
             for lvl, (name, c) in enumerate(ENC):
                 out = self.S[lvl][..., p * c:(p + 1) * c]
                 gout = self.gS[lvl][..., p * c:(p + 1) * c]
+                if p == 0:      # pass 0's entries run last in backward: after them this level's segments are final
+                    self._marks[len(self._tape)] = self.store.off(name + ".0.weight")
                 self._double_conv(src, name, out, p, gsrc, gout)
                 if lvl < 4:
                     nh, nw = out.shape[1] // 2, out.shape[2] // 2
@@ -339,6 +346,7 @@ class SiameseEngine(_Net):
                     self._tape.append(lambda o=out, gp=gpooled, go=gout: ops.maxpool2x2_bwd(o, gp, go, True))
                     src, gsrc = pooled, gpooled
         prev, gprev = self.S[4], self.gS[4]          # bottleneck pair (2048 channels)
+        self._marks[len(self._tape)] = self.store.off(DEC[0][0] + ".W_g.0.weight")   # gates, decoder blocks, conv_last
         for i, (gate, block, fg, fl, cout) in enumerate(DEC):
             lvl = 3 - i
             d, gd = self.D[i], self.gD[i]
@@ -358,13 +366,16 @@ class SiameseEngine(_Net):
         return self.logits
 
     # -- backward --------------------------------------------------------------------------------------
+    @_on_device
     def backward(self) -> None:
         """Consumes self.dlogits (fp32 [n, h, w]); accumulates every parameter gradient."""
         dl = self.dlogits.view(-1)
         ops.conv1x1_cout1_wgrad(dl, self._last, self.store.seg(self.store.g, "conv_last.weight"), self.grad("conv_last.bias"))
         ops.conv1x1_cout1_dgrad(dl, self.store.seg(self.store.p, "conv_last.weight"), self._glast)
-        for fn in reversed(self._tape):
-            fn()
+        for idx in range(len(self._tape) - 1, -1, -1):
+            self._tape[idx]()
+            if self.reducer is not None and idx in self._marks:
+                self.reducer.ready_from(self._marks[idx])
         self._tape = []
 
     # -- one training iteration (train.py:137-146) ------------------------------------------------------
@@ -383,16 +394,22 @@ class SiameseEngine(_Net):
             raise ValueError(f"unknown loss {kind!r}")
         return self.loss_out
 
+    @_on_device
     def train_step(self, img1: torch.Tensor, img2: torch.Tensor, labels: torch.Tensor, lr: float = 1.0152e-4,
                    weight_decay: float = 1.118e-5, kind: str = "combined", grad_scale: float = 1.0, allreduce=None,
                    **loss_kw) -> torch.Tensor:
-        """zero_grad -> forward -> criterion -> backward -> AdamW step (train.py:140-144)."""
+        """zero_grad -> forward -> criterion -> backward -> AdamW step (train.py:140-144).  Data parallel: set
+        `self.reducer = parallel.TailReducer(self.store.g)` (or pass `allreduce`) and grad_scale = 1 / world."""
         self.training = True
         self.zero_grad()
         self.forward(img1, img2)
         loss = self.loss_and_grad(labels, kind, **loss_kw)
+        if self.reducer is not None:        # data parallel: SUM all-reduce of the gradient tail while backward continues
+            self.reducer.begin()
         self.backward()
-        if allreduce is not None:
+        if self.reducer is not None:
+            self.reducer.finish()
+        elif allreduce is not None:
             allreduce(self.store.g)
         self.adam_step(lr, (0.9, 0.999), 1e-8, weight_decay, decoupled=True, grad_scale=grad_scale)
         return loss

@@ -144,3 +144,72 @@ def test_grad_bucket_reducer_world2_overlapped_protocol():
         assert launched[0] == 0 and launched[1] == 0                      # bucket 0 = {s0,s1,s2} not complete yet
         assert launched[2] >= 1                                           # ... until s1 arrives
         assert launched[-1] >= 2 and launched[-1] < n_buckets             # buckets went out during "backward"
+
+
+# ---------------------------------------------------------------------------------------------------
+# TailReducer (Siamese engine: flat buffer in forward order, finalised from the tail) and the replica
+# broadcast / checksum helpers
+# ---------------------------------------------------------------------------------------------------
+class _FakeStore:
+    def __init__(self, p):
+        self.p, self.m, self.v = p, torch.zeros_like(p), torch.zeros_like(p)
+        self.step, self.step_dev = 0, None
+
+
+class _FakeNet:
+    def __init__(self, p):
+        self.store, self.bns, self.repacked = _FakeStore(p), {}, 0
+
+    def repack(self):
+        self.repacked += 1
+
+
+def _tail_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gan_aug_pfa_b200.parallel import TailReducer, broadcast_replica_state, replica_param_max_abs_diff
+        g = torch.Generator().manual_seed(7 + rank)
+        flat = torch.randn(1000, generator=g)
+        local = flat.clone()
+        red = TailReducer(flat, min_elems=200)
+        red.begin()
+        for off in (900, 760, 750, 400, 390):      # watermarks only move down; small steps are merged
+            red.ready_from(off)
+        before_finish = list(red.launched)
+        red.finish()
+        # replicas built from different seeds differ until rank 0's state is broadcast
+        net = _FakeNet(torch.randn(64, generator=g))
+        d0 = replica_param_max_abs_diff([net])
+        broadcast_replica_state([net])
+        d1 = replica_param_max_abs_diff([net])
+        q.put((rank, local.numpy(), flat.numpy(), before_finish, list(red.launched), d0, d1, net.repacked))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tail_reducer_and_replica_sync_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tail_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = torch.from_numpy(res[0][1]) + torch.from_numpy(res[1][1])
+    for _, _, reduced, before, launched, d0, d1, repacked in res:
+        assert torch.allclose(torch.from_numpy(reduced), total, rtol=1e-6, atol=1e-9)    # every element reduced exactly once
+        assert before == [(760, 1000), (400, 760)]          # 900 and 750/390 were too small a step: merged into the next
+        assert launched == before + [(0, 400)]               # finish() flushes the head
+        assert d0 > 0.0 and d1 == 0.0 and repacked == 1
+    import pytest as _pt
+    from gan_aug_pfa_b200.parallel import TailReducer
+    r = TailReducer(torch.zeros(10), min_elems=1)
+    r.begin()
+    r.hi = 5
+    with _pt.raises(ValueError):
+        r.ready_from(7)

@@ -239,13 +239,21 @@ def test_full_batch64_train_step_against_oracle():
     assert abs(float(losses[1]) - lg) < 2e-3 * max(1, abs(lg)), (float(losses[1]), lg)
     fake = tr.G.output_nchw().cpu()
     assert rel(fake, aux["fake_B"]) < 2e-2
-    worst, worst_k = 1.0, None
-    for net, grads in ((tr.D, aux["grads_d"]), (tr.G, aux["grads_g"])):
+    # per-tensor gradient cosine >= 0.97, or — where torch's OWN bf16 arithmetic does worse than that on this very
+    # fixture (tests/golden/gan_yardstick_b64.json, made by make_gan_yardstick.py: the oracle under CPU bf16 autocast
+    # reaches only 0.9645 on the depth-4 down-norm bias and 0.926 on a discriminator norm bias) — within 1.5 x the
+    # yardstick's error:  1 - cos <= max(0.03, 2.25 x (1 - yardstick cos))
+    import json
+    from pathlib import Path
+    yard = json.loads((Path(__file__).resolve().parent / "golden" / "gan_yardstick_b64.json").read_text())
+    assert abs(yard["loss_d"] - ld) < 1e-4 * abs(ld) and abs(yard["loss_g"] - lg) < 1e-4 * abs(lg)   # same fixture
+    bad = []
+    for net, grads, yc in ((tr.D, aux["grads_d"], yard["cos_d"]), (tr.G, aux["grads_g"], yard["cos_g"])):
         for k, gref in grads.items():
             c = cos(net.grad(k).cpu(), gref)
-            if c < worst:
-                worst, worst_k = c, k
-    assert worst >= 0.97, f"worst per-tensor gradient cosine {worst} ({worst_k})"
+            if 1 - c > max(0.03, 2.25 * (1 - yc[k])):
+                bad.append((k, round(c, 4), round(yc[k], 4)))
+    assert not bad, f"gradient cosines outside the bf16 band (tensor, ours, torch-bf16 yardstick): {bad}"
     assert rel(tr.G.grad("model.model.3.weight").cpu(), aux["grads_g"]["model.model.3.weight"]) < 2e-2
     assert rel(tr.D.grad("model.11.weight").cpu(), aux["grads_d"]["model.11.weight"]) < 2e-2
     for net, sd, inc in ((tr.G, sd_g, 2), (tr.D, sd_d, 3)):
