@@ -97,10 +97,10 @@ _SIGNATURES = {
     "gap_bce_logits_const": (C.c_int, [_P, _L, _F, _F, _P, _L, _P, _P]),
     "gap_bce_logits_const_f32": (C.c_int, [_P, _L, _F, _F, _P, _P, _P, _P]),
     "gap_sum_f32": (C.c_int, [_P, _L, _P, _P]),
-    "gap_cout1_conv_fwd": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "gap_cout1_conv_fwd": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _F, _P]),
     "gap_cout1_conv_dgrad": (C.c_int, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _L, _I, _I, _P]),
     "gap_cout1_conv_dgrad_bwd": (C.c_int, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _L, _I, _I, _P, _L, _P, _P, _F, _P, _P]),
-    "gap_cout1_conv_wgrad": (C.c_int, [_P, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P]),
+    "gap_cout1_conv_wgrad": (C.c_int, [_P, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P]),
     "gap_thin_conv_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _P, _P, _I, _P, _L, _I, _P, _L, _I, _P]),
     "gap_thin_conv_wgrad": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P, _P]),
     "gap_thin_convT_fwd": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P, _I, _P, _L, _P, _L, _P, _P]),

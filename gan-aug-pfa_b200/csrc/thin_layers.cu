@@ -29,21 +29,60 @@ __device__ __forceinline__ void cp_async_wait() {
 // filter — every input element is read once (the 16 shifted sums are formed in stage 2 from z).
 // CTA = 128 pixels, warp = 16 pixels x 16 taps, K = channels in chunks of 64.
 // ------------------------------------------------------------------------------------------------
+// PRE: the input is the raw (pre-BatchNorm) conv output y of the layer below and x = LeakyReLU(y*scale + shift) is
+// formed while staging it (training-mode BatchNorm apply fused into the consumer: the activated tensor never exists
+// in HBM).  The next 64-channel chunk's global loads are issued before the current chunk's MMAs.
+struct Cout1Pre {
+  const float* scale;
+  const float* shift;
+  float slope;
+};
+
+// y*scale + shift, then x > 0 ? x : slope*x, on eight packed bf16 channels
+__device__ __forceinline__ uint4 bn_act8(uint4 v, const float* __restrict__ sc, const float* __restrict__ sh, float slope) {
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = fmaf(bf16_lo(w[j]), sc[2 * j], sh[2 * j]);
+    float b = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sh[2 * j + 1]);
+    a = a > 0.f ? a : slope * a;
+    b = b > 0.f ? b : slope * b;
+    w[j] = pack_bf16x2(a, b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool PRE>
 __global__ void __launch_bounds__(256) cout1_z_kernel(const bf16* __restrict__ x, long long ld_x, long long npix,
-                                                      int c, const bf16* __restrict__ w, float* __restrict__ z) {
+                                                      int c, const bf16* __restrict__ w, float* __restrict__ z,
+                                                      const Cout1Pre pre) {
   __shared__ __align__(16) bf16 xs[128][72];
   __shared__ __align__(16) bf16 ws[16][72];
+  __shared__ __align__(16) float par[PRE ? 1024 : 4];   // scale[512] | shift[512]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t xs_a = smem_u32(&xs[0][0]), ws_a = smem_u32(&ws[0][0]);
+  if (PRE) {
+    for (int i = tid; i < c; i += 256) {
+      par[i] = __ldg(pre.scale + i);
+      par[512 + i] = __ldg(pre.shift + i);
+    }
+    __syncthreads();
+  }
   for (long long tile = blockIdx.x; tile * 128 < npix; tile += gridDim.x) {
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    uint4 nxt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = tid + i * 256, px = v >> 3, seg = v & 7;
+      const long long pix = tile * 128 + px;
+      nxt[i] = pix < npix ? ldg128(x + pix * ld_x + seg * 8) : make_uint4(0, 0, 0, 0);
+    }
     for (int c0 = 0; c0 < c; c0 += 64) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int v = tid + i * 256, px = v >> 3, seg = v & 7;
-        const long long pix = tile * 128 + px;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (pix < npix) val = ldg128(x + pix * ld_x + c0 + seg * 8);
+        uint4 val = nxt[i];
+        if (PRE && tile * 128 + px < npix) val = bn_act8(val, par + c0 + seg * 8, par + 512 + c0 + seg * 8, pre.slope);
         *reinterpret_cast<uint4*>(&xs[px][seg * 8]) = val;
       }
       if (tid < 128) {
@@ -51,6 +90,14 @@ __global__ void __launch_bounds__(256) cout1_z_kernel(const bf16* __restrict__ x
         *reinterpret_cast<uint4*>(&ws[t][seg * 8]) = ldg128(w + static_cast<long long>(t) * c + c0 + seg * 8);
       }
       __syncthreads();
+      if (c0 + 64 < c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = tid + i * 256, px = v >> 3, seg = v & 7;
+          const long long pix = tile * 128 + px;
+          nxt[i] = pix < npix ? ldg128(x + pix * ld_x + c0 + 64 + seg * 8) : make_uint4(0, 0, 0, 0);
+        }
+      }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t a[4], b[4];
@@ -258,14 +305,19 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
 // CTA = a contiguous range of input pixels; warp = one 64-channel range (c <= 512).
 // dynamic smem: xs[16][c + 8] | ut[16][24]   (bf16)
 // ------------------------------------------------------------------------------------------------
+// PRE: x = LeakyReLU(y*scale + shift) is formed from the raw conv output y while staging (see cout1_z_kernel).
+// The next 16-pixel slab's global loads are in flight while the current slab's MMAs run (register prefetch;
+// kVec = uint4 per thread and slab = 16 * c / 8 / 256, i.e. 4 for c = 512).
+template <bool PRE>
 __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restrict__ dlog, int ih, int iw, int oh, int ow,
                                                           int pad, long long npix, long long chunk,
                                                           const bf16* __restrict__ x, long long ld_x, int c,
-                                                          float* __restrict__ dw) {
+                                                          float* __restrict__ dw, const Cout1Pre pre) {
   extern __shared__ __align__(16) uint8_t dsm[];
   bf16* xs = reinterpret_cast<bf16*>(dsm);
   const int xstride = c + 8;
   bf16* ut = xs + 16 * xstride;
+  float* par = reinterpret_cast<float*>(ut + 16 * 24);   // scale[c] | shift[c] (PRE only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const long long p0 = blockIdx.x * chunk, p1 = min(npix, p0 + chunk);
@@ -278,20 +330,46 @@ __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
   const int vec_per_px = c >> 3;
-  for (long long k0 = p0; k0 < p1; k0 += 16) {
-    for (int idx = tid; idx < 16 * vec_per_px; idx += 256) {
-      const int px = idx / vec_per_px, seg = idx - px * vec_per_px;
-      const long long pix = k0 + px;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (pix < p1) val = ldg128(x + pix * ld_x + seg * 8);
-      *reinterpret_cast<uint4*>(xs + px * xstride + seg * 8) = val;
-    }
-    {
-      const int tap = tid >> 4, px = tid & 15;
-      const long long pix = k0 + px;
-      ut[tap * 24 + px] = __float2bfloat16(pix < p1 ? gather_dlogit(dlog, pix, npix, tap, ih, iw, oh, ow, pad) : 0.f);
+  const int n_vec = 16 * vec_per_px;        // <= 1024 (c <= 512): at most 4 per thread
+  if (PRE) {
+    for (int i = tid; i < c; i += 256) {
+      par[i] = __ldg(pre.scale + i);
+      par[c + i] = __ldg(pre.shift + i);
     }
     __syncthreads();
+  }
+  uint4 nxt[4];
+  float unxt = 0.f;
+  auto fetch = [&](long long k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      nxt[i] = make_uint4(0, 0, 0, 0);
+      if (idx < n_vec) {
+        const int px = idx / vec_per_px, seg = idx - px * vec_per_px;
+        const long long pix = k0 + px;
+        if (pix < p1) nxt[i] = ldg128(x + pix * ld_x + seg * 8);
+      }
+    }
+    const int tap = tid >> 4, px = tid & 15;
+    const long long pix = k0 + px;
+    unxt = pix < p1 ? gather_dlogit(dlog, pix, npix, tap, ih, iw, oh, ow, pad) : 0.f;
+  };
+  if (p0 < p1) fetch(p0);
+  for (long long k0 = p0; k0 < p1; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      if (idx < n_vec) {
+        const int px = idx / vec_per_px, seg = idx - px * vec_per_px;
+        uint4 val = nxt[i];
+        if (PRE && k0 + px < p1) val = bn_act8(val, par + seg * 8, par + c + seg * 8, pre.slope);
+        *reinterpret_cast<uint4*>(xs + px * xstride + seg * 8) = val;
+      }
+    }
+    ut[(tid >> 4) * 24 + (tid & 15)] = __float2bfloat16(unxt);
+    __syncthreads();
+    if (k0 + 16 < p1) fetch(k0 + 16);
     if (active) {
       uint32_t a[4];
       lda_16x16(a, ut_a, 48, lane);
@@ -936,9 +1014,12 @@ using namespace gap;
 extern "C" {
 
 int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c, const void* w, const float* bias,
-                       int ksize, int pad, float* z_ws, float* logits, void* stream) {
+                       int ksize, int pad, float* z_ws, float* logits, const float* in_scale, const float* in_shift,
+                       float in_slope, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GAP_CHECK_ARG(x && w && z_ws && logits && n > 0 && ih > 0 && iw > 0, "gap_cout1_conv_fwd: bad arguments");
+  GAP_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr) && (!in_scale || c <= 512),
+                "gap_cout1_conv_fwd: in_scale / in_shift come together and need c <= 512");
   if (ksize != 4 || c % 64 != 0 || c <= 0 || ld_x % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) ||
       (reinterpret_cast<uintptr_t>(w) & 15)) {
     set_error("gap_cout1_conv_fwd: needs ksize 4, channels %% 64 == 0 and 16-byte aligned rows (c=%d ld=%lld)", c,
@@ -949,8 +1030,13 @@ int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c
   GAP_CHECK_ARG(oh > 0 && ow > 0, "gap_cout1_conv_fwd: empty output");
   const long long npix = static_cast<long long>(n) * ih * iw;
   const int tiles = static_cast<int>((npix + 127) / 128);
-  cout1_z_kernel<<<std::min(tiles, 8 * sm_count()), 256, 0, st>>>(static_cast<const bf16*>(x), ld_x, npix, c,
-                                                                   static_cast<const bf16*>(w), z_ws);
+  const Cout1Pre pre{in_scale, in_shift, in_slope};
+  if (in_scale)
+    cout1_z_kernel<true><<<std::min(tiles, 8 * sm_count()), 256, 0, st>>>(static_cast<const bf16*>(x), ld_x, npix, c,
+                                                                           static_cast<const bf16*>(w), z_ws, pre);
+  else
+    cout1_z_kernel<false><<<std::min(tiles, 8 * sm_count()), 256, 0, st>>>(static_cast<const bf16*>(x), ld_x, npix, c,
+                                                                            static_cast<const bf16*>(w), z_ws, pre);
   GAP_CUDA(cudaGetLastError());
   const long long total = static_cast<long long>(n) * oh * ow;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * sm_count()));
@@ -1012,21 +1098,28 @@ int gap_cout1_conv_dgrad_bwd(const float* dlogits, int n, int oh, int ow, const 
 }
 
 int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void* x, int64_t ld_x, int ih, int iw, int c,
-                         int ksize, int pad, float* dw, void* stream) {
+                         int ksize, int pad, float* dw, const float* in_scale, const float* in_shift, float in_slope,
+                         void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GAP_CHECK_ARG(dlogits && x && dw && n > 0 && oh > 0 && ow > 0 && ih > 0 && iw > 0, "gap_cout1_conv_wgrad: bad arguments");
+  GAP_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "gap_cout1_conv_wgrad: in_scale / in_shift come together");
   if (ksize != 4 || c % 64 != 0 || c <= 0 || c > 512 || ld_x % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) {
     set_error("gap_cout1_conv_wgrad: needs ksize 4, channels %% 64 == 0, <= 512, 16-byte aligned rows");
     return GAP_ERR_UNSUPPORTED;
   }
   const long long npix = static_cast<long long>(n) * ih * iw;
-  const size_t smem = (static_cast<size_t>(16) * (c + 8) + 16 * 24) * sizeof(bf16);
+  const size_t smem = (static_cast<size_t>(16) * (c + 8) + 16 * 24) * sizeof(bf16) + (in_scale ? 2 * c * sizeof(float) : 0);
   const int want = 4 * sm_count();
   long long chunk = (npix + want - 1) / want;
   chunk = (chunk + 15) / 16 * 16;
   const int grid = static_cast<int>((npix + chunk - 1) / chunk);
-  cout1_wgrad_kernel<<<grid, 256, smem, st>>>(dlogits, ih, iw, oh, ow, pad, npix, chunk, static_cast<const bf16*>(x),
-                                              ld_x, c, dw);
+  const Cout1Pre pre{in_scale, in_shift, in_slope};
+  if (in_scale)
+    cout1_wgrad_kernel<true><<<grid, 256, smem, st>>>(dlogits, ih, iw, oh, ow, pad, npix, chunk,
+                                                       static_cast<const bf16*>(x), ld_x, c, dw, pre);
+  else
+    cout1_wgrad_kernel<false><<<grid, 256, smem, st>>>(dlogits, ih, iw, oh, ow, pad, npix, chunk,
+                                                        static_cast<const bf16*>(x), ld_x, c, dw, pre);
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -327,10 +327,21 @@ def sum_f32(x: torch.Tensor, out: torch.Tensor) -> None:
     _lib.check(_lib.lib().gap_sum_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "gap_sum_f32")
 
 
+def _pre(pre: Optional[tuple], c: int):
+    """(scale, shift, slope) of a fused input transform LeakyReLU_slope(x*scale + shift) -> ctypes arguments."""
+    if pre is None:
+        return None, None, 0.0
+    sc, sh, slope = pre
+    if sc.dtype != torch.float32 or sh.dtype != torch.float32 or sc.numel() < c or sh.numel() < c:
+        raise ValueError("pre = (scale, shift, slope) needs fp32 vectors with >= c elements")
+    return _ptr(sc), _ptr(sh), float(slope)
+
+
 def cout1_conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], z_ws: torch.Tensor,
-                   logits: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:
+                   logits: torch.Tensor, ksize: int = 4, pad: int = 1, pre: Optional[tuple] = None) -> None:
     """Conv2d(C -> 1, k4, s1, p1) + bias (models.py:243): x NHWC bf16, w bf16 [16*C] ([kh][kw][c]), logits fp32
-    [n, oh, ow(, 1)]."""
+    [n, oh, ow(, 1)].  pre = (scale, shift, slope): x is the raw conv output below and BatchNorm + LeakyReLU
+    (models.py:239-240) are applied while it is read."""
     n, ih, iw, c, ld = _nhwc_view(x)
     if z_ws.dtype != torch.float32 or z_ws.numel() < n * ih * iw * 16 or logits.dtype != torch.float32:
         raise ValueError("z_ws / logits must be fp32 (z_ws >= n*ih*iw*16 elements)")
@@ -338,8 +349,9 @@ def cout1_conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
         raise ValueError("w must be bf16 [k*k*C]")
     if logits.numel() != n * (ih + 2 * pad - ksize + 1) * (iw + 2 * pad - ksize + 1):
         raise ValueError("logits shape mismatch")
+    sc, sh, slope = _pre(pre, c)
     _lib.check(_lib.lib().gap_cout1_conv_fwd(_ptr(x), ld, n, ih, iw, c, _ptr(w), _ptr(bias), ksize, pad, _ptr(z_ws),
-                                             _ptr(logits), _stream()), "gap_cout1_conv_fwd")
+                                             _ptr(logits), sc, sh, slope, _stream()), "gap_cout1_conv_fwd")
 
 
 def cout1_conv_dgrad(dlogits: torch.Tensor, w: torch.Tensor, gx: torch.Tensor, ksize: int = 4, pad: int = 1,
@@ -364,15 +376,17 @@ def cout1_conv_dgrad(dlogits: torch.Tensor, w: torch.Tensor, gx: torch.Tensor, k
                "gap_cout1_conv_dgrad_bwd")
 
 
-def cout1_conv_wgrad(dlogits: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksize: int = 4, pad: int = 1) -> None:
+def cout1_conv_wgrad(dlogits: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ksize: int = 4, pad: int = 1,
+                     pre: Optional[tuple] = None) -> None:
     n, ih, iw, c, ld = _nhwc_view(x)
     oh, ow = ih + 2 * pad - ksize + 1, iw + 2 * pad - ksize + 1
     if dlogits.dtype != torch.float32 or dlogits.numel() != n * oh * ow:
         raise ValueError("dlogits must be fp32 [n, oh, ow]")
     if dw.dtype != torch.float32 or dw.numel() != ksize * ksize * c:
         raise ValueError("dw must be fp32 [k*k*C]")
+    sc, sh, slope = _pre(pre, c)
     _lib.check(_lib.lib().gap_cout1_conv_wgrad(_ptr(dlogits), n, oh, ow, _ptr(x), ld, ih, iw, c, ksize, pad, _ptr(dw),
-                                               _stream()), "gap_cout1_conv_wgrad")
+                                               sc, sh, slope, _stream()), "gap_cout1_conv_wgrad")
 
 
 def thin_conv_fwd(s0: torch.Tensor, s1: Optional[torch.Tensor], wpk: torch.Tensor, bias: Optional[torch.Tensor],

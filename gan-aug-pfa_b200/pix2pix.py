@@ -330,6 +330,17 @@ class _Net:
         ops.bn_eval_scale_shift(gamma, beta, bn.running_mean, bn.running_var, BN_EPS, bn.scale, bn.shift)
         ops.bn_act(y, bn.scale, bn.shift, out1, act1, out2, act2)
 
+    def _bn_scale_shift(self, bn: _BN, y: torch.Tensor, repeat: int = 1) -> None:
+        """BatchNorm reduced to per-channel (scale, shift) WITHOUT an apply pass: the consumer kernel normalises and
+        activates while it reads the raw tensor.  Training: batch statistics from the conv epilogue's sums (+ running
+        buffers, saved mean / invstd for backward); eval: running statistics."""
+        gamma, beta = self.param(bn.name + ".weight"), self.param(bn.name + ".bias")
+        if self.training:
+            ops.bn_finalize(bn.stats, y.numel() // y.shape[-1], gamma, beta, BN_EPS, BN_MOMENTUM, repeat, bn.running_mean,
+                            bn.running_var, bn.nbt, bn.scale, bn.shift, bn.mean, bn.invstd)
+        else:
+            ops.bn_eval_scale_shift(gamma, beta, bn.running_mean, bn.running_var, BN_EPS, bn.scale, bn.shift)
+
     def _bn_eval(self, bn: _BN) -> None:
         """eval-mode BatchNorm as (scale, shift) from the running statistics (generate_synthetic_data.py:55)."""
         ops.bn_eval_scale_shift(self.param(bn.name + ".weight"), self.param(bn.name + ".bias"), bn.running_mean,
@@ -614,6 +625,10 @@ class GeneratorEngine(_Net):
 class DiscriminatorEngine(_Net):
     """NLayerDiscriminator(input_nc=6, ndf, n_layers, BatchNorm2d)."""
 
+    # BatchNorm + LeakyReLU of the last normalised layer (models.py:239-240) applied inside the Cout = 1 head's forward
+    # and wgrad kernels instead of a separate pass that writes H (63 MB written + re-read per forward at batch 64)
+    fuse_head = True
+
     _BUFFER_ATTRS = ("hs", "ws", "H", "y", "logits", "z_ws", "dlogits", "gH", "dy", "dfake", "_xa", "_xb")
 
     def __init__(self, device, input_nc: int = 6, ndf: int = 64, n_layers: int = 3, init: bool = True) -> None:
@@ -706,13 +721,16 @@ class DiscriminatorEngine(_Net):
                 hs.append(hs[-1] - 1)
                 ws.append(ws[-1] - 1)
         self.hs, self.ws = hs, ws
-        self.H = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
+        # H[k] = LeakyReLU(BN(y[k])): the input of conv k+1.  The last one is never materialised: the Cout = 1 head
+        # (forward and wgrad) normalises + activates the raw y while reading it (fuse_head).
+        self.H = [None if (self.fuse_head and k == self.n_conv - 2) else torch.empty(n, hs[k], ws[k], C[k], **bf)
+                  for k in range(self.n_conv - 1)]
         self.y = [None] + [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(1, self.n_conv - 1)]
         self.logits = torch.empty(n, hs[-1], ws[-1], 1, device=self.dev)
         self.z_ws = torch.empty(n * hs[-2] * ws[-2], 16, device=self.dev)      # per-pixel tap products of the last conv
         self.dlogits = torch.zeros(n, hs[-1], ws[-1], device=self.dev)            # fp32 d(loss)/d(logits)
-        self.gH = [torch.empty_like(t) for t in self.H]
-        self.dy = [torch.empty_like(t) for t in self.H]
+        self.gH = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
+        self.dy = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
         self.dfake = torch.zeros(n, h, w, 4, device=self.dev)
         self._n = (n, h, w)
         self.alloc_gen += 1
@@ -731,10 +749,18 @@ class DiscriminatorEngine(_Net):
             bn = self.bn[k]
             ops.conv_gemm([self.H[k - 1]], self.w_fwd[k], ops.geom_conv_fwd(4, self.stride(k), 1), self.y[k], C[k],
                           (self.hs[k], self.ws[k]), stats=bn.stats if self.training else None)
-            self._bn_forward(bn, self.y[k], self.H[k], ACT_LRELU)
+            if self.H[k] is None:
+                self._bn_scale_shift(bn, self.y[k])          # applied by the head's kernels on the fly
+            else:
+                self._bn_forward(bn, self.y[k], self.H[k], ACT_LRELU)
         k = self.n_conv - 1
-        ops.cout1_conv_fwd(self.H[k - 1], self.w_fwd[k].view(-1), self.param(self.k_conv[k] + ".bias"), self.z_ws,
-                           self.logits)
+        if self.H[k - 1] is None:
+            hb = self.bn[k - 1]
+            ops.cout1_conv_fwd(self.y[k - 1], self.w_fwd[k].view(-1), self.param(self.k_conv[k] + ".bias"), self.z_ws,
+                               self.logits, pre=(hb.scale, hb.shift, 0.2))
+        else:
+            ops.cout1_conv_fwd(self.H[k - 1], self.w_fwd[k].view(-1), self.param(self.k_conv[k] + ".bias"), self.z_ws,
+                               self.logits)
         return self.logits
 
     @_on_device
@@ -746,11 +772,15 @@ class DiscriminatorEngine(_Net):
         last = self.n_conv - 1
         g = self.store.g
         self._join_wgrad()
-        if wgrad:
-            self._fork_wgrad(lambda: ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1],
-                                                          self.store.seg(g, self.k_conv[last] + ".weight")))
-        # the Cout = 1 dgrad kernel applies the LeakyReLU backward of the last BatchNorm layer and accumulates its sums
         lb = self.bn[last - 1]
+        if wgrad:
+            wseg = self.store.seg(g, self.k_conv[last] + ".weight")
+            if self.H[last - 1] is None:
+                self._fork_wgrad(lambda: ops.cout1_conv_wgrad(self.dlogits, self.y[last - 1], wseg,
+                                                              pre=(lb.scale, lb.shift, 0.2)))
+            else:
+                self._fork_wgrad(lambda: ops.cout1_conv_wgrad(self.dlogits, self.H[last - 1], wseg))
+        # the Cout = 1 dgrad kernel applies the LeakyReLU backward of the last BatchNorm layer and accumulates its sums
         ops.cout1_conv_dgrad(self.dlogits, self.w_fwd[last].view(-1), self.gH[last - 1],
                              bwd=dict(y=self.y[last - 1], scale=lb.scale, shift=lb.shift, slope=0.2, sums=lb.sums))
         for k in range(last - 1, 0, -1):

@@ -208,9 +208,13 @@ int gap_sum_f32(const float* x, int64_t count, float* out, void* stream);
  *   wgrad: dw[tap][c] += sum_pix  dlogits[n][y-kh+pad][x-kw+pad] * x[pix][c]            (fp32)
  * x / gx: NHWC bf16 (pixel stride ld, multiple of 8); w: bf16 [16][c] ([kh][kw][c], the packed
  * forward operand); logits / dlogits: fp32 [n][oh][ow]; z_ws: fp32 workspace [n*ih*iw*16].
+ * in_scale / in_shift (fp32 [c], both or neither; c <= 512) + in_slope: x is then the RAW conv output of the layer below
+ * and the kernels form LeakyReLU_slope(x*in_scale + in_shift) while staging it -- the BatchNorm apply + activation of
+ * models.py:239-240 fused into its consumer, so the activated tensor never makes an HBM round trip.
  * ---------------------------------------------------------------------------------------------- */
 int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c, const void* w, const float* bias,
-                       int ksize, int pad, float* z_ws, float* logits, void* stream);
+                       int ksize, int pad, float* z_ws, float* logits, const float* in_scale, const float* in_shift,
+                       float in_slope, void* stream);
 int gap_cout1_conv_dgrad(const float* dlogits, int n, int oh, int ow, const void* w, int ksize, int pad, int c, void* gx,
                          int64_t ld_gx, int ih, int iw, void* stream);
 /* The same dgrad with the activation backward of the layer below and its BatchNorm-backward sums fused into the
@@ -220,7 +224,8 @@ int gap_cout1_conv_dgrad_bwd(const float* dlogits, int n, int oh, int ow, const 
                              int64_t ld_gx, int ih, int iw, const void* y, int64_t ld_y, const float* scale,
                              const float* shift, float slope, double* sums, void* stream);
 int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void* x, int64_t ld_x, int ih, int iw, int c,
-                         int ksize, int pad, float* dw, void* stream);
+                         int ksize, int pad, float* dw, const float* in_scale, const float* in_shift, float in_slope,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Thin-input Conv2d(k4, s2, p1) as one fused warp-MMA kernel (no im2col buffer): the generator's first

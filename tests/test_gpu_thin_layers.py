@@ -232,3 +232,37 @@ def test_uint8_image_input_and_output_paths():
     assert torch.equal(ou8.cpu(), want)
     ref_u8 = ((nhwc(y) * 0.5 + 0.5) * 255).to(torch.uint8).int()
     assert int((ou8.cpu().int() - ref_u8).abs().max()) <= 1                               # vs the fp32 reference: +-1 level
+
+
+@pytest.mark.parametrize("n,c,h", [(2, 512, 31), (3, 128, 9), (64, 512, 31)])
+def test_cout1_conv_with_batchnorm_leakyrelu_fused_into_the_loads(n, c, h):
+    """gap_cout1_conv_fwd / _wgrad with in_scale / in_shift / in_slope: the head reads the RAW conv output y of the layer
+    below and forms LeakyReLU(y*scale + shift) on the fly (models.py:239-240 fused into models.py:243) — same results as
+    running on the materialised activated tensor, which then never exists in HBM."""
+    g = torch.Generator().manual_seed(41 + c + n)
+    y = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16)
+    scale = torch.rand(c, generator=g) + 0.5
+    shift = torch.randn(c, generator=g) * 0.3
+    w = (torch.randn(1, c, 4, 4, generator=g) / (16 * c) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(1, generator=g)
+    act = F.leaky_relu(y.float() * scale + shift, 0.2).to(torch.bfloat16)             # what bn_act would have stored
+    wd = w.permute(0, 2, 3, 1).reshape(-1).contiguous().to(DEV)
+    yd, ad = y.to(DEV), act.to(DEV)
+    z = torch.empty(n * h * h, 16, device=DEV)
+    want = torch.empty(n, h - 1, h - 1, device=DEV)
+    got = torch.full_like(want, float("nan"))
+    ops.cout1_conv_fwd(ad, wd, b.to(DEV), z, want)
+    ops.cout1_conv_fwd(yd, wd, b.to(DEV), z, got, pre=(scale.to(DEV), shift.to(DEV), 0.2))
+    assert rel(got.cpu(), want.cpu()) < 2e-3          # one differently-rounded fma per element at most
+    ref = F.conv2d(act.float().permute(0, 3, 1, 2), w.float(), b, stride=1, padding=1)[:, 0]
+    assert rel(got.cpu(), ref) < 3e-3
+    dl = (torch.randn(n, h - 1, h - 1, generator=g) * 0.01).to(DEV)
+    dw_want = torch.zeros(16 * c, device=DEV)
+    dw_got = torch.zeros(16 * c, device=DEV)
+    ops.cout1_conv_wgrad(dl, ad, dw_want)
+    ops.cout1_conv_wgrad(dl, yd, dw_got, pre=(scale.to(DEV), shift.to(DEV), 0.2))
+    assert rel(dw_got.cpu(), dw_want.cpu()) < 2e-3
+    # a ragged last slab / zero rows must stay zero after the transform (BN(0) != 0): compare against fp32 torch
+    xr = act.float().permute(0, 3, 1, 2)
+    ref_w = torch.nn.grad.conv2d_weight(xr, (1, c, 4, 4), dl.cpu().unsqueeze(1), 1, 1)
+    assert rel(dw_got.cpu().view(4, 4, c), ref_w[0].permute(1, 2, 0)) < 6e-3
