@@ -114,6 +114,7 @@ _SIGNATURES = {
     "gap_add_inplace_bf16": (C.c_int, [_P, _L, _P, _L, _L, _I, _P]),
     "gap_att_add_relu_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "gap_relu_bwd": (C.c_int, [_P, _P, _P, _L, _P]),
+    "gap_lrelu_bwd_bf16": (C.c_int, [_P, _L, _P, _L, _F, _P, _L, _L, _I, _I, _P]),
     "gap_att_gate_fwd": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _L, _L, _I, _P]),
     "gap_att_gate_bwd": (C.c_int, [_P, _L, _P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
     "gap_vec_stats": (C.c_int, [_P, _L, _P, _P]),

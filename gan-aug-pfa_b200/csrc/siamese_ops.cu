@@ -333,6 +333,28 @@ __global__ void relu_bwd_kernel(const bf16* __restrict__ s, const bf16* __restri
   }
 }
 
+// LeakyReLU backward with strided operands: d (+)= y > 0 ? g : slope * g   (y = the activation's output or input: same sign)
+__global__ void lrelu_bwd_kernel(const bf16* __restrict__ y, long long ldy, const bf16* __restrict__ g, long long ldg,
+                                 float slope, bf16* __restrict__ d, long long ldd, long long pixels, int c, int accumulate) {
+  const int cv = c >> 3;
+  const long long total = pixels * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c8 = static_cast<int>(i - pix * cv) << 3;
+    float a[8], b[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + c8)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(g + pix * ldg + c8)), b);
+    if (accumulate) unpack8(*reinterpret_cast<const uint4*>(d + pix * ldd + c8), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = a[j] > 0.f ? b[j] : slope * b[j];
+      o[j] = accumulate ? o[j] + v : v;
+    }
+    *reinterpret_cast<uint4*>(d + pix * ldd + c8) = pack8(o);
+  }
+}
+
 // psi = sigmoid(ypsi*scale + shift); out[pix][c] = x[pix][c] * psi[pix]
 __global__ void att_gate_fwd_kernel(const float* __restrict__ ypsi, const float* __restrict__ scale,
                                     const float* __restrict__ shift, float* __restrict__ psi, const bf16* __restrict__ x,
@@ -705,6 +727,16 @@ int gap_relu_bwd(const void* s, const void* gs, void* d, int64_t count, void* st
   GAP_CHECK_ARG(s && gs && d && count > 0 && count % 8 == 0, "gap_relu_bwd: bad arguments");
   relu_bwd_kernel<<<grid_of(count / 8, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(s), static_cast<const bf16*>(gs), static_cast<bf16*>(d), count / 8);
+  SI_LAUNCH_OK();
+}
+
+int gap_lrelu_bwd_bf16(const void* y, int64_t ldy, const void* g, int64_t ldg, float slope, void* d, int64_t ldd,
+                       int64_t pixels, int c, int accumulate, void* stream) {
+  GAP_CHECK_ARG(y && g && d && pixels > 0 && c > 0 && c % 8 == 0 && ldy % 8 == 0 && ldg % 8 == 0 && ldd % 8 == 0,
+                "gap_lrelu_bwd_bf16: bad arguments");
+  lrelu_bwd_kernel<<<grid_of(pixels * (c / 8), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(y), ldy, static_cast<const bf16*>(g), ldg, slope, static_cast<bf16*>(d), ldd, pixels, c,
+      accumulate);
   SI_LAUNCH_OK();
 }
 

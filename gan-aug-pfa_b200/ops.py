@@ -662,6 +662,12 @@ def relu_bwd(s: torch.Tensor, gs: torch.Tensor, d: torch.Tensor) -> None:
     _lib.check(_lib.lib().gap_relu_bwd(_ptr(s), _ptr(gs), _ptr(d), s.numel(), _stream()), "gap_relu_bwd")
 
 
+def lrelu_bwd(y: torch.Tensor, g: torch.Tensor, slope: float, d: torch.Tensor, accumulate: bool) -> None:
+    """d (+)= (y > 0) ? g : slope*g on NHWC bf16 tensors / channel slices of the same shape."""
+    _lib.check(_lib.lib().gap_lrelu_bwd_bf16(_ptr(y), y.stride(-2), _ptr(g), g.stride(-2), slope, _ptr(d), d.stride(-2),
+                                             _px(y), y.shape[-1], 1 if accumulate else 0, _stream()), "gap_lrelu_bwd_bf16")
+
+
 def att_gate_fwd(ypsi, scale, shift, psi, x, out) -> None:
     _lib.check(_lib.lib().gap_att_gate_fwd(_ptr(ypsi), _ptr(scale), _ptr(shift), _ptr(psi), _ptr(x), x.stride(-2), _ptr(out),
                                            out.stride(-2), _px(x), x.shape[-1], _stream()), "gap_att_gate_fwd")

@@ -708,7 +708,7 @@ class DiscriminatorEngine(_Net):
         return plan
 
     def _alloc(self, n: int, h: int, w: int) -> None:
-        if self._n == (n, h, w):
+        if self._n == (n, h, w, self.fuse_head):
             return
         C = self.C
         bf = dict(device=self.dev, dtype=torch.bfloat16)
@@ -732,7 +732,7 @@ class DiscriminatorEngine(_Net):
         self.gH = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
         self.dy = [torch.empty(n, hs[k], ws[k], C[k], **bf) for k in range(self.n_conv - 1)]
         self.dfake = torch.zeros(n, h, w, 4, device=self.dev)
-        self._n = (n, h, w)
+        self._n = (n, h, w, self.fuse_head)
         self.alloc_gen += 1
 
     @_on_device

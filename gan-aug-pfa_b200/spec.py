@@ -37,22 +37,53 @@ class GeneratorSpec:
     conv `k_up[j]` (2*C[j] or C[j] -> C[j-1]); down norm `k_dbn[j]` exists for 1 <= j <= L-2, up norm
     `k_ubn[j]` for 1 <= j <= L-1."""
 
-    def __init__(self, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64) -> None:
-        if num_downs < 5:
-            raise ValueError("UNetGenerator needs num_downs >= 5 (models.py:155-161)")
-        self.input_nc, self.output_nc, self.L, self.ngf = input_nc, output_nc, num_downs, ngf
-        L = num_downs
-        # models.py:155-161: innermost ngf*8, (num_downs-5) x ngf*8, then ngf*8->4, 4->2, 2->1, outermost
-        inner = [ngf, ngf * 2, ngf * 4] + [ngf * 8] * (L - 3)
-        self.C: List[int] = inner
-        pref = ["model.model"]
-        for j in range(1, L):
-            pref.append(pref[-1] + (".1.model" if j == 1 else ".3.model"))
+    def __init__(self, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64,
+                 C: Optional[List[int]] = None, root: str = "model.model", virtual0: bool = False) -> None:
+        """`C`, `root`, `virtual0` describe a stand-alone UnetSkipConnectionBlock chain (see `for_block_chain`);
+        by default the layout is UNetGenerator's."""
+        if C is None:
+            if num_downs < 5:
+                raise ValueError("UNetGenerator needs num_downs >= 5 (models.py:155-161)")
+            # models.py:155-161: innermost ngf*8, (num_downs-5) x ngf*8, then ngf*8->4, 4->2, 2->1, outermost
+            C = [ngf, ngf * 2, ngf * 4] + [ngf * 8] * (num_downs - 3)
+        self.input_nc, self.output_nc, self.L, self.ngf = input_nc, output_nc, len(C), ngf
+        self.virtual0 = virtual0
+        L = self.L
+        self.C: List[int] = list(C)
+        # Sequential index of the sub-block inside its parent: 1 in the outermost block, 3 in a middle block
+        if virtual0:      # level 0 does not exist: level 1 is the called block itself, its Sequential is `root`
+            pref = [None, root]
+            for j in range(2, L):
+                pref.append(pref[-1] + ".3.model")
+        else:
+            pref = [root]
+            for j in range(1, L):
+                pref.append(pref[-1] + (".1.model" if j == 1 else ".3.model"))
         self.pref = pref
-        self.k_down = [pref[0] + ".0"] + [pref[j] + ".1" for j in range(1, L)]
+        first = None if virtual0 else pref[0] + ".0"
+        self.k_down = [first] + [pref[j] + ".1" for j in range(1, L)]
         self.k_dbn: List[Optional[str]] = [None] + [pref[j] + ".2" for j in range(1, L - 1)] + [None]
-        self.k_up = [pref[0] + ".3"] + [pref[j] + ".5" for j in range(1, L - 1)] + [pref[L - 1] + ".3"]
+        self.k_up = [None if virtual0 else pref[0] + ".3"] + [pref[j] + ".5" for j in range(1, L - 1)] + [pref[L - 1] + ".3"]
         self.k_ubn: List[Optional[str]] = [None] + [pref[j] + ".6" for j in range(1, L - 1)] + [pref[L - 1] + ".4"]
+        if L == 1:
+            raise ValueError("a U-Net needs at least one nested block")
+
+    @classmethod
+    def for_block_chain(cls, chain) -> "GeneratorSpec":
+        """Layout of a stand-alone UnetSkipConnectionBlock (models.py:167-208) and the blocks nested inside it.
+        `chain` lists (outer_nc, inner_nc, input_nc, outermost, innermost) from the called block inwards."""
+        outer0, inner0, in0, outermost0, _ = chain[0]
+        for (o, i, inp, om, im), nxt in zip(chain, chain[1:] + [None]):
+            if nxt is None:
+                if not im:
+                    raise NotImplementedError("the innermost nested block must be built with innermost=True")
+            elif nxt[0] != i or nxt[2] != i or nxt[3]:
+                raise NotImplementedError("nested blocks must chain outer_nc == input_nc == the parent's inner_nc")
+        if outermost0:
+            return cls(in0, outer0, C=[c[1] for c in chain], root="model")
+        if in0 != outer0:
+            raise NotImplementedError("a stand-alone inner block needs input_nc == outer_nc (the reference's default)")
+        return cls(in0, outer0, C=[in0] + [c[1] for c in chain], root="model", virtual0=True)
 
     def down_shape(self, j: int):
         return (self.C[j], self.input_nc if j == 0 else self.C[j - 1], 4, 4)
@@ -67,6 +98,8 @@ class GeneratorSpec:
 
         def block(j: int) -> List[str]:
             if j == 0:
+                if self.virtual0:
+                    return block(1)
                 return [self.k_down[0] + ".weight"] + block(1) + [self.k_up[0] + ".weight", self.k_up[0] + ".bias"]
             keys = [self.k_down[j] + ".weight"]
             if j < L - 1:
@@ -82,7 +115,7 @@ class GeneratorSpec:
         """Default torch init consuming the global CPU RNG exactly like UNetGenerator.__init__: blocks are
         built innermost first (models.py:155-161); within a block downconv, then upconv (+bias)."""
         sd: Dict[str, torch.Tensor] = {}
-        for j in range(self.L - 1, -1, -1):
+        for j in range(self.L - 1, 0 if self.virtual0 else -1, -1):
             w = torch.empty(*self.down_shape(j))
             _kaiming_uniform_(w)
             sd[self.k_down[j] + ".weight"] = w

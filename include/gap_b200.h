@@ -287,6 +287,10 @@ int gap_add_inplace_bf16(void* dst, int64_t ldd, const void* src, int64_t lds, i
 int gap_att_add_relu_fwd(const void* yg, const float* scale_g, const float* shift_g, const void* yx, const float* scale_x,
                          const float* shift_x, void* s, int64_t pixels, int c, void* stream);
 int gap_relu_bwd(const void* s, const void* gs, void* d, int64_t count, void* stream);
+/* LeakyReLU backward on NHWC bf16 channel slices: d (+)= (y > 0) ? g : slope*g.  Used by the stand-alone
+ * UnetSkipConnectionBlock path (models.py:178,208: the block's skip output is LeakyReLU(x) itself). */
+int gap_lrelu_bwd_bf16(const void* y, int64_t ldy, const void* g, int64_t ldg, float slope, void* d, int64_t ldd,
+                       int64_t pixels, int c, int accumulate, void* stream);
 int gap_att_gate_fwd(const float* ypsi, const float* scale, const float* shift, float* psi, const void* x, int64_t ldx,
                      void* out, int64_t ldo, int64_t pixels, int c, void* stream);
 int gap_att_gate_bwd(const void* gout, int64_t ldg, const void* x, int64_t ldx, const float* psi, void* gx, int64_t ldgx,

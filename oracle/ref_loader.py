@@ -1,4 +1,4 @@
-"""Import the staged reference (oracle/_ref/*.pyc, see stage_ref.py).  TEST INFRASTRUCTURE ONLY: tests/ and bench.py's
+"""Import the staged reference (oracle/_ref/*.gapref, see stage_ref.py).  TEST INFRASTRUCTURE ONLY: tests/ and bench.py's
 reference / library-baseline legs are the only callers.
 
 `load(models=None)` returns a namespace with the reference's modules (`models`, `dataset`, `train_gan`, `train`).
@@ -19,10 +19,11 @@ import types
 from pathlib import Path
 
 REF_DIR = Path(__file__).resolve().parent / "_ref"
+EXT = ".gapref"
 
 
 def available() -> bool:
-    return (REF_DIR / "models.pyc").exists() and (REF_DIR / "train_gan.pyc").exists()
+    return (REF_DIR / ("models" + EXT)).exists() and (REF_DIR / ("train_gan" + EXT)).exists()
 
 
 class _NoBar:
@@ -37,7 +38,7 @@ class _NoBar:
 
 
 def _import_pyc(name: str, alias: str):
-    path = REF_DIR / f"{name}.pyc"
+    path = REF_DIR / (name + EXT)
     loader = importlib.machinery.SourcelessFileLoader(alias, str(path))
     spec = importlib.util.spec_from_loader(alias, loader)
     mod = importlib.util.module_from_spec(spec)
