@@ -38,8 +38,15 @@ struct Cout1Pre {
   float slope;
 };
 
+// eight consecutive fp32 parameters (32-byte aligned shared memory) as two 128-bit loads
+__device__ __forceinline__ void lds8(const float* p, float (&r)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+  r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+
 // y*scale + shift, then x > 0 ? x : slope*x, on eight packed bf16 channels
-__device__ __forceinline__ uint4 bn_act8(uint4 v, const float* __restrict__ sc, const float* __restrict__ sh, float slope) {
+__device__ __forceinline__ uint4 bn_act8(uint4 v, const float (&sc)[8], const float (&sh)[8], float slope) {
   uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -53,7 +60,7 @@ __device__ __forceinline__ uint4 bn_act8(uint4 v, const float* __restrict__ sc, 
 }
 
 template <bool PRE>
-__global__ void __launch_bounds__(256) cout1_z_kernel(const bf16* __restrict__ x, long long ld_x, long long npix,
+__global__ void __launch_bounds__(256, 4) cout1_z_kernel(const bf16* __restrict__ x, long long ld_x, long long npix,
                                                       int c, const bf16* __restrict__ w, float* __restrict__ z,
                                                       const Cout1Pre pre) {
   __shared__ __align__(16) bf16 xs[128][72];
@@ -78,11 +85,16 @@ __global__ void __launch_bounds__(256) cout1_z_kernel(const bf16* __restrict__ x
       nxt[i] = pix < npix ? ldg128(x + pix * ld_x + seg * 8) : make_uint4(0, 0, 0, 0);
     }
     for (int c0 = 0; c0 < c; c0 += 64) {
+      float sc[8], sh[8];       // this thread always stages the same 8 channels of a chunk (seg = tid & 7)
+      if (PRE) {
+        lds8(par + c0 + (tid & 7) * 8, sc);
+        lds8(par + 512 + c0 + (tid & 7) * 8, sh);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int v = tid + i * 256, px = v >> 3, seg = v & 7;
         uint4 val = nxt[i];
-        if (PRE && tile * 128 + px < npix) val = bn_act8(val, par + c0 + seg * 8, par + 512 + c0 + seg * 8, pre.slope);
+        if (PRE && tile * 128 + px < npix) val = bn_act8(val, sc, sh, pre.slope);
         *reinterpret_cast<uint4*>(&xs[px][seg * 8]) = val;
       }
       if (tid < 128) {
@@ -309,7 +321,7 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
 // The next 16-pixel slab's global loads are in flight while the current slab's MMAs run (register prefetch;
 // kVec = uint4 per thread and slab = 16 * c / 8 / 256, i.e. 4 for c = 512).
 template <bool PRE>
-__global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restrict__ dlog, int ih, int iw, int oh, int ow,
+__global__ void __launch_bounds__(256, 4) cout1_wgrad_kernel(const float* __restrict__ dlog, int ih, int iw, int oh, int ow,
                                                           int pad, long long npix, long long chunk,
                                                           const bf16* __restrict__ x, long long ld_x, int c,
                                                           float* __restrict__ dw, const Cout1Pre pre) {
@@ -331,6 +343,9 @@ __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restric
     for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
   const int vec_per_px = c >> 3;
   const int n_vec = 16 * vec_per_px;        // <= 1024 (c <= 512): at most 4 per thread
+  // vec_per_px (c / 8) divides 256 for the supported c in {64, 128, 256, 512}: idx % vec_per_px = tid % vec_per_px for
+  // every i, so a thread always stages the same 8 channels; their scale / shift sit in shared memory as one 32-byte row
+  // per channel group (two 128-bit loads per slab: registers are needed for the 32 accumulators and the prefetch)
   if (PRE) {
     for (int i = tid; i < c; i += 256) {
       par[i] = __ldg(pre.scale + i);
@@ -338,6 +353,7 @@ __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restric
     }
     __syncthreads();
   }
+  const int my_ch = (tid % vec_per_px) * 8;
   uint4 nxt[4];
   float unxt = 0.f;
   auto fetch = [&](long long k0) {
@@ -363,7 +379,12 @@ __global__ void __launch_bounds__(256) cout1_wgrad_kernel(const float* __restric
       if (idx < n_vec) {
         const int px = idx / vec_per_px, seg = idx - px * vec_per_px;
         uint4 val = nxt[i];
-        if (PRE && k0 + px < p1) val = bn_act8(val, par + seg * 8, par + c + seg * 8, pre.slope);
+        if (PRE && k0 + px < p1) {
+          float sc[8], sh[8];
+          lds8(par + my_ch, sc);
+          lds8(par + c + my_ch, sh);
+          val = bn_act8(val, sc, sh, pre.slope);
+        }
         *reinterpret_cast<uint4*>(xs + px * xstride + seg * 8) = val;
       }
     }
@@ -1103,6 +1124,7 @@ int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GAP_CHECK_ARG(dlogits && x && dw && n > 0 && oh > 0 && ow > 0 && ih > 0 && iw > 0, "gap_cout1_conv_wgrad: bad arguments");
   GAP_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "gap_cout1_conv_wgrad: in_scale / in_shift come together");
+  GAP_CHECK_ARG(!in_scale || 256 % (c / 8) == 0, "gap_cout1_conv_wgrad: the fused input transform needs c in {64, 128, 256, 512}");
   if (ksize != 4 || c % 64 != 0 || c <= 0 || c > 512 || ld_x % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) {
     set_error("gap_cout1_conv_wgrad: needs ksize 4, channels %% 64 == 0, <= 512, 16-byte aligned rows");
     return GAP_ERR_UNSUPPORTED;

@@ -27,40 +27,16 @@ from .pix2pix import DiscriminatorEngine, GeneratorEngine
 # ------------------------------------------------------------------------------------------------
 # module skeletons: identical structure to the reference so that keys and RNG consumption match
 # ------------------------------------------------------------------------------------------------
-class UnetSkipConnectionBlock(nn.Module):
-    """One U-Net level (models.py:167-208).  Kept as a container of the reference's layers; the
-    computation happens in UNetGenerator.forward through the native engine."""
-
-    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
-                 norm_layer=nn.BatchNorm2d, use_dropout=False):
-        super().__init__()
-        self.outermost = outermost
-        if type(norm_layer) == functools.partial:
-            use_bias = norm_layer.func == nn.InstanceNorm2d
-        else:
-            use_bias = norm_layer == nn.InstanceNorm2d
-        if input_nc is None:
-            input_nc = outer_nc
-        downconv = nn.Conv2d(input_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
-        downrelu = nn.LeakyReLU(0.2, True)
-        downnorm = norm_layer(inner_nc)
-        uprelu = nn.ReLU(True)
-        upnorm = norm_layer(outer_nc)
-        if outermost:
-            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
-            layers = [downconv, submodule, uprelu, upconv, nn.Tanh()]
-        elif innermost:
-            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
-            layers = [downrelu, downconv, uprelu, upconv, upnorm]
-        else:
-            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
-            layers = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
-            if use_dropout:
-                layers.append(nn.Dropout(0.5))
-        self.model = nn.Sequential(*layers)
-
-    def forward(self, x):  # pragma: no cover - the enclosing generator owns the computation
-        raise RuntimeError("UnetSkipConnectionBlock is executed by UNetGenerator.forward (native engine)")
+def _is_dense_permutation(t: torch.Tensor) -> bool:
+    """True when the tensor's elements tile a contiguous block of memory exactly once in SOME dimension order (what
+    torch calls non-overlapping and dense): foreach optimizers keep their fast path for such parameters."""
+    dims = sorted((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1)
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
 
 
 class _NativeModule(nn.Module):
@@ -88,7 +64,7 @@ class _NativeModule(nn.Module):
             for name, q in self.named_parameters():
                 view = eng.param(name)
                 view.copy_(q)
-                if view.is_non_overlapping_and_dense():
+                if _is_dense_permutation(view):
                     q.data = view              # same Parameter object (optimizers keep working), engine-owned storage
                 else:
                     copied.append((name, q))
@@ -139,6 +115,112 @@ class _NativeModule(nn.Module):
         eng._join_wgrad()
         flat = eng.store.g.clone()
         return [eng.view(flat, name) for name in names]
+
+
+class _BlockFn(torch.autograd.Function):
+    """A stand-alone UnetSkipConnectionBlock through the native engine (forward, input gradient, parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, module, x, grad_mode, *params):
+        eng = module._engine()
+        eng.forward(x.detach().contiguous().float())
+        out = eng.output_nchw()
+        need = grad_mode and (x.requires_grad or any(p.requires_grad for p in params))
+        ctx.module = module
+        ctx.x_grad = x.requires_grad
+        ctx.snap = eng.detach_buffers() if need else None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        module = ctx.module
+        eng = module._engine_obj
+        eng.attach_buffers(ctx.snap)
+        eng.zero_grad()
+        names = [name for name, _ in module.named_parameters()]
+        gx = None
+        if eng.virtual0:
+            n, c2, h, w = gout.shape
+            ops.nchw_to_nhwc_bf16(gout.contiguous().float(), eng.gR[0])      # gradient of cat([x, model(x)], 1)
+            eng.backward()
+            if ctx.x_grad:
+                gx = torch.empty(n, c2 // 2, h, w, device=gout.device)
+                ops.nhwc_to_nchw_f32(eng.dyd[0], gx, c2 // 2)
+        else:
+            if ctx.x_grad:
+                raise NotImplementedError("gradient w.r.t. the image input of the outermost block is not provided")
+            ops.tanh_bwd(gout.contiguous().float(), eng.fake_f32, eng.dpre)
+            eng.backward()
+        grads = module._grads_for_autograd(eng, names)
+        return (None, gx, None, *grads)
+
+
+class UnetSkipConnectionBlock(_NativeModule):
+    """One U-Net level (models.py:167-208).  Kept as a container of the reference's layers; the
+    computation happens in UNetGenerator.forward through the native engine."""
+
+    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
+                 norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super().__init__()
+        self.outermost = outermost
+        # structure record for the native engine of a direct call on this block (object.__setattr__: the nested block is
+        # registered once, as part of self.model, like in the reference)
+        object.__setattr__(self, "_sub", submodule)
+        object.__setattr__(self, "_shape", (outer_nc, inner_nc, outer_nc if input_nc is None else input_nc,
+                                            bool(outermost), bool(innermost)))
+        object.__setattr__(self, "_has_dropout", bool(use_dropout) or
+                           (submodule is not None and getattr(submodule, "_has_dropout", False)))
+        if type(norm_layer) == functools.partial:
+            use_bias = norm_layer.func == nn.InstanceNorm2d
+        else:
+            use_bias = norm_layer == nn.InstanceNorm2d
+        if input_nc is None:
+            input_nc = outer_nc
+        downconv = nn.Conv2d(input_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+        downrelu = nn.LeakyReLU(0.2, True)
+        downnorm = norm_layer(inner_nc)
+        uprelu = nn.ReLU(True)
+        upnorm = norm_layer(outer_nc)
+        if outermost:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            layers = [downconv, submodule, uprelu, upconv, nn.Tanh()]
+        elif innermost:
+            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            layers = [downrelu, downconv, uprelu, upconv, upnorm]
+        else:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            layers = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
+            if use_dropout:
+                layers.append(nn.Dropout(0.5))
+        self.model = nn.Sequential(*layers)
+
+    def _chain(self):
+        """(outer_nc, inner_nc, input_nc, outermost, innermost) of this block and the blocks nested in it."""
+        out, blk = [], self
+        while blk is not None:
+            if not isinstance(blk, UnetSkipConnectionBlock):
+                raise NotImplementedError("the native path needs UnetSkipConnectionBlock sub-modules")
+            out.append(blk._shape)
+            blk = blk._sub
+        return out
+
+    def _make_engine(self, device):
+        from .spec import GeneratorSpec
+        if self._has_dropout:
+            raise NotImplementedError("stand-alone blocks with use_dropout=True are not implemented natively "
+                                      "(UNetGenerator(use_dropout=True) is)")
+        return GeneratorEngine(device, init=False, spec=GeneratorSpec.for_block_chain(self._chain()))
+
+    def forward(self, x):
+        """models.py:204-208: `self.model(x)` for the outermost block, else `torch.cat([x, self.model(x)], 1)` — where x
+        has already been through the block's in-place LeakyReLU, so the skip half is LeakyReLU(x) (and, like the
+        reference, the caller's tensor is modified in place to match).  Inside a UNetGenerator the generator's fused
+        engine runs the whole stack; this entry point serves direct calls on a block."""
+        out = _BlockFn.apply(self, x, torch.is_grad_enabled(), *self.parameters())
+        if not self.outermost and not (torch.is_grad_enabled() and x.requires_grad):
+            with torch.no_grad():
+                x.copy_(out[:, :x.shape[1]])          # nn.LeakyReLU(0.2, True) mutated the caller's tensor (models.py:178)
+        return out
 
 
 class _GeneratorFn(torch.autograd.Function):
@@ -284,19 +366,96 @@ def double_conv(in_channels, out_channels):
     )
 
 
-class AttentionGate(nn.Module):
-    """Attention gate (models.py:18-44); executed by the enclosing SiameseUNet through the native engine."""
+class _GateFn(torch.autograd.Function):
+    """A stand-alone AttentionGate through siamese.GateEngine (forward, both input gradients, parameter gradients).
+    The engine keeps the activations of its most recent forward: backward must follow its forward."""
+
+    @staticmethod
+    def forward(ctx, module, g, x, *params):
+        eng = module._engine()
+        out = eng.forward(g.detach(), x.detach())
+        n, h, w, fl = out.shape
+        res = torch.empty(n, fl, h, w, device=out.device)
+        ops.nhwc_to_nchw_f32(out, res, fl)
+        ctx.module = module
+        ctx.needs = (g.requires_grad, x.requires_grad)
+        return res
+
+    @staticmethod
+    def backward(ctx, gout):
+        module = ctx.module
+        eng = module._engine_obj
+        eng.zero_grad()
+        ops.nchw_to_nhwc_bf16(gout.contiguous().float(), eng.gout)
+        eng.backward()
+        grads_in = []
+        for need, buf in zip(ctx.needs, (eng.gg, eng.gxs)):
+            if need:
+                n, h, w, c = buf.shape
+                t = torch.empty(n, c, h, w, device=gout.device)
+                ops.nhwc_to_nchw_f32(buf, t, c)
+                grads_in.append(t)
+            else:
+                grads_in.append(None)
+        grads = module._grads_for_autograd(eng, [name for name, _ in module.named_parameters()])
+        return (None, *grads_in, *grads)
+
+
+class AttentionGate(_NativeModule):
+    """Attention gate (models.py:18-44).  Inside SiameseUNet the network's fused engine executes it; a direct call runs
+    the same kernels through a stand-alone siamese.GateEngine."""
 
     def __init__(self, F_g, F_l, F_int):
         super().__init__()
+        self._cfg = (F_g, F_l, F_int)
         self.W_g = nn.Sequential(nn.Conv2d(F_g, F_int, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(F_int))
         self.W_x = nn.Sequential(nn.Conv2d(F_l, F_int, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(F_int))
         self.psi = nn.Sequential(nn.Conv2d(F_int, 1, kernel_size=1, stride=1, padding=0, bias=True), nn.BatchNorm2d(1),
                                  nn.Sigmoid())
         self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, g, x):  # pragma: no cover
-        raise RuntimeError("AttentionGate is executed by SiameseUNet.forward (native engine)")
+    def _make_engine(self, device):
+        from .siamese import GateEngine
+        return GateEngine(device, *self._cfg)
+
+    def forward(self, g, x):
+        """x * Sigmoid(BN(psi(ReLU(BN(W_g g) + BN(W_x x)))))   (models.py:39-44)"""
+        return _GateFn.apply(self, g, x, *self.parameters())
+
+
+class _EncoderFn(torch.autograd.Function):
+    """SiameseUNet.forward_encoder on its own: one pass of the shared encoder through the network's engine."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module._engine()
+        if x.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the input images are not provided (the reference never needs them)")
+        feats = eng.forward_encoder(x.detach())
+        outs = []
+        for f in feats:
+            n, h, w, c = f.shape
+            t = torch.empty(n, c, h, w, device=f.device)
+            ops.nhwc_to_nchw_f32(f, t, c)
+            outs.append(t)
+        ctx.module = module
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        module = ctx.module
+        eng = module._engine_obj
+        eng.zero_grad()
+        for lvl, g in enumerate(gouts):
+            c = g.shape[1] if g is not None else eng.gS[lvl].shape[-1] // 2
+            slot = eng.gS[lvl][..., :c]
+            if g is None:
+                slot.zero_()
+            else:
+                ops.nchw_to_nhwc_bf16(g.contiguous().float(), slot)
+        eng.backward_encoder()
+        grads = module._grads_for_autograd(eng, [name for name, _ in module.named_parameters()])
+        return (None, None, *grads)
 
 
 class _SiameseFn(torch.autograd.Function):
@@ -352,8 +511,10 @@ class SiameseUNet(_NativeModule):
         from .siamese import SiameseEngine
         return SiameseEngine(device, self.n_channels, self.n_classes)
 
-    def forward_encoder(self, x):  # pragma: no cover - kept for API compatibility (models.py:92-102)
-        raise RuntimeError("forward_encoder is fused into SiameseUNet.forward (native engine)")
+    def forward_encoder(self, x):
+        """One pass of the shared encoder (models.py:92-102): returns (conv1, conv2, conv3, conv4, bottleneck).  forward()
+        runs both passes and the decoder inside one fused engine call; this entry point serves direct calls."""
+        return _EncoderFn.apply(self, x, *self.parameters())
 
     def forward(self, x1, x2):
         return _SiameseFn.apply(self, x1, x2, *self.parameters())

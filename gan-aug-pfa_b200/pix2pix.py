@@ -364,10 +364,14 @@ class GeneratorEngine(_Net):
     """UNetGenerator(input_nc=3, output_nc=3, num_downs, ngf, BatchNorm2d, use_dropout=False)."""
 
     _BUFFER_ATTRS = ("S", "x_nhwc", "A", "R", "Rin", "yd", "yu", "fake_bf", "fake_f32", "dpre", "gR", "gRin", "gA",
-                     "dyu", "dyd")
+                     "dyu", "dyd", "xin", "out_cat")
 
     def __init__(self, device, input_nc: int = 3, output_nc: int = 3, num_downs: int = 7, ngf: int = 64,
-                 init: bool = True, use_dropout: bool = False, dropout_seed: int = 0) -> None:
+                 init: bool = True, use_dropout: bool = False, dropout_seed: int = 0,
+                 spec: Optional[GeneratorSpec] = None) -> None:
+        """`spec` (GeneratorSpec.for_block_chain) builds the engine of a stand-alone UnetSkipConnectionBlock instead of a
+        whole UNetGenerator.  With spec.virtual0 the chain starts at an inner block: level 0 has no layers, the input
+        is the block's C[0]-channel feature map and the output is torch.cat([x, model(x)], 1) (models.py:208)."""
         super().__init__(device)
         # nn.Dropout(0.5) after the up-norm of the num_downs-5 blocks at ngf*8 (models.py:156-157,197-198); their up
         # outputs are yu[j] for j = L-2 ... L-1-(num_downs-5)
@@ -375,17 +379,26 @@ class GeneratorEngine(_Net):
         self.dropout_seed = dropout_seed
         self.dropout_calls = 0          # forward counter: every forward draws fresh masks
         self._drop_off: Dict[int, int] = {}
-        if input_nc != 3 or output_nc != 3:
-            raise NotImplementedError("the native generator supports input_nc = output_nc = 3")
-        if ngf % 64 != 0 or num_downs < 5:
-            raise NotImplementedError("ngf must be a multiple of 64 and num_downs >= 5")
-        self.spec = sp = GeneratorSpec(input_nc, output_nc, num_downs, ngf)
-        self.L = L = num_downs
+        if spec is None:
+            if input_nc != 3 or output_nc != 3:
+                raise NotImplementedError("the native generator supports input_nc = output_nc = 3")
+            if ngf % 64 != 0 or num_downs < 5:
+                raise NotImplementedError("ngf must be a multiple of 64 and num_downs >= 5")
+            spec = GeneratorSpec(input_nc, output_nc, num_downs, ngf)
+        else:
+            if use_dropout:
+                raise NotImplementedError("stand-alone blocks with dropout are not implemented natively")
+            if any(c % 64 for c in spec.C) or (not spec.virtual0 and (spec.input_nc != 3 or spec.output_nc != 3)):
+                raise NotImplementedError("native blocks need channel counts that are multiples of 64 (3 at the image side)")
+        self.spec = sp = spec
+        self.virtual0 = v0 = sp.virtual0
+        self.L = L = sp.L
         self.C = C = sp.C
         self.k_down, self.k_dbn, self.k_up, self.k_ubn = sp.k_down, sp.k_dbn, sp.k_up, sp.k_ubn
         # flat-buffer order = order in which gradients complete in backward (DP buckets)
-        self._reg_small(self.k_up[0] + ".weight", 2 * C[0], 3, 64)
-        self._reg_vec(self.k_up[0] + ".bias", 3)
+        if not v0:
+            self._reg_small(self.k_up[0] + ".weight", 2 * C[0], 3, 64)
+            self._reg_vec(self.k_up[0] + ".bias", 3)
         self.ubn: List[Optional[_BN]] = [None] * L
         self.dbn: List[Optional[_BN]] = [None] * L
         for j in range(1, L):
@@ -396,7 +409,8 @@ class GeneratorEngine(_Net):
             self._reg_conv(self.k_down[j] + ".weight", C[j], C[j - 1])
             if self.k_dbn[j] is not None:
                 self.dbn[j] = self._reg_bn(self.k_dbn[j], C[j])
-        self._reg_small(self.k_down[0] + ".weight", C[0], 3, 64)
+        if not v0:
+            self._reg_small(self.k_down[0] + ".weight", C[0], 3, 64)
         self.store.allocate(device)
         for bn in self.bns.values():
             bn.allocate(device)
@@ -408,10 +422,13 @@ class GeneratorEngine(_Net):
         self.w_d_dg = [None] + [torch.zeros(4, C[j - 1], 4 * C[j], **bf) for j in range(1, L)]
         self.w_u_fwd = [None]
         self.w_u_dg = [None]
-        self.w_u_T2 = torch.zeros(48, 2 * C[0], **bf)        # last ConvTranspose2d, forward: [(kh*4+kw)*3 + co][Cin]
-        # thin-layer operands [rows][16 taps x 4 channel slots] (3 channels + a zero slot)
-        self.w_d_thin = torch.zeros(C[0], 64, **bf)          # first conv, models.py:177
-        self.w_u_thin = torch.zeros(2 * C[0], 64, **bf)      # last ConvTranspose2d seen from its dgrad
+        if not v0:
+            self.w_u_T2 = torch.zeros(48, 2 * C[0], **bf)        # last ConvTranspose2d, forward: [(kh*4+kw)*3 + co][Cin]
+            # thin-layer operands [rows][16 taps x 4 channel slots] (3 channels + a zero slot)
+            self.w_d_thin = torch.zeros(C[0], 64, **bf)          # first conv, models.py:177
+            self.w_u_thin = torch.zeros(2 * C[0], 64, **bf)      # last ConvTranspose2d seen from its dgrad
+        else:
+            self._ident = (torch.ones(C[0], device=device), torch.zeros(C[0], device=device))
         for j in range(1, L):
             cin = C[j] if j == L - 1 else 2 * C[j]
             self.w_u_fwd.append(torch.zeros(4, C[j - 1], 4 * cin, **bf))
@@ -441,11 +458,12 @@ class GeneratorEngine(_Net):
             o = off(self.k_down[j] + ".weight")
             plan.add(p, o, self.w_d_fwd[j], 0, 1, co, co, (4, 4), ci, ci, 16 * ci, (16 * ci, 1, 4 * ci, ci))
             plan.add(p, o, self.w_d_dg[j], 2, 4, ci, ci, (2, 2), co, co, 4 * co, (1, 16 * ci, 4 * ci, ci))
-        k0 = off(self.k_up[0] + ".weight")
-        c2 = 2 * C[0]
-        plan.add(p, k0, self.w_u_T2, 0, 1, 48, 48, (1, 1), c2, c2, c2, (1, 64, 0, 0))
-        plan.add(p, off(self.k_down[0] + ".weight"), self.w_d_thin, 0, 1, C[0], C[0], (4, 4), 3, 4, 64, (64, 1, 12, 3))
-        plan.add(p, k0, self.w_u_thin, 0, 1, c2, c2, (4, 4), 3, 4, 64, (64, 1, 12, 3))
+        if not self.virtual0:
+            k0 = off(self.k_up[0] + ".weight")
+            c2 = 2 * C[0]
+            plan.add(p, k0, self.w_u_T2, 0, 1, 48, 48, (1, 1), c2, c2, c2, (1, 64, 0, 0))
+            plan.add(p, off(self.k_down[0] + ".weight"), self.w_d_thin, 0, 1, C[0], C[0], (4, 4), 3, 4, 64, (64, 1, 12, 3))
+            plan.add(p, k0, self.w_u_thin, 0, 1, c2, c2, (4, 4), 3, 4, 64, (64, 1, 12, 3))
         for j in range(1, L):
             ci = C[j] if j == L - 1 else 2 * C[j]
             co = C[j - 1]
@@ -458,22 +476,32 @@ class GeneratorEngine(_Net):
     def _alloc(self, n: int, h: int, w: int) -> None:
         if self._n == (n, h, w):
             return
-        L, C = self.L, self.C
-        if h % (1 << L) or w % (1 << L):
-            raise ValueError(f"input {h}x{w} must be divisible by 2^{L}")
+        L, C, v0 = self.L, self.C, self.virtual0
+        depth = L - 1 if v0 else L                  # number of stride-2 down convs applied to the input
+        if h % (1 << depth) or w % (1 << depth):
+            raise ValueError(f"input {h}x{w} must be divisible by 2^{depth}")
         bf = dict(device=self.dev, dtype=torch.bfloat16)
-        S = [(h >> (j + 1), w >> (j + 1)) for j in range(L)]
+        base = 0 if v0 else 1                       # S[j]: spatial size of level j's feature maps
+        S = [(h >> (j + base), w >> (j + base)) for j in range(L)]
         self.S = S
-        self.x_nhwc = torch.zeros(n, h, w, 4, **bf)
-        self.A = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
-        self.R = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
+        if v0:
+            # stand-alone inner block: xin = the block's input, out_cat = cat([LeakyReLU(x), BN(ConvT(...))], 1); A[0] is
+            # its first half (the in-place LeakyReLU of models.py:178 is what the skip carries, models.py:208)
+            self.xin = torch.empty(n, h, w, C[0], **bf)
+            self.out_cat = torch.empty(n, h, w, 2 * C[0], **bf)
+            self.A = [self.out_cat[..., :C[0]]] + [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(1, L - 1)]
+            self.R = [None] + [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(1, L - 1)]
+        else:
+            self.x_nhwc = torch.zeros(n, h, w, 4, **bf)
+            self.A = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
+            self.R = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
+            self.fake_bf = torch.zeros(n, h, w, 4, **bf)
+            self.fake_f32 = torch.zeros(n, h, w, 4, device=self.dev)
+            self.dpre = torch.zeros(n, h, w, 4, **bf)
         self.Rin = torch.empty(n, S[L - 1][0], S[L - 1][1], C[L - 1], **bf)
         self.yd = [None] + [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(1, L - 1)] + [None]
         self.yu = [None] + [torch.empty(n, S[j - 1][0], S[j - 1][1], C[j - 1], **bf) for j in range(1, L)]
-        self.fake_bf = torch.zeros(n, h, w, 4, **bf)
-        self.fake_f32 = torch.zeros(n, h, w, 4, device=self.dev)
         # backward scratch
-        self.dpre = torch.zeros(n, h, w, 4, **bf)
         self.gR = [torch.empty(n, S[j][0], S[j][1], 2 * C[j], **bf) for j in range(L - 1)]
         self.gRin = torch.empty_like(self.Rin)
         self.gA = [torch.empty(n, S[j][0], S[j][1], C[j], **bf) for j in range(L - 1)]
@@ -507,13 +535,23 @@ class GeneratorEngine(_Net):
         generate_synthetic_data.py:69-88 saves, written by the last layer's epilogue.  x_ready: prepare_input(x) has
         already run (the trainer converts the input before it forks the generator onto its own stream)."""
         self._join_wgrad()
-        if not x_ready:
+        v0 = self.virtual0
+        if v0:
+            # stand-alone inner block: x is its fp32 NCHW feature map; A[0] = LeakyReLU(x) (models.py:178, in place)
+            n, c, h, w = x_nchw.shape
+            if c != self.C[0]:
+                raise ValueError(f"block input has {c} channels, expected {self.C[0]}")
+            self._alloc(n, h, w)
+            ops.nchw_to_nhwc_bf16(x_nchw.contiguous().float(), self.xin)
+            ops.bn_act(self.xin, self._ident[0], self._ident[1], self.A[0], ACT_LRELU)
+        elif not x_ready:
             self.prepare_input(x_nchw)
         L, C, S = self.L, self.C, self.S
         g_s2 = ops.geom_conv_fwd(4, 2, 1)
         g_1x1 = ops.geom_conv_fwd(1, 1, 0)
         g_ph = ops.geom_phase_k4s2p1()
-        ops.thin_conv_fwd(self.x_nhwc, None, self.w_d_thin, None, self.A[0], ACT_LRELU, self.R[0][..., :C[0]], ACT_RELU)
+        if not v0:
+            ops.thin_conv_fwd(self.x_nhwc, None, self.w_d_thin, None, self.A[0], ACT_LRELU, self.R[0][..., :C[0]], ACT_RELU)
         for j in range(1, L - 1):
             bn = self.dbn[j]
             if not self.training:      # eval: BatchNorm folds into the conv epilogue (scale, shift), no extra pass
@@ -527,18 +565,22 @@ class GeneratorEngine(_Net):
         for j in range(L - 1, 0, -1):
             src = self.Rin if j == L - 1 else self.R[j]
             bn = self.ubn[j]
+            # the parent's in-place ReLU (models.py:180) acts on the concatenated tensor; a stand-alone block returns
+            # its up-norm output un-activated
+            dst, act = (self.out_cat[..., C[0]:], ACT_NONE) if (v0 and j == 1) else (self.R[j - 1][..., C[j - 1]:], ACT_RELU)
             if not self.training:
                 self._bn_eval(bn)
-                ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.R[j - 1][..., C[j - 1]:], C[j - 1], S[j], act=ACT_RELU,
-                              scale=bn.scale, bias=bn.shift)
+                ops.conv_gemm([src], self.w_u_fwd[j], g_ph, dst, C[j - 1], S[j], act=act, scale=bn.scale, bias=bn.shift)
                 continue
             ops.conv_gemm([src], self.w_u_fwd[j], g_ph, self.yu[j], C[j - 1], S[j], stats=bn.stats)
-            self._bn_forward(bn, self.yu[j], self.R[j - 1][..., C[j - 1]:], ACT_RELU, repeat=bn_repeat)
+            self._bn_forward(bn, self.yu[j], dst, act, repeat=bn_repeat)
             if self._dropout_layer(j):
                 # ReLU(Dropout(v)) = Dropout(ReLU(v)): the mask multiplies the slot the parent block reads
                 slot = self.R[j - 1][..., C[j - 1]:]
                 self._drop_off[j] = (self.dropout_calls << 40) + (j << 34)
                 ops.dropout_(slot, 0.5, self.dropout_seed, self._drop_off[j])
+        if v0:
+            return self.out_cat
         ops.thin_convT_fwd(self.R[0], self.w_u_T2, self.param(self.k_up[0] + ".bias"), ACT_TANH, self.fake_bf, self.fake_f32,
                            out_u8)
         self.dropout_calls += 1
@@ -551,6 +593,10 @@ class GeneratorEngine(_Net):
     @_on_device
     def output_nchw(self) -> torch.Tensor:
         n, h, w = self._n
+        if self.virtual0:
+            out = torch.empty(n, 2 * self.C[0], h, w, device=self.dev)
+            ops.nhwc_to_nchw_f32(self.out_cat, out, 2 * self.C[0])
+            return out
         out = torch.empty(n, 3, h, w, device=self.dev)
         ops.nhwc_to_nchw_f32(self.fake_f32, out, 3)
         return out
@@ -565,15 +611,17 @@ class GeneratorEngine(_Net):
         g_1x1 = ops.geom_conv_fwd(1, 1, 0)
         g_ph = ops.geom_phase_k4s2p1()
         self._join_wgrad()
+        v0 = self.virtual0
         gseg = lambda key: self.store.seg(self.store.g, key)
-        # outermost up-conv
+        # outermost up-conv (a stand-alone inner block starts from gR[0] = the gradient of its concatenated output)
 
         def _w0():
             ops.thin_conv_wgrad(self.R[0], self.dpre, None, gseg(self.k_up[0] + ".weight"), 64)
             ops.colsum_bf16(self.dpre, 3, self.grad(self.k_up[0] + ".bias"))
-        self._fork_wgrad(_w0)
-        self._ready(self.k_up[0] + ".weight", self.k_up[0] + ".bias", side=True)
-        ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
+        if not v0:
+            self._fork_wgrad(_w0)
+            self._ready(self.k_up[0] + ".weight", self.k_up[0] + ".bias", side=True)
+            ops.thin_conv_fwd(self.dpre, None, self.w_u_thin, None, self.gR[0])
         # up path, outer -> inner.  Every dgrad GEMM applies the activation backward of the layer below in its
         # epilogue and accumulates that layer's BatchNorm-backward sums (no separate reduce pass).
         for j in range(1, L):
@@ -582,7 +630,8 @@ class GeneratorEngine(_Net):
             if self._dropout_layer(j):
                 ops.dropout_(self.gR[j - 1][..., co:], 0.5, self.dropout_seed, self._drop_off[j])   # same mask as forward
             if j == 1 or self._dropout_layer(j):      # gR[0] comes from the thin-layer kernel: classic reduce + apply
-                self._bn_backward(bn, self.yu[j], self.gR[j - 1][..., co:], None, 0.0, self.dyu[j])
+                # (slope 1: a stand-alone block's up-norm output is not followed by the parent's ReLU)
+                self._bn_backward(bn, self.yu[j], self.gR[j - 1][..., co:], None, 1.0 if (v0 and j == 1) else 0.0, self.dyu[j])
             else:
                 self._bn_backward_fused(bn, self.yu[j], self.gR[j - 1][..., co:], self.dyu[j])
             src = self.Rin if j == L - 1 else self.R[j]
@@ -612,9 +661,17 @@ class GeneratorEngine(_Net):
                 ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.gA[jj], C[jj], S[j], stats=bn.sums,
                               bwd=self._bwd_epilogue(bn, self.yd[jj], 0.2, g2=skip))
                 self._bn_backward_fused(bn, self.yd[jj], self.gA[jj], self.dyd[jj])
+            elif v0:
+                # stand-alone block: the skip half of the output IS LeakyReLU(x), so its gradient passes the LeakyReLU
+                # derivative too:  dx = LeakyReLU'(x) * (dgrad + g_skip)
+                ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.dyd[0], C[0], S[j],
+                              bwd=self._bwd_epilogue(None, self.A[0], 0.2))
+                ops.lrelu_bwd(self.A[0], skip, 0.2, self.dyd[0], accumulate=True)
             else:
                 ops.conv_gemm([self.dyd[j]], self.w_d_dg[j], g_ph, self.dyd[0], C[0], S[j],
                               bwd=self._bwd_epilogue(None, self.A[0], 0.2, g2=skip))
+        if v0:
+            return
         self._fork_wgrad(lambda: ops.thin_conv_wgrad(self.dyd[0], self.x_nhwc, None, gseg(self.k_down[0] + ".weight"), 64))
         self._ready(self.k_down[0] + ".weight", side=True)
 

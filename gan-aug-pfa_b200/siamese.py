@@ -27,6 +27,11 @@ DEC = (("att3", "dconv_up3", 2048, 1024, 512), ("att2", "dconv_up2", 512, 512, 2
        ("att_last", "dconv_last", 128, 128, 64))      # (gate, block, F_g, F_l, block out channels)
 
 
+def _k(name: str, leaf: str) -> str:
+    """state_dict key of `leaf` inside the sub-module `name` ("" = the engine's root module is that sub-module)."""
+    return leaf if not name else name + "." + leaf
+
+
 class _Saved:
     """BatchNorm statistics of one layer evaluation (the shared encoder evaluates each layer twice)."""
 
@@ -102,14 +107,14 @@ class SiameseEngine(_Net):
         self._reg_bn_keys(name + ".4", cout)
 
     def _reg_gate(self, name: str, fg: int, fl: int, fint: int) -> None:
-        self._reg_convk(name + ".W_g.0", fint, fg, 1, True)
-        self._reg_bn_keys(name + ".W_g.1", fint)
-        self._reg_convk(name + ".W_x.0", fint, fl, 1, True)
-        self._reg_bn_keys(name + ".W_x.1", fint)
-        self._reg(name + ".psi.0.weight", fint, (1, fint, 1, 1), (fint, 1, 1, 1))
-        self._reg_vec(name + ".psi.0.bias", 1)
-        self.key_order += [name + ".psi.0.weight", name + ".psi.0.bias"]
-        self._reg_bn_keys(name + ".psi.1", 1)
+        self._reg_convk(_k(name, "W_g.0"), fint, fg, 1, True)
+        self._reg_bn_keys(_k(name, "W_g.1"), fint)
+        self._reg_convk(_k(name, "W_x.0"), fint, fl, 1, True)
+        self._reg_bn_keys(_k(name, "W_x.1"), fint)
+        self._reg(_k(name, "psi.0.weight"), fint, (1, fint, 1, 1), (fint, 1, 1, 1))
+        self._reg_vec(_k(name, "psi.0.bias"), 1)
+        self.key_order += [_k(name, "psi.0.weight"), _k(name, "psi.0.bias")]
+        self._reg_bn_keys(_k(name, "psi.1"), 1)
 
     # -- operands ------------------------------------------------------------------------------------
     def repack(self) -> None:
@@ -285,17 +290,17 @@ class SiameseEngine(_Net):
         gg / gxs: gradient buffers of g / x; gout: gradient buffer of out.  The gate writes the FIRST contribution to
         gxs (through x * psi); the W_g / W_x input gradients are added to gg / gxs."""
         n, h, w, fl = x.shape
-        fint = fl // 2
+        fint = self.conv_meta[_k(name, "W_g.0")][0]
         pix = n * h * w
-        yg, svg, bwd_g = self._conv1x1_bn(g, name + ".W_g.0", gg)
-        yx, svx, bwd_x = self._conv1x1_bn(x, name + ".W_x.0", gxs)
+        yg, svg, bwd_g = self._conv1x1_bn(g, _k(name, "W_g.0"), gg)
+        yx, svx, bwd_x = self._conv1x1_bn(x, _k(name, "W_x.0"), gxs)
         s = self._scratch(f"s.{name}", (n, h, w, fint))
         ops.att_add_relu_fwd(yg, svg.scale, svg.shift, yx, svx.scale, svx.shift, s)
         ypsi = self._scratch(f"ypsi.{name}", (pix,), torch.float32)
         psi = self._scratch(f"psi.{name}", (pix,), torch.float32)
-        wpsi, bpsi = self.store.seg(self.store.p, name + ".psi.0.weight"), self.param(name + ".psi.0.bias")
+        wpsi, bpsi = self.store.seg(self.store.p, _k(name, "psi.0.weight")), self.param(_k(name, "psi.0.bias"))
         ops.conv1x1_cout1_fwd(s, wpsi, bpsi, ypsi)
-        bn = self.bns[name + ".psi.1"]
+        bn = self.bns[_k(name, "psi.1")]
         sv = self._sv(bn.name, 0, 1)
         if self.training:
             ops.vec_stats(ypsi, bn.stats)
@@ -308,8 +313,8 @@ class SiameseEngine(_Net):
             ops.att_gate_bwd(gout, x, psi, gxs, False, dz)
             ops.vec_bn_bwd(ypsi, dz, sv.scale, sv.mean, sv.invstd, bn.sums, dyp)
             ops.bn_param_grads(bn.sums, self.grad(bn.name + ".weight"), self.grad(bn.name + ".bias"))
-            ops.conv1x1_cout1_wgrad(dyp, s, self.store.seg(self.store.g, name + ".psi.0.weight"),
-                                    self.grad(name + ".psi.0.bias"))
+            ops.conv1x1_cout1_wgrad(dyp, s, self.store.seg(self.store.g, _k(name, "psi.0.weight")),
+                                    self.grad(_k(name, "psi.0.bias")))
             gs = self._scratch("gs", (n, h, w, fint))
             ops.conv1x1_cout1_dgrad(dyp, wpsi, gs)
             d = self._scratch("d", (n, h, w, fint))
@@ -320,6 +325,45 @@ class SiameseEngine(_Net):
         self._tape.append(backward)
 
     # -- forward ---------------------------------------------------------------------------------------
+    def _encode(self, p: int, x: torch.Tensor) -> None:
+        """forward_encoder (models.py:92-102) for branch p: 4 x (double_conv + MaxPool2d(2)) + bottleneck; the features
+        land in the channel slots p of the concatenated skip buffers S[0..4]."""
+        n = x.shape[0]
+        ops.nchw_to_nhwc_bf16(x.contiguous().float(), self.x_in[p])
+        ops.im2col_k3s1p1_c3(self.x_in[p], self.col[p])
+        src, gsrc = self.col[p], None
+        for lvl, (name, c) in enumerate(ENC):
+            out = self.S[lvl][..., p * c:(p + 1) * c]
+            gout = self.gS[lvl][..., p * c:(p + 1) * c]
+            if p == 0:      # pass 0's entries run last in backward: after them this level's segments are final
+                self._marks[len(self._tape)] = self.store.off(name + ".0.weight")
+            self._double_conv(src, name, out, p, gsrc, gout)
+            if lvl < 4:
+                nh, nw = out.shape[1] // 2, out.shape[2] // 2
+                pooled = self._scratch(f"pool.{lvl}.{p}", (n, nh, nw, c))
+                gpooled = self._scratch(f"gpool.{lvl}.{p}", (n, nh, nw, c))
+                ops.maxpool2x2_fwd(out, pooled)
+                # the skip tensor already holds the decoder's gradient when the pool backward runs: accumulate
+                self._tape.append(lambda o=out, gp=gpooled, go=gout: ops.maxpool2x2_bwd(o, gp, go, True))
+                src, gsrc = pooled, gpooled
+
+    @_on_device
+    def forward_encoder(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """SiameseUNet.forward_encoder(x) (models.py:92-102) on its own: returns (conv1, conv2, conv3, conv4, bottleneck)
+        as NHWC bf16 views.  backward_encoder() expects the gradients of those five tensors in self.gS[lvl][..., :c]."""
+        n, _, h, w = x.shape
+        self._alloc(n, h, w)
+        self._tape = []
+        self._marks = {}
+        self._encode(0, x)
+        return [self.S[lvl][..., :c] for lvl, (_, c) in enumerate(ENC)]
+
+    @_on_device
+    def backward_encoder(self) -> None:
+        for idx in range(len(self._tape) - 1, -1, -1):
+            self._tape[idx]()
+        self._tape = []
+
     @_on_device
     def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
         """x1, x2: fp32 NCHW on the device.  Returns fp32 logits [n, h, w] (n_classes = 1)."""
@@ -328,23 +372,7 @@ class SiameseEngine(_Net):
         self._tape = []
         self._marks = {}
         for p, x in enumerate((x1, x2)):
-            ops.nchw_to_nhwc_bf16(x.contiguous().float(), self.x_in[p])
-            ops.im2col_k3s1p1_c3(self.x_in[p], self.col[p])
-            src, gsrc = self.col[p], None
-            for lvl, (name, c) in enumerate(ENC):
-                out = self.S[lvl][..., p * c:(p + 1) * c]
-                gout = self.gS[lvl][..., p * c:(p + 1) * c]
-                if p == 0:      # pass 0's entries run last in backward: after them this level's segments are final
-                    self._marks[len(self._tape)] = self.store.off(name + ".0.weight")
-                self._double_conv(src, name, out, p, gsrc, gout)
-                if lvl < 4:
-                    nh, nw = out.shape[1] // 2, out.shape[2] // 2
-                    pooled = self._scratch(f"pool.{lvl}.{p}", (n, nh, nw, c))
-                    gpooled = self._scratch(f"gpool.{lvl}.{p}", (n, nh, nw, c))
-                    ops.maxpool2x2_fwd(out, pooled)
-                    # the skip tensor already holds the decoder's gradient when the pool backward runs: accumulate
-                    self._tape.append(lambda o=out, gp=gpooled, go=gout: ops.maxpool2x2_bwd(o, gp, go, True))
-                    src, gsrc = pooled, gpooled
+            self._encode(p, x)
         prev, gprev = self.S[4], self.gS[4]          # bottleneck pair (2048 channels)
         self._marks[len(self._tape)] = self.store.off(DEC[0][0] + ".W_g.0.weight")   # gates, decoder blocks, conv_last
         for i, (gate, block, fg, fl, cout) in enumerate(DEC):
@@ -413,3 +441,59 @@ class SiameseEngine(_Net):
             allreduce(self.store.g)
         self.adam_step(lr, (0.9, 0.999), 1e-8, weight_decay, decoupled=True, grad_scale=grad_scale)
         return loss
+
+
+class GateEngine(SiameseEngine):
+    """A stand-alone AttentionGate(F_g, F_l, F_int) (models.py:18-44): the gate layers of SiameseEngine with their own
+    parameter store, so `AttentionGate.forward(g, x)` computes through the same kernels."""
+
+    def __init__(self, device, F_g: int, F_l: int, F_int: int) -> None:
+        _Net.__init__(self, device)
+        if F_g % 64 or F_l % 64 or F_int % 8:
+            raise NotImplementedError("the native attention gate needs F_g, F_l multiples of 64 and F_int a multiple of 8")
+        self.cfg = (F_g, F_l, F_int)
+        self.key_order = []
+        self.conv_meta = {}
+        self._reg_gate("", F_g, F_l, F_int)
+        self.store.allocate(device)
+        for bn in self.bns.values():
+            bn.allocate(device)
+        bf = dict(device=device, dtype=torch.bfloat16)
+        self.w_fwd, self.w_dg = {}, {}
+        for key, (co, ci, k) in self.conv_meta.items():
+            self.w_fwd[key] = torch.zeros(1, co, ci, **bf)
+            self.w_dg[key] = torch.zeros(1, ci, co, **bf)
+        self._plan = None
+        self._n = None
+        self._tape = []
+        self._marks = {}
+        self.reducer = None
+        self.tmp, self.saved = {}, {}
+
+    @_on_device
+    def forward(self, g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """g [n, F_g, h, w], x [n, F_l, h, w] fp32 NCHW -> x * psi as NHWC bf16 [n, h, w, F_l]."""
+        fg, fl, _ = self.cfg
+        n, cg, h, w = g.shape
+        if cg != fg or tuple(x.shape) != (n, fl, h, w):
+            raise ValueError(f"AttentionGate expects g [n,{fg},h,w] and x [n,{fl},h,w], got {tuple(g.shape)} / {tuple(x.shape)}")
+        if self._n != (n, h, w):
+            bf = dict(device=self.dev, dtype=torch.bfloat16)
+            self.g_in, self.gg = torch.empty(n, h, w, fg, **bf), torch.empty(n, h, w, fg, **bf)
+            self.x_in2, self.gxs = torch.empty(n, h, w, fl, **bf), torch.empty(n, h, w, fl, **bf)
+            self.out, self.gout = torch.empty(n, h, w, fl, **bf), torch.empty(n, h, w, fl, **bf)
+            self.tmp, self.saved = {}, {}
+            self._n = (n, h, w)
+        self._tape = []
+        ops.nchw_to_nhwc_bf16(g.contiguous().float(), self.g_in)
+        ops.nchw_to_nhwc_bf16(x.contiguous().float(), self.x_in2)
+        self._gate("", self.g_in, self.gg, self.x_in2, self.gxs, self.out, self.gout)
+        return self.out
+
+    @_on_device
+    def backward(self) -> None:
+        """Consumes self.gout (gradient of the output, NHWC bf16); leaves the input gradients in self.gg / self.gxs."""
+        self.gg.zero_()
+        for fn in reversed(self._tape):
+            fn()
+        self._tape = []

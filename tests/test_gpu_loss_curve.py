@@ -1,16 +1,23 @@
-"""Loss-curve parity over 300 GAN iterations against the reference's own train_gan_one_epoch run
-(tests/golden/gan_curve.json, produced by tests/golden/make_curve.py from the unmodified reference on the
-deterministic learnable pairs of tests/curve_data.py; batch 1, 256x256, seed 0).
+"""Loss-curve parity over 1000 GAN iterations against the reference's own train_gan_one_epoch runs.
 
-GAN training is chaotic: the reference re-run with its initial weights merely rounded to bf16
-(tests/golden/gan_curve_perturbed.json) already drifts from itself (EMA loss_g by up to 4.1 %, EMA loss_d by up to
-44 %), and two native runs differ from each other through fp32-atomic ordering (EMA loss_d by ~25 % mid-run).  The
-band is therefore stated on EMA(0.98)-smoothed curves after a 50-step burn-in:
-  loss_g  pointwise within max(3 x the reference's own perturbation deviation, 10 %)   (measured: 2.8 %)
-  loss_d  mean over steps 100..299 within 40 % of the reference's, pointwise EMA within a factor of 3
-          (measured over several runs: mean within 20 %; pointwise the EMA swings between -52 % and +73 % of the
-          reference's because the discriminator's short-term wins and losses are not reproducible — the reference
-          perturbed by one bf16 rounding does the same)."""
+Fixtures (tests/golden/, produced by make_curve.py from the UNMODIFIED reference on the deterministic learnable pairs of
+tests/curve_data.py; batch 1, 256x256, seed 0, 1000 iterations each):
+  gan_curve.json              the reference
+  gan_curve_perturbed.json    the reference with its initial weights rounded once to bf16
+  gan_curve_perturbed{1,2}.json   ... multiplied by (1 + 2^-9 u), u ~ U(-1, 1), seeds 1 and 2
+The three perturbed runs measure how far the REFERENCE drifts from itself under a perturbation the size of one bf16
+rounding.  GAN training is chaotic: up to ~250 iterations the four runs stay close (EMA(0.98) loss_g within 4 %,
+loss_d within 15 %); from ~300 on the discriminator's short-term wins and collapses happen at different times in every
+run (100-iteration window means differ by up to 2.6x for loss_g and 30x for loss_d between reference runs), while the
+long-run level is stable (mean over iterations 300-999: loss_g 5.74 ... 6.41, loss_d 0.20 ... 0.30).  The band is
+therefore stated in three parts, all on the native run vs the reference family:
+  1. iterations 50-249, pointwise on EMA(0.98) curves:  |native - reference| <= max(3 x the family's own deviation
+     from the reference at that iteration, 10 % for loss_g / 40 % for loss_d)          (measured: 0.29-0.55 of the band)
+  2. iterations 300-999, long-run level: the native mean lies in [0.85 x family min, 1.15 x family max] for loss_g and
+     [0.6 x min, 1.6 x max] for loss_d                   (measured loss_g 5.67-6.43 in [4.88, 7.37]; loss_d 0.18-0.29 in [0.12, 0.49])
+  3. iterations 300-999, pointwise EMA envelope (no blow-up, no collapse): loss_g within [family min / 1.5, family max x 1.5],
+     loss_d within [family min / 10, family max x 3]     (measured ratios: loss_g 0.88 ... 1.21, loss_d 0.17 ... 1.82)
+plus the first iteration (not chaotic yet) to 5e-3 and real training progress."""
 import json
 from pathlib import Path
 
@@ -22,13 +29,14 @@ pytestmark = pytest.mark.gpu
 from curve_data import ema, pairs  # noqa: E402
 
 GOLD = Path(__file__).resolve().parent / "golden"
+FAMILY = ("gan_curve.json", "gan_curve_perturbed.json", "gan_curve_perturbed1.json", "gan_curve_perturbed2.json")
 
 
-def test_gan_loss_curves_stay_in_the_reference_band():
+def test_gan_loss_curves_stay_in_the_reference_band_over_1000_iterations():
     from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
-    ref = json.loads((GOLD / "gan_curve.json").read_text())
-    per = json.loads((GOLD / "gan_curve_perturbed.json").read_text())
-    steps = ref["steps"]
+    fam = [json.loads((GOLD / f).read_text()) for f in FAMILY]
+    steps = fam[0]["steps"]
+    assert steps == 1000 and all(f["steps"] == steps for f in fam)
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     tr = Pix2PixTrainer(dev)
@@ -38,19 +46,29 @@ def test_gan_loss_curves_stay_in_the_reference_band():
         a, b = data[s % len(data)]
         out.append(tr.train_step(a, b))
     got = torch.stack(out).cpu().tolist()
-    r = ema([x[1] for x in ref["loss_d_g"]])
-    p = ema([x[1] for x in per["loss_d_g"]])
-    g = ema([x[1] for x in got])
-    worst = max(abs(g[i] - r[i]) / abs(r[i]) / max(3.0 * abs(p[i] - r[i]) / abs(r[i]), 0.10) for i in range(50, steps))
-    assert worst <= 1.0, f"loss_g: EMA curve leaves the band (worst deviation / band = {worst:.2f})"
-    rd = ema([x[0] for x in ref["loss_d_g"]])
-    gd = ema([x[0] for x in got])
-    mean_r = sum(x[0] for x in ref["loss_d_g"][100:]) / (steps - 100)
-    mean_g = sum(x[0] for x in got[100:]) / (steps - 100)
-    assert abs(mean_g - mean_r) < 0.40 * mean_r, (mean_g, mean_r)
-    assert all(rd[i] / 3.0 < gd[i] < 3.0 * rd[i] for i in range(50, steps))
+    assert all(torch.isfinite(torch.tensor(got)).flatten())
+    for col, name, floor, lvl_lo, lvl_hi, env_lo, env_hi in ((1, "loss_g", 0.10, 0.85, 1.15, 1.5, 1.5),
+                                                             (0, "loss_d", 0.40, 0.60, 1.60, 10.0, 3.0)):
+        fe = [ema([x[col] for x in f["loss_d_g"]]) for f in fam]
+        g = ema([x[col] for x in got])
+        ref = fe[0]
+        # 1. early, pointwise
+        worst = 0.0
+        for i in range(50, 250):
+            env = max(abs(e[i] - ref[i]) for e in fe[1:]) / abs(ref[i])
+            worst = max(worst, abs(g[i] - ref[i]) / abs(ref[i]) / max(3.0 * env, floor))
+        assert worst <= 1.0, f"{name}: EMA curve leaves the early band (worst deviation / band = {worst:.2f})"
+        # 2. long-run level
+        fm = [sum(x[col] for x in f["loss_d_g"][300:]) / (steps - 300) for f in fam]
+        gm = sum(x[col] for x in got[300:]) / (steps - 300)
+        assert lvl_lo * min(fm) <= gm <= lvl_hi * max(fm), f"{name}: long-run mean {gm:.4f} vs reference family {fm}"
+        # 3. pointwise envelope
+        for i in range(300, steps):
+            lo, hi = min(e[i] for e in fe), max(e[i] for e in fe)
+            assert lo / env_lo <= g[i] <= hi * env_hi, f"{name}: EMA {g[i]:.4f} at iteration {i} outside [{lo:.4f}/{env_lo}, {hi:.4f}x{env_hi}]"
     # the first iteration is not chaotic yet: it must match the reference closely
-    assert abs(got[0][0] - ref["loss_d_g"][0][0]) < 5e-3
-    assert abs(got[0][1] - ref["loss_d_g"][0][1]) < 5e-3 * ref["loss_d_g"][0][1]
+    first = fam[0]["loss_d_g"][0]
+    assert abs(got[0][0] - first[0]) < 5e-3
+    assert abs(got[0][1] - first[1]) < 5e-3 * first[1]
     # and training must actually make progress on this learnable data
     assert ema([x[1] for x in got])[-1] < 0.3 * got[0][1]
