@@ -449,8 +449,8 @@ class GateEngine(SiameseEngine):
 
     def __init__(self, device, F_g: int, F_l: int, F_int: int) -> None:
         _Net.__init__(self, device)
-        if F_g % 64 or F_l % 64 or F_int % 8:
-            raise NotImplementedError("the native attention gate needs F_g, F_l multiples of 64 and F_int a multiple of 8")
+        if F_g % 64 or F_l % 64 or F_int % 64:
+            raise NotImplementedError("the native attention gate needs F_g, F_l and F_int to be multiples of 64 (the reference uses 64 ... 2048)")
         self.cfg = (F_g, F_l, F_int)
         self.key_order = []
         self.conv_meta = {}

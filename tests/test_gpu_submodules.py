@@ -98,7 +98,7 @@ def test_outermost_unet_block_called_directly_is_a_small_generator():
 
 def test_attention_gate_called_directly():
     torch.manual_seed(5)
-    gate = M.AttentionGate(F_g=128, F_l=64, F_int=32)
+    gate = M.AttentionGate(F_g=128, F_l=64, F_int=64)
     sd, names = _sd_with_grad(gate)
     psd = {"att." + k: v for k, v in sd.items()}
     gen = torch.Generator().manual_seed(7)
