@@ -89,13 +89,6 @@ struct alignas(64) FpropParams {
   int a_load_bytes;    // bytes one A TMA load delivers
   int b_per_stage;     // B tiles per pipeline stage (1, or halo_taps)
   int chunks_tot;      // 64-channel chunks over both sources
-  // Resident-B mode (halo mode, one N tile): the whole packed weight slice of the CTA's phase sits in shared memory for
-  // the kernel's lifetime (k_blocks tiles of block_n x 128 B, loaded once), so the pipeline stages carry A tiles only.
-  // With N = 64 the B re-fetch per M tile was a third of the TMA traffic (16 of 52 KiB per stage), and TMA / L2 feed is
-  // what bounds these layers.  A CTA keeps one phase because its work items advance by gridDim.x (a multiple of 4).
-  int bres;            // 0 / 1
-  int bres_bytes;      // bytes of the resident region (multiple of 1024)
-  int bres_blocks;     // 64-wide K blocks of one phase = taps_h * taps_w * chunks_tot
   // Split-K (kEpi = 2): small-M layers (deep U-Net levels, small batches) do not have enough output tiles for 148 SMs,
   // so the K loop is cut into `splits` ranges; partial tiles are added into an fp32 workspace [pixel][n_out] with
   // red.global.add.v4.f32 and splitk_finish_kernel applies the epilogue (and re-zeroes the workspace).
@@ -234,16 +227,14 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int a_bytes = p.mt * p.a_tile_bytes;
-  const int stage_bytes = a_bytes + (p.bres ? 0 : p.b_per_stage * p.block_n * 128);
-  const uint32_t stage_base = smem_base + p.bres_bytes;      // [resident B | pipeline stages | barriers ...]
-  const uint32_t bar_base = stage_base + p.num_stages * stage_bytes;
+  const int stage_bytes = a_bytes + p.b_per_stage * p.block_n * 128;
+  const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
   // barrier slots (8 bytes each): full[0..7], empty[8..15], tfull[16..17], tempty[18..19]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
-  const uint32_t bres_bar = bar_base + 8u * 22;   // slot 20 holds the TMEM base address
-  uint8_t* bar_gen = smem_gen + p.bres_bytes + p.num_stages * stage_bytes;
+  uint8_t* bar_gen = smem_gen + p.num_stages * stage_bytes;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 20);
   double* stats_sm = reinterpret_cast<double*>(bar_gen + kBarrierBytes);
   float* par_sm = reinterpret_cast<float*>(bar_gen + kBarrierBytes + kStatsBytes);  // [2][256] scale | shift
@@ -267,7 +258,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiWarps);
     }
-    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -295,13 +285,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       uint32_t it = 0;
       int stage = 0;
       uint32_t phase = 0;
-      if (p.bres && warp == 0 && static_cast<int>(blockIdx.x) < p.total_tiles) {
-        // this CTA's phase never changes: fetch its whole weight slice once
-        const WorkCoord w0 = decode_work(p, blockIdx.x);
-        mbar_expect_tx(bres_bar, static_cast<uint32_t>(p.bres_blocks * p.block_n * 128));
-        for (int kb = 0; kb < p.bres_blocks; ++kb)
-          tma_load_3d(smem_base + kb * p.block_n * 128, &p.tmB, bres_bar, kb * kBlockK, w0.n_tile * p.block_n, w0.phase);
-      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const WorkCoord wc = decode_work(p, tile);
         const MTile m0 = decode_mtile(p, wc.sm * p.mt);
@@ -326,7 +309,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             if ((it++ & 1u) == my_par) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               mbar_expect_tx(full_bar(stage), tx_bytes);
-              const uint32_t a_dst = stage_base + stage * stage_bytes;
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
               tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
               if (has1) tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
               tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kk * kBlockK, b_row, wc.phase);
@@ -339,8 +322,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           continue;
         }
         if (p.halo) {
-          const uint32_t txh =
-              static_cast<uint32_t>((p.bres ? 0 : p.halo_taps * p.block_n * 128) + (has1 ? 2 : 1) * p.a_load_bytes);
+          const uint32_t txh = static_cast<uint32_t>(p.halo_taps * p.block_n * 128 + (has1 ? 2 : 1) * p.a_load_bytes);
           for (int t_w = 0; t_w < p.taps_w; ++t_w) {
             for (int g = 0; g < p.halo_groups; ++g) {
               int cc = 0;
@@ -349,11 +331,11 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
                   if ((it++ & 1u) == my_par) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), txh);
-                    const uint32_t a_dst = stage_base + stage * stage_bytes;
+                    const uint32_t a_dst = smem_base + stage * stage_bytes;
                     tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + g, n0);
                     if (has1)
                       tma_load_4d(a_dst + p.a_tile_bytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + g, n1);
-                    for (int i = 0; i < (p.bres ? 0 : p.halo_taps); ++i) {
+                    for (int i = 0; i < p.halo_taps; ++i) {
                       const int t_h = g + p.halo_groups * i;
                       tma_load_3d(a_dst + a_bytes + i * p.block_n * 128, &p.tmB, full_bar(stage),
                                   ((t_h * p.taps_w + t_w) * p.chunks_tot + cc) * kBlockK, b_row, wc.phase);
@@ -377,7 +359,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
                 if ((it++ & 1u) == my_par) {
                   mbar_wait(empty_bar(stage), phase ^ 1u);
                   mbar_expect_tx(full_bar(stage), tx_bytes);
-                  const uint32_t a_dst = stage_base + stage * stage_bytes;
+                  const uint32_t a_dst = smem_base + stage * stage_bytes;
                   tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
                   if (has1)
                     tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
@@ -401,10 +383,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (p.bres && static_cast<int>(blockIdx.x) < p.total_tiles) {
-        mbar_wait(bres_bar, 0u);      // the resident weight slice has landed
-        tc_fence_after();
-      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const WorkCoord wc = decode_work(p, tile);
         const int mt_eff = min(p.mt, p.m_tiles_pp - wc.sm * p.mt);
@@ -418,24 +396,16 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
         for (int k_iter = 0; k_iter < k_count; ++k_iter) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = stage_base + stage * stage_bytes;
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
           const uint32_t b_addr = a_addr + a_bytes;
           if (p.halo) {
             const uint32_t row_shift = static_cast<uint32_t>(128 << p.log_bw);   // one input row of the tile = BW pixels
-            // resident B: K block of tap (t_h = g + groups*i, t_w) and chunk cc, in the producer's iteration order
-            const int per_tw = p.halo_groups * p.chunks_tot;
-            const int r_tw = k_iter / per_tw, r_rem = k_iter - r_tw * per_tw;
-            const int r_g = r_rem / p.chunks_tot, r_cc = r_rem - r_g * p.chunks_tot;
             for (int j = 0; j < mt_eff; ++j) {
               for (int i = 0; i < p.halo_taps; ++i) {
-                const uint32_t b_tile =
-                    p.bres ? smem_base + static_cast<uint32_t>((((r_g + p.halo_groups * i) * p.taps_w + r_tw) * p.chunks_tot + r_cc) *
-                                                               p.block_n * 128)
-                           : b_addr + i * p.block_n * 128;
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                   const uint64_t adesc = make_sw128_desc(a_addr + j * p.a_tile_bytes + i * row_shift + k * 32, 16, 1024);
-                  const uint64_t bdesc = make_sw128_desc(b_tile + k * 32, 16, 1024);
+                  const uint64_t bdesc = make_sw128_desc(b_addr + i * p.block_n * 128 + k * 32, 16, 1024);
                   umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | i | k) != 0 ? 1u : 0u);
                 }
               }
@@ -1002,29 +972,13 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
                    : 0;
   p.skip = debug_get("fprop_skip", 0);
 
-  // Resident-B mode (see FpropParams): halo layers with one N tile whose per-phase weight slice leaves room for at
-  // least three A stages; every CTA must keep its phase, i.e. the grid is a multiple of n_phase.
-  const int fixed_smem = 1024 + kBarrierBytes + kStatsBytes + kParamBytes + kColStageBytes;
-  const int grid_sz = std::min(p.total_tiles, sms);
-  {
-    const int kb = a->taps_h * a->taps_w * (ctot / 64);
-    const long long bytes = static_cast<long long>(kb) * block_n * 128;
-    const bool fits = bytes + 3LL * mt * p.a_tile_bytes + fixed_smem <= kSmemBudget;
-    const int want = debug_get("fprop_bres", 1);
-    if (halo && splits == 1 && n_tiles == 1 && fits && grid_sz % a->n_phase == 0 && (block_n * 128) % 1024 == 0 &&
-        (want == 1 || (want == 2 && bytes + 2LL * mt * p.a_tile_bytes + fixed_smem <= kSmemBudget))) {
-      p.bres = 1;
-      p.bres_bytes = static_cast<int>(bytes);
-      p.bres_blocks = kb;
-    }
-  }
-  const int stage_bytes = mt * p.a_tile_bytes + (p.bres ? 0 : p.b_per_stage * block_n * 128);
-  int stages = (kSmemBudget - fixed_smem - p.bres_bytes) / stage_bytes;
+  const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * block_n * 128;
+  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes - kColStageBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);
   if (force_st > 0) stages = std::min(force_st, stages);
   p.num_stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(fixed_smem) + p.bres_bytes + static_cast<size_t>(stages) * stage_bytes;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes + kParamBytes + kColStageBytes;
 
   // ---- tensor maps
   const uint32_t bx_w = static_cast<uint32_t>(BW * a->in_stride);
