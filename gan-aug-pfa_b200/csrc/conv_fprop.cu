@@ -89,6 +89,10 @@ struct alignas(64) FpropParams {
   int a_load_bytes;    // bytes one A TMA load delivers
   int b_per_stage;     // B tiles per pipeline stage (1, or halo_taps)
   int chunks_tot;      // 64-channel chunks over both sources
+  // CTA-pair mode (kPair, see ptx.cuh "CTA pairs"): a cluster of two CTAs works on ONE work item of 2*mt M tiles; CTA
+  // rank r owns M tiles (2*sm + r)*mt .. +mt and stages rows [r*block_n/2, (r+1)*block_n/2) of the B tile; the leader
+  // issues tcgen05.mma.cta_group::2 (M = 256).  sm_tiles / total_tiles then count PAIR items.
+  int pair;
   // Split-K (kEpi = 2): small-M layers (deep U-Net levels, small batches) do not have enough output tiles for 148 SMs,
   // so the K loop is cut into `splits` ranges; partial tiles are added into an fp32 workspace [pixel][n_out] with
   // red.global.add.v4.f32 and splitk_finish_kernel applies the epilogue (and re-zeroes the workspace).
@@ -219,15 +223,20 @@ __device__ __noinline__ void epilogue_store_generic(const FpropParams& p, float4
   }
 }
 
-template <int kEpi>
+template <int kEpi, bool kPair = false>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
+  // pair mode: this CTA's half of the B rows; rank 0 (the leader) issues the MMAs for both CTAs
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const int bn_cta = kPair ? (p.block_n >> 1) : p.block_n;
+  const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int a_bytes = p.mt * p.a_tile_bytes;
-  const int stage_bytes = a_bytes + p.b_per_stage * p.block_n * 128;
+  const int stage_bytes = a_bytes + p.b_per_stage * bn_cta * 128;
   const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
   // barrier slots (8 bytes each): full[0..7], empty[8..15], tfull[16..17], tempty[18..19]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -256,16 +265,24 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tempty_bar(a), kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogue warps release the leader
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair)
+    cluster_sync();      // the peer's barriers are initialised before anything signals them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();   // the next kernel's CTAs may be scheduled as SMs drain; they block in their own pdl_wait()
@@ -285,19 +302,38 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       uint32_t it = 0;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      // pair mode: every load reports its bytes to the LEADER's full barrier (the leader arms it for both CTAs); a
+      // tile that does not exist is still fetched (its coordinates are out of range: zero fill, same byte count)
+      auto ld_a = [&](uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (kPair)
+          tma_load_4d_pair(dst, tm, bar, c0, c1, c2, c3);
+        else
+          tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+      };
+      auto ld_b = [&](uint32_t dst, uint32_t bar, int c0, int c1, int c2) {
+        if (kPair)
+          tma_load_3d_pair(dst, &p.tmB, bar, c0, c1, c2);
+        else
+          tma_load_3d(dst, &p.tmB, bar, c0, c1, c2);
+      };
+      auto fbar = [&](int s) { return kPair ? mapa_cluster(full_bar(s), 0u) : full_bar(s); };
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         const WorkCoord wc = decode_work(p, tile);
-        const MTile m0 = decode_mtile(p, wc.sm * p.mt);
-        const MTile m1 = decode_mtile(p, wc.sm * p.mt + 1);
-        const bool has1 = p.mt > 1 && m1.exists;
+        const int sm_own = kPair ? (wc.sm * 2 + static_cast<int>(cta_rank)) : wc.sm;
+        const MTile m0 = decode_mtile(p, sm_own * p.mt);
+        const MTile m1 = decode_mtile(p, sm_own * p.mt + 1);
+        const bool has1 = p.mt > 1 && (m1.exists || kPair);
         const int x0 = m0.tw * BW * p.in_stride + p.in_off_w[wc.pw];
         const int y0 = m0.th * BH * p.in_stride + p.in_off_h[wc.ph];
         const int n0 = m0.tn * BNI;
         const int x1 = m1.tw * BW * p.in_stride + p.in_off_w[wc.pw];
         const int y1 = m1.th * BH * p.in_stride + p.in_off_h[wc.ph];
         const int n1 = m1.tn * BNI;
-        const uint32_t tx_bytes = static_cast<uint32_t>(p.block_n * 128 + (has1 ? 2 : 1) * kATileBytes);
-        const int b_row = wc.n_tile * p.block_n;
+        // bytes one CTA receives per stage; the leader of a pair arms its barrier for both CTAs
+        const uint32_t tx_bytes =
+            static_cast<uint32_t>(bn_cta * 128 + (has1 ? 2 : 1) * kATileBytes) * (kPair ? 2u : 1u);
+        const int b_row = wc.n_tile * p.block_n + static_cast<int>(cta_rank) * bn_cta;
+        const bool arm = !kPair || cta_rank == 0;
         if (kEpi == 2) {
           const int k_lo = static_cast<int>(static_cast<long long>(p.k_iters) * wc.split / p.splits);
           const int k_hi = static_cast<int>(static_cast<long long>(p.k_iters) * (wc.split + 1) / p.splits);
@@ -322,7 +358,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           continue;
         }
         if (p.halo) {
-          const uint32_t txh = static_cast<uint32_t>(p.halo_taps * p.block_n * 128 + (has1 ? 2 : 1) * p.a_load_bytes);
+          const uint32_t txh =
+              static_cast<uint32_t>(p.halo_taps * bn_cta * 128 + (has1 ? 2 : 1) * p.a_load_bytes) * (kPair ? 2u : 1u);
           for (int t_w = 0; t_w < p.taps_w; ++t_w) {
             for (int g = 0; g < p.halo_groups; ++g) {
               int cc = 0;
@@ -330,15 +367,15 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
                 for (int c = 0; c < p.src_chunks[s]; ++c, ++cc) {
                   if ((it++ & 1u) == my_par) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), txh);
+                    if (arm) mbar_expect_tx(full_bar(stage), txh);
+                    const uint32_t fb = fbar(stage);
                     const uint32_t a_dst = smem_base + stage * stage_bytes;
-                    tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + g, n0);
-                    if (has1)
-                      tma_load_4d(a_dst + p.a_tile_bytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + g, n1);
+                    ld_a(a_dst, &p.tmA[s], fb, c * kBlockK, x0 + t_w, y0 + g, n0);
+                    if (has1) ld_a(a_dst + p.a_tile_bytes, &p.tmA[s], fb, c * kBlockK, x1 + t_w, y1 + g, n1);
                     for (int i = 0; i < p.halo_taps; ++i) {
                       const int t_h = g + p.halo_groups * i;
-                      tma_load_3d(a_dst + a_bytes + i * p.block_n * 128, &p.tmB, full_bar(stage),
-                                  ((t_h * p.taps_w + t_w) * p.chunks_tot + cc) * kBlockK, b_row, wc.phase);
+                      ld_b(a_dst + a_bytes + i * bn_cta * 128, fb, ((t_h * p.taps_w + t_w) * p.chunks_tot + cc) * kBlockK,
+                           b_row, wc.phase);
                     }
                   }
                   if (++stage == p.num_stages) {
@@ -358,12 +395,12 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               for (int c = 0; c < p.src_chunks[s]; ++c) {
                 if ((it++ & 1u) == my_par) {
                   mbar_wait(empty_bar(stage), phase ^ 1u);
-                  mbar_expect_tx(full_bar(stage), tx_bytes);
+                  if (arm) mbar_expect_tx(full_bar(stage), tx_bytes);
+                  const uint32_t fb = fbar(stage);
                   const uint32_t a_dst = smem_base + stage * stage_bytes;
-                  tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
-                  if (has1)
-                    tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
-                  tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kcol, b_row, wc.phase);
+                  ld_a(a_dst, &p.tmA[s], fb, c * kBlockK, x0 + t_w, y0 + t_h, n0);
+                  if (has1) ld_a(a_dst + kATileBytes, &p.tmA[s], fb, c * kBlockK, x1 + t_w, y1 + t_h, n1);
+                  ld_b(a_dst + a_bytes, fb, kcol, b_row, wc.phase);
                 }
                 kcol += kBlockK;
                 if (++stage == p.num_stages) {
@@ -377,15 +414,27 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accum) {
+      if (kPair)
+        umma_bf16_pair(d, ad, bd, p.idesc, accum);
+      else
+        umma_bf16(d, ad, bd, p.idesc, accum);
+    };
+    auto commit = [&](uint32_t bar) {      // pair mode: the arrival lands on the same barrier of BOTH CTAs
+      if (kPair)
+        umma_commit_pair(bar, 0x3);
+      else
+        umma_commit(bar);
+    };
+    if ((!kPair || cta_rank == 0) && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
         const WorkCoord wc = decode_work(p, tile);
-        const int mt_eff = min(p.mt, p.m_tiles_pp - wc.sm * p.mt);
+        const int mt_eff = kPair ? p.mt : min(p.mt, p.m_tiles_pp - wc.sm * p.mt);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -405,8 +454,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                   const uint64_t adesc = make_sw128_desc(a_addr + j * p.a_tile_bytes + i * row_shift + k * 32, 16, 1024);
-                  const uint64_t bdesc = make_sw128_desc(b_addr + i * p.block_n * 128 + k * 32, 16, 1024);
-                  umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | i | k) != 0 ? 1u : 0u);
+                  const uint64_t bdesc = make_sw128_desc(b_addr + i * bn_cta * 128 + k * 32, 16, 1024);
+                  mma(d_tmem + j * p.block_n, adesc, bdesc, (k_iter | i | k) != 0 ? 1u : 0u);
                 }
               }
             }
@@ -416,17 +465,17 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               for (int k = 0; k < kBlockK / 16; ++k) {
                 const uint64_t adesc = make_sw128_desc(a_addr + j * kATileBytes + k * 32, 16, 1024);
                 const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-                umma_bf16(d_tmem + j * p.block_n, adesc, bdesc, p.idesc, (k_iter | k) != 0 ? 1u : 0u);
+                mma(d_tmem + j * p.block_n, adesc, bdesc, (k_iter | k) != 0 ? 1u : 0u);
               }
             }
           }
-          umma_commit(empty_bar(stage));
+          commit(empty_bar(stage));
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));
+        commit(tfull_bar(acc));
         if (++acc == p.acc_stages) {
           acc = 0;
           acc_phase ^= 1u;
@@ -465,8 +514,9 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       const WorkCoord wc = decode_work(p, tile);
+      const int sm_own = kPair ? (wc.sm * 2 + static_cast<int>(cta_rank)) : wc.sm;
       if ((do_stats || kEpi == 1) && wc.n_tile != cur_ntile) {
         if (do_stats && cur_ntile >= 0) flush_stats(cur_ntile);
         if (do_stats) {
@@ -494,7 +544,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       tc_fence_after();
       const int n_chunks = p.block_n >> 4;
       for (int j = 0; j < p.mt; ++j) {
-        const MTile mtile = decode_mtile(p, wc.sm * p.mt + j);
+        const MTile mtile = decode_mtile(p, sm_own * p.mt + j);
         const int wi = row & (BW - 1);
         const int hi = (row >> p.log_bw) & (BH - 1);
         const int ni = row >> (p.log_bw + p.log_bh);
@@ -650,7 +700,12 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (kPair)
+          mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0u));     // the leader's MMA lane waits for both CTAs
+        else
+          mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == p.acc_stages) {
         acc = 0;
         acc_phase ^= 1u;
@@ -660,10 +715,16 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair)
+    cluster_sync();      // neither CTA frees its TMEM / exits while the peer's MMAs or remote arrivals may still touch it
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair)
+      tmem_dealloc_pair(tmem_base, kTmemCols);
+    else
+      tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -886,9 +947,19 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   if (model_mt > 0) mt = model_mt;
   const int force_mt = debug_get("fprop_mt", 0);
   if (force_mt > 0) mt = std::min(force_mt, 2);
+  // CTA pairs (cta_group::2, see FpropParams::pair): per SM half of every B tile is written by TMA and read by the tensor
+  // core, and shared-memory bandwidth (MMA operand reads + TMA writes, ~128 B/clk) is what bounds these kernels: at
+  // N = 256 a single CTA needs 156 B/clk at full MMA rate, a pair 110; at N = 128 219 -> 174.  Used when every cluster
+  // still gets at least one work item (the under-filled bottleneck layers keep the single-CTA path and its cost model).
+  bool pair = debug_get("fprop_pair", 1) != 0 && splits == 1 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32;
+  if (pair) {
+    const long long pair_items = static_cast<long long>((m_tiles_pp + 2 * mt - 1) / (2 * mt)) * a->n_phase * n_tiles;
+    if (pair_items < sms / 2) pair = false;
+  }
+  p.pair = pair ? 1 : 0;
   p.mt = mt;
   p.m_tiles_pp = m_tiles_pp;
-  p.sm_tiles = (m_tiles_pp + mt - 1) / mt;
+  p.sm_tiles = pair ? (m_tiles_pp + 2 * mt - 1) / (2 * mt) : (m_tiles_pp + mt - 1) / mt;
   p.acc_stages = (mt * block_n <= kAccStride) ? 2 : 1;
   p.block_n = block_n;
   p.n_tiles = n_tiles;
@@ -932,7 +1003,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.bias = a->bias;
   p.scale = a->scale;
   p.stats = a->stats;
-  p.idesc = make_idesc_bf16(kBlockM, block_n, 0, 0);
+  p.idesc = make_idesc_bf16(pair ? 2 * kBlockM : kBlockM, block_n, 0, 0);
   const bool vec32 =
       vec_ok && a->out_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 31) == 0 &&
       (!a->out2 || (a->out2_ld % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out2) & 31) == 0));
@@ -972,7 +1043,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
                    : 0;
   p.skip = debug_get("fprop_skip", 0);
 
-  const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * block_n * 128;
+  const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * (pair ? block_n / 2 : block_n) * 128;
   int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes - kColStageBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);
@@ -1002,7 +1073,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     const uint64_t ktot = static_cast<uint64_t>(a->taps_h) * a->taps_w * ctot;
     uint64_t dims[3] = {ktot, static_cast<uint64_t>(a->w_rows), static_cast<uint64_t>(a->n_phase)};
     uint64_t strides[2] = {ktot * 2, ktot * 2 * a->w_rows};
-    uint32_t box[3] = {64, static_cast<uint32_t>(block_n), 1};
+    uint32_t box[3] = {64, static_cast<uint32_t>(pair ? block_n / 2 : block_n), 1};
     int rc = encode_tmap_bf16(&p.tmB, a->wpk, 3, dims, strides, box, nullptr, true);
     if (rc) return rc;
   }
@@ -1012,8 +1083,19 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(splitk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
+  }
+  if (pair) {
+    const int grid2 = std::min(2 * p.total_tiles, sms) & ~1;
+    if (bwd)
+      GAP_CUDA(launch_pair(conv_fprop_kernel<1, true>, dim3(grid2), dim3(kFpropThreads), smem_bytes, stream, p));
+    else
+      GAP_CUDA(launch_pair(conv_fprop_kernel<0, true>, dim3(grid2), dim3(kFpropThreads), smem_bytes, stream, p));
+    GAP_CUDA(cudaGetLastError());
+    return 0;
   }
   const int grid = std::min(p.total_tiles, sms);
   if (splits > 1) {
