@@ -6,6 +6,7 @@ raises — it never routes around the CUDA kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
@@ -105,6 +106,8 @@ _SIGNATURES = {
     "gap_thin_conv_wgrad": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P, _P]),
     "gap_thin_convT_fwd": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P, _I, _P, _L, _P, _L, _P, _P]),
     "gap_u8_hwc_to_nhwc_bf16": (C.c_int, [_P, _P, _L, _L, _P]),
+    "gap_resize_u8_to_nhwc_bf16": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
+    "gap_resize_nearest_i64": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "gap_im2col_k3s1p1_c3": (C.c_int, [_P, _L, _P, _I, _I, _I, _P]),
     "gap_maxpool2x2_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "gap_maxpool2x2_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P]),
@@ -159,6 +162,11 @@ def lib() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # bring-up A/B runs: GAP_DEBUG="knob=value,knob=value" presets gap_debug_set knobs (none are set in production)
+        for item in filter(None, os.environ.get("GAP_DEBUG", "").split(",")):
+            k, _, v = item.partition("=")
+            DEBUG_KNOBS[k.strip()] = int(v)
+            handle.gap_debug_set(k.strip().encode(), int(v))
     return _lib
 
 

@@ -948,10 +948,14 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   const int force_mt = debug_get("fprop_mt", 0);
   if (force_mt > 0) mt = std::min(force_mt, 2);
   // CTA pairs (cta_group::2, see FpropParams::pair): per SM half of every B tile is written by TMA and read by the tensor
-  // core, and shared-memory bandwidth (MMA operand reads + TMA writes, ~128 B/clk) is what bounds these kernels: at
-  // N = 256 a single CTA needs 156 B/clk at full MMA rate, a pair 110; at N = 128 219 -> 174.  Used when every cluster
-  // still gets at least one work item (the under-filled bottleneck layers keep the single-CTA path and its cost model).
-  bool pair = debug_get("fprop_pair", 1) != 0 && splits == 1 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32;
+  // core.  MEASURED per layer (profiles/r2_pair_mode_per_layer.txt, serialised launches of the batch-64 step): the
+  // 256-wide N tiles with long K loops gain 1.5-6 % (512->256 s1: 1323 -> 1353 TFLOP/s, 256->1024: 1189 -> 1258), the
+  // N <= 128 and four-phase layers LOSE 3-12 % (the two CTAs run in lock step and every release crosses the cluster),
+  // so pairs are used only for single-phase launches with a 256-wide N tile, >= 64 K iterations and enough work items
+  // for every cluster.  fprop_pair = 2 forces pairs wherever they are legal (tests, A/B runs), 0 disables them.
+  const int pair_knob = debug_get("fprop_pair", 1);
+  bool pair = pair_knob != 0 && splits == 1 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32;
+  if (pair && pair_knob != 2 && !(block_n == 256 && a->n_phase == 1 && k_iters_full >= 64)) pair = false;
   if (pair) {
     const long long pair_items = static_cast<long long>((m_tiles_pp + 2 * mt - 1) / (2 * mt)) * a->n_phase * n_tiles;
     if (pair_items < sms / 2) pair = false;

@@ -1011,6 +1011,79 @@ __global__ void u8_hwc_to_nhwc_bf16_kernel(const uint8_t* __restrict__ x, bf16* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dataset.py's JointResize + JointNormalize on the device (dataset.py:136-159): uint8 HWC image -> bilinear resize of
+// the [0, 1] tensor -> x*2 - 1 -> NHWC bf16 with 4 channel slots.  The reference resizes TENSORS with
+// torchvision.transforms.functional.resize(BILINEAR), i.e. F.interpolate(mode="bilinear", align_corners=False,
+// antialias=True): a separable triangle filter whose support grows with the down-scaling factor (ATen
+// upsample_bilinear2d_aa; identical to plain bilinear when up-scaling).  Per output index i along an axis:
+//   scale = in / out; support = max(scale, 1); center = scale * (i + 0.5)
+//   taps j in [max(0, int(center - support + 0.5)), min(in, int(center + support + 0.5)));
+//   w_j = max(0, 1 - |(j - center + 0.5) / max(scale, 1)|), normalised to sum 1.
+// One thread per output pixel, all three channels; the 2-D weights are the product of the two 1-D ones.
+// ------------------------------------------------------------------------------------------------
+struct AaAxis {
+  int lo, n;
+  float center, inv, total;
+};
+__device__ __forceinline__ AaAxis aa_axis(int i, int in, float scale) {
+  AaAxis a;
+  const float support = fmaxf(scale, 1.f);
+  a.center = scale * (i + 0.5f);
+  a.inv = 1.f / support;
+  a.lo = max(0, static_cast<int>(a.center - support + 0.5f));
+  a.n = min(in, static_cast<int>(a.center + support + 0.5f)) - a.lo;
+  a.total = 0.f;
+  for (int j = 0; j < a.n; ++j) a.total += fmaxf(0.f, 1.f - fabsf((j + a.lo - a.center + 0.5f) * a.inv));
+  return a;
+}
+__global__ void resize_u8_to_nhwc_bf16_kernel(const uint8_t* __restrict__ x, int n, int ih, int iw, int oh, int ow,
+                                              bf16* __restrict__ out, long long ld, float* __restrict__ out_nchw) {
+  const long long total = static_cast<long long>(n) * oh * ow;
+  const float sh = static_cast<float>(ih) / oh, sw = static_cast<float>(iw) / ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % ow), oy = static_cast<int>((i / ow) % oh);
+    const long long img = i / (static_cast<long long>(ow) * oh);
+    const AaAxis ay = aa_axis(oy, ih, sh), ax = aa_axis(ox, iw, sw);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int jy = 0; jy < ay.n; ++jy) {
+      const float wy = fmaxf(0.f, 1.f - fabsf((jy + ay.lo - ay.center + 0.5f) * ay.inv)) / ay.total;
+      const uint8_t* row = x + ((img * ih + ay.lo + jy) * iw + ax.lo) * 3;
+      float r[3] = {0.f, 0.f, 0.f};
+      for (int jx = 0; jx < ax.n; ++jx) {
+        const float wx = fmaxf(0.f, 1.f - fabsf((jx + ax.lo - ax.center + 0.5f) * ax.inv)) / ax.total;
+        r[0] = fmaf(wx, row[jx * 3], r[0]);
+        r[1] = fmaf(wx, row[jx * 3 + 1], r[1]);
+        r[2] = fmaf(wx, row[jx * 3 + 2], r[2]);
+      }
+      acc[0] = fmaf(wy, r[0], acc[0]);
+      acc[1] = fmaf(wy, r[1], acc[1]);
+      acc[2] = fmaf(wy, r[2], acc[2]);
+    }
+    const float a = acc[0] * (2.f / 255.f) - 1.f, b = acc[1] * (2.f / 255.f) - 1.f, c = acc[2] * (2.f / 255.f) - 1.f;
+    if (out != nullptr) *reinterpret_cast<uint2*>(out + i * ld) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, 0.f));
+    if (out_nchw != nullptr) {      // what the reference's DataLoader yields: fp32 [n][3][oh][ow]
+      const long long hw = static_cast<long long>(oh) * ow, pix = static_cast<long long>(oy) * ow + ox;
+      out_nchw[(img * 3 + 0) * hw + pix] = a;
+      out_nchw[(img * 3 + 1) * hw + pix] = b;
+      out_nchw[(img * 3 + 2) * hw + pix] = c;
+    }
+  }
+}
+
+// JointResize of the label map (dataset.py:143-146): NEAREST on the int64 {0,1} tensor, src = min(floor(dst*scale), in-1)
+__global__ void resize_nearest_i64_kernel(const long long* __restrict__ x, int n, int ih, int iw, int oh, int ow,
+                                          long long* __restrict__ out) {
+  const long long total = static_cast<long long>(n) * oh * ow;
+  const float sh = static_cast<float>(ih) / oh, sw = static_cast<float>(iw) / ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % ow), oy = static_cast<int>((i / ow) % oh);
+    const long long img = i / (static_cast<long long>(ow) * oh);
+    const int sy = min(static_cast<int>(floorf(oy * sh)), ih - 1), sx = min(static_cast<int>(floorf(ox * sw)), iw - 1);
+    out[i] = x[(img * ih + sy) * iw + sx];
+  }
+}
+
 __global__ void sum_f32_kernel(const float* __restrict__ x, long long count, float* __restrict__ out) {
   float part = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
@@ -1351,6 +1424,29 @@ int gap_u8_hwc_to_nhwc_bf16(const uint8_t* x, void* out, int64_t out_ld, int64_t
                 "gap_u8_hwc_to_nhwc_bf16: bad arguments");
   const int blocks = static_cast<int>(std::min<int64_t>((pixels + 255) / 256, 148 * 16));
   u8_hwc_to_nhwc_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<bf16*>(out), out_ld, pixels);
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_resize_u8_to_nhwc_bf16(const uint8_t* x, int n, int ih, int iw, int oh, int ow, void* out, int64_t out_ld,
+                               float* out_nchw_f32, void* stream) {
+  GAP_CHECK_ARG(x && (out || out_nchw_f32) && n > 0 && ih > 0 && iw > 0 && oh > 0 && ow > 0 &&
+                    (!out || (out_ld >= 4 && out_ld % 4 == 0)),
+                "gap_resize_u8_to_nhwc_bf16: bad arguments");
+  const long long total = static_cast<long long>(n) * oh * ow;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  resize_u8_to_nhwc_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, ih, iw, oh, ow, static_cast<bf16*>(out), out_ld, out_nchw_f32);
+  GAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gap_resize_nearest_i64(const int64_t* x, int n, int ih, int iw, int oh, int ow, int64_t* out, void* stream) {
+  GAP_CHECK_ARG(x && out && n > 0 && ih > 0 && iw > 0 && oh > 0 && ow > 0, "gap_resize_nearest_i64: bad arguments");
+  const long long total = static_cast<long long>(n) * oh * ow;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  resize_nearest_i64_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(x), n, ih, iw, oh, ow, reinterpret_cast<long long*>(out));
   GAP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,9 +7,30 @@ computes, batch i+1 is copied into the other staging slot; the consumer calls `r
 work that reads the current slot, which lets the copy stream refill it two iterations later."""
 from __future__ import annotations
 
-from typing import Iterable, Iterator, List, Sequence, Tuple
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import torch
+
+from . import ops
+
+
+def load_pair_u8(a_u8: torch.Tensor, b_u8: torch.Tensor, size: Tuple[int, int],
+                 label: Optional[torch.Tensor] = None):
+    """The tensor half of BaseChangeDetectionDataset.__getitem__ (dataset.py:191, transform list at 185-191) on the
+    device, for raw uint8 [n, h, w, 3] image batches of any size: ToTensor -> JointResize(size, BILINEAR; labels
+    NEAREST) -> JointNormalize.  Returns fp32 NCHW [n, 3, H, W] tensors in [-1, 1] — what the reference's DataLoader
+    yields and `train_step` / the drop-in modules accept — and the resized int64 label map if one was given."""
+    H, W = size
+    outs = []
+    for x in (a_u8, b_u8):
+        f = torch.empty(x.shape[0], 3, H, W, device=x.device)
+        ops.resize_u8_to_nhwc_bf16(x.contiguous(), None, f)
+        outs.append(f)
+    if label is not None:
+        lab = torch.empty(label.shape[0], H, W, device=label.device, dtype=torch.int64)
+        ops.resize_nearest_i64(label.contiguous(), lab)
+        outs.append(lab)
+    return tuple(outs)
 
 
 class PairPrefetcher:

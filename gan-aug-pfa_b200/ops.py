@@ -446,6 +446,40 @@ def u8_hwc_to_nhwc_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
                "gap_u8_hwc_to_nhwc_bf16")
 
 
+def resize_u8_to_nhwc_bf16(x: torch.Tensor, out: Optional[torch.Tensor], out_nchw_f32: Optional[torch.Tensor] = None) -> None:
+    """dataset.py's ToTensor + JointResize(BILINEAR, antialias) + JointNormalize on the device: uint8 [n,ih,iw,3] ->
+    NHWC bf16 [n,oh,ow,4 slots] and / or the fp32 NCHW [n,3,oh,ow] tensor the reference's DataLoader yields (the output
+    tensors' h / w are the target size)."""
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[-1] != 3 or not x.is_contiguous() or not x.is_cuda:
+        raise ValueError("expected a contiguous CUDA uint8 [n,h,w,3] tensor")
+    n = x.shape[0]
+    ld = 0
+    if out is not None:
+        on, oh, ow, _, ld = _nhwc_view(out)
+        if on != n or out.shape[-1] < 4:
+            raise ValueError("output must be NHWC bf16 [n, oh, ow, >=4]")
+    if out_nchw_f32 is not None:
+        f = out_nchw_f32
+        if f.dtype != torch.float32 or f.dim() != 4 or f.shape[0] != n or f.shape[1] != 3 or not f.is_contiguous() or not f.is_cuda:
+            raise ValueError("out_nchw_f32 must be a contiguous CUDA fp32 [n,3,oh,ow] tensor")
+        if out is not None and (f.shape[2], f.shape[3]) != (oh, ow):
+            raise ValueError("both outputs must have the same size")
+        oh, ow = f.shape[2], f.shape[3]
+    if out is None and out_nchw_f32 is None:
+        raise ValueError("no output given")
+    _lib.check(_lib.lib().gap_resize_u8_to_nhwc_bf16(_ptr(x), n, x.shape[1], x.shape[2], oh, ow, _ptr(out), ld,
+                                                     _ptr(out_nchw_f32), _stream()), "gap_resize_u8_to_nhwc_bf16")
+
+
+def resize_nearest_i64(x: torch.Tensor, out: torch.Tensor) -> None:
+    """JointResize's label half (dataset.py:143-146): nearest-neighbour resize of an int64 [n,ih,iw] map into [n,oh,ow]."""
+    if x.dtype != torch.int64 or out.dtype != torch.int64 or x.dim() != 3 or out.dim() != 3 or x.shape[0] != out.shape[0] \
+            or not (x.is_contiguous() and out.is_contiguous() and x.is_cuda and out.is_cuda):
+        raise ValueError("expected contiguous CUDA int64 [n,h,w] tensors")
+    _lib.check(_lib.lib().gap_resize_nearest_i64(_ptr(x), x.shape[0], x.shape[1], x.shape[2], out.shape[1], out.shape[2],
+                                                 _ptr(out), _stream()), "gap_resize_nearest_i64")
+
+
 def thin_convT_fwd(wide: torch.Tensor, wcol: torch.Tensor, bias: Optional[torch.Tensor], act: int,
                    out_bf16: Optional[torch.Tensor], out_f32: Optional[torch.Tensor],
                    out_u8: Optional[torch.Tensor] = None) -> None:

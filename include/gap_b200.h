@@ -260,6 +260,14 @@ int gap_thin_convT_fwd(const void* wide, int64_t ld_w, int n, int ih, int iw, in
  * the last layer's epilogue; gap_u8_hwc_to_nhwc_bf16 is dataset.py's ToTensor + Normalize(0.5, 0.5) (dataset.py:155-159)
  * on the device: uint8 HWC [pixels][3] -> NHWC bf16 with 4 channel slots, x*(2/255) - 1. */
 int gap_u8_hwc_to_nhwc_bf16(const uint8_t* x, void* out, int64_t out_ld, int64_t pixels, void* stream);
+/* The same with dataset.py's JointResize in front (dataset.py:136-153; ToTensor -> resize(BILINEAR) -> Normalize): uint8
+ * HWC [n][ih][iw][3] -> antialiased bilinear resize (torchvision's tensor path = F.interpolate(mode="bilinear",
+ * align_corners=False, antialias=True)) -> x*2 - 1 -> NHWC bf16 [n][oh][ow][4 slots] and / or (out_nchw_f32) the fp32
+ * [n][3][oh][ow] tensor the reference's DataLoader yields (either output may be NULL).  gap_resize_nearest_i64 is the
+ * label half of JointResize (InterpolationMode.NEAREST on the int64 {0,1} map, dataset.py:143-146). */
+int gap_resize_u8_to_nhwc_bf16(const uint8_t* x, int n, int ih, int iw, int oh, int ow, void* out, int64_t out_ld,
+                               float* out_nchw_f32, void* stream);
+int gap_resize_nearest_i64(const int64_t* x, int n, int ih, int iw, int oh, int ow, int64_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Siamese U-Net extras (models.py:47-145, train.py:34-128); NHWC bf16 activations, 8-channel vectors

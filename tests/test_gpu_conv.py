@@ -256,3 +256,80 @@ def test_full_size_adjointness_property():
     rhs = float((x.double() * gy.double()).sum())
     scale = float(fx.double().norm() * y.double().norm())
     assert abs(lhs - rhs) / scale < 1e-4
+
+
+@pytest.fixture
+def force_cta_pairs():
+    """fprop_pair = 2: tcgen05 cta_group::2 (M = 256 across two CTAs of a cluster) on every launch where it is legal; by
+    default only the 256-wide single-phase layers with long K loops use it (profiles/r2_pair_mode_per_layer.txt)."""
+    from gan_aug_pfa_b200 import _lib
+    _lib.debug_set("fprop_pair", 2)
+    yield
+    _lib.debug_set("fprop_pair", 1)
+
+
+def test_cta_pair_mode_on_every_geometry(force_cta_pairs):
+    """The CTA-pair path (each CTA stages half of the B rows, the leader issues the MMAs, completion multicast to both
+    CTAs) against fp32 CPU convolutions: stride-2 forward with statistics, the four-phase transposed geometry, halo
+    mode (k3 s1), a ragged stride-1 grid, two N tiles, and the backward-fused epilogue."""
+    g = torch.Generator().manual_seed(77)
+    # stride-2 forward + BatchNorm statistics (N = 128)
+    n, cin, cout, h = 16, 64, 128, 64
+    x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 4, 4, generator=g) / 32).to(torch.bfloat16)
+    out = torch.full((n, h // 2, h // 2, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * cout, device=DEV, dtype=torch.float64)
+    ops.conv_gemm([nhwc(x).to(DEV)], pack_conv(w).to(DEV), ops.geom_conv_fwd(4, 2, 1), out, cout, (h // 2, h // 2), stats=stats)
+    assert rel(out.cpu().float(), nhwc(F.conv2d(x.float(), w.float(), None, 2, 1))) < FWD_TOL
+    o = out.double()
+    assert rel(stats[cout:].cpu(), (o ** 2).sum((0, 1, 2)).cpu()) < 1e-5
+    # ConvTranspose2d forward: four phases, halo tiles (N = 64)
+    n, cin, cout, h = 8, 128, 64, 32
+    x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cin, cout, 4, 4, generator=g) / 24).to(torch.bfloat16)
+    out = torch.full((n, 2 * h, 2 * h, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv_gemm([nhwc(x).to(DEV)], pack_phase(w.permute(1, 0, 2, 3)).to(DEV), ops.geom_phase_k4s2p1(), out, cout, (h, h))
+    assert rel(out.cpu().float(), nhwc(F.conv_transpose2d(x.float(), w.float(), None, 2, 1))) < FWD_TOL
+    # stride-1 k4 on a ragged 31x31 grid with two 256-wide N tiles (the PatchGAN layer, models.py:238)
+    n, cin, cout, h = 8, 128, 512, 32
+    x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 4, 4, generator=g) / 45).to(torch.bfloat16)
+    out = torch.full((n, h - 1, h - 1, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv_gemm([nhwc(x).to(DEV)], pack_conv(w).to(DEV), ops.geom_conv_fwd(4, 1, 1), out, cout, (h - 1, h - 1))
+    assert rel(out.cpu().float(), nhwc(F.conv2d(x.float(), w.float(), None, 1, 1))) < FWD_TOL
+    # k3 s1 p1 (Siamese double_conv) with an odd number of M tiles per phase: the last pair has a missing partner tile
+    n, cin, cout, h = 5, 64, 64, 48
+    x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / 24).to(torch.bfloat16)
+    out = torch.full((n, h, h, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv_gemm([nhwc(x).to(DEV)], pack_conv(w).to(DEV), ops.geom_conv_fwd(3, 1, 1), out, cout, (h, h))
+    assert rel(out.cpu().float(), nhwc(F.conv2d(x.float(), w.float(), None, 1, 1))) < FWD_TOL
+    assert not torch.isnan(out.float()).any()
+    # backward-fused epilogue under pairs
+    _pair_bwd_epilogue(g)
+
+
+def _pair_bwd_epilogue(g):
+    n, cin, cout, h, slope = 16, 128, 256, 32, 0.2
+    dy = torch.randn(n, cout, h // 2, h // 2, generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 4, 4, generator=g) / 64.0
+    x = torch.zeros(n, cin, h, h, requires_grad=True)
+    (gref,) = torch.autograd.grad(F.conv2d(x, w.to(torch.bfloat16).float(), None, 2, 1), x, dy.float())
+    gref = nhwc(gref)
+    y = torch.randn(n, h, h, cin, generator=g).to(torch.bfloat16)
+    g2 = torch.randn(n, h, h, cin, generator=g).to(torch.bfloat16)
+    scale, shift = torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.3
+    yh = y.float() * scale + shift
+    dref = torch.where(yh > 0, gref + g2.float(), slope * gref)
+    out = torch.full((n, h, h, cin), float("nan"), device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * cin, device=DEV, dtype=torch.float64)
+    ops.conv_gemm([nhwc(dy).to(DEV)], pack_phase(w.to(torch.bfloat16).permute(1, 0, 2, 3)).to(DEV), ops.geom_phase_k4s2p1(),
+                  out, cin, (h // 2, h // 2), stats=stats,
+                  bwd=dict(y=y.to(DEV), slope=slope, g2=g2.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV)))
+    o = out.cpu().float()
+    safe = yh.abs() > 1e-3
+    assert float(((o - dref) * safe).norm() / dref.norm()) < FWD_TOL
+    od = o.double()
+    denom = (od ** 2).sum((0, 1, 2)).sqrt().max()
+    assert float((stats[:cin].cpu() - od.sum((0, 1, 2))).abs().max() / denom) < 1e-5
+    assert float((stats[cin:].cpu() - (od * y.double()).sum((0, 1, 2))).abs().max() / denom) < 1e-5

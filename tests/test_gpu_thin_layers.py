@@ -266,3 +266,30 @@ def test_cout1_conv_with_batchnorm_leakyrelu_fused_into_the_loads(n, c, h):
     xr = act.float().permute(0, 3, 1, 2)
     ref_w = torch.nn.grad.conv2d_weight(xr, (1, c, 4, 4), dl.cpu().unsqueeze(1), 1, 1)
     assert rel(dw_got.cpu().view(4, 4, c), ref_w[0].permute(1, 2, 0)) < 6e-3
+
+
+@pytest.mark.parametrize("ih,iw,oh,ow", [(300, 420, 256, 256), (512, 512, 256, 256), (100, 90, 256, 256), (256, 256, 256, 256),
+                                         (777, 333, 128, 128)])
+def test_on_device_resize_matches_the_reference_dataset_transforms(ih, iw, oh, ow):
+    """gap_resize_u8_to_nhwc_bf16 == dataset.py's ToTensor -> JointResize -> JointNormalize (dataset.py:28-29,136-159):
+    torchvision's tensor resize with BILINEAR is F.interpolate(mode="bilinear", align_corners=False, antialias=True)
+    (pinned on the CPU against torchvision itself in tests/test_oracle_golden.py).  bf16 output: rel-L2 <= 4e-3 and every
+    pixel within one bf16 ulp of the fp32 value.  Labels: NEAREST, bit-exact."""
+    g = torch.Generator().manual_seed(ih + iw)
+    img = torch.randint(0, 256, (2, ih, iw, 3), generator=g, dtype=torch.uint8)
+    x = img.permute(0, 3, 1, 2).float() / 255.0                                        # ToTensor
+    ref = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True) * 2.0 - 1.0
+    out = torch.full((2, oh, ow, 4), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.resize_u8_to_nhwc_bf16(img.to(DEV), out)
+    got = out.cpu().float()
+    assert rel(got[..., :3], nhwc(ref)) < 4e-3
+    assert float((got[..., :3] - nhwc(ref)).abs().max()) <= 2.0 ** -7             # bf16 spacing below 2 is 2^-7 at most... one ulp
+    assert float(got[..., 3].abs().max()) == 0.0
+    f32 = torch.full((2, 3, oh, ow), float("nan"), device=DEV)
+    ops.resize_u8_to_nhwc_bf16(img.to(DEV), None, f32)                            # the DataLoader's fp32 NCHW form
+    assert float((f32.cpu() - ref).abs().max()) < 2e-6
+    lab = (torch.rand(2, ih, iw, generator=g) < 0.3).long()
+    want = F.interpolate(lab.unsqueeze(1).float(), size=(oh, ow), mode="nearest").squeeze(1).long()
+    res = torch.full((2, oh, ow), -1, device=DEV, dtype=torch.int64)
+    ops.resize_nearest_i64(lab.to(DEV), res)
+    assert torch.equal(res.cpu(), want)
