@@ -91,8 +91,6 @@ _SIGNATURES = {
     "gap_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _P]),
     "gap_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _L, _I, _I, _P]),
     "gap_tanh_bwd": (C.c_int, [_P, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
-    "gap_im2col_k4s2p1": (C.c_int, [_P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _P]),
-    "gap_col2im_k4s2p1": (C.c_int, [_P, _L, _I, _I, _I, _P, _I, _P, _L, _P, _L, _I, _I, _I, _P]),
     "gap_gen_out_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _L, _L, _I, _P, _P]),
     "gap_gen_out_bwd_u8": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _L, _L, _I, _P, _P]),
     "gap_bce_logits_const": (C.c_int, [_P, _L, _F, _F, _P, _L, _P, _P]),

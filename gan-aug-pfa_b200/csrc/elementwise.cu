@@ -103,90 +103,6 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ gout, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// im2col for Conv2d(k4,s2,p1) over tiny-channel NHWC inputs (first layers, Cin = 3 or 6):
-//   col[(n,oh,ow)][(kh*4+kw)*ctot + c] = cat(src0, src1)[n, 2oh-1+kh, 2ow-1+kw, c], zero padded
-// One thread builds one full row (krow elements) in registers and writes it as 16-byte vectors.
-// ------------------------------------------------------------------------------------------------
-template <int CTOT, int KROW>
-__global__ void im2col_k4s2p1_kernel(const __nv_bfloat16* __restrict__ s0, int c0, long long ld0,
-                                     const __nv_bfloat16* __restrict__ s1, int c1, long long ld1,
-                                     __nv_bfloat16* __restrict__ col, int n, int h, int w) {
-  const int ho = h / 2, wo = w / 2;
-  const long long total = static_cast<long long>(n) * ho * wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ow = static_cast<int>(i % wo);
-    const int oh = static_cast<int>((i / wo) % ho);
-    const long long img = i / (static_cast<long long>(wo) * ho);
-    __align__(16) __nv_bfloat16 row[KROW];
-#pragma unroll
-    for (int k = 0; k < KROW; ++k) row[k] = __float2bfloat16(0.f);
-#pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-      const int y = 2 * oh - 1 + kh;
-#pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int x = 2 * ow - 1 + kw;
-        if (y >= 0 && y < h && x >= 0 && x < w) {
-          const long long pix = (img * h + y) * w + x;
-#pragma unroll
-          for (int c = 0; c < CTOT; ++c) {
-            const __nv_bfloat16 v = (c < c0) ? s0[pix * ld0 + c] : s1[pix * ld1 + (c - c0)];
-            row[(kh * 4 + kw) * CTOT + c] = v;
-          }
-        }
-      }
-    }
-    uint4* dst = reinterpret_cast<uint4*>(col + i * KROW);
-    const uint4* srcv = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-    for (int k = 0; k < KROW / 8; ++k) dst[k] = srcv[k];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// col2im for the k4,s2,p1 transposed geometry:
-//   out[n,y,x,c] = act( bias[c] + sum over (kh,kw) with (y+1-kh), (x+1-kw) even and in range of
-//                  col[(n,(y+1-kh)/2,(x+1-kw)/2)][(kh*4+kw)*ctot + c0 + c] )
-// Used for the generator's last ConvTranspose2d (+bias, Tanh; models.py:184,186) and for the
-// input gradient of the discriminator's first conv (channel slice of the col gradient).
-// ------------------------------------------------------------------------------------------------
-__global__ void col2im_k4s2p1_kernel(const __nv_bfloat16* __restrict__ col, long long ldc, int ctot, int c0,
-                                     int cn, const float* __restrict__ bias, int act,
-                                     __nv_bfloat16* __restrict__ out_bf, long long ld_bf,
-                                     float* __restrict__ out_f32, long long ld_f32, int n, int hi, int wi) {
-  const int ho = hi * 2, wo = wi * 2;
-  const long long total = static_cast<long long>(n) * ho * wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = static_cast<int>(i % wo);
-    const int y = static_cast<int>((i / wo) % ho);
-    const long long img = i / (static_cast<long long>(wo) * ho);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int kh = ((y + 1) & 1) + 2 * a;
-      const int iy = (y + 1 - kh) >> 1;
-      if (iy < 0 || iy >= hi) continue;
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int kw = ((x + 1) & 1) + 2 * b;
-        const int ix = (x + 1 - kw) >> 1;
-        if (ix < 0 || ix >= wi) continue;
-        const __nv_bfloat16* src = col + ((img * hi + iy) * wi + ix) * ldc + (kh * 4 + kw) * ctot + c0;
-        for (int c = 0; c < cn; ++c) acc[c] += __bfloat162float(src[c]);
-      }
-    }
-    for (int c = 0; c < cn; ++c) {
-      float v = acc[c] + (bias ? bias[c] : 0.f);
-      v = act_fwd(v, act);
-      if (out_bf) out_bf[i * ld_bf + c] = __float2bfloat16(v);
-      if (out_f32) out_f32[i * ld_f32 + c] = v;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Generator output backward + L1 loss (train_gan.py:68-70 through Tanh, models.py:186):
 //   l1 += sum |fake - real|;  g = dfake_d + l1_scale * sign(fake - real);  dpre = g * (1 - fake^2)
 // fake: fp32 NHWC (ld_f), real: fp32 NCHW (the caller's tensor), dfake_d: fp32 NHWC (ld_d, may be
@@ -987,41 +903,6 @@ int gap_tanh_bwd(const float* gout_nchw, const float* y_nhwc, int64_t ld_y, void
   const long long hw = static_cast<long long>(h) * w;
   tanh_bwd_kernel<<<grid_for(n * hw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       gout_nchw, y_nhwc, ld_y, static_cast<__nv_bfloat16*>(dpre), ld_p, n, c, hw);
-  GAP_LAUNCH_CHECK();
-  return 0;
-}
-
-int gap_im2col_k4s2p1(const void* s0, int c0, int64_t ld0, const void* s1, int c1, int64_t ld1, void* col,
-                      int krow, int n, int h, int w, void* stream) {
-  GAP_CHECK_ARG(s0 && col && n > 0 && h % 2 == 0 && w % 2 == 0, "gap_im2col_k4s2p1: bad arguments");
-  GAP_CHECK_ARG(c1 == 0 || s1, "gap_im2col_k4s2p1: src1 is null");
-  const int ctot = c0 + c1;
-  const long long rows = static_cast<long long>(n) * (h / 2) * (w / 2);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(s0);
-  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(s1);
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(col);
-  if (ctot == 3 && krow == 64)
-    im2col_k4s2p1_kernel<3, 64><<<grid_for(rows, 128), 128, 0, st>>>(a, c0, ld0, b, c1, ld1, o, n, h, w);
-  else if (ctot == 6 && krow == 128)
-    im2col_k4s2p1_kernel<6, 128><<<grid_for(rows, 128), 128, 0, st>>>(a, c0, ld0, b, c1, ld1, o, n, h, w);
-  else {
-    set_error("gap_im2col_k4s2p1: unsupported (channels %d, row %d); supported: (3,64), (6,128)", ctot, krow);
-    return GAP_ERR_UNSUPPORTED;
-  }
-  GAP_LAUNCH_CHECK();
-  return 0;
-}
-
-int gap_col2im_k4s2p1(const void* col, int64_t ldc, int ctot, int c0, int cn, const float* bias, int act,
-                      void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, int n, int hi, int wi,
-                      void* stream) {
-  GAP_CHECK_ARG(col && (out_bf16 || out_f32) && cn >= 1 && cn <= 4 && c0 + cn <= ctot && n > 0,
-                "gap_col2im_k4s2p1: bad arguments");
-  const long long total = static_cast<long long>(n) * hi * wi * 4;
-  col2im_k4s2p1_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(col), ldc, ctot, c0, cn, bias, act, static_cast<__nv_bfloat16*>(out_bf16),
-      ld_bf16, out_f32, ld_f32, n, hi, wi);
   GAP_LAUNCH_CHECK();
   return 0;
 }

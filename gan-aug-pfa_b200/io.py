@@ -50,6 +50,13 @@ class PairPrefetcher:
         self._cur = -1
         self.h2d_bytes = 0
 
+    def preallocate(self, example: Sequence[torch.Tensor]) -> "PairPrefetcher":
+        """Create the device staging buffers for batches shaped like `example` up front (a cudaMalloc inside the loop
+        would synchronise the device)."""
+        while len(self._stage) < self.slots:
+            self._stage.append(tuple(torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in example))
+        return self
+
     def _issue(self, k: int, batch: Sequence[torch.Tensor]) -> None:
         for t in batch:
             if not t.is_pinned():

@@ -266,22 +266,6 @@ def tanh_bwd(gout_nchw: torch.Tensor, y_nhwc_f32: torch.Tensor, dpre: torch.Tens
                                        dpre.stride(2), n, c, h, w, _stream()), "gap_tanh_bwd")
 
 
-def im2col_k4s2p1(s0: torch.Tensor, c0: int, s1: Optional[torch.Tensor], c1: int, col: torch.Tensor) -> None:
-    n, h, w, _ = s0.shape
-    _lib.check(_lib.lib().gap_im2col_k4s2p1(_ptr(s0), c0, s0.stride(2), _ptr(s1), c1,
-                                            0 if s1 is None else s1.stride(2), _ptr(col), col.shape[-1], n, h, w,
-                                            _stream()), "gap_im2col_k4s2p1")
-
-
-def col2im_k4s2p1(col: torch.Tensor, ctot: int, c0: int, cn: int, bias: Optional[torch.Tensor], act: int,
-                  out_bf16: Optional[torch.Tensor], out_f32: Optional[torch.Tensor]) -> None:
-    n, hi, wi, ldc = col.shape
-    _lib.check(_lib.lib().gap_col2im_k4s2p1(
-        _ptr(col), ldc, ctot, c0, cn, _ptr(bias), act, _ptr(out_bf16),
-        0 if out_bf16 is None else out_bf16.stride(2), _ptr(out_f32), 0 if out_f32 is None else out_f32.stride(2),
-        n, hi, wi, _stream()), "gap_col2im_k4s2p1")
-
-
 def gen_out_bwd(fake_f32: torch.Tensor, real: torch.Tensor, dfake_d: Optional[torch.Tensor], l1_scale: float,
                 dpre: torch.Tensor, loss_acc: torch.Tensor) -> None:
     """L1 * lambda + Tanh backward.  ``real`` is real_B either as fp32 NCHW (what the reference's DataLoader yields) or

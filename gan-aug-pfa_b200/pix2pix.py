@@ -951,11 +951,14 @@ class Pix2PixTrainer:
         return self._g_out.clone()
 
     @_on_device
-    def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor) -> torch.Tensor:
+    def train_step(self, real_A: torch.Tensor, real_B: torch.Tensor,
+                   loss_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """real_A / real_B: fp32 NCHW in [-1, 1] on the device (what the reference's DataLoader yields), or BOTH as raw
         uint8 [n, h, w, 3] images: the ToTensor + JointNormalize of dataset.py:28-29,155-159 then runs on the device
         inside the first kernels (4x less host->device traffic).  Returns a device tensor [loss_d, loss_g] (fp64); no
-        host synchronisation happens here."""
+        host synchronisation happens here.  loss_host: a PINNED host fp64[2] tensor — the step's last kernel then stores
+        the two losses straight into host memory (zero-copy over PCIe; valid once the stream has passed that kernel) and
+        that tensor is returned: the per-step `.item()` of train_gan.py:72-74 without a memcpy node in the stream."""
         G, D = self.G, self.D
         u8 = real_A.dtype == torch.uint8
         if u8 != (real_B.dtype == torch.uint8):
@@ -1024,5 +1027,10 @@ class Pix2PixTrainer:
         elif self.allreduce is not None:
             self.allreduce(G.store.g)
         G.adam_step(self.lr_g, self.betas, grad_scale=1.0 / self.world)   # :71
+        if loss_host is not None:
+            if not loss_host.is_pinned() or loss_host.dtype != torch.float64 or loss_host.numel() < 2:
+                raise ValueError("loss_host must be a pinned fp64 host tensor with 2 elements")
+            ops.gan_losses(self.loss_acc, cnt, LAMBDA_L1, numel, loss_host)      # :61, :68-69, written over PCIe
+            return loss_host
         ops.gan_losses(self.loss_acc, cnt, LAMBDA_L1, numel, self.loss_out)      # :61, :68-69
         return self.loss_out.clone()     # (callers may keep the result across steps)

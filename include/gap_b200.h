@@ -164,19 +164,6 @@ int gap_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* out, int n, int c, 
 int gap_tanh_bwd(const float* gout_nchw, const float* y_nhwc, int64_t ld_y, void* dpre, int64_t ld_p, int n, int c,
                  int h, int w, void* stream);
 
-/* First-layer im2col for Conv2d(k4,s2,p1) with 3 or 6 input channels (models.py:177 outermost,
- * models.py:223; the 6-channel input is torch.cat((real_A, B), 1), train_gan.py:57,59,66):
- * col[(n,oh,ow)][(kh*4+kw)*(c0+c1) + c], zero padded to `krow` (64 for 3 channels, 128 for 6). */
-int gap_im2col_k4s2p1(const void* src0, int c0, int64_t ld0, const void* src1, int c1, int64_t ld1, void* col,
-                      int krow, int n, int h, int w, void* stream);
-
-/* col2im of the k4,s2,p1 transposed geometry (+bias, activation): the generator's last
- * ConvTranspose2d + Tanh (models.py:184,186) after its GEMM, and the input gradient of the
- * discriminator's first conv (channel slice [c0, c0+cn) of the col gradient). */
-int gap_col2im_k4s2p1(const void* col, int64_t ldc, int ctot, int c0, int cn, const float* bias, int act,
-                      void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, int n, int hi, int wi,
-                      void* stream);
-
 /* L1Loss(fake, real) * lambda (train_gan.py:43,68) fused with the Tanh backward:
  * loss_acc += sum|fake-real|; dpre = (dfake_d + l1_scale*sign(fake-real)) * (1 - fake^2). */
 int gap_gen_out_bwd(const float* fake, int64_t ld_f, const float* real_nchw, int64_t hw, const float* dfake_d,
