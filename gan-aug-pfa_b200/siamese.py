@@ -224,7 +224,9 @@ class SiameseEngine(_Net):
         ops.bn_act(y, sv.scale, sv.shift, out, ACT_RELU)
 
         def backward() -> None:
-            dy = self._scratch("dy", (n, h, w, co))
+            # (one dy buffer per layer evaluation: the weight gradient runs on the side stream and may still be reading
+            # it when the next layer's backward starts)
+            dy = self._scratch(f"dy.{key}.{pass_id}", (n, h, w, co))
             if gout_premasked:
                 ops.bn_bwd_finalize(bn.sums, sv.mean, sv.invstd, self.grad(bn.name + ".weight"),
                                     self.grad(bn.name + ".bias"), bn.sums2)
@@ -232,10 +234,13 @@ class SiameseEngine(_Net):
             else:
                 self._bn_bwd(bn, sv, y, gout, 0.0, dy)
             wseg = self.store.seg(self.store.g, key + ".weight")
+            # weight gradients are off the critical path: they run on the side stream (tensor-bound) underneath the
+            # HBM-bound BatchNorm / pooling / gate passes of the layers that follow
             if ci == 3:
-                ops.conv_wgrad(dy, x, wseg, (1, 1), 1, (0, 0), 64, 0, flops=2.0 * n * h * w * co * 27)
+                self._fork_wgrad(lambda: ops.conv_wgrad(dy, x, wseg, (1, 1), 1, (0, 0), 64, 0,
+                                                        flops=2.0 * n * h * w * co * 27))
                 return
-            ops.conv_wgrad(dy, x, wseg, (3, 3), 1, (-1, -1), 9 * ci, ci)
+            self._fork_wgrad(lambda: ops.conv_wgrad(dy, x, wseg, (3, 3), 1, (-1, -1), 9 * ci, ci))
             if gx is None:
                 return
             if gx_accumulate:
@@ -362,6 +367,7 @@ class SiameseEngine(_Net):
     def backward_encoder(self) -> None:
         for idx in range(len(self._tape) - 1, -1, -1):
             self._tape[idx]()
+        self._join_wgrad()
         self._tape = []
 
     @_on_device
@@ -403,7 +409,9 @@ class SiameseEngine(_Net):
         for idx in range(len(self._tape) - 1, -1, -1):
             self._tape[idx]()
             if self.reducer is not None and idx in self._marks:
+                self._join_wgrad()          # the segments' side-stream weight gradients are part of what gets reduced
                 self.reducer.ready_from(self._marks[idx])
+        self._join_wgrad()
         self._tape = []
 
     # -- one training iteration (train.py:137-146) ------------------------------------------------------
