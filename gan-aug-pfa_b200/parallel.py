@@ -16,6 +16,11 @@ import torch
 import torch.distributed as dist
 
 
+import os as _os
+
+_SKIP = _os.environ.get("GAP_DP_SKIP_ALLREDUCE", "0") == "1"     # bring-up only: measures what the collectives cost
+
+
 def make_allreduce(world: int, bucket_elems: int = 8 << 20) -> Optional[Callable[[torch.Tensor], None]]:
     """Returns f(flat_grad) that sum-reduces the buffer in place across ranks, in buckets (no overlap)."""
     if world <= 1:
@@ -80,7 +85,8 @@ class GradBucketReducer:
                 ev.record(st)
                 self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(view, op=dist.ReduceOp.SUM)
+                if not _SKIP:
+                    dist.all_reduce(view, op=dist.ReduceOp.SUM)
         else:
             dist.all_reduce(view, op=dist.ReduceOp.SUM)
 

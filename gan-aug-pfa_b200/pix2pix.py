@@ -901,7 +901,9 @@ class Pix2PixTrainer:
         self._graph_sig = None
         self._g_stream = None
         if world > 1 and allreduce is None:
+            import os
             from .parallel import GradBucketReducer
+            bucket_elems = int(os.environ.get("GAP_BUCKET_ELEMS", bucket_elems))      # bring-up sweeps
             self.g_reducer = GradBucketReducer(self.G.store.g, self.G.grad_segments(), bucket_elems=bucket_elems)
             self.d_reducer = GradBucketReducer(self.D.store.g, self.D.grad_segments(), bucket_elems=1 << 30,
                                                comm_stream=self.g_reducer.comm_stream)
