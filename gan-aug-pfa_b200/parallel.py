@@ -34,17 +34,34 @@ def make_allreduce(world: int, bucket_elems: int = 8 << 20) -> Optional[Callable
     return allreduce
 
 
-def plan_buckets(segments: Sequence[Tuple[str, int, int]], total: int, bucket_elems: int) -> List[Tuple[int, int, List[str]]]:
+def plan_buckets(segments: Sequence[Tuple[str, int, int]], total: int, bucket_elems: int,
+                 tail_elems: int = 0) -> List[Tuple[int, int, List[str]]]:
     """Group consecutive segments (name, offset, numel — in buffer order) into buckets of at least
-    ``bucket_elems`` elements.  Returns (begin, end, segment names); buckets tile [0, total)."""
+    ``bucket_elems`` elements.  Returns (begin, end, segment names); buckets tile [0, total).
+    ``tail_elems`` > 0 additionally splits off the trailing segments (as many as fit in ``tail_elems`` elements) as the
+    LAST bucket: that bucket can only be reduced after the backward pass has finished, so its transfer is exposed and
+    should be small, while the bucket before it still overlaps the last layers."""
+    n_tail = 0
+    if tail_elems > 0 and len(segments) > 1:
+        acc = 0
+        for i in range(len(segments) - 1, 0, -1):
+            end = segments[i + 1][1] if i + 1 < len(segments) else total
+            if acc + (end - segments[i][1]) > tail_elems:
+                break
+            acc += end - segments[i][1]
+            n_tail += 1
+    head = segments[:len(segments) - n_tail] if n_tail else segments
+    head_total = segments[len(segments) - n_tail][1] if n_tail else total
     buckets: List[Tuple[int, int, List[str]]] = []
     begin, names = 0, []
-    for i, (name, off, numel) in enumerate(segments):
+    for i, (name, off, numel) in enumerate(head):
         names.append(name)
-        end = segments[i + 1][1] if i + 1 < len(segments) else total
-        if end - begin >= bucket_elems or i + 1 == len(segments):
+        end = head[i + 1][1] if i + 1 < len(head) else head_total
+        if end - begin >= bucket_elems or i + 1 == len(head):
             buckets.append((begin, end, names))
             begin, names = end, []
+    if n_tail:
+        buckets.append((head_total, total, [s[0] for s in segments[len(segments) - n_tail:]]))
     return buckets
 
 
@@ -58,9 +75,9 @@ class GradBucketReducer:
     what is left and makes the compute stream wait for the reductions."""
 
     def __init__(self, flat: torch.Tensor, segments: Sequence[Tuple[str, int, int]], bucket_elems: int = 8 << 20,
-                 comm_stream: Optional["torch.cuda.Stream"] = None) -> None:
+                 comm_stream: Optional["torch.cuda.Stream"] = None, tail_elems: int = 0) -> None:
         self.flat = flat
-        self.buckets = plan_buckets(segments, flat.numel(), bucket_elems)
+        self.buckets = plan_buckets(segments, flat.numel(), bucket_elems, tail_elems)
         self.bucket_of: Dict[str, int] = {n: b for b, (_, _, names) in enumerate(self.buckets) for n in names}
         self.cuda = flat.is_cuda
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream(flat.device) if self.cuda else None)
@@ -128,33 +145,41 @@ class TailReducer:
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream(flat.device) if self.cuda else None)
         self.hi = flat.numel()
         self.launched: List[Tuple[int, int]] = []      # (begin, end) of the reductions of the last step
+        self._streams: set = set()
 
     def begin(self) -> None:
         self.hi = self.flat.numel()
         self.launched = []
+        self._streams = set()
 
-    def _launch(self, lo: int) -> None:
+    def _launch(self, lo: int, streams=()) -> None:
         view = self.flat[lo:self.hi]
         if self.cuda:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.flat.device))
-            self.comm_stream.wait_event(ev)
+            for st in {torch.cuda.current_stream(self.flat.device), *[s for s in streams if s is not None]}:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(view, op=dist.ReduceOp.SUM)
+                if not _SKIP:
+                    dist.all_reduce(view, op=dist.ReduceOp.SUM)
         else:
             dist.all_reduce(view, op=dist.ReduceOp.SUM)
         self.launched.append((lo, self.hi))
         self.hi = lo
 
-    def ready_from(self, offset: int) -> None:
+    def ready_from(self, offset: int, streams=()) -> None:
+        """``streams``: side streams (besides the current one) that produced part of [offset, watermark)."""
         if offset < 0 or offset > self.hi:
             raise ValueError(f"watermark {offset} must move down from {self.hi}")
+        self._streams.update(s for s in streams if s is not None)
         if self.hi - offset >= self.min_elems:
-            self._launch(offset)
+            self._launch(offset, self._streams)
+            self._streams = set()
 
     def finish(self) -> None:
         if self.hi > 0:
-            self._launch(0)
+            self._launch(0, self._streams)
+            self._streams = set()
         if self.cuda:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
 

@@ -821,10 +821,13 @@ class DiscriminatorEngine(_Net):
         return self.logits
 
     @_on_device
-    def backward(self, wgrad: bool, input_grad: bool, input_grad_a: bool = False) -> Optional[torch.Tensor]:
+    def backward(self, wgrad: bool, input_grad: bool, input_grad_a: bool = False, final_hook=None) -> Optional[torch.Tensor]:
         """Consumes self.dlogits (fp32 [n, h', w']).  wgrad=False skips every parameter gradient (the G step);
         input_grad=True returns d(loss)/d(xb) as fp32 NHWC.  The last conv's bias gradient (sum of dlogits) is
-        produced by whoever wrote dlogits (gap_bce_logits_const_f32 / gap_sum_f32)."""
+        produced by whoever wrote dlogits (gap_bce_logits_const_f32 / gap_sum_f32).  final_hook(offset, stream): called
+        when this pass has enqueued the last contribution to every gradient from `offset` to the end of the flat buffer
+        (the buffer is in forward order, backward finalises it from the tail): the data-parallel reducer starts reducing
+        that tail while the rest of the pass runs."""
         C = self.C
         last = self.n_conv - 1
         g = self.store.g
@@ -847,6 +850,8 @@ class DiscriminatorEngine(_Net):
                 self._fork_wgrad(lambda k=k, s=s: ops.conv_wgrad(
                     self.dy[k], self.H[k - 1], self.store.seg(g, self.k_conv[k] + ".weight"), (4, 4), s, (-1, -1),
                     16 * C[k - 1], C[k - 1]))
+                if final_hook is not None:
+                    final_hook(self.store.off(self.k_conv[k] + ".weight"), self._wgrad_stream if self._wgrad_used else None)
             geom = ops.geom_phase_k4s2p1() if s == 2 else ops.geom_conv_dgrad_s1(4, 1)
             grid = (self.hs[k], self.ws[k]) if s == 2 else (self.hs[k - 1], self.ws[k - 1])
             # algorithmic FLOPs of a dgrad = those of the layer's forward (the stride-1 dgrad runs its GEMM over the
@@ -904,9 +909,13 @@ class Pix2PixTrainer:
             import os
             from .parallel import GradBucketReducer
             bucket_elems = int(os.environ.get("GAP_BUCKET_ELEMS", bucket_elems))      # bring-up sweeps
-            self.g_reducer = GradBucketReducer(self.G.store.g, self.G.grad_segments(), bucket_elems=bucket_elems)
-            self.d_reducer = GradBucketReducer(self.D.store.g, self.D.grad_segments(), bucket_elems=1 << 30,
-                                               comm_stream=self.g_reducer.comm_stream)
+            from .parallel import TailReducer
+            # generator: buckets in backward-completion order; the LAST bucket (reduced after the pass, i.e. exposed)
+            # holds only the trailing small segments.  discriminator: its buffer is in forward order, so it is reduced
+            # from the tail (the 2.1 M-parameter conv right after the head's gradients, under the rest of the pass).
+            self.g_reducer = GradBucketReducer(self.G.store.g, self.G.grad_segments(), bucket_elems=bucket_elems,
+                                               tail_elems=int(os.environ.get("GAP_TAIL_ELEMS", 1 << 20)))
+            self.d_reducer = TailReducer(self.D.store.g, min_elems=1 << 20, comm_stream=self.g_reducer.comm_stream)
             self.G.grad_hook = self.g_reducer.mark_ready
         if world > 1:
             self.sync_replicas()
@@ -1003,10 +1012,14 @@ class Pix2PixTrainer:
             cur.wait_stream(self._g_stream)
         logits = D.forward(a_nhwc, G.fake_bf)              # :59
         ops.bce_logits_const_f32(logits, 0.0, 0.5 / cnt, D.dlogits, self.loss_acc[1:2], d_bias_last)   # :60,61
-        D.backward(wgrad=True, input_grad=False)           # :62
-        D._join_wgrad()
         if self.d_reducer is not None:
             self.d_reducer.begin()
+            D.backward(wgrad=True, input_grad=False,       # :62 — this pass completes the D gradients
+                       final_hook=lambda off, st: self.d_reducer.ready_from(off, (st,)))
+        else:
+            D.backward(wgrad=True, input_grad=False)       # :62
+        D._join_wgrad()
+        if self.d_reducer is not None:
             self.d_reducer.finish()
         elif self.allreduce is not None:
             self.allreduce(D.store.g)

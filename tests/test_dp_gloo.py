@@ -213,3 +213,18 @@ def test_tail_reducer_and_replica_sync_world2():
     r.hi = 5
     with _pt.raises(ValueError):
         r.ready_from(7)
+
+
+def test_plan_buckets_splits_off_a_small_exposed_tail():
+    """tail_elems: the bucket that can only be reduced after the backward pass holds just the trailing small segments."""
+    from gan_aug_pfa_b200.parallel import plan_buckets
+    segs = [("up", 0, 4000), ("d6", 4000, 4000), ("d5", 8000, 4000), ("d4", 12000, 4000), ("d3", 16000, 2000),
+            ("d2", 18000, 500), ("d1", 18500, 128), ("d0", 18628, 4)]
+    plain = plan_buckets(segs, 18632, 8000)
+    assert plain[-1][2] == ["d3", "d2", "d1", "d0"]                         # 2632 elements wait for the end of backward
+    split = plan_buckets(segs, 18632, 8000, tail_elems=1000)
+    assert split[-1] == (18000, 18632, ["d2", "d1", "d0"])                  # only 632 do now
+    assert split[-2][2] == ["d3"] and split[-2][1] == 18000
+    assert split[0][0] == 0 and all(a[1] == b[0] for a, b in zip(split, split[1:]))
+    assert [n for _, _, names in split for n in names] == [s[0] for s in segs]
+    assert plan_buckets(segs, 18632, 8000, tail_elems=2) == plain           # nothing fits: unchanged
