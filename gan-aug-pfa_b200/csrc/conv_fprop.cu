@@ -540,67 +540,53 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       }
       // (Tried: prefetch.global.L2 of the next work item's y / g2 rows here.  5 % SLOWER: the loads wait on the L1
       // data pipe, which the tensor-core operand reads and TMA writes keep ~70 % busy, not on DRAM.)
-      // Backward-fused epilogue: the y / g2 rows a warp needs are fetched in groups of two 16-column chunks, one group
-      // AHEAD of the group being processed (and the first group of a work item before the wait for its accumulator):
-      // ncu (profiles/r2_ncu_bwd_epilogue.md) showed the small-N dgrads epilogue-bound — the epilogue warps never wait
-      // for the MMA, the MMA lane waits for them — with 26 % of the epilogue warps' time on the first use of y.
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
       const int n_chunks = p.block_n >> 4;
-      const int my_chunks = (n_chunks - half + 1) >> 1;        // chunks half, half + 2, ... of every M tile
-      const int ng = (my_chunks + 1) >> 1;                      // groups of two per M tile
-      const int total_groups = p.mt * ng;
-      auto tile_pixel = [&](int j, bool& valid, bool& exists) -> long long {
+      for (int j = 0; j < p.mt; ++j) {
         const MTile mtile = decode_mtile(p, sm_own * p.mt + j);
         const int wi = row & (BW - 1);
         const int hi = (row >> p.log_bw) & (BH - 1);
         const int ni = row >> (p.log_bw + p.log_bh);
         const int gx = mtile.tw * BW + wi, gy = mtile.th * BH + hi, n = mtile.tn * BNI + ni;
-        exists = mtile.exists;
-        valid = mtile.exists && (gx < p.gw) && (gy < p.gh) && (n < p.n_img);
-        return (static_cast<long long>(n) * p.OH + (gy * p.out_stride + wc.ph)) * p.OW + (gx * p.out_stride + wc.pw);
-      };
-      auto load_group = [&](int g, uint4 (&yq)[2][2], uint4 (&gq)[2][2]) {
-        const int j = g / ng, cg0 = half + 4 * (g - j * ng);
-        bool valid, exists;
-        const long long pix = tile_pixel(j, valid, exists);
+        const bool valid = mtile.exists && (gx < p.gw) && (gy < p.gh) && (n < p.n_img);
+        const long long pix =
+            (static_cast<long long>(n) * p.OH + (gy * p.out_stride + wc.ph)) * p.OW + (gx * p.out_stride + wc.pw);
+        const uint32_t t_row =
+            tmem_base + acc * kAccStride + j * p.block_n + (static_cast<uint32_t>(q * 32) << 16);
+        if (!mtile.exists) continue;
+        const bool fast = valid && p.fast_store;
+        for (int cg = half; cg < n_chunks; cg += 8) {
+          // backward-fused epilogue: issue the y / g2 loads of up to four chunks before touching TMEM, so their
+          // latency overlaps (the epilogue is latency-bound otherwise: only four warps per CTA)
+          uint4 yq[4][2], gq[4][2];
+          if (kEpi == 1) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          yq[i][0] = yq[i][1] = gq[i][0] = gq[i][1] = make_uint4(0, 0, 0, 0);
-          const int colp = wc.n_tile * p.block_n + (cg0 + 2 * i) * 16;
-          if (valid && cg0 + 2 * i < n_chunks && colp >= p.bwd_c0 && colp < p.n_out && !(p.skip & 2)) {
-            const __nv_bfloat16* yp = p.bwd_y + pix * p.bwd_y_ld + (colp - p.bwd_c0);
-            if (p.bwd_ld32) {
-              ld_global_nc_32B(yp, yq[i][0], yq[i][1]);
-            } else {
-              yq[i][0] = __ldg(reinterpret_cast<const uint4*>(yp));
-              yq[i][1] = __ldg(reinterpret_cast<const uint4*>(yp) + 1);
-            }
-            if (p.bwd_g2 != nullptr) {
-              const __nv_bfloat16* gp = p.bwd_g2 + pix * p.bwd_g2_ld + (colp - p.bwd_c0);
-              if (p.bwd_ld32) {
-                ld_global_nc_32B(gp, gq[i][0], gq[i][1]);
-              } else {
-                gq[i][0] = __ldg(reinterpret_cast<const uint4*>(gp));
-                gq[i][1] = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
+            for (int i = 0; i < 4; ++i) {
+              yq[i][0] = yq[i][1] = gq[i][0] = gq[i][1] = make_uint4(0, 0, 0, 0);
+              const int colp = wc.n_tile * p.block_n + (cg + 2 * i) * 16;
+              if (valid && cg + 2 * i < n_chunks && colp >= p.bwd_c0 && colp < p.n_out && !(p.skip & 2)) {
+                const __nv_bfloat16* yp = p.bwd_y + pix * p.bwd_y_ld + (colp - p.bwd_c0);
+                if (p.bwd_ld32) {
+                  ld_global_nc_32B(yp, yq[i][0], yq[i][1]);
+                } else {
+                  yq[i][0] = __ldg(reinterpret_cast<const uint4*>(yp));
+                  yq[i][1] = __ldg(reinterpret_cast<const uint4*>(yp) + 1);
+                }
+                if (p.bwd_g2 != nullptr) {
+                  const __nv_bfloat16* gp = p.bwd_g2 + pix * p.bwd_g2_ld + (colp - p.bwd_c0);
+                  if (p.bwd_ld32) {
+                    ld_global_nc_32B(gp, gq[i][0], gq[i][1]);
+                  } else {
+                    gq[i][0] = __ldg(reinterpret_cast<const uint4*>(gp));
+                    gq[i][1] = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
+                  }
+                }
               }
             }
           }
-        }
-      };
-      uint4 yq[2][2], gq[2][2], yn[2][2], gn[2][2];
-      if (kEpi == 1) load_group(0, yq, gq);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      for (int g = 0; g < total_groups; ++g) {
-        const int j = g / ng, cg = half + 4 * (g - j * ng);
-        if (kEpi == 1 && g + 1 < total_groups) load_group(g + 1, yn, gn);
-        bool valid, exists;
-        const long long pix = tile_pixel(j, valid, exists);
-        const uint32_t t_row =
-            tmem_base + acc * kAccStride + j * p.block_n + (static_cast<uint32_t>(q * 32) << 16);
-        const bool fast = valid && p.fast_store;
-        if (exists) {
 #pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
+          for (int ci = 0; ci < 4; ++ci) {
           const int c = cg + 2 * ci;
           if (c >= n_chunks) break;
           uint32_t raw[16];
@@ -709,15 +695,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
                                    make_float4(f[8], f[9], f[10], f[11]), make_float4(f[12], f[13], f[14], f[15]), pix,
                                    col0);
           }
-          }
-        }
-        if (kEpi == 1) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            yq[i][0] = yn[i][0];
-            yq[i][1] = yn[i][1];
-            gq[i][0] = gn[i][0];
-            gq[i][1] = gn[i][1];
           }
         }
       }
