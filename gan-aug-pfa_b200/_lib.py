@@ -86,7 +86,6 @@ _SIGNATURES = {
     "gap_version": (C.c_int, []),
     "gap_sm_count": (C.c_int, []),
     "gap_debug_set": (C.c_int, [C.c_char_p, C.c_int]),
-    "gap_set_sm_limit": (C.c_int, [C.c_int]),
     "gap_conv_gemm": (C.c_int, [C.POINTER(ConvGemmArgs), C.c_void_p]),
     "gap_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "gap_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _L, _P]),

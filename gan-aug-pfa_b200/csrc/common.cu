@@ -19,10 +19,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// SMs the persistent kernels spread over.  gap_set_sm_limit(n) (data parallel: pix2pix.Pix2PixTrainer) leaves the
-// remaining SMs to the NCCL all-reduce kernels: a persistent GEMM CTA takes an SM's whole shared memory, so a collective
-// launched underneath a full-width GEMM only progresses in the gaps between kernels.
-static std::atomic<int> g_sm_limit{0};
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -33,8 +29,7 @@ int sm_count() {
     else
       return 148;
   }
-  const int lim = g_sm_limit.load(std::memory_order_relaxed);
-  return lim > 0 && lim < cached ? lim : cached;
+  return cached;
 }
 
 static std::mutex g_dbg_mu;
@@ -123,10 +118,6 @@ extern "C" {
 const char* gap_last_error_string(void) { return gap::g_err; }
 int gap_version(void) { return 100; }
 int gap_sm_count(void) { return gap::sm_count(); }
-int gap_set_sm_limit(int n) {
-  gap::g_sm_limit.store(n > 0 ? n : 0, std::memory_order_relaxed);
-  return gap::sm_count();
-}
 int gap_debug_set(const char* key, int value) {
   std::lock_guard<std::mutex> lk(gap::g_dbg_mu);
   gap::dbg_map()[key] = value;

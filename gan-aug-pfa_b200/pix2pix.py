@@ -909,8 +909,6 @@ class Pix2PixTrainer:
             import os
             from .parallel import GradBucketReducer
             bucket_elems = int(os.environ.get("GAP_BUCKET_ELEMS", bucket_elems))      # bring-up sweeps
-            from . import _lib
-            _lib.lib().gap_set_sm_limit(int(os.environ.get("GAP_SM_LIMIT", "0")))
             from .parallel import TailReducer
             # generator: buckets in backward-completion order; the LAST bucket (reduced after the pass, i.e. exposed)
             # holds only the trailing small segments.  discriminator: its buffer is in forward order, so it is reduced

@@ -49,9 +49,6 @@ const char* gap_last_error_string(void);
 int gap_version(void);
 /* Number of SMs the persistent kernels size their grids for (148 on B200). */
 int gap_sm_count(void);
-/* Cap the number of SMs the persistent kernels use (0 = all).  Data-parallel training leaves a few SMs to the NCCL
- * all-reduce kernels that run underneath the backward pass.  Returns the effective count. */
-int gap_set_sm_limit(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution engine (tcgen05 / TMEM / TMA).
