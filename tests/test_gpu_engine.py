@@ -278,3 +278,37 @@ def test_generator_with_dropout_trains_and_evaluates():
     assert int(t_drop.G.state_dict()["model.model.1.model.2.num_batches_tracked"]) == nbt0 + 2
     g = t_drop.G.store.g
     assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+def test_graphed_step_recaptures_when_buffers_or_hyperparameters_change():
+    """a captured iteration bakes in the engines' activation buffers (raw pointers, TMA maps) and lr / betas.
+    An eager step at another batch size re-allocates those buffers; the next graphed call at the original shape must
+    re-capture instead of replaying into freed memory, results of successive replays must not alias, and the host step
+    counters must follow the device-side ones."""
+    from gan_aug_pfa_b200.pix2pix import Pix2PixTrainer
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(21)
+    mk = lambda n: ((torch.rand(n, 3, 64, 64, generator=gen) * 2 - 1).to(dev), (torch.rand(n, 3, 64, 64, generator=gen) * 2 - 1).to(dev))
+    b2 = [mk(2) for _ in range(4)]
+    b3 = mk(3)
+    seqs = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        tr = Pix2PixTrainer(dev, num_downs=5)
+        fn = tr.train_step_graphed if graphed else tr.train_step
+        out = [fn(*b2[0]), fn(*b2[1])]
+        if graphed:
+            assert out[0].data_ptr() != out[1].data_ptr()          # replays hand out fresh tensors
+            sig = tr._graph_sig
+        tr.train_step(*b3)                                          # eager, another shape: buffers are re-allocated
+        out.append(fn(*b2[2]))                                      # must re-capture (graphed) — not replay a stale graph
+        if graphed:
+            assert tr._graph_sig != sig
+            sig = tr._graph_sig
+        tr.lr_g = 5e-5                                              # a kernel argument of the captured Adam launch
+        out.append(fn(*b2[3]))
+        if graphed:
+            assert tr._graph_sig != sig
+            assert int(tr.G.store.step_dev) == tr.G.store.step == 5 and tr.D.store.step == 5
+        seqs.append(torch.stack([o.cpu() for o in out]))
+    assert torch.allclose(seqs[0], seqs[1], rtol=3e-3, atol=3e-4), (seqs[0], seqs[1])
