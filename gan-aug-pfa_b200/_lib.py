@@ -47,7 +47,6 @@ class ConvGemmArgs(C.Structure):
         ("bwd_g2", C.c_void_p), ("bwd_g2_ld", C.c_int64),
         ("bwd_slope", C.c_float), ("bwd_c0", C.c_int),
         ("scale", C.c_void_p),
-        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_size_t),
     ]
 
 
@@ -132,11 +131,6 @@ _SIGNATURES = {
     "gap_bn_bwd_apply": (C.c_int, [_P, _L, _P, _L, _P, _L, _F, _P, _P, _P, _P, _L, _I, _P, _D, _P, _L, _P]),
     "gap_bn_param_grads": (C.c_int, [_P, _I, _P, _P, _P]),
     "gap_bn_bwd_finalize": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P]),
-    # y ld d ld scale shift mean invstd pixels c raw count dgamma dbeta ticket dy ld stream
-    "gap_bn_bwd_apply_raw": (C.c_int, [_P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _P, _D, _P, _P, _P, _P, _L, _P]),
-    # stats count gamma beta eps momentum repeat rm rv nbt scale shift mean invstd ticket y ld pixels c o1 ld1 a1 o2 ld2 a2 stream
-    "gap_bn_train_act": (C.c_int, [_P, _D, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _L,
-                                   _I, _P, _L, _I, _P]),
     "gap_colsum_bf16": (C.c_int, [_P, _L, _L, _I, _P, _P]),
     "gap_adam_flat": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _F, _P]),
     "gap_adam_flat_devstep": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
@@ -179,7 +173,7 @@ def check(rc: int, what: str = "gap call") -> None:
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")
 
 
-DEBUG_KNOBS: dict = {}      # what was set through debug_set (the launchers consult it, e.g. for the split-K workspace)
+DEBUG_KNOBS: dict = {}      # what was set through debug_set (read back by tools and tests)
 
 
 def debug_set(key: str, value: int) -> None:

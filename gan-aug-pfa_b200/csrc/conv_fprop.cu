@@ -93,11 +93,6 @@ struct alignas(64) FpropParams {
   // rank r owns M tiles (2*sm + r)*mt .. +mt and stages rows [r*block_n/2, (r+1)*block_n/2) of the B tile; the leader
   // issues tcgen05.mma.cta_group::2 (M = 256).  sm_tiles / total_tiles then count PAIR items.
   int pair;
-  // Split-K (kEpi = 2): small-M layers (deep U-Net levels, small batches) do not have enough output tiles for 148 SMs,
-  // so the K loop is cut into `splits` ranges; partial tiles are added into an fp32 workspace [pixel][n_out] with
-  // red.global.add.v4.f32 and splitk_finish_kernel applies the epilogue (and re-zeroes the workspace).
-  int splits;
-  float* ws;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -116,7 +111,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 struct WorkCoord {
-  int n_tile, sm, ph, pw, phase, split;
+  int n_tile, sm, ph, pw, phase;
 };
 struct MTile {
   int tw, th, tn;
@@ -132,8 +127,7 @@ __device__ __forceinline__ WorkCoord decode_work(const FpropParams& p, int t) {
   t /= p.n_tiles;
   c.phase = t % p.n_phase;
   t /= p.n_phase;
-  c.sm = t % p.sm_tiles;
-  c.split = t / p.sm_tiles;
+  c.sm = t;
   c.ph = c.phase >> 1;
   c.pw = c.phase & 1;
   return c;
@@ -334,29 +328,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
             static_cast<uint32_t>(bn_cta * 128 + (has1 ? 2 : 1) * kATileBytes) * (kPair ? 2u : 1u);
         const int b_row = wc.n_tile * p.block_n + static_cast<int>(cta_rank) * bn_cta;
         const bool arm = !kPair || cta_rank == 0;
-        if (kEpi == 2) {
-          const int k_lo = static_cast<int>(static_cast<long long>(p.k_iters) * wc.split / p.splits);
-          const int k_hi = static_cast<int>(static_cast<long long>(p.k_iters) * (wc.split + 1) / p.splits);
-          for (int kk = k_lo; kk < k_hi; ++kk) {
-            const int tap = kk / p.chunks_tot, cc = kk - tap * p.chunks_tot;
-            const int t_h = tap / p.taps_w, t_w = tap - t_h * p.taps_w;
-            const int s = cc >= p.src_chunks[0] ? 1 : 0;
-            const int c = cc - (s ? p.src_chunks[0] : 0);
-            if ((it++ & 1u) == my_par) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              const uint32_t a_dst = smem_base + stage * stage_bytes;
-              tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), c * kBlockK, x0 + t_w, y0 + t_h, n0);
-              if (has1) tma_load_4d(a_dst + kATileBytes, &p.tmA[s], full_bar(stage), c * kBlockK, x1 + t_w, y1 + t_h, n1);
-              tma_load_3d(a_dst + a_bytes, &p.tmB, full_bar(stage), kk * kBlockK, b_row, wc.phase);
-            }
-            if (++stage == p.num_stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-          continue;
-        }
         if (p.halo) {
           const uint32_t txh =
               static_cast<uint32_t>(p.halo_taps * bn_cta * 128 + (has1 ? 2 : 1) * p.a_load_bytes) * (kPair ? 2u : 1u);
@@ -438,11 +409,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        int k_count = p.k_iters;
-        if (kEpi == 2)
-          k_count = static_cast<int>(static_cast<long long>(p.k_iters) * (wc.split + 1) / p.splits) -
-                    static_cast<int>(static_cast<long long>(p.k_iters) * wc.split / p.splits);
-        for (int k_iter = 0; k_iter < k_count; ++k_iter) {
+        for (int k_iter = 0; k_iter < p.k_iters; ++k_iter) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
@@ -492,7 +459,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     uint32_t acc_phase = 0;
     int cur_ntile = -1;
     double* my_stats = stats_sm + q * 512;  // [256 sum][256 sumsq]
-    const bool do_stats = p.stats != nullptr && !(p.skip & 4) && kEpi != 2;
+    const bool do_stats = p.stats != nullptr && !(p.skip & 4);
     const uint32_t colstage = colstage_base + static_cast<uint32_t>(warp - 2) * 1024u;
     const bool stat_holder = (lane >> 3) == (lane & 3u);  // lanes 4m + (m >> 1): columns m and m + 8 of a chunk
     const int stat_col = static_cast<int>(lane >> 2);
@@ -596,15 +563,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           float f[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(raw[jj]);
-          if (kEpi == 2) {
-            if (valid && col0 < p.n_out) {
-              float* wrow = p.ws + pix * p.n_out + col0;
-#pragma unroll
-              for (int jj = 0; jj < 16; jj += 4)
-                if (col0 + jj < p.n_out) red_add_v4_f32(wrow + jj, f[jj], f[jj + 1], f[jj + 2], f[jj + 3]);
-            }
-            continue;
-          }
           if (kEpi == 1 && col0 >= p.bwd_c0) {
             // d = mask(y) ? g (+ g2) : slope * g  with mask = (y*scale + shift > 0); sums of d and d*y
             const uint32_t* yw = reinterpret_cast<const uint32_t*>(yq[ci]);
@@ -728,79 +686,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   }
 }
 
-// Epilogue of a split-K launch: v = ws[pix][c] (re-zeroed), then exactly what the fused epilogues do — scale / bias,
-// BatchNorm statistics, activation(s) and up to two bf16 (or one fp32) outputs, or the backward-fused variant.
-// Thread layout: threadIdx.x walks 8-channel groups, threadIdx.y walks pixels (the tensors are small).
-__global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constant__ FpropParams p, long long pixels) {
-  extern __shared__ float fin_red[];   // [blockDim.y][n8*8][2]
-  const int n8 = (p.n_out + 7) >> 3;
-  const bool bwd = p.bwd_y != nullptr;
-  const bool do_stats = p.stats != nullptr;
-  for (int cg = threadIdx.x; cg < n8; cg += blockDim.x) {
-    const int c8 = cg << 3;
-    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long pix = blockIdx.x * (long long)blockDim.y + threadIdx.y; pix < pixels;
-         pix += (long long)gridDim.x * blockDim.y) {
-      float v[8], y[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c8 + j;
-        v[j] = 0.f;
-        y[j] = 0.f;
-        if (c < p.n_out) {
-          float* w = p.ws + pix * p.n_out + c;
-          v[j] = *w;
-          *w = 0.f;
-          if (p.scale) v[j] *= p.scale[c];
-          if (p.bias) v[j] += p.bias[c];
-          if (bwd && c >= p.bwd_c0) {
-            const int cb = c - p.bwd_c0;
-            y[j] = __bfloat162float(p.bwd_y[pix * p.bwd_y_ld + cb]);
-            const float yh = p.bwd_scale ? fmaf(y[j], p.bwd_scale[cb], p.bwd_shift[cb]) : y[j];
-            const float g2 = p.bwd_g2 ? __bfloat162float(p.bwd_g2[pix * p.bwd_g2_ld + cb]) : 0.f;
-            v[j] = yh > 0.f ? v[j] + g2 : p.bwd_slope * v[j];
-          }
-          if (bwd) {
-            if (c >= p.bwd_c0) {
-              s1[j] += v[j];
-              s2[j] += v[j] * y[j];
-            }
-          } else {
-            s1[j] += v[j];
-            s2[j] += v[j] * v[j];
-          }
-          if (p.out_f32) {
-            reinterpret_cast<float*>(p.out)[pix * p.out_ld + c] = apply_act(v[j], p.act);
-          } else {
-            p.out[pix * p.out_ld + c] = __float2bfloat16(apply_act(v[j], p.act));
-            if (p.out2) p.out2[pix * p.out2_ld + c] = __float2bfloat16(apply_act(v[j], p.act2));
-          }
-        }
-      }
-    }
-    if (do_stats) {
-      float* slot = fin_red + (static_cast<size_t>(threadIdx.y) * n8 * 8 + c8) * 2;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        slot[2 * j] = s1[j];
-        slot[2 * j + 1] = s2[j];
-      }
-    }
-  }
-  if (do_stats) {
-    __syncthreads();
-    const int c0 = bwd ? p.bwd_c0 : 0;
-    const int n_stats = p.n_out - c0;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-    for (int i = tid; i < n_stats * 2; i += nthr) {
-      const int ch = c0 + (i >> 1), which = i & 1;
-      double tot = 0.0;
-      for (int r = 0; r < blockDim.y; ++r) tot += fin_red[(static_cast<size_t>(r) * n8 * 8 + ch) * 2 + which];
-      atomicAdd(p.stats + which * n_stats + (ch - c0), tot);
-    }
-  }
-}
-
 static int ilog2_ceil(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -913,31 +798,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     }
     n_tiles = (n_pad + block_n - 1) / block_n;
   }
-  // Split-K for layers with too few output tiles (see FpropParams): keep a wide N tile and cut K instead.
-  // Measured (tools/sweep_splitk.py): only the M = 256 layers gain (38 -> 27 us), M >= 1024 lose to the finish pass and
-  // the fp32 atomics make results run-to-run non-deterministic, so it is OFF unless gap_debug_set("fprop_splitk", 1).
-  int splits = 1;
   const int k_iters_full = a->taps_h * a->taps_w * ((a->src_c[0] + a->src_c[1]) / 64);
-  const long long ws_need = static_cast<long long>(a->n) * a->oh * a->ow * a->n_out * 4;
-  if (!halo && force_bn == 0 && a->splitk_ws != nullptr && static_cast<long long>(a->splitk_ws_bytes) >= ws_need &&
-      a->n_out % 4 == 0 && debug_get("fprop_splitk", 0) != 0) {
-    int bn_wide = ((n_pad + (n_pad + 255) / 256 - 1) / ((n_pad + 255) / 256) + 15) / 16 * 16;
-    const int nt_wide = (n_pad + bn_wide - 1) / bn_wide;
-    const int items = m_tiles * nt_wide;
-    if (items * 3 <= sms && k_iters_full >= 16) {
-      splits = std::min(k_iters_full / 4, (sms + items - 1) / items);
-      if (splits >= 2) {
-        block_n = bn_wide;
-        n_tiles = nt_wide;
-      } else {
-        splits = 1;
-      }
-    }
-  }
-  const int force_splits = debug_get("fprop_splits", 0);
-  if (force_splits > 0 && !halo && a->splitk_ws != nullptr && static_cast<long long>(a->splitk_ws_bytes) >= ws_need &&
-      a->n_out % 4 == 0)
-    splits = std::min(force_splits, std::max(1, k_iters_full));
   // Two M tiles per work item share each B tile (halves the weight traffic from L2) when there is
   // still at least ~2 waves of work items left.
   int mt = (m_tiles_pp >= 2 && (m_tiles / 2) * n_tiles >= 2 * sms) ? 2 : 1;
@@ -954,7 +815,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   // so pairs are used only for single-phase launches with a 256-wide N tile, >= 64 K iterations and enough work items
   // for every cluster.  fprop_pair = 2 forces pairs wherever they are legal (tests, A/B runs), 0 disables them.
   const int pair_knob = debug_get("fprop_pair", 1);
-  bool pair = pair_knob != 0 && splits == 1 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32;
+  bool pair = pair_knob != 0 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32;
   if (pair && pair_knob != 2 && !(block_n == 256 && a->n_phase == 1 && k_iters_full >= 64)) pair = false;
   if (pair) {
     const long long pair_items = static_cast<long long>((m_tiles_pp + 2 * mt - 1) / (2 * mt)) * a->n_phase * n_tiles;
@@ -967,9 +828,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   p.acc_stages = (mt * block_n <= kAccStride) ? 2 : 1;
   p.block_n = block_n;
   p.n_tiles = n_tiles;
-  p.splits = splits;
-  p.ws = static_cast<float*>(a->splitk_ws);
-  p.total_tiles = p.sm_tiles * a->n_phase * n_tiles * splits;
+  p.total_tiles = p.sm_tiles * a->n_phase * n_tiles;
   const int ctot = a->src_c[0] + a->src_c[1];
   p.src_chunks[0] = a->src_c[0] / 64;
   p.src_chunks[1] = a->src_c[1] / 64;
@@ -1086,10 +945,8 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   if (!attr_set) {
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    GAP_CUDA(cudaFuncSetAttribute(splitk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
   if (pair) {
@@ -1102,22 +959,6 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     return 0;
   }
   const int grid = std::min(p.total_tiles, sms);
-  if (splits > 1) {
-    GAP_CUDA(launch_pdl(conv_fprop_kernel<2>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
-    GAP_CUDA(cudaGetLastError());
-    const long long pixels = static_cast<long long>(a->n) * a->oh * a->ow;
-    const int n8 = (a->n_out + 7) / 8;
-    const int bx = std::min(n8, 128), by = std::max(1, 256 / bx);
-    const size_t fsm = a->stats ? static_cast<size_t>(by) * n8 * 8 * 2 * sizeof(float) : 0;
-    if (fsm > 96 * 1024) {
-      set_error("gap_conv_gemm: split-K finish needs %zu bytes of shared memory", fsm);
-      return GAP_ERR_UNSUPPORTED;
-    }
-    const int fgrid = static_cast<int>(std::min<long long>((pixels + by - 1) / by, 4LL * sms));
-    splitk_finish_kernel<<<fgrid, dim3(bx, by), fsm, stream>>>(p, pixels);
-    GAP_CUDA(cudaGetLastError());
-    return 0;
-  }
   if (bwd)
     GAP_CUDA(launch_pdl(conv_fprop_kernel<1>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
   else

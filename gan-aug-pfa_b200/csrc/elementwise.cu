@@ -282,111 +282,6 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, long long ld_
   }
 }
 
-// Training-mode BatchNorm in ONE launch: every block derives scale / shift for all channels from the fp64 batch sums
-// the conv epilogue accumulated (a few hundred cycles), block 0 also writes them out together with mean / invstd (the
-// backward pass needs them) and updates the running statistics; then the same apply + activation loop as
-// bn_act_kernel with the per-channel constants in shared memory.  The last block to finish re-zeroes the sums (ticket
-// counter), so the launch is self-contained and replayable inside a CUDA graph.  Replaces bn_finalize + bn_act.
-__global__ void bn_train_act_kernel(double* __restrict__ stats, double count, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, float eps, float momentum, int repeat,
-                                    float* __restrict__ running_mean, float* __restrict__ running_var,
-                                    long long* __restrict__ nbt, float* __restrict__ scale, float* __restrict__ shift,
-                                    float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                    unsigned int* __restrict__ ticket, const __nv_bfloat16* __restrict__ y,
-                                    long long ld_y, long long pixels, int c, __nv_bfloat16* __restrict__ o1,
-                                    long long ld1, int act1, __nv_bfloat16* __restrict__ o2, long long ld2, int act2) {
-  extern __shared__ float bn_par[];  // [c] scale | [c] shift
-  // (every block repeats this for all channels: keep fp64 to the cancellation-prone E[x^2] - mean^2 and do the
-  // square root / reciprocal in fp32 -- fp64 division and sqrt in 2000+ blocks cost more than the launch they save)
-  const double inv_count = 1.0 / count;
-  for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const double mean = stats[i] * inv_count;
-    double var = fma(-mean, mean, stats[c + i] * inv_count);
-    if (var < 0.0) var = 0.0;
-    const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
-    const float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
-    const float sc = g * invstd;
-    const float sh = b - static_cast<float>(mean) * sc;
-    bn_par[i] = sc;
-    bn_par[c + i] = sh;
-    if (blockIdx.x == 0) {
-      scale[i] = sc;
-      shift[i] = sh;
-      if (save_mean) save_mean[i] = static_cast<float>(mean);
-      if (save_invstd) save_invstd[i] = invstd;
-      if (running_mean) {
-        const float unbiased = static_cast<float>(count > 1.0 ? var * count / (count - 1.0) : var);
-        float rm = running_mean[i], rv = running_var[i];
-        for (int r = 0; r < repeat; ++r) {
-          rm = (1.f - momentum) * rm + momentum * static_cast<float>(mean);
-          rv = (1.f - momentum) * rv + momentum * unbiased;
-        }
-        running_mean[i] = rm;
-        running_var[i] = rv;
-      }
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += repeat;
-  __syncthreads();
-  const int cv = c >> 3;
-  const long long total = pixels * cv;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  constexpr int U = 4;
-  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
-    uint4 raw[U];
-    long long pixv[U];
-    int c8v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      pixv[u] = i / cv;
-      c8v[u] = static_cast<int>(i - pixv[u] * cv) << 3;
-      if (i < total) raw[u] = __ldg(reinterpret_cast<const uint4*>(y + pixv[u] * ld_y + c8v[u]));
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i0 + u * stride >= total) break;
-      const long long pix = pixv[u];
-      const int c8 = c8v[u];
-      const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[2 * j] = bf16_lo(w[j]);
-        v[2 * j + 1] = bf16_hi(w[j]);
-      }
-      const float4 s0 = *reinterpret_cast<const float4*>(bn_par + c8), s1 = *reinterpret_cast<const float4*>(bn_par + c8 + 4);
-      const float4 h0 = *reinterpret_cast<const float4*>(bn_par + c + c8);
-      const float4 h1 = *reinterpret_cast<const float4*>(bn_par + c + c8 + 4);
-      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-      uint32_t pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act1), act_fwd(v[2 * j + 1], act1));
-      *reinterpret_cast<uint4*>(o1 + pix * ld1 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      if (o2) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(act_fwd(v[2 * j], act2), act_fwd(v[2 * j + 1], act2));
-        *reinterpret_cast<uint4*>(o2 + pix * ld2 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-    }
-  }
-  // every block has read the sums before it takes a ticket; the last one re-zeroes them for the next pass
-  __shared__ bool is_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (is_last) {
-    for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) stats[i] = 0.0;
-    if (threadIdx.x == 0) *ticket = 0u;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // BatchNorm + activation backward.
 //   yhat = y*scale + shift;  xhat = (y - mean) * invstd
@@ -414,12 +309,6 @@ struct BnBwdArgs {
   double inv_count;
   __nv_bfloat16* dy;
   long long ld_dy;
-  // raw mode (apply only): sums = [sum d, sum d*y] straight from a dgrad epilogue; the kernel converts them, block 0
-  // accumulates dgamma / dbeta, the last block re-zeroes them (ticket)
-  int raw_mode;
-  float* dgamma;
-  float* dbeta;
-  unsigned int* ticket;
 };
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
@@ -444,7 +333,7 @@ __device__ __forceinline__ void loadf8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-template <bool APPLY, bool RAW>
+template <bool APPLY>
 __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -469,15 +358,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const double t1 = a.sums[c8 + j];
-        double t2 = a.sums[a.c + c8 + j];
-        if (RAW) {
-          // sum d*xhat = invstd * (sum d*y - mean * sum d); parameter gradients written once (block 0, first row)
-          t2 = static_cast<double>(a.invstd[c8 + j]) * (t2 - static_cast<double>(a.mean[c8 + j]) * t1);
-          if (blockIdx.x == 0 && threadIdx.y == 0) {
-            if (a.dbeta) a.dbeta[c8 + j] += static_cast<float>(t1);
-            if (a.dgamma) a.dgamma[c8 + j] += static_cast<float>(t2);
-          }
-        }
+        const double t2 = a.sums[a.c + c8 + j];
         const float m1 = static_cast<float>(t1 * a.inv_count);
         const float m2 = static_cast<float>(t2 * a.inv_count);
         ca[j] = -sc[j] * m2 * a.invstd[c8 + j];
@@ -543,20 +424,6 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
         slot[2 * j] = s1[j];
         slot[2 * j + 1] = is * (s2[j] - mu * s1[j]);
       }
-    }
-  }
-  if (APPLY && RAW) {
-    __shared__ bool is_last;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (is_last) {
-      for (int i = tid; i < a.c * 2; i += blockDim.x * blockDim.y) a.sums[i] = 0.0;
-      if (tid == 0) *a.ticket = 0u;
     }
   }
   if (!APPLY) {
@@ -976,26 +843,6 @@ int gap_bn_act(const void* y, int64_t ld_y, const float* scale, const float* shi
   return 0;
 }
 
-int gap_bn_train_act(double* stats, double count, const float* gamma, const float* beta, float eps, float momentum,
-                     int repeat, float* running_mean, float* running_var, int64_t* nbt, float* scale, float* shift,
-                     float* save_mean, float* save_invstd, uint32_t* ticket, const void* y, int64_t ld_y,
-                     int64_t pixels, int c, void* out1, int64_t ld1, int act1, void* out2, int64_t ld2, int act2,
-                     void* stream) {
-  GAP_CHECK_ARG(stats && scale && shift && ticket && y && out1 && pixels > 0 && c > 0 && c % 8 == 0 && count > 0 &&
-                    c <= 4096,
-                "gap_bn_train_act: bad arguments");
-  if (ld_y % 8 || ld1 % 8 || (out2 && ld2 % 8)) {
-    set_error("gap_bn_train_act: pixel strides must be multiples of 8");
-    return GAP_ERR_ALIGNMENT;
-  }
-  bn_train_act_kernel<<<grid_for(pixels * (c / 8), 256), 256, 2 * c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, reinterpret_cast<long long*>(nbt),
-      scale, shift, save_mean, save_invstd, ticket, static_cast<const __nv_bfloat16*>(y), ld_y, pixels, c,
-      static_cast<__nv_bfloat16*>(out1), ld1, act1, static_cast<__nv_bfloat16*>(out2), ld2, act2);
-  GAP_LAUNCH_CHECK();
-  return 0;
-}
-
 static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
   const int cv = a.c / 8;
   int bx = cv < 128 ? cv : 128;
@@ -1004,20 +851,18 @@ static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
   dim3 block(bx, by);
   const long long slabs = (a.pixels + by - 1) / by;
   const int grid = grid_even(slabs, 4, 148 * debug_get("bn_bwd_bps", 2));   // 4 pixel slabs per block and sweep (U in the kernel); resident blocks only
-  if (apply && a.raw_mode) {
-    GAP_CUDA(launch_pdl(bn_bwd_kernel<true, true>, dim3(grid), block, 0, st, a));
-  } else if (apply) {
-    GAP_CUDA(launch_pdl(bn_bwd_kernel<true, false>, dim3(grid), block, 0, st, a));
+  if (apply) {
+    GAP_CUDA(launch_pdl(bn_bwd_kernel<true>, dim3(grid), block, 0, st, a));
   } else {
     const size_t smem = static_cast<size_t>(by) * a.c * 2 * sizeof(float);
     if (smem > 48 * 1024) {
       static bool set = false;
       if (!set) {
-        GAP_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        GAP_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         set = true;
       }
     }
-    GAP_CUDA(launch_pdl(bn_bwd_kernel<false, false>, dim3(grid), block, smem, st, a));
+    GAP_CUDA(launch_pdl(bn_bwd_kernel<false>, dim3(grid), block, smem, st, a));
   }
   GAP_CUDA(cudaGetLastError());
   return 0;
@@ -1030,7 +875,7 @@ int gap_bn_bwd_reduce(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1
                 "gap_bn_bwd_reduce: bad arguments");
   BnBwdArgs a{static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(g1), ld_g1,
               static_cast<const __nv_bfloat16*>(g2), ld_g2, slope, scale, shift, mean, invstd, pixels, c, sums,
-              0.0, nullptr, 0, 0, nullptr, nullptr, nullptr};
+              0.0, nullptr, 0};
   return bn_bwd_launch(false, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -1043,21 +888,7 @@ int gap_bn_bwd_apply(const void* y, int64_t ld_y, const void* g1, int64_t ld_g1,
                 "gap_bn_bwd_apply: BatchNorm mode needs shift/mean/invstd/sums/count");
   BnBwdArgs a{static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(g1), ld_g1,
               static_cast<const __nv_bfloat16*>(g2), ld_g2, slope, scale, shift, mean, invstd, pixels, c,
-              const_cast<double*>(sums), count > 0 ? 1.0 / count : 0.0, static_cast<__nv_bfloat16*>(dy), ld_dy,
-              0, nullptr, nullptr, nullptr};
-  return bn_bwd_launch(true, a, static_cast<cudaStream_t>(stream));
-}
-
-int gap_bn_bwd_apply_raw(const void* y, int64_t ld_y, const void* d, int64_t ld_d, const float* scale,
-                         const float* shift, const float* mean, const float* invstd, int64_t pixels, int c,
-                         double* raw, double count, float* dgamma, float* dbeta, uint32_t* ticket, void* dy,
-                         int64_t ld_dy, void* stream) {
-  GAP_CHECK_ARG(y && d && dy && scale && shift && mean && invstd && raw && ticket && pixels > 0 && c > 0 &&
-                    c % 8 == 0 && count > 0,
-                "gap_bn_bwd_apply_raw: bad arguments");
-  BnBwdArgs a{static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(d), ld_d, nullptr, 0, 1.f,
-              scale, shift, mean, invstd, pixels, c, raw, 1.0 / count, static_cast<__nv_bfloat16*>(dy), ld_dy,
-              1, dgamma, dbeta, ticket};
+              const_cast<double*>(sums), count > 0 ? 1.0 / count : 0.0, static_cast<__nv_bfloat16*>(dy), ld_dy};
   return bn_bwd_launch(true, a, static_cast<cudaStream_t>(stream));
 }
 

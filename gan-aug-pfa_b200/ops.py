@@ -81,21 +81,6 @@ def geom_phase_k4s2p1() -> Geometry:
     return Geometry(4, 2, 2, 1, (-1, 0), (-1, 0), 2)
 
 
-_SPLITK_WS: dict = {}
-
-
-def _splitk_workspace(device: torch.device) -> torch.Tensor:
-    """Zero-filled fp32 scratch for split-K launches (gap_conv_gemm_args.splitk_ws); the kernels leave it zeroed.
-    One per (device, stream): the trainer runs conv_gemm concurrently on several streams, and two split-K launches
-    must never accumulate into the same buffer."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
-    ws = _SPLITK_WS.get(key)
-    if ws is None:
-        ws = torch.zeros(8 << 20, device=device, dtype=torch.float32)      # 32 MiB: n*oh*ow*n_out <= 8 Mi elements
-        _SPLITK_WS[key] = ws
-    return ws
-
-
 def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, out: torch.Tensor,
               n_out: int, grid_hw: tuple[int, int], *, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, act2: int = ACT_NONE,
@@ -194,11 +179,6 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
         a.bwd_c0 = c0
     else:
         a.bwd_y = None
-    if _lib.DEBUG_KNOBS.get("fprop_splitk", 0) or _lib.DEBUG_KNOBS.get("fprop_splits", 0):
-        ws = _splitk_workspace(out.device)      # split-K is an opt-in experiment (off by default, see conv_fprop.cu)
-        a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
-    else:
-        a.splitk_ws, a.splitk_ws_bytes = None, 0
     if flops is None:
         flops = 2.0 * n * grid_hw[0] * grid_hw[1] * geom.n_phase * n_out * geom.taps_h * geom.taps_w * ctot
     _timed("conv_fprop_kernel", flops,
@@ -527,27 +507,6 @@ def bn_bwd_finalize(raw, mean, invstd, dgamma, dbeta, sums) -> None:
     """raw [sum d, sum d*y] (re-zeroed) -> sums [sum d, sum d*xhat]; dgamma / dbeta accumulated (may be None)."""
     _lib.check(_lib.lib().gap_bn_bwd_finalize(_ptr(raw), _ptr(mean), _ptr(invstd), mean.numel(), _ptr(dgamma),
                                               _ptr(dbeta), _ptr(sums), _stream()), "gap_bn_bwd_finalize")
-
-
-def bn_bwd_apply_raw(y, d, scale, shift, mean, invstd, raw, count, dgamma, dbeta, ticket, dy) -> None:
-    """bn_bwd_finalize + bn_bwd_apply in one launch (raw sums re-zeroed by the kernel's last block)."""
-    pixels, c, ld = _rows_ld(y)
-    _lib.check(_lib.lib().gap_bn_bwd_apply_raw(_ptr(y), ld, _ptr(d), d.stride(-2), _ptr(scale), _ptr(shift), _ptr(mean),
-                                               _ptr(invstd), pixels, c, _ptr(raw), float(count), _ptr(dgamma),
-                                               _ptr(dbeta), _ptr(ticket), _ptr(dy), dy.stride(-2), _stream()),
-               "gap_bn_bwd_apply_raw")
-
-
-def bn_train_act(stats, count, gamma, beta, eps, momentum, repeat, running_mean, running_var, nbt, scale, shift,
-                 save_mean, save_invstd, ticket, y, out1, act1, out2=None, act2: int = ACT_NONE) -> None:
-    """Training-mode BatchNorm forward in one launch (= bn_finalize + bn_act)."""
-    pixels, c, ld = _rows_ld(y)
-    _lib.check(_lib.lib().gap_bn_train_act(_ptr(stats), float(count), _ptr(gamma), _ptr(beta), eps, momentum, repeat,
-                                           _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(scale), _ptr(shift),
-                                           _ptr(save_mean), _ptr(save_invstd), _ptr(ticket), _ptr(y), ld, pixels, c,
-                                           _ptr(out1), out1.stride(-2), act1, _ptr(out2),
-                                           0 if out2 is None else out2.stride(-2), act2, _stream()),
-               "gap_bn_train_act")
 
 
 def colsum_bf16(x: torch.Tensor, c: int, out: torch.Tensor) -> None:

@@ -97,9 +97,6 @@ class _BN:
     shift: torch.Tensor = None
     mean: torch.Tensor = None
     invstd: torch.Tensor = None
-    tickets: torch.Tensor = None    # two device counters (forward / backward "last block re-zeroes the sums")
-    ticket_f: torch.Tensor = None
-    ticket_b: torch.Tensor = None
 
     def allocate(self, dev: torch.device) -> None:
         self.running_mean = torch.zeros(self.c, device=dev)
@@ -112,8 +109,6 @@ class _BN:
         self.shift = torch.empty(self.c, device=dev)
         self.mean = torch.empty(self.c, device=dev)
         self.invstd = torch.empty(self.c, device=dev)
-        self.tickets = torch.zeros(2, device=dev, dtype=torch.int32)
-        self.ticket_f, self.ticket_b = self.tickets[0:1], self.tickets[1:2]
 
 
 class _Net:
@@ -140,12 +135,6 @@ class _Net:
     # enqueued on a side stream: the block scheduler fills the SMs that the dgrad chain leaves idle (small deep layers,
     # tail waves of the persistent GEMMs) with wgrad CTAs.  Joined before anything they read is overwritten.
     overlap_wgrad = True
-    # One-launch BatchNorm forward (gap_bn_train_act) / backward apply (gap_bn_bwd_apply_raw).  Measured with
-    # tools/layer_profile.py (serialised): the fused launches are SLOWER than the finalize + apply pairs they replace
-    # (747 vs 645 us and 937 vs 870 us per step): every one of the ~2400 blocks repeats the per-channel prologue and
-    # holds more registers.  Kept as tested entry points, off by default.
-    fused_bn_fwd = False
-    fused_bn_bwd = False
     _wgrad_stream = None
     _wgrad_used = False
 
@@ -298,34 +287,21 @@ class _Net:
         """BatchNorm backward when the producing dgrad epilogue already applied the activation backward and
         accumulated [sum d, sum d*y] into bn.sums: finalize (+ parameter gradients), then one apply pass."""
         count = y.numel() // y.shape[-1]
-        if not self.fused_bn_bwd:
-            dgo = self.grad(bn.name + ".weight") if param_grads else None
-            dbo = self.grad(bn.name + ".bias") if param_grads else None
-            ops.bn_bwd_finalize(bn.sums, bn.mean, bn.invstd, dgo, dbo, bn.sums2)
-            ops.bn_bwd_apply(y, d, None, 1.0, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums2, count, dy)
-            if param_grads:
-                self._ready(bn.name + ".weight", bn.name + ".bias")
-            return
         dg = self.grad(bn.name + ".weight") if param_grads else None
         db = self.grad(bn.name + ".bias") if param_grads else None
-        ops.bn_bwd_apply_raw(y, d, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums, count, dg, db, bn.ticket_b, dy)
+        ops.bn_bwd_finalize(bn.sums, bn.mean, bn.invstd, dg, db, bn.sums2)
+        ops.bn_bwd_apply(y, d, None, 1.0, bn.scale, bn.shift, bn.mean, bn.invstd, bn.sums2, count, dy)
         if param_grads:
             self._ready(bn.name + ".weight", bn.name + ".bias")
 
     def _bn_forward(self, bn: _BN, y: torch.Tensor, out1, act1, out2=None, act2=ACT_NONE, repeat: int = 1) -> None:
         gamma = self.param(bn.name + ".weight")
         beta = self.param(bn.name + ".bias")
-        if self.training and not self.fused_bn_fwd:
+        if self.training:
             count = y.numel() // y.shape[-1]
             ops.bn_finalize(bn.stats, count, gamma, beta, BN_EPS, BN_MOMENTUM, repeat, bn.running_mean,
                             bn.running_var, bn.nbt, bn.scale, bn.shift, bn.mean, bn.invstd)
             ops.bn_act(y, bn.scale, bn.shift, out1, act1, out2, act2)
-            return
-        if self.training:
-            count = y.numel() // y.shape[-1]
-            ops.bn_train_act(bn.stats, count, gamma, beta, BN_EPS, BN_MOMENTUM, repeat, bn.running_mean,
-                             bn.running_var, bn.nbt, bn.scale, bn.shift, bn.mean, bn.invstd, bn.ticket_f, y, out1,
-                             act1, out2, act2)
             return
         ops.bn_eval_scale_shift(gamma, beta, bn.running_mean, bn.running_var, BN_EPS, bn.scale, bn.shift)
         ops.bn_act(y, bn.scale, bn.shift, out1, act1, out2, act2)

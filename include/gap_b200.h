@@ -115,11 +115,6 @@ typedef struct gap_conv_gemm_args {
    * Eval-mode BatchNorm (generate_synthetic_data.py:55, train.py:151, evaluate.py:146) folds into the conv this way
    * (scale = gamma/sqrt(running_var+eps), bias = beta - running_mean*scale), so no normalisation pass runs. */
   const float* scale;
-  /* Optional split-K workspace (device, fp32, ZERO-filled, >= n*oh*ow*n_out*4 bytes): layers with too few output
-   * tiles for the GPU (deep U-Net levels, small batches) split the K loop over CTAs, accumulate partial tiles here and
-   * finish with a small epilogue kernel that leaves the workspace zeroed again.  NULL disables split-K. */
-  void* splitk_ws;
-  size_t splitk_ws_bytes;
 } gap_conv_gemm_args;
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);
@@ -344,21 +339,6 @@ int gap_bn_param_grads(double* sums, int c, float* dgamma, float* dbeta, void* s
  * dbeta += sum d, dgamma += sum d*xhat (either may be NULL). */
 int gap_bn_bwd_finalize(double* raw, const float* mean, const float* invstd, int c, float* dgamma, float* dbeta,
                         double* sums, void* stream);
-/* gap_bn_bwd_finalize + gap_bn_bwd_apply (slope 1, no g2) in one launch: raw = [sum d, sum d*y] from the dgrad
- * epilogue is converted by every block, dgamma / dbeta (may be NULL) are accumulated once, and the last block to
- * finish re-zeroes raw (*ticket: a zero-initialised device counter, returned to zero). */
-int gap_bn_bwd_apply_raw(const void* y, int64_t ld_y, const void* d, int64_t ld_d, const float* scale,
-                         const float* shift, const float* mean, const float* invstd, int64_t pixels, int c,
-                         double* raw, double count, float* dgamma, float* dbeta, uint32_t* ticket, void* dy,
-                         int64_t ld_dy, void* stream);
-/* Training-mode nn.BatchNorm2d forward (models.py:179,181,231,239) in one launch = gap_bn_finalize + gap_bn_act:
- * scale / shift / mean / invstd from the batch sums in stats (re-zeroed by the last block through *ticket), running
- * statistics updated `repeat` times, out1 = act1(y*scale+shift), out2 = act2(...) (optional). */
-int gap_bn_train_act(double* stats, double count, const float* gamma, const float* beta, float eps, float momentum,
-                     int repeat, float* running_mean, float* running_var, int64_t* nbt, float* scale, float* shift,
-                     float* save_mean, float* save_invstd, uint32_t* ticket, const void* y, int64_t ld_y,
-                     int64_t pixels, int c, void* out1, int64_t ld1, int act1, void* out2, int64_t ld2, int act2,
-                     void* stream);
 /* bias gradient: out[c] += sum over pixels of x[pixel][c] */
 int gap_colsum_bf16(const void* x, int64_t ld, int64_t pixels, int c, float* out, void* stream);
 

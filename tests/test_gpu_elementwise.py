@@ -49,59 +49,44 @@ def test_bn_finalize_act_and_buffers():
 
 
 @pytest.mark.parametrize("n,h,c", [(3, 10, 64), (64, 2, 512), (5, 33, 128)])
-def test_fused_bn_launches_match_the_two_kernel_path(n, h, c):
-    """gap_bn_train_act == gap_bn_finalize + gap_bn_act and gap_bn_bwd_apply_raw == gap_bn_bwd_finalize +
-    gap_bn_bwd_apply (same formulas, one launch; backward bit for bit); the sums are re-zeroed and the tickets return to 0,
-    so a second call (CUDA-graph replay) gives the same answer."""
+def test_bn_backward_from_dgrad_epilogue_sums(n, h, c):
+    """gap_bn_bwd_finalize turns the raw [sum d, sum d*y] a backward-fused dgrad epilogue leaves behind into the
+    [sum d, sum d*xhat] gap_bn_bwd_apply expects: same dy, dgamma, dbeta as the stand-alone reduce pass (slope 1 = the
+    activation backward already applied), the raw sums are re-zeroed, parameter gradients are accumulated."""
     g = torch.Generator().manual_seed(n + c)
     y = (torch.randn(n, h, h, c, generator=g) * 2 + 0.5).to(torch.bfloat16).to(DEV)
-    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), torch.randn(c, generator=g).to(DEV)
-    yd = y.double()
-    stats0 = torch.cat([yd.sum((0, 1, 2)), (yd ** 2).sum((0, 1, 2))])
-    count = n * h * h
-
-    def buffers():
-        return dict(rm=torch.zeros(c, device=DEV), rv=torch.ones(c, device=DEV),
-                    nbt=torch.zeros((), device=DEV, dtype=torch.int64),
-                    par=[torch.empty(c, device=DEV) for _ in range(4)],
-                    o1=torch.empty(n, h, h, c, device=DEV, dtype=torch.bfloat16),
-                    o2=torch.zeros(n, h, h, 2 * c, device=DEV, dtype=torch.bfloat16))
-
-    a, b = buffers(), buffers()
-    st = stats0.clone()
-    ops.bn_finalize(st, count, gamma, beta, 1e-5, 0.1, 2, a["rm"], a["rv"], a["nbt"], *a["par"])
-    ops.bn_act(y, a["par"][0], a["par"][1], a["o1"], ops.ACT_LRELU, a["o2"][..., c:], ops.ACT_RELU)
-    ticket = torch.zeros(1, device=DEV, dtype=torch.int32)
-    for rep in range(2):
-        st = stats0.clone()
-        ops.bn_train_act(st, count, gamma, beta, 1e-5, 0.1, 2, b["rm"], b["rv"], b["nbt"], *b["par"], ticket, y, b["o1"],
-                         ops.ACT_LRELU, b["o2"][..., c:], ops.ACT_RELU)
-        assert float(st.abs().max()) == 0.0 and int(ticket) == 0
-        # (the fused kernel takes 1/sqrt in fp32, the two-kernel path in fp64: last-bit differences only)
-        assert rel(b["o1"].float(), a["o1"].float()) < 1e-3 and rel(b["o2"].float(), a["o2"].float()) < 1e-3
-        for pa, pb in zip(a["par"], b["par"]):
-            assert torch.allclose(pa, pb, rtol=2e-6, atol=1e-7)
-        if rep == 0:
-            assert torch.allclose(a["rm"], b["rm"], rtol=1e-6, atol=1e-8) and int(b["nbt"]) == 2
-            assert torch.allclose(a["rv"], b["rv"], rtol=1e-6, atol=1e-8)
-    assert int(b["nbt"]) == 4
-    # backward
     d = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16).to(DEV)
-    raw0 = torch.cat([d.double().sum((0, 1, 2)), (d.double() * yd).sum((0, 1, 2))])
-    scale, shift, mean, invstd = a["par"]
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), torch.randn(c, generator=g).to(DEV)
+    yd, dd = y.double(), d.double()
+    count = n * h * h
+    mean64 = yd.mean((0, 1, 2))
+    var64 = (yd ** 2).mean((0, 1, 2)) - mean64 ** 2
+    invstd = torch.rsqrt(var64 + 1e-5).float()
+    mean = mean64.float()
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    raw = torch.cat([dd.sum((0, 1, 2)), (dd * yd).sum((0, 1, 2))])
     dg_a, db_a = torch.ones(c, device=DEV), torch.ones(c, device=DEV)
     sums = torch.zeros(2 * c, device=DEV, dtype=torch.float64)
-    dy_a = torch.empty_like(d)
-    raw = raw0.clone()
+    dy_a = torch.full_like(d, float("nan"))
     ops.bn_bwd_finalize(raw, mean, invstd, dg_a, db_a, sums)
+    assert float(raw.abs().max()) == 0.0
     ops.bn_bwd_apply(y, d, None, 1.0, scale, shift, mean, invstd, sums, count, dy_a)
-    for rep in range(2):
-        dg_b, db_b = torch.ones(c, device=DEV), torch.ones(c, device=DEV)
-        dy_b = torch.full_like(d, float("nan"))
-        raw = raw0.clone()
-        ops.bn_bwd_apply_raw(y, d, scale, shift, mean, invstd, raw, count, dg_b, db_b, ticket, dy_b)
-        assert float(raw.abs().max()) == 0.0 and int(ticket) == 0
-        assert torch.equal(dy_a, dy_b) and torch.equal(dg_a, dg_b) and torch.equal(db_a, db_b)
+    # the stand-alone path: reduce (slope 1: d passes through whatever the sign of yhat) + apply + parameter gradients
+    sums_b = torch.zeros(2 * c, device=DEV, dtype=torch.float64)
+    dy_b = torch.full_like(d, float("nan"))
+    ops.bn_bwd_reduce(y, d, None, 1.0, scale, shift, mean, invstd, sums_b)
+    ops.bn_bwd_apply(y, d, None, 1.0, scale, shift, mean, invstd, sums_b, count, dy_b)
+    dg_b, db_b = torch.ones(c, device=DEV), torch.ones(c, device=DEV)
+    ops.bn_param_grads(sums_b, dg_b, db_b)
+    assert rel(dy_a.float(), dy_b.float()) < 4e-3
+    assert rel(dg_a, dg_b) < 1e-4 and rel(db_a, db_b) < 1e-5
+    # and fp64 math
+    xhat = (yd - mean64) * invstd.double()
+    db_ref, dg_ref = dd.sum((0, 1, 2)), (dd * xhat).sum((0, 1, 2))
+    dy_ref = scale.double() * (dd - db_ref / count - xhat * dg_ref / count)
+    assert rel(dy_a.double(), dy_ref) < 4e-3
+    assert rel(dg_a.double() - 1.0, dg_ref) < 1e-4 and rel(db_a.double() - 1.0, db_ref) < 1e-4
 
 
 @pytest.mark.parametrize("c,slope,two", [(64, 0.2, True), (512, 0.0, False), (128, 0.2, False)])

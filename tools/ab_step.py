@@ -1,5 +1,5 @@
 """A/B of engine switches inside one process (same box, same clocks): python tools/ab_step.py attr [attr...]
-Each attr is a boolean class attribute of the engines (e.g. fused_bn, overlap_wgrad); every combination is timed
+Each attr is a boolean class attribute of the engines (e.g. overlap_wgrad, fuse_head); every combination is timed
 as eager and graph-replayed steps, interleaved twice."""
 import itertools
 import sys
@@ -13,7 +13,7 @@ N = 64
 gen = torch.Generator().manual_seed(1234)
 A = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
 B = (torch.rand(N, 3, 256, 256, generator=gen) * 2 - 1).to(dev)
-attrs = sys.argv[1:] or ["fused_bn"]
+attrs = sys.argv[1:] or ["overlap_wgrad"]
 
 
 def timeit(fn, iters=15):
