@@ -86,6 +86,9 @@ if WORK == "siamese":
         def train_step(self, a, b):
             return self.e.train_step(a, b, LAB, kind="combined")
     tr = _T()
+    import os
+    if os.environ.get("GAP_NO_OVERLAP"):
+        tr.e.overlap_wgrad = False
     A = (torch.rand(N, 3, 512, 512, generator=gen) * 2 - 1).to(dev)
     B = (torch.rand(N, 3, 512, 512, generator=gen) * 2 - 1).to(dev)
     LAB = (torch.rand(N, 512, 512, generator=gen) < 0.05).long().to(dev)
