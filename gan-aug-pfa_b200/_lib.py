@@ -47,6 +47,7 @@ class ConvGemmArgs(C.Structure):
         ("bwd_g2", C.c_void_p), ("bwd_g2_ld", C.c_int64),
         ("bwd_slope", C.c_float), ("bwd_c0", C.c_int),
         ("scale", C.c_void_p),
+        ("accumulate", C.c_int),
     ]
 
 

@@ -79,6 +79,7 @@ struct alignas(64) FpropParams {
   int bwd_c0;
   int bwd_ld32;   // y / g2 rows allow 256-bit loads
   int skip;  // bring-up ablation: 1 no global stores, 2 no y / g2 loads, 4 no statistics
+  int accum;  // kEpi = 2: out[pix][c] = act(v) + out[pix][c] (a gradient with several contributors)
   // Halo mode: the taps of one kernel column that differ only by whole input rows (th = g + in_stride*i) share ONE
   // A tile of BH + halo_taps - 1 rows; tap i reads it through a descriptor shifted by i*BW rows (BW % 8 == 0, so the
   // shift is a whole number of 1024-byte swizzle atoms).  Cuts the A-operand TMA traffic of small-N layers.
@@ -206,12 +207,13 @@ __device__ __noinline__ void epilogue_store_generic(const FpropParams& p, float4
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < p.n_out) o[j] = apply_act(f[j], p.act);
+      if (col0 + j < p.n_out) o[j] = apply_act(f[j], p.act) + (p.accum ? o[j] : 0.f);
     return;
   }
   for (int j = 0; j < 16; ++j) {
     if (col0 + j < p.n_out) {
-      p.out[pix * p.out_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act));
+      const float prev = p.accum ? __bfloat162float(p.out[pix * p.out_ld + col0 + j]) : 0.f;
+      p.out[pix * p.out_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act) + prev);
       if (p.out2 != nullptr) p.out2[pix * p.out2_ld + col0 + j] = __float2bfloat16(apply_act(f[j], p.act2));
     }
   }
@@ -552,6 +554,17 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
               }
             }
           }
+          if (kEpi == 2) {
+            // accumulate mode: the values already in `out`, fetched the same way (coherent loads: this thread
+            // overwrites them below)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              yq[i][0] = yq[i][1] = make_uint4(0, 0, 0, 0);
+              const int colp = wc.n_tile * p.block_n + (cg + 2 * i) * 16;
+              if (fast && cg + 2 * i < n_chunks && colp + 16 <= p.n_out)
+                ld_global_32B(p.out + pix * p.out_ld + colp, yq[i][0], yq[i][1]);
+            }
+          }
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
           const int c = cg + 2 * ci;
@@ -617,7 +630,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) f[jj] += __ldg(p.bias + min(col0 + jj, p.n_out - 1));
           }
-          if (do_stats && kEpi == 0) {
+          if (do_stats && kEpi != 1) {
             // BatchNorm batch statistics (sum, sum of squares) of the bf16-rounded pre-activation values
             uint32_t pr[8];
 #pragma unroll
@@ -637,7 +650,13 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const float a0 = f[2 * jj], a1 = f[2 * jj + 1];
-              pk[jj] = pack_bf16x2(a0 * (a0 > 0.f ? 1.f : p.slope1), a1 * (a1 > 0.f ? 1.f : p.slope1));
+              float v0 = a0 * (a0 > 0.f ? 1.f : p.slope1), v1 = a1 * (a1 > 0.f ? 1.f : p.slope1);
+              if (kEpi == 2) {
+                const uint32_t prev = reinterpret_cast<const uint32_t*>(yq[ci])[jj];
+                v0 += bf16_lo(prev);
+                v1 += bf16_hi(prev);
+              }
+              pk[jj] = pack_bf16x2(v0, v1);
             }
             st_global_32B(p.out + pix * p.out_ld + col0, pk, true);
             if (p.out2 != nullptr) {
@@ -815,7 +834,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   // so pairs are used only for single-phase launches with a 256-wide N tile, >= 64 K iterations and enough work items
   // for every cluster.  fprop_pair = 2 forces pairs wherever they are legal (tests, A/B runs), 0 disables them.
   const int pair_knob = debug_get("fprop_pair", 1);
-  bool pair = pair_knob != 0 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32;
+  bool pair = pair_knob != 0 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32 && !a->accumulate;
   if (pair && pair_knob != 2 && !(block_n == 256 && a->n_phase == 1 && k_iters_full >= 64)) pair = false;
   if (pair) {
     const long long pair_items = static_cast<long long>((m_tiles_pp + 2 * mt - 1) / (2 * mt)) * a->n_phase * n_tiles;
@@ -905,6 +924,9 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
                    ? 1
                    : 0;
   p.skip = debug_get("fprop_skip", 0);
+  p.accum = a->accumulate ? 1 : 0;
+  GAP_CHECK_ARG(!(a->accumulate && (bwd || a->out2 || a->stats)),
+                "gap_conv_gemm: accumulate excludes the backward-fused epilogue, out2 and stats");
 
   const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * (pair ? block_n / 2 : block_n) * 128;
   int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes - kColStageBytes) / stage_bytes;
@@ -947,6 +969,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   if (pair) {
@@ -961,6 +984,8 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   const int grid = std::min(p.total_tiles, sms);
   if (bwd)
     GAP_CUDA(launch_pdl(conv_fprop_kernel<1>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
+  else if (p.accum)
+    GAP_CUDA(launch_pdl(conv_fprop_kernel<2>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
   else
     GAP_CUDA(launch_pdl(conv_fprop_kernel<0>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
   GAP_CUDA(cudaGetLastError());

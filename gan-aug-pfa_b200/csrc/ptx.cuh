@@ -310,6 +310,14 @@ __device__ __forceinline__ void ld_global_nc_32B(const void* src, uint4& lo, uin
                : "l"(src));
 }
 
+// the same through the coherent path (for data this kernel also writes)
+__device__ __forceinline__ void ld_global_32B(const void* src, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(src)
+               : "memory");
+}
+
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor in the stream is still running; it must not touch global memory before pdl_wait() (which
 // returns once the predecessor grid has completed and flushed).  pdl_trigger() lets the NEXT kernel's CTAs be

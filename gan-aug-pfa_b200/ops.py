@@ -85,9 +85,11 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
               n_out: int, grid_hw: tuple[int, int], *, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, act2: int = ACT_NONE,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              flops: Optional[float] = None, bwd: Optional[dict] = None, scale: Optional[torch.Tensor] = None) -> None:
+              flops: Optional[float] = None, bwd: Optional[dict] = None, scale: Optional[torch.Tensor] = None,
+              accumulate: bool = False) -> None:
     """Launch the implicit-GEMM engine.  ``wpk`` is [n_phase, rows, taps*ctot] bf16.  ``flops`` overrides
-    the algorithmic FLOP count reported to the profiler (layers that pad channels pass the true one)."""
+    the algorithmic FLOP count reported to the profiler (layers that pad channels pass the true one).
+    ``accumulate``: add the result to what ``out`` already holds instead of overwriting it."""
     a = _lib.ConvGemmArgs()
     n = ih = iw = None
     for i in range(2):
@@ -151,6 +153,7 @@ def conv_gemm(srcs: Sequence[torch.Tensor], wpk: torch.Tensor, geom: Geometry, o
         a.scale = scale.data_ptr()
     else:
         a.scale = None
+    a.accumulate = 1 if accumulate else 0
     if stats is not None:
         if stats.dtype != torch.float64 or stats.numel() != 2 * (n_out - c0):
             raise ValueError("stats must be fp64 [2*(n_out - c0)]")

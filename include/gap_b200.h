@@ -115,6 +115,10 @@ typedef struct gap_conv_gemm_args {
    * Eval-mode BatchNorm (generate_synthetic_data.py:55, train.py:151, evaluate.py:146) folds into the conv this way
    * (scale = gamma/sqrt(running_var+eps), bias = beta - running_mean*scale), so no normalisation pass runs. */
   const float* scale;
+  /* 1: out[pix][co] = act(v) + out[pix][co] instead of a plain store -- a gradient buffer that collects several
+   * contributions (autograd's accumulation for a tensor with more than one consumer: the Siamese skips, gate inputs
+   * and concatenated decoder inputs, models.py:104-135).  Excludes out2, stats and the backward-fused epilogue. */
+  int accumulate;
 } gap_conv_gemm_args;
 
 int gap_conv_gemm(const gap_conv_gemm_args* args, void* stream);

@@ -230,6 +230,31 @@ def test_conv_transpose2d_wgrad_and_row_mask():
     assert float(o1[1].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n,cin,cout,h,k,p,slot", [(2, 64, 64, 20, 3, 1, False),     # Siamese 3x3 dgrad shape
+                                                   (1, 128, 192, 16, 3, 1, True),    # into a channel slot of a wider buffer
+                                                   (3, 256, 64, 12, 1, 0, False),    # gate 1x1
+                                                   (2, 64, 24, 8, 1, 0, False)])     # ragged last chunk: scalar path
+def test_accumulating_epilogue(n, cin, cout, h, k, p, slot):
+    """accumulate=True adds the result to what `out` holds (gradient buffers with several contributors): one rounding
+    of prev + acc from fp32, vector and scalar store paths, neighbouring channel slots untouched."""
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    prev = torch.randn(n, h, h, cout, generator=g).to(torch.bfloat16)
+    wide = torch.full((n, h, h, cout + 32), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = wide[..., 16:16 + cout] if slot else torch.empty(n, h, h, cout, device=DEV, dtype=torch.bfloat16)
+    out.copy_(prev.to(DEV))
+    ops.conv_gemm([nhwc(x).to(DEV)], pack_conv(w).to(DEV), ops.geom_conv_fwd(k, 1, p), out, cout, (h, h),
+                  accumulate=True)
+    ref = nhwc(F.conv2d(x.float(), w.to(torch.bfloat16).float(), None, stride=1, padding=p)) + prev.float()
+    assert rel(out.cpu().float(), ref) < FWD_TOL
+    if slot:
+        assert float((wide[..., :16] - 7.0).abs().max()) == 0 and float((wide[..., 16 + cout:] - 7.0).abs().max()) == 0
+    with pytest.raises(RuntimeError, match="accumulate excludes"):
+        ops.conv_gemm([nhwc(x).to(DEV)], pack_conv(w).to(DEV), ops.geom_conv_fwd(k, 1, p), out, cout, (h, h),
+                      accumulate=True, stats=torch.zeros(2 * cout, device=DEV, dtype=torch.float64))
+
+
 def test_invalid_configurations_are_errors():
     x = torch.zeros(1, 4, 4, 48, device=DEV, dtype=torch.bfloat16)     # 48 channels: not a multiple of 64
     w = torch.zeros(1, 64, 48, device=DEV, dtype=torch.bfloat16)

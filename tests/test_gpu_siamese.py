@@ -48,19 +48,33 @@ def test_maxpool_forward_backward_with_ties():
     assert torch.equal(gin.cpu().float(), nhwc(xr.grad))
 
 
-def test_upsample_bilinear_align_corners_forward_backward():
-    g = torch.Generator().manual_seed(2)
-    x = torch.randn(2, 16, 5, 7, generator=g).to(torch.bfloat16).float()
+@pytest.mark.parametrize("n,c,h,w", [(2, 16, 5, 7),      # odd sizes
+                                     (1, 24, 1, 9),      # one input row (scale 0), channel groups not a power of two
+                                     (2, 8, 6, 1),       # one input column
+                                     (1, 128, 40, 72),   # rows longer than one 1024-element segment, ragged last one
+                                     (3, 256, 32, 32)])
+def test_upsample_bilinear_align_corners_forward_backward(n, c, h, w):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (models.py:64) against torch, forward and
+    backward (written and accumulated), through channel slices of wider buffers like the decoder's concat slots."""
+    g = torch.Generator().manual_seed(2 + c + h)
+    x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16).float()
     xr = x.clone().requires_grad_(True)
     y = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)
     gy = torch.randn(y.shape, generator=g).to(torch.bfloat16).float()
     y.backward(gy)
-    out = torch.empty(2, 10, 14, 16, device=DEV, dtype=torch.bfloat16)
+    wide = torch.zeros(n, 2 * h, 2 * w, c + 16, device=DEV, dtype=torch.bfloat16)
+    out = wide[..., 8:8 + c]
     ops.upsample2x_fwd(nhwc(x).to(torch.bfloat16).to(DEV), out)
     assert rel(out.cpu().float(), nhwc(y.detach())) < 4e-3
-    gin = torch.empty(2, 5, 7, 16, device=DEV, dtype=torch.bfloat16)
-    ops.upsample2x_bwd(nhwc(gy).to(torch.bfloat16).to(DEV), gin, False)
+    assert float(wide[..., :8].abs().max()) == 0.0 and float(wide[..., 8 + c:].abs().max()) == 0.0
+    gwide = torch.zeros(n, 2 * h, 2 * w, c + 8, device=DEV, dtype=torch.bfloat16)
+    gwide[..., 8:] = nhwc(gy).to(torch.bfloat16).to(DEV)
+    gin = torch.full((n, h, w, c), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.upsample2x_bwd(gwide[..., 8:], gin, False)
     assert rel(gin.cpu().float(), nhwc(xr.grad)) < 4e-3
+    gin.fill_(1.0)
+    ops.upsample2x_bwd(gwide[..., 8:], gin, True)                                             # accumulate onto ones
+    assert rel(gin.cpu().float(), nhwc(xr.grad) + 1.0) < 6e-3
 
 
 @pytest.mark.parametrize("mode", [0, 1])

@@ -163,3 +163,16 @@ def test_uint8_normalisation_matches_the_reference_transforms():
     sample = ds.JointNormalize()(ds.JointToTensor()(sample))
     mine = ((u8.float() / 255.0) * 2.0 - 1.0).permute(2, 0, 1)
     assert torch.equal(sample["image1"], mine) and torch.equal(sample["image2"], mine)
+
+
+def test_attention_gate_conv_biases_have_zero_gradient_in_the_reference(ref_models):
+    """AttentionGate's W_g / W_x / psi convs carry a bias and feed a training-mode BatchNorm (models.py:21-34), which
+    subtracts the batch mean: d(loss)/d(bias) is identically zero and autograd returns rounding noise.  The native
+    engine therefore leaves the W_g / W_x bias gradients at zero instead of summing dy (siamese.py _conv1x1_bn)."""
+    torch.manual_seed(3)
+    gate = ref_models.AttentionGate(F_g=16, F_l=16, F_int=8).train()
+    g, x = torch.randn(2, 16, 12, 12), torch.randn(2, 16, 12, 12)
+    (gate(g, x) * torch.randn(2, 16, 12, 12)).sum().backward()
+    for conv in (gate.W_g[0], gate.W_x[0], gate.psi[0]):
+        assert float(conv.weight.grad.abs().max()) > 1e-3
+        assert float(conv.bias.grad.abs().max()) < 1e-5 * float(conv.weight.grad.abs().max())
