@@ -112,7 +112,6 @@ _SIGNATURES = {
     "gap_upsample_bilinear2x_fwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "gap_upsample_bilinear2x_bwd": (C.c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P]),
     "gap_dropout_bf16": (C.c_int, [_P, _L, _L, _I, _F, C.c_uint64, C.c_uint64, _P]),
-    "gap_add_inplace_bf16": (C.c_int, [_P, _L, _P, _L, _L, _I, _P]),
     "gap_att_add_relu_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "gap_relu_bwd": (C.c_int, [_P, _P, _P, _L, _P]),
     "gap_lrelu_bwd_bf16": (C.c_int, [_P, _L, _P, _L, _F, _P, _L, _L, _I, _I, _P]),

@@ -310,24 +310,6 @@ __global__ void dropout_kernel(bf16* __restrict__ x, long long ld, long long pix
   }
 }
 
-// dst += src  (bf16, 8 channels per thread; gradient accumulation for activations with several consumers)
-__global__ void add_inplace_kernel(bf16* __restrict__ dst, long long ldd, const bf16* __restrict__ src, long long lds,
-                                   long long pixels, int c) {
-  const int cv = c >> 3;
-  const long long total = pixels * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c8 = static_cast<int>(i - pix * cv) << 3;
-    float a[8], b[8];
-    unpack8(*reinterpret_cast<const uint4*>(dst + pix * ldd + c8), a);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(src + pix * lds + c8)), b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += b[j];
-    *reinterpret_cast<uint4*>(dst + pix * ldd + c8) = pack8(a);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // AttentionGate (models.py:18-44) elementwise pieces
 //   s   = ReLU(BN_g(yg) + BN_x(yx))                        (add_relu)
@@ -748,13 +730,6 @@ int gap_dropout_bf16(void* x, int64_t ld, int64_t pixels, int c, float p_drop, u
   GAP_CHECK_ARG(x && pixels > 0 && c % 8 == 0 && ld % 8 == 0 && p_drop >= 0.f && p_drop < 1.f, "gap_dropout_bf16: bad arguments");
   dropout_kernel<<<grid_of(pixels * (c / 8), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<bf16*>(x), ld, pixels, c, p_drop, 1.f / (1.f - p_drop), seed, offset);
-  SI_LAUNCH_OK();
-}
-
-int gap_add_inplace_bf16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t pixels, int c, void* stream) {
-  GAP_CHECK_ARG(dst && src && pixels > 0 && c % 8 == 0 && ldd % 8 == 0 && lds % 8 == 0, "gap_add_inplace_bf16: bad arguments");
-  add_inplace_kernel<<<grid_of(pixels * (c / 8), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<bf16*>(dst), ldd, static_cast<const bf16*>(src), lds, pixels, c);
   SI_LAUNCH_OK();
 }
 

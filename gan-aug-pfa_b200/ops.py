@@ -628,11 +628,6 @@ def dropout_(x: torch.Tensor, p_drop: float, seed: int, offset: int) -> None:
                                            offset & (2**64 - 1), _stream()), "gap_dropout_bf16")
 
 
-def add_inplace(dst: torch.Tensor, src: torch.Tensor) -> None:
-    _lib.check(_lib.lib().gap_add_inplace_bf16(_ptr(dst), dst.stride(-2), _ptr(src), src.stride(-2), _px(dst),
-                                               dst.shape[-1], _stream()), "gap_add_inplace_bf16")
-
-
 def att_add_relu_fwd(yg, scg, shg, yx, scx, shx, s) -> None:
     _lib.check(_lib.lib().gap_att_add_relu_fwd(_ptr(yg), _ptr(scg), _ptr(shg), _ptr(yx), _ptr(scx), _ptr(shx), _ptr(s),
                                                _px(s), s.shape[-1], _stream()), "gap_att_add_relu_fwd")

@@ -274,8 +274,6 @@ int gap_upsample_bilinear2x_bwd(const void* gout, int64_t ldg, void* gin, int64_
  * keep = hash(seed, offset + element index) — forward and backward call it with the same (seed, offset), on the
  * activation and on its gradient.  Not bit-compatible with torch's Philox stream (statistical parity only). */
 int gap_dropout_bf16(void* x, int64_t ld, int64_t pixels, int c, float p_drop, uint64_t seed, uint64_t offset, void* stream);
-/* dst += src: gradient accumulation for activations with several consumers (skip tensors) */
-int gap_add_inplace_bf16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t pixels, int c, void* stream);
 /* AttentionGate (models.py:18-44): s = ReLU(BN(yg) + BN(yx)) (dense [pixels][c]); d = (s > 0) ? gs : 0;
  * psi = Sigmoid(BN(ypsi)), out = x * psi;  gate backward: gx (+)= gout * psi, dz = (sum_c gout * x) * psi * (1 - psi) */
 int gap_att_add_relu_fwd(const void* yg, const float* scale_g, const float* shift_g, const void* yx, const float* scale_x,
