@@ -1204,7 +1204,7 @@ int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void
   }
   const long long npix = static_cast<long long>(n) * ih * iw;
   const size_t smem = (static_cast<size_t>(16) * (c + 8) + 16 * 24) * sizeof(bf16) + (in_scale ? 2 * c * sizeof(float) : 0);
-  const int want = 4 * sm_count();
+  const int want = debug_get("cout1_wg_mult", 4) * sm_count();
   long long chunk = (npix + want - 1) / want;
   chunk = (chunk + 15) / 16 * 16;
   const int grid = static_cast<int>((npix + chunk - 1) / chunk);
