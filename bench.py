@@ -718,6 +718,22 @@ def measure_secondary(workload: str, steps: int, warmup: int, dist, world: int, 
     _barrier(dist, world)
     ms_e2e = e0.elapsed_time(e1)
     ms, ms_e2e = _max_over_ranks(dist, world, dev, ms, ms_e2e)
+    if workload == "siamese_train":
+        # the criterion train.py's main() actually builds (train.py:294, Optuna's constants): same step, other loss kernel
+        fd = dict(kind="focal_dice", focal_alpha=0.6030489822904476, gamma=1.7930869982898021, beta=0.6699803915247974,
+                  smooth=1.956571276926647e-06, grad_scale=1.0 / world)
+        n_fd = max(2, min(steps, 5))
+        for i in range(2):
+            eng.train_step(*devb[i % 2], **fd)
+        _barrier(dist, world)
+        e0.record()
+        for i in range(n_fd):
+            eng.train_step(*devb[i % 2], **fd)
+        e1.record()
+        _barrier(dist, world)
+        (ms_fd,) = _max_over_ranks(dist, world, dev, e0.elapsed_time(e1))
+        extra["focal_dice_loss"] = {"value": world * units * n_fd / (ms_fd * 1e-3), "unit": unit, "steps": n_fd,
+                                    "loss": "FocalDiceLoss(train.py:294 constants)"}
     if workload == "siamese_train" and world > 1:
         from gan_aug_pfa_b200 import parallel
         extra["replica_param_max_abs_diff"] = parallel.replica_param_max_abs_diff([eng])

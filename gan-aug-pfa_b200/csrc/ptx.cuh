@@ -117,6 +117,8 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed stores have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -261,6 +263,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// The same without swizzling (layout type 0, "interleave"): a K-major operand is made of 8-row x 16-byte core
+// matrices whose rows sit 16 bytes apart; sbo = distance between consecutive 8-row groups, lbo = distance between
+// the two 16-byte K chunks of one K = 16 instruction.  Neither has to be the dense value: overlapping or strided
+// core matrices are how thin_layers.cu reads im2col rows straight out of staged image rows.
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(256, 4) cout1_wgrad_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 struct ThinFwdParams {
   CUtensorMap tm_out[2];   // out1 / out2 as [n][oh][ow][cw] bf16: box 64 ch x 16 x 8 x 1, 128B swizzle (TMA store)
+  CUtensorMap tm_row[2];   // the same tensors, box 64 ch x 128 x 1 x 1: one output row (tcgen05 row kernel)
   const bf16* s0;
   long long ld0;
   const bf16* s1;
@@ -614,6 +615,272 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __grid_constan
   if (tid == 0) tma_store_wait_all();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same convolution on tcgen05 for full-width rows (w_in = 256, dense 4-slot sources): one output row of 128 pixels
+// is one M = 128 accumulator tile, and the im2col matrix is never built -- the A descriptors read it straight out of
+// the staged image rows with the un-swizzled K-major layout (ptx.cuh make_nosw_desc), whose 8-row core matrices only
+// need rows 16 bytes apart:
+//   CT = 8 (two sources, 16 B per concatenated pixel): a row is staged as two planes of 130 entries, odd pixels
+//     (entry i = pixel 2i+1, entry -1 = the left padding) and even pixels (entry i = pixel 2i, entry 128 = the right
+//     padding).  Output pixel ow reads taps kw = 0..3 from odd[ow-1], even[ow], odd[ow], even[ow+1]: for the tap pairs
+//     (0,1) and (2,3) that is start = odd[-1] / odd[0], row pitch 16 B, and the same plane distance + 16 B between the
+//     two K chunks (lbo).  One K = 16 instruction per (kh, tap pair): 8 per output row.
+//   CT = 4 (one source, 8 B per pixel): the row is staged shifted by one pixel, so the 16-byte entry ow holds pixels
+//     (2ow-1, 2ow) and entry ow+1 holds (2ow+1, 2ow+2): start = entry 0, lbo = 16 B (overlapping core matrices).  One
+//     K = 16 instruction per kh: 4 per output row.
+// Input rows come in PAIRS (rows 2p-1, 2p; output row oh needs pairs oh and oh+1) through a ring of kTcSlots pair slots
+// filled by cp.async (8-byte pieces, zero-filled outside the image), one stager warp per pair, four pairs in flight.
+// Every CTA takes one contiguous range of output rows (two CTAs per SM).  Warp 0 issues the MMAs, warps 1-4 stage,
+// warps 5-12 drain the accumulators (256 / cw TMEM stages): + bias, bf16, activation(s) into 128B-swizzled row tiles
+// that leave through TMA stores (whole output rows, full lines).
+// dynamic smem: out_s[2 rows][outputs][cw/64][128 px][128 B] | ws[16*CT/8][cw][16 B] | ring[kTcSlots][2 rows][kRowBytes] |
+//               mbarriers | TMEM address
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcSlots = 6;      // ring of row pairs (8320 B each for two sources)
+constexpr int kTcPlane = 130 * 16;
+constexpr int kTcStagers = 32;   // arrivals per staged pair: one stager warp (of four, warps 1-4) copies a whole pair
+constexpr int kTcThreads = 416;  // warp 0 MMA | warps 1-4 staging | warps 5-12 epilogue (TMEM lane quarter = warp % 4;
+                                 // two warps per quarter split each 64-column half: 4 warps were latency-bound)
+
+template <int CT>
+__global__ void __launch_bounds__(kTcThreads, 2) thin_conv_fwd_tc_kernel(const __grid_constant__ ThinFwdParams p) {
+  constexpr int kRowBytes = (CT == 8 ? 2 : 1) * kTcPlane;
+  constexpr int kSlotBytes = 2 * kRowBytes;
+  constexpr int KC = 16 * CT / 8;            // 16-byte K chunks per weight row
+  extern __shared__ uint8_t tc_raw[];
+  const uint32_t base_a = (smem_u32(tc_raw) + 1023u) & ~1023u;
+  uint8_t* base = tc_raw + (base_a - smem_u32(tc_raw));
+  const int cw = p.cw;
+  const int halves = cw >> 6;                // 64-channel output tiles per row
+  const int outs_bytes = 2 * (p.out2 != nullptr ? 2 : 1) * halves * 16384;   // out_s[2 rows][outputs][halves][128 px][128 B], 128B-swizzled
+  const int ws_bytes = KC * cw * 16;
+  const uint32_t outs_a = base_a, ws_a = base_a + outs_bytes, ring_a = ws_a + ws_bytes;
+  const uint32_t bar_a = ring_a + kTcSlots * kSlotBytes;
+  uint8_t* ws = base + outs_bytes;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(ws + ws_bytes + kTcSlots * kSlotBytes + (2 * kTcSlots + 8) * 8);
+  const int n_acc = 256 / cw;                // 4 (cw = 64) or 2 (cw = 128)
+  auto pair_full = [&](int s) { return bar_a + s * 8; };
+  auto pair_empty = [&](int s) { return bar_a + (kTcSlots + s) * 8; };
+  auto acc_full = [&](int a) { return bar_a + (2 * kTcSlots + a) * 8; };
+  auto acc_empty = [&](int a) { return bar_a + (2 * kTcSlots + 4 + a) * 8; };
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // weights: ws[kc][n][8] <- w[n][kc*8 .. +8]   (core matrices of 8 output channels x 16 bytes)
+  for (int idx = tid; idx < cw * KC; idx += kTcThreads) {
+    const int n = idx / KC, kc = idx - n * KC;
+    *reinterpret_cast<uint4*>(ws + (kc * cw + n) * 16) = ldg128(p.w + static_cast<long long>(n) * (16 * CT) + kc * 8);
+  }
+  for (int idx = tid; idx < kTcSlots * kSlotBytes / 16; idx += kTcThreads)      // padding entries stay zero for good
+    *reinterpret_cast<uint4*>(ws + ws_bytes + idx * 16) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < kTcSlots; ++s) {
+      mbar_init(pair_full(s), kTcStagers);
+      mbar_init(pair_empty(s), 1);
+    }
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 8);
+    }
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 0) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work split: every CTA takes one contiguous range of output rows (all images concatenated); a range is walked
+  // in segments that stay inside one image (a segment of nrows output rows needs nrows + 1 row pairs)
+  const int rows_total = p.n * p.oh;
+  const int g_begin = static_cast<int>(static_cast<long long>(rows_total) * blockIdx.x / gridDim.x);
+  const int g_end = static_cast<int>(static_cast<long long>(rows_total) * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, cw, 0, 0);
+      uint32_t c = 0, rs = 0;
+      for (int g = g_begin; g < g_end;) {
+        const int oh0 = g % p.oh;
+        const int nrows = min(p.oh - oh0, g_end - g);
+        g += nrows;
+        for (int j = 0; j < nrows; ++j, ++rs) {
+          const uint32_t a = rs % n_acc, aph = (rs / n_acc) & 1u;
+          const uint32_t c0 = c + j;
+          mbar_wait(acc_empty(a), aph ^ 1u);
+          if (j == 0) mbar_wait(pair_full(c0 % kTcSlots), (c0 / kTcSlots) & 1u);   // (later rows saw it as c0 + 1)
+          mbar_wait(pair_full((c0 + 1) % kTcSlots), ((c0 + 1) / kTcSlots) & 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + a * cw;
+#pragma unroll
+          for (int kh = 0; kh < 4; ++kh) {
+            const uint32_t cc = c0 + (kh >> 1);
+            const uint32_t row_a = ring_a + (cc % kTcSlots) * kSlotBytes + (kh & 1) * kRowBytes;
+            if (CT == 8) {
+#pragma unroll
+              for (int tp = 0; tp < 2; ++tp) {
+                const uint64_t ad = make_nosw_desc(row_a + tp * 16, kTcPlane + 16, 128);
+                const uint64_t bd = make_nosw_desc(ws_a + (kh * 4 + tp * 2) * cw * 16, cw * 16, 128);
+                umma_bf16(d_tmem, ad, bd, idesc, (kh | tp) != 0);
+              }
+            } else {
+              const uint64_t ad = make_nosw_desc(row_a, 16, 128);
+              const uint64_t bd = make_nosw_desc(ws_a + (kh * 2) * cw * 16, cw * 16, 128);
+              umma_bf16(d_tmem, ad, bd, idesc, kh != 0);
+            }
+          }
+          umma_commit(acc_full(a));
+          umma_commit(pair_empty(c0 % kTcSlots));                    // rows 2oh-1, 2oh are not needed again
+          if (j == nrows - 1) umma_commit(pair_empty((c0 + 1) % kTcSlots));
+        }
+        c += nrows + 1;
+      }
+    }
+  } else if (warp < 5) {
+    // ------------------------------------------------------------------ staging
+    // Stager warp sw copies the pairs whose running index is sw (mod 4), whole pairs on its own: cp.async, wait for ITS
+    // copies, fence.proxy.async, 32 arrivals.  Four pairs are in flight per CTA without any thread having to fence
+    // while younger copies are pending (a proxy fence waits for every outstanding cp.async of the thread, which
+    // serialised a one-pair-per-iteration scheme at the memory latency).
+    const int sw = warp - 1;
+    const long long row_elems = static_cast<long long>(p.w_in) * 4;
+    uint32_t c = 0;                            // running pair index
+    for (int g = g_begin; g < g_end;) {
+      const int img = g / p.oh;
+      const int oh0 = g - img * p.oh;
+      const int nrows = min(p.oh - oh0, g_end - g);
+      g += nrows;
+      const long long img_off = static_cast<long long>(img) * p.h * row_elems;
+      for (int pj = 0; pj <= nrows; ++pj, ++c) {
+        if ((c & 3u) != static_cast<uint32_t>(sw)) continue;
+        const uint32_t slot = c % kTcSlots;
+        mbar_wait(pair_empty(slot), ((c / kTcSlots) & 1u) ^ 1u);
+        const int r0 = 2 * (oh0 + pj) - 1;
+        const uint32_t dst0 = ring_a + slot * kSlotBytes;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = r0 + rr;
+          const bool ok = static_cast<unsigned>(r) < static_cast<unsigned>(p.h) && !(p.skip & 4);
+          const int nb = ok ? 8 : 0;
+          const long long off_r = img_off + (ok ? r * row_elems : 0);
+          const uint32_t d = dst0 + rr * kRowBytes;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int i = lane + 32 * t;       // pixels 2i (even) and 2i + 1 (odd)
+            const long long off = off_r + i * 8;
+            // CT = 8: even pixel -> even plane entry i, odd pixel -> odd plane entry i (entry -1 sits at byte 0)
+            // CT = 4: pixel x at byte (x + 1) * 8
+            const uint32_t d_even = CT == 8 ? kTcPlane + (i + 1) * 16 : (2 * i + 1) * 8;
+            const uint32_t d_odd = CT == 8 ? (i + 1) * 16 : (2 * i + 2) * 8;
+            cp_async8(d + d_even, p.s0 + off, nb);
+            cp_async8(d + d_odd, p.s0 + off + 4, nb);
+            if (CT == 8) {
+              cp_async8(d + d_even + 8, p.s1 + off, nb);
+              cp_async8(d + d_odd + 8, p.s1 + off + 4, nb);
+            }
+          }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        mbar_arrive(pair_full(slot));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    // TMEM -> registers -> (+bias, bf16, activation(s)) -> 128B-swizzled smem row tiles -> TMA stores of whole output
+    // rows (full lines; per-thread global stores of a pixel's 128 bytes made the store path the bottleneck).  One bulk
+    // group per output row; the tiles are double-buffered by row parity.
+    const int q = warp & 3;
+    const int e_tid = tid - 160;               // 0 .. 255
+    const int eh = (warp - 5) >> 2;            // which 32 columns of every 64-column half
+    const int row = q * 32 + lane;             // pixel of the output row = TMEM lane
+    const int n_pass = p.out2 != nullptr ? 2 : 1;
+    const __nv_bfloat162 slope_a = __float2bfloat162_rn(p.slope1), slope_b = __float2bfloat162_rn(p.slope2);
+    uint32_t rs = 0;
+    for (int g = g_begin; g < g_end;) {
+      const int img = g / p.oh;
+      const int oh0 = g - img * p.oh;
+      const int nrows = min(p.oh - oh0, g_end - g);
+      g += nrows;
+      for (int j = 0; j < nrows; ++j, ++rs) {
+        const uint32_t a = rs % n_acc, aph = (rs / n_acc) & 1u;
+        const uint32_t buf_a = outs_a + (rs & 1u) * n_pass * halves * 16384;     // [pass][half][128 px][128 B]
+        mbar_wait(acc_full(a), aph);
+        tc_fence_after();
+        // the TMA stores that last read these tiles (two rows ago) have finished reading them
+        if (e_tid == 0) tma_store_wait_read1();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t t_row = tmem_base + a * cw + (static_cast<uint32_t>(q * 32) << 16);
+        for (int hb = 0; hb < halves; ++hb) {
+          uint32_t r[2][16];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) tmem_ld16(t_row + hb * 64 + eh * 32 + i * 16, r[i]);
+          tmem_ld_wait();
+          if (hb == halves - 1) {                // accumulator drained: hand it back before the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(a));
+          }
+#pragma unroll
+          for (int cl = 0; cl < 4; ++cl) {       // this warp's 16-byte chunks of the row's 128 bytes
+            const int ch = eh * 4 + cl;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[cl >> 1][(cl & 1) * 8 + k]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + hb * 64 + ch * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + hb * 64 + ch * 8 + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            __nv_bfloat162 t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            // act(v) = max(v, slope*v) for slope in [0, 1], on the packed bf16 pair (the tile kernel's arithmetic);
+            // 16-byte chunk c of row r lives at chunk c ^ (r & 7) of the 128-byte row
+            const uint32_t dst = buf_a + hb * 16384 + row * 128 + ((ch ^ (row & 7)) << 4);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              if (pass == n_pass) break;
+              const float slope = pass == 0 ? p.slope1 : p.slope2;
+              const __nv_bfloat162 s2 = pass == 0 ? slope_a : slope_b;
+              uint32_t pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 u = slope != 1.f ? __hmax2(t[k], __hmul2(t[k], s2)) : t[k];
+                pk[k] = *reinterpret_cast<const uint32_t*>(&u);
+              }
+              st_shared_v4(dst + pass * halves * 16384, pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (e_tid == 0 && !(p.skip & 2)) {
+          for (int pass = 0; pass < n_pass; ++pass)
+            for (int hb = 0; hb < halves; ++hb)
+              tma_store_4d(&p.tm_row[pass], buf_a + (pass * halves + hb) * 16384, hb * 64, 0, oh0 + j, img);
+          tma_store_commit();
+        }
+      }
+    }
+    if (e_tid == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Thin-input Conv2d(k4, s2, p1) weight gradient (and the last ConvTranspose2d's, with roles swapped):
@@ -1280,6 +1547,34 @@ int gap_thin_conv_fwd(const void* src0, int64_t ld0, const void* src1, int64_t l
     uint32_t box[4] = {64, 16, 8, 1};
     int rc = encode_tmap_bf16(&p.tm_out[o], base, 4, dims, strides, box, nullptr, true);
     if (rc) return rc;
+    if (p.ow == 128) {
+      uint32_t box_row[4] = {64, 128, 1, 1};
+      rc = encode_tmap_bf16(&p.tm_row[o], base, 4, dims, strides, box_row, nullptr, true);
+      if (rc) return rc;
+    }
+  }
+  // full-width dense rows: the tcgen05 row kernel (see thin_conv_fwd_tc_kernel)
+  const bool tc_ok = w == 256 && ld0 == 4 && (!src1 || ld1 == 4) && ldo1 % 16 == 0 && (!out2 || ldo2 % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(out1) & 31) == 0 && (reinterpret_cast<uintptr_t>(out2) & 31) == 0 &&
+                     (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(cw == 128 && out2) &&
+                     debug_get("thin_tc", 1) != 0;
+  if (tc_ok) {
+    const int kc = 16 * ct / 8;
+    const size_t smem_tc = 1024 + static_cast<size_t>(2) * (out2 ? 2 : 1) * (cw / 64) * 16384 + static_cast<size_t>(kc) * cw * 16 +
+                           kTcSlots * 2 * (ct == 8 ? 2 : 1) * kTcPlane + (2 * kTcSlots + 8) * 8 + 16;
+    const int grid_tc = std::min(n * p.oh, 2 * sm_count());
+    static bool set_tc = false;
+    if (!set_tc) {
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      set_tc = true;
+    }
+    if (ct == 8)
+      thin_conv_fwd_tc_kernel<8><<<grid_tc, kTcThreads, smem_tc, st>>>(p);
+    else
+      thin_conv_fwd_tc_kernel<4><<<grid_tc, kTcThreads, smem_tc, st>>>(p);
+    GAP_CUDA(cudaGetLastError());
+    return 0;
   }
   const size_t smem = 1024 + static_cast<size_t>(cw / 64) * 16384 + 2 * 18 * 34 * ct * 2 +
                       static_cast<size_t>(cw) * (16 * ct + 8) * 2;

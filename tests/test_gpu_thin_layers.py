@@ -134,6 +134,12 @@ def _pack_thin(w, groups):
     (1, 8, 8, 64, 1, False, True),        # image smaller than one tile: the TMA store box exceeds the tensor
     (2, 4, 12, 64, 2, True, False),
     (1, 256, 256, 64, 2, True, False),
+    # 256-pixel rows: the tcgen05 row kernel (A operand read out of the staged image rows, no im2col)
+    (2, 12, 256, 64, 2, True, False),     # one ragged unit of 6 output rows per image
+    (1, 40, 256, 64, 1, False, True),     # one source, two outputs; units of 8, 8, 4 rows
+    (3, 18, 256, 128, 1, False, False),   # 128 output channels (two TMEM stages), 9 rows
+    (2, 2, 256, 64, 2, False, False),     # a single output row: both neighbours are padding
+    (5, 64, 256, 64, 2, True, False),     # more units than one wave of CTAs handles at once on small grids
 ])
 def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
     g = torch.Generator().manual_seed(h + cw)

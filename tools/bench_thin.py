@@ -10,13 +10,24 @@ N = 64
 
 
 def timeit(fn, iters=10):
+    """Device time per call: the launches are replayed from a CUDA graph, so the host's launch cost (tensor-map
+    encodes, ctypes) is not what is measured when a kernel is shorter than its launch."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(iters):
-        fn()
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
@@ -49,9 +60,11 @@ t7 = timeit(lambda: ops.thin_conv_wgrad(o64, xa, None, dw4, 48, None))
 print(f"G.last fwd (convT 128->3, tanh, bf16+f32 out) {t4:.1f} us | D.0 input grad (convT 64->3, bf16 out) {t5:.1f} us | "
       f"D.0 wgrad {t6:.1f} us | G.0 wgrad {t7:.1f} us", flush=True)
 for cps in [int(a) for a in sys.argv[1:]] or [0]:
+  for tc in (1, 0, 1, 0):
+    _lib.debug_set("thin_tc", tc)          # 1: tcgen05 row kernel (256-pixel rows), 0: the mma.sync tile kernel
     _lib.debug_set("thin_skip", cps)
     t1 = timeit(lambda: ops.thin_conv_fwd(xa, xb, w8, bias, o64, ops.ACT_LRELU))
     t2 = timeit(lambda: ops.thin_conv_fwd(xa, None, w4, None, o64, ops.ACT_LRELU, o64b, ops.ACT_RELU))
     t3 = timeit(lambda: ops.thin_conv_fwd(xa, None, w4b, None, o128))
-    print(f"skip {cps}: D.0 fwd (6->64) {t1:.1f} us | G.0 fwd (3->64, 2 outs) {t2:.1f} us | G.last dgrad (3->128) {t3:.1f} us",
+    print(f"tc {tc} skip {cps}: D.0 fwd (6->64) {t1:.1f} us | G.0 fwd (3->64, 2 outs) {t2:.1f} us | G.last dgrad (3->128) {t3:.1f} us",
           flush=True)
