@@ -895,6 +895,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) thin_conv_fwd_tc_kernel(const _
 // ------------------------------------------------------------------------------------------------
 struct ThinWgradParams {
   CUtensorMap tm_wide;   // [n][oh][ow][cw] bf16: box 64 ch x 16 x 8 x 1, 128B swizzle, ragged tiles zero-filled
+  CUtensorMap tm_row;    // the same tensor, box 64 ch x 128 x 1 x 1: one output row (tcgen05 row kernel)
   const bf16* wide;
   long long ld_w;
   const bf16* s0;
@@ -1056,6 +1057,268 @@ __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const __grid_const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same weight gradient on tcgen05 for 256-pixel rows (dense 4-slot sources):
+//   D[m][co] += sum_ow  A[m][ow] * dy[ow][co],   m = (kh*4 + kw)*CT + slot   (A = the im2col matrix, transposed)
+// accumulated in ONE TMEM tile over all the output rows a CTA owns (K = pixels) and flushed with atomics at the end.
+// Both operands are MN-major: dy rows arrive by TMA as 128B-swizzled [128 px][64 co] tiles, and A is read straight
+// out of staged copies of the image rows through an un-swizzled MN-major descriptor -- 16-byte M chunks `sbo` apart,
+// eight consecutive ow 16 bytes apart.  A chunk is one (kh, kw) tap of the concatenated 8-slot pixel (CT = 8) or one
+// (kh, pixel pair) of the single source (CT = 4); a uniform chunk pitch needs every x row staged as four (two) shifted
+// planes of 128 entries: plane kw, entry ow = pixel 2ow - 1 + kw (CT = 8); plane ps, entry ow = pixels 2ow - 1 + 2ps,
+// 2ow + 2ps (CT = 4).  Rows are staged in PAIRS (rows 2p-1, 2p = kh 0,1 of output row p and kh 2,3 of row p-1) into a
+// ring of four 8-plane slots; an output row reads two consecutive slots with one descriptor, so the pair that lands
+// in slot 0 is also written to a mirror slot behind slot 3.  CT = 4 has only 64 valid M rows: the upper 64 TMEM lanes
+// accumulate whatever follows in shared memory and are never read.
+// Warp 0 issues the MMAs (8 per output row), warps 1-4 stage x (cp.async, one warp per pair), warp 5 issues the dy
+// TMA loads, warps 6-9 sum the dy tiles for the bias gradient and flush the accumulator at the end.
+// dynamic smem (1 KiB aligned): dy_s[4][cw/64][128 px][128 B] | ring[(5 + 3) slots][8 planes][2 KiB (CT/8)] | mbarriers |
+//                               bias partial sums [2][16][64] fp32
+// ------------------------------------------------------------------------------------------------
+constexpr int kWtThreads = 320;
+constexpr int kWtSlots = 4;
+
+template <int CT>
+__global__ void __launch_bounds__(kWtThreads, 1) thin_conv_wgrad_tc_kernel(const __grid_constant__ ThinWgradParams p) {
+  constexpr int kPlane = 2048;                           // 128 entries x 16 B
+  constexpr int kPlanesPerRow = CT == 8 ? 4 : 2;
+  constexpr int kSlotBytes = 2 * kPlanesPerRow * kPlane;   // one pair of x rows
+  constexpr int kRingSlots = kWtSlots + 1 + 3;           // + mirror of slot 0 + slack the CT = 4 descriptor runs into
+  extern __shared__ uint8_t wt_raw[];
+  const uint32_t base_a = (smem_u32(wt_raw) + 1023u) & ~1023u;
+  uint8_t* base = wt_raw + (base_a - smem_u32(wt_raw));
+  const int cw = p.cw, halves = cw >> 6;
+  const int dy_bytes = halves * 16384;
+  const uint32_t dy_a = base_a, ring_a = base_a + 4 * dy_bytes;
+  const uint32_t bar_a = ring_a + kRingSlots * kSlotBytes;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base + 4 * dy_bytes + kRingSlots * kSlotBytes + 20 * 8);
+  auto xfull = [&](int s) { return bar_a + s * 8; };
+  auto xempty = [&](int s) { return bar_a + (4 + s) * 8; };
+  auto dfull = [&](int s) { return bar_a + (8 + s) * 8; };
+  auto dempty = [&](int s) { return bar_a + (12 + s) * 8; };
+  const uint32_t acc_done = bar_a + 16 * 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool do_bias = p.dbias != nullptr;
+
+  for (int idx = tid; idx < kRingSlots * kSlotBytes / 16; idx += kWtThreads)      // edge entries stay zero for good
+    *reinterpret_cast<uint4*>(base + 4 * dy_bytes + idx * 16) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s2 = 0; s2 < 4; ++s2) {
+      mbar_init(xfull(s2), 32);
+      mbar_init(xempty(s2), 1);
+      mbar_init(dfull(s2), 1);
+      mbar_init(dempty(s2), do_bias ? 5 : 1);
+    }
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 0) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int rows_total = p.n * p.oh;
+  const int g_begin = static_cast<int>(static_cast<long long>(rows_total) * blockIdx.x / gridDim.x);
+  const int g_end = static_cast<int>(static_cast<long long>(rows_total) * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, cw, 1, 1);
+      uint32_t c = 0, rs = 0;
+      for (int g = g_begin; g < g_end;) {
+        const int oh0 = g % p.oh;
+        const int nrows = min(p.oh - oh0, g_end - g);
+        g += nrows;
+        for (int j = 0; j < nrows; ++j, ++rs) {
+          const uint32_t c0 = c + j, s0 = c0 & 3u;      // pairs c0, c0 + 1 sit in slots s0, s0 + 1 (mirror when s0 = 3)
+          if (j == 0) mbar_wait(xfull(s0), (c0 >> 2) & 1u);
+          mbar_wait(xfull((c0 + 1) & 3u), ((c0 + 1) >> 2) & 1u);
+          mbar_wait(dfull(rs & 3u), (rs >> 2) & 1u);
+          tc_fence_after();
+          const uint32_t a_row = ring_a + s0 * kSlotBytes, b_row = dy_a + (rs & 3u) * dy_bytes;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {                  // 16 output pixels per instruction
+            const uint64_t ad = make_nosw_desc(a_row + k * 256, 128, kPlane);
+            const uint64_t bd = make_sw128_desc(b_row + k * 2048, 16384, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (rs | k) != 0);
+          }
+          umma_commit(xempty(s0));                       // rows 2oh-1, 2oh are not needed again
+          if (j == nrows - 1) umma_commit(xempty((c0 + 1) & 3u));
+          umma_commit(dempty(rs & 3u));
+        }
+        c += nrows + 1;
+      }
+      umma_commit(acc_done);
+    }
+  } else if (warp < 5) {
+    // ------------------------------------------------------------------ x staging: one warp per pair
+    const int sw = warp - 1;
+    const long long row_elems = static_cast<long long>(p.w_in) * 4;
+    uint32_t c = 0;
+    for (int g = g_begin; g < g_end;) {
+      const int img = g / p.oh;
+      const int oh0 = g - img * p.oh;
+      const int nrows = min(p.oh - oh0, g_end - g);
+      g += nrows;
+      const long long img_off = static_cast<long long>(img) * p.h * row_elems;
+      for (int pj = 0; pj <= nrows; ++pj, ++c) {
+        if ((c & 3u) != static_cast<uint32_t>(sw)) continue;
+        const uint32_t slot = c & 3u;
+        mbar_wait(xempty(slot), ((c >> 2) & 1u) ^ 1u);
+        const int r0 = 2 * (oh0 + pj) - 1;
+        for (int copy = 0; copy < ((slot == 0 && c > 0) ? 2 : 1); ++copy) {
+          const uint32_t dst0 = ring_a + (copy ? kWtSlots : slot) * kSlotBytes;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = r0 + rr;
+            const bool ok = static_cast<unsigned>(r) < static_cast<unsigned>(p.h);
+            const int nb = ok ? 8 : 0;
+            const long long off_r = img_off + (ok ? r * row_elems : 0);
+            const uint32_t d = dst0 + rr * kPlanesPerRow * kPlane;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = lane + 32 * t;               // pixels 2i (even) and 2i + 1 (odd)
+              const long long off = off_r + i * 8;
+              if (CT == 8) {
+                // even pixel 2i: plane 1 entry i, plane 3 entry i-1; odd pixel 2i+1: plane 0 entry i+1, plane 2 entry i
+                cp_async8(d + 1 * kPlane + i * 16, p.s0 + off, nb);
+                cp_async8(d + 1 * kPlane + i * 16 + 8, p.s1 + off, nb);
+                if (i > 0) {
+                  cp_async8(d + 3 * kPlane + (i - 1) * 16, p.s0 + off, nb);
+                  cp_async8(d + 3 * kPlane + (i - 1) * 16 + 8, p.s1 + off, nb);
+                }
+                if (i < 127) {
+                  cp_async8(d + 0 * kPlane + (i + 1) * 16, p.s0 + off + 4, nb);
+                  cp_async8(d + 0 * kPlane + (i + 1) * 16 + 8, p.s1 + off + 4, nb);
+                }
+                cp_async8(d + 2 * kPlane + i * 16, p.s0 + off + 4, nb);
+                cp_async8(d + 2 * kPlane + i * 16 + 8, p.s1 + off + 4, nb);
+              } else {
+                // plane ps, entry e = pixels (2e-1+2ps, 2e+2ps): even pixel 2i -> second half of (0, i) and (1, i-1);
+                // odd pixel 2i+1 -> first half of (0, i+1) and (1, i)
+                cp_async8(d + 0 * kPlane + i * 16 + 8, p.s0 + off, nb);
+                if (i > 0) cp_async8(d + 1 * kPlane + (i - 1) * 16 + 8, p.s0 + off, nb);
+                if (i < 127) cp_async8(d + 0 * kPlane + (i + 1) * 16, p.s0 + off + 4, nb);
+                cp_async8(d + 1 * kPlane + i * 16, p.s0 + off + 4, nb);
+              }
+            }
+          }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        mbar_arrive(xfull(slot));
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ dy rows by TMA
+    if (lane == 0) {
+      uint32_t rs = 0;
+      for (int g = g_begin; g < g_end; ++g, ++rs) {
+        const int img = g / p.oh, oh = g - img * p.oh;
+        const uint32_t slot = rs & 3u;
+        mbar_wait(dempty(slot), ((rs >> 2) & 1u) ^ 1u);
+        mbar_expect_tx(dfull(slot), dy_bytes);
+        for (int hb = 0; hb < halves; ++hb)
+          tma_load_4d(dy_a + slot * dy_bytes + hb * 16384, &p.tm_row, dfull(slot), hb * 64, 0, oh, img);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ bias sums per row, accumulator flush at the end
+    const int q = warp & 3;
+    const int e_tid = tid - 192;               // 0 .. 127
+    // thread -> 16-byte column chunk it always reads (the swizzle XOR is constant along its pixels r0 + 16 i)
+    const int r0 = e_tid >> 3, chunk = (e_tid & 7) ^ (r0 & 7);
+    float bs[2][8];
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bs[hb][k] = 0.f;
+    if (do_bias) {
+      uint32_t rs = 0;
+      for (int g = g_begin; g < g_end; ++g, ++rs) {
+        const uint32_t slot = rs & 3u;
+        mbar_wait(dfull(slot), (rs >> 2) & 1u);
+        const uint8_t* tile = base + slot * dy_bytes;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {       // (static bounds: bs[][] must stay in registers)
+          if (hb >= halves) break;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(tile + hb * 16384 + (r0 + 16 * i) * 128 + (e_tid & 7) * 16);
+            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              bs[hb][2 * k] += bf16_lo(w4[k]);
+              bs[hb][2 * k + 1] += bf16_hi(w4[k]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dempty(slot));
+      }
+      // 16 threads (r0 = 0 .. 15) hold partial sums of the same 8 channels: combine them in shared memory so that every
+      // CTA adds ONE value per channel (16 x 148 same-address atomics per channel cost more than the whole kernel)
+      float* red = reinterpret_cast<float*>(base + 4 * dy_bytes + kRingSlots * kSlotBytes + 32 * 8);   // [2][16][64]
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        if (hb >= halves) break;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[(hb * 16 + r0) * 64 + chunk * 8 + k] = bs[hb][k];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int col = e_tid; col < cw; col += 128) {
+        const int hb = col >> 6, cc = col & 63;
+        float tot = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tot += red[(hb * 16 + r) * 64 + cc];
+        atomicAdd(p.dbias + col, tot);
+      }
+    }
+    if (g_end > g_begin) {
+      mbar_wait(acc_done, 0u);
+      tc_fence_after();
+      const int m = q * 32 + lane;             // TMEM lane = im2col row
+      int tap, ch;
+      bool valid;
+      if (CT == 8) {
+        const int s8 = m & 7;
+        tap = m >> 3;
+        valid = (s8 & 3) != 3;
+        ch = s8 < 3 ? s8 : s8 - 1;
+      } else {
+        const int s4 = m & 3;
+        tap = m >> 2;
+        valid = m < 64 && s4 != 3;
+        ch = s4;
+      }
+      float* dst = p.dw + tap * p.c_real + ch;
+      for (int c0 = 0; c0 < cw; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + c0 + (static_cast<uint32_t>(q * 32) << 16), r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) atomicAdd(dst + static_cast<long long>(c0 + k) * p.ld_m, __uint_as_float(r[k]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Thin-output ConvTranspose2d(cw -> 3, k4, s2, p1): the generator's last layer (+bias, Tanh; models.py:184,186)
@@ -1639,6 +1902,31 @@ int gap_thin_conv_wgrad(const void* wide, int64_t ld_w, const void* src0, int64_
     uint32_t box[4] = {64, 16, 8, 1};
     int rc = encode_tmap_bf16(&p.tm_wide, wide, 4, dims, strides, box, nullptr, true);
     if (rc) return rc;
+  }
+  // full-width dense rows: the tcgen05 row kernel (see thin_conv_wgrad_tc_kernel)
+  if (w == 256 && ld0 == 4 && (!src1 || ld1 == 4) && debug_get("thin_tc", 1) != 0) {
+    const uint64_t ld_b = static_cast<uint64_t>(ld_w) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(cw), static_cast<uint64_t>(p.ow), static_cast<uint64_t>(p.oh),
+                        static_cast<uint64_t>(n)};
+    uint64_t strides[3] = {ld_b, ld_b * p.ow, ld_b * p.ow * p.oh};
+    uint32_t box_row[4] = {64, 128, 1, 1};
+    int rc = encode_tmap_bf16(&p.tm_row, wide, 4, dims, strides, box_row, nullptr, true);
+    if (rc) return rc;
+    const size_t smem_tc = 1024 + 4 * static_cast<size_t>(cw / 64) * 16384 + 8 * 2 * (ct == 8 ? 4 : 2) * 2048 + 32 * 8 +
+                           2 * 16 * 64 * 4;
+    const int grid_tc = std::min(n * p.oh, sm_count());
+    static bool set_tc = false;
+    if (!set_tc) {
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_wgrad_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      GAP_CUDA(cudaFuncSetAttribute(thin_conv_wgrad_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      set_tc = true;
+    }
+    if (ct == 8)
+      thin_conv_wgrad_tc_kernel<8><<<grid_tc, kWtThreads, smem_tc, st>>>(p);
+    else
+      thin_conv_wgrad_tc_kernel<4><<<grid_tc, kWtThreads, smem_tc, st>>>(p);
+    GAP_CUDA(cudaGetLastError());
+    return 0;
   }
   const size_t smem = 1024 + 2 * static_cast<size_t>(cw / 64) * 16384 + 2 * 18 * 34 * ct * 2 + 16;
   const int threads = 128 * (cw / 64);

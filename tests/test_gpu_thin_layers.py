@@ -167,6 +167,13 @@ def test_thin_conv_fwd(n, h, w, cw, groups, bias, two_out):
     (2, 20, 36, 128, 1, False),      # generator last ConvT wgrad (wide = its input); partial tiles
     (1, 8, 8, 64, 1, False),         # image smaller than one tile (TMA box exceeds the tensor)
     (5, 64, 64, 64, 2, True),
+    # 256-pixel rows: the tcgen05 row kernel (im2col matrix read out of staged image rows, one TMEM tile per CTA)
+    (2, 12, 256, 64, 2, True),       # two sources + bias gradient; every CTA owns one output row
+    (1, 40, 256, 64, 1, False),      # one source (64 valid im2col rows)
+    (3, 18, 256, 128, 1, False),     # 128 wide channels (two dy tiles per row), 9 rows per image
+    (2, 2, 256, 64, 2, True),        # a single output row per image: both neighbours are padding
+    (3, 256, 256, 64, 2, True),      # 384 rows over 148 CTAs: ranges cross image boundaries, ring and mirror wrap
+    (2, 256, 256, 64, 1, False),
 ])
 def test_thin_conv_wgrad(n, h, w, cw, groups, bias):
     g = torch.Generator().manual_seed(h * 3 + cw)

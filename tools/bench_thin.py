@@ -52,6 +52,7 @@ fake_bf = torch.zeros(N, 256, 256, 4, **bf)
 fake_f32 = torch.zeros(N, 256, 256, 4, device=dev)
 dw8 = torch.zeros(64, 96, device=dev)
 dw4 = torch.zeros(64, 48, device=dev)
+dw4l = torch.zeros(128, 48, device=dev)
 db = torch.zeros(64, device=dev)
 t4 = timeit(lambda: ops.thin_convT_fwd(wide128, wcol128, b3, ops.ACT_TANH, fake_bf, fake_f32))
 t5 = timeit(lambda: ops.thin_convT_fwd(wide64, wcol64, None, ops.ACT_NONE, fake_bf, None))
@@ -66,5 +67,11 @@ for cps in [int(a) for a in sys.argv[1:]] or [0]:
     t1 = timeit(lambda: ops.thin_conv_fwd(xa, xb, w8, bias, o64, ops.ACT_LRELU))
     t2 = timeit(lambda: ops.thin_conv_fwd(xa, None, w4, None, o64, ops.ACT_LRELU, o64b, ops.ACT_RELU))
     t3 = timeit(lambda: ops.thin_conv_fwd(xa, None, w4b, None, o128))
+    t6 = timeit(lambda: ops.thin_conv_wgrad(o64, xa, xb, dw8, 96, db))
+    t7 = timeit(lambda: ops.thin_conv_wgrad(o64, xa, None, dw4, 48, None))
+    t8 = timeit(lambda: ops.thin_conv_wgrad(wide128, xa, None, dw4l, 48, None))
+    t6b = timeit(lambda: ops.thin_conv_wgrad(o64, xa, xb, dw8, 96, None))
+    print(f"tc {tc}: D.0 wgrad without the bias gradient {t6b:.1f} us", flush=True)
+    print(f"tc {tc}: D.0 wgrad {t6:.1f} us | G.0 wgrad {t7:.1f} us | G.last wgrad (128 wide) {t8:.1f} us", flush=True)
     print(f"tc {tc} skip {cps}: D.0 fwd (6->64) {t1:.1f} us | G.0 fwd (3->64, 2 outs) {t2:.1f} us | G.last dgrad (3->128) {t3:.1f} us",
           flush=True)

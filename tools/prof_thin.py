@@ -15,6 +15,8 @@ w4 = torch.randn(64, 64, **bf)
 bias = torch.randn(64, device=dev)
 o64 = torch.empty(N, 128, 128, 64, **bf)
 o64b = torch.empty(N, 128, 128, 64, **bf)
+o128 = torch.empty(N, 128, 128, 128, **bf)
+w4b = torch.randn(128, 64, **bf)
 dw8 = torch.zeros(64, 96, device=dev)
 dw4 = torch.zeros(64, 48, device=dev)
 db = torch.zeros(64, device=dev)
@@ -26,6 +28,7 @@ fake_f32 = torch.zeros(N, 256, 256, 4, device=dev)
 for _ in range(2):
     ops.thin_conv_fwd(xa, xb, w8, bias, o64, ops.ACT_LRELU)                              # D.0 forward
     ops.thin_conv_fwd(xa, None, w4, None, o64, ops.ACT_LRELU, o64b, ops.ACT_RELU)         # G.0 forward
+    ops.thin_conv_fwd(xa, None, w4b, None, o128)                                         # G.last input gradient
     ops.thin_conv_wgrad(o64, xa, xb, dw8, 96, db)                                        # D.0 wgrad
     ops.thin_conv_wgrad(o64, xa, None, dw4, 48, None)                                    # G.0 wgrad
     ops.thin_convT_fwd(wide128, wcol, b3, ops.ACT_TANH, fake_bf, fake_f32)               # G.last forward
