@@ -972,8 +972,20 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
+  // Persistent grid: with W = ceil(items / slots) passes over the work list, ceil(items / W) CTAs finish at the same
+  // time as `slots` would (the 3.46-wave launches of the 512-tile layers: 128 CTAs x 4 items instead of 148 CTAs of which
+  // 80 idle through the last pass) and leave the other SMs to the kernels of the concurrent streams (weight gradients,
+  // the generator forward next to the discriminator).  fprop_balance = 0: one CTA per SM as before.  Measured on the
+  // whole iteration (tools/ab_knob.py, ABBA): 7.888 -> 7.842 ms.  (Also tried: walking the work list from the last M
+  // tile down so that a conv reads first what the BatchNorm pass before it wrote last, i.e. what is still in L2:
+  // 7.879 vs 7.875 ms, no effect -- the GEMMs are not DRAM-bound -- not kept.)
+  auto balanced = [&](int items, int slots) {
+    if (items <= slots || debug_get("fprop_balance", 1) == 0) return std::min(items, slots);
+    const int passes = (items + slots - 1) / slots;
+    return (items + passes - 1) / passes;
+  };
   if (pair) {
-    const int grid2 = std::min(2 * p.total_tiles, sms) & ~1;
+    const int grid2 = 2 * balanced(p.total_tiles, sms / 2);
     if (bwd)
       GAP_CUDA(launch_pair(conv_fprop_kernel<1, true>, dim3(grid2), dim3(kFpropThreads), smem_bytes, stream, p));
     else
@@ -981,7 +993,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     GAP_CUDA(cudaGetLastError());
     return 0;
   }
-  const int grid = std::min(p.total_tiles, sms);
+  const int grid = balanced(p.total_tiles, sms);
   if (bwd)
     GAP_CUDA(launch_pdl(conv_fprop_kernel<1>, dim3(grid), dim3(kFpropThreads), smem_bytes, stream, p));
   else if (p.accum)

@@ -403,14 +403,28 @@ __global__ void __launch_bounds__(256, 4) cout1_wgrad_kernel(const float* __rest
     }
     __syncthreads();
   }
-  if (active && p1 > p0) {
+  if (active && p1 > p0) {       // (warp-uniform: the shuffles below are executed by whole warps)
+    // One 128-bit reduction per lane and 8-column block instead of four scalar ones (every CTA adds its whole
+    // 16 x c partial to the same 16 x c words: the L2 atomic units, not the loads, bounded this kernel): lanes t and
+    // t ^ 1 swap halves so that the even lane owns 4 consecutive columns of tap row g, the odd lane those of row g + 8.
+    const bool odd = t & 1;
+    const bool vec = (reinterpret_cast<uintptr_t>(dw) & 15) == 0;      // c % 64 == 0 keeps every row 16-byte aligned
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int col = n0 + nt * 8 + 2 * t;
-      atomicAdd(dw + static_cast<long long>(g) * c + col, acc[nt][0]);
-      atomicAdd(dw + static_cast<long long>(g) * c + col + 1, acc[nt][1]);
-      atomicAdd(dw + static_cast<long long>(g + 8) * c + col, acc[nt][2]);
-      atomicAdd(dw + static_cast<long long>(g + 8) * c + col + 1, acc[nt][3]);
+      const float s0 = odd ? acc[nt][0] : acc[nt][2], s1 = odd ? acc[nt][1] : acc[nt][3];
+      const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const int col = n0 + nt * 8 + 4 * (t >> 1);
+      float* dst = dw + static_cast<long long>(odd ? g + 8 : g) * c + col;
+      const float v0 = odd ? r0 : acc[nt][0], v1 = odd ? r1 : acc[nt][1];
+      const float v2 = odd ? acc[nt][2] : r0, v3 = odd ? acc[nt][3] : r1;
+      if (vec) {
+        red_add_v4_f32(dst, v0, v1, v2, v3);
+      } else {
+        atomicAdd(dst, v0);
+        atomicAdd(dst + 1, v1);
+        atomicAdd(dst + 2, v2);
+        atomicAdd(dst + 3, v3);
+      }
     }
   }
 }
