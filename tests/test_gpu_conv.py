@@ -381,8 +381,9 @@ def test_cluster_split_k_on_the_bottleneck_geometries(split):
                       bias=b.to(DEV), stats=stats, act=ops.ACT_LRELU)
         ref = nhwc(F.conv2d(x.float(), w.float(), b, 2, 1))
         assert rel(out.cpu().float(), F.leaky_relu(ref, 0.2)) < FWD_TOL
-        assert rel(stats[:cout].cpu(), ref.double().sum((0, 1, 2))) < 5e-3
-        assert rel(stats[cout:].cpu(), (ref.double() ** 2).sum((0, 1, 2))) < 5e-3
+        s2 = (ref.double() ** 2).sum((0, 1, 2))
+        assert float((stats[:cout].cpu() - ref.double().sum((0, 1, 2))).abs().max() / s2.sqrt().max()) < 5e-3
+        assert rel(stats[cout:].cpu(), s2) < 5e-3
         # ConvTranspose2d 512 -> 512 forward, 1x1 -> 2x2, batch 48 (one half-empty M tile per phase, K = 32 iterations)
         n, cin, cout, h = 48, 512, 512, 1
         x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
