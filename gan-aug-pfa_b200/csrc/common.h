@@ -44,11 +44,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// Launch as clusters of `cluster_x` CTAs; launch_pair: two (a CTA pair on the two SMs of one TPC: tcgen05 cta_group::2
-// kernels).
+// Launch as clusters of two CTAs (a CTA pair on the two SMs of one TPC: tcgen05 cta_group::2 kernels).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                  Args&&... args) {
+inline cudaError_t launch_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -56,7 +54,7 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+  attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -64,10 +62,6 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 
   cfg.attrs = attr;
   cfg.numAttrs = debug_get("pdl", 0) != 0 ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
-}
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  return launch_cluster(kernel, 2, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 #define GAP_CHECK_ARG(cond, ...)      \

@@ -94,15 +94,6 @@ struct alignas(64) FpropParams {
   // rank r owns M tiles (2*sm + r)*mt .. +mt and stages rows [r*block_n/2, (r+1)*block_n/2) of the B tile; the leader
   // issues tcgen05.mma.cta_group::2 (M = 256).  sm_tiles / total_tiles then count PAIR items.
   int pair;
-  // Split-K across a thread-block cluster (kSplit): the `split` CTAs of a cluster work on the SAME work item, CTA rank r
-  // runs pipeline iterations [k_iters*r/split, k_iters*(r+1)/split) into its own TMEM accumulator; ranks > 0 then park
-  // their fp32 partial tile in their own shared memory ([mt*128 rows][block_n floats + 16 B pad]) and arrive on the
-  // leader's mbarrier; the leader's epilogue adds the partials, rank by rank (deterministic), through distributed shared
-  // memory (ld.shared::cluster) and runs the normal fused epilogue.  For the under-filled 8x8 .. 2x2 layers, whose
-  // launches are one or two latency-bound K loops of 32-128 iterations on a fraction of the SMs.  One work item per
-  // cluster (grid = items * split), so the partial buffers are written once.
-  int split;
-  int part_stride;     // bytes per row of the partial buffer
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -228,7 +219,7 @@ __device__ __noinline__ void epilogue_store_generic(const FpropParams& p, float4
   }
 }
 
-template <int kEpi, bool kPair = false, bool kSplit = false>
+template <int kEpi, bool kPair = false>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -238,14 +229,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   // pair mode: this CTA's half of the B rows; rank 0 (the leader) issues the MMAs for both CTAs
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const int bn_cta = kPair ? (p.block_n >> 1) : p.block_n;
-  // split mode: rank of this CTA in its cluster = its slice of the K loop
-  const uint32_t k_rank = kSplit ? cluster_ctarank() : 0u;
-  const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1)
-                          : (kSplit ? static_cast<int>(blockIdx.x) / p.split : static_cast<int>(blockIdx.x));
-  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1)
-                              : (kSplit ? static_cast<int>(gridDim.x) / p.split : static_cast<int>(gridDim.x));
-  const int k_lo = kSplit ? static_cast<int>(static_cast<long long>(p.k_iters) * k_rank / p.split) : 0;
-  const int k_hi = kSplit ? static_cast<int>(static_cast<long long>(p.k_iters) * (k_rank + 1) / p.split) : p.k_iters;
+  const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int a_bytes = p.mt * p.a_tile_bytes;
   const int stage_bytes = a_bytes + p.b_per_stage * bn_cta * 128;
   const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
@@ -254,13 +239,11 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
-  const uint32_t part_bar = bar_base + 8u * (2 * kMaxStages + 5);     // split mode: the peers' partial tiles are parked
   uint8_t* bar_gen = smem_gen + p.num_stages * stage_bytes;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * 20);
   double* stats_sm = reinterpret_cast<double*>(bar_gen + kBarrierBytes);
   float* par_sm = reinterpret_cast<float*>(bar_gen + kBarrierBytes + kStatsBytes);  // [2][256] scale | shift
   const uint32_t colstage_base = bar_base + kBarrierBytes + kStatsBytes + kParamBytes;  // [kEpiWarps][1 KiB]
-  const uint32_t part_base = colstage_base + kColStageBytes;   // split mode: [mt * 128][part_stride] fp32 partial tile
 
   // Warp index broadcast from lane 0: the role dispatch and the producer / MMA loops are then
   // warp-uniform for the compiler, so TMA / MMA operands stay in uniform registers (a per-lane
@@ -280,7 +263,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogue warps release the leader
     }
-    if (kSplit) mbar_init(part_bar, (p.split - 1) * kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -293,7 +275,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
     }
   }
   tc_fence_before();
-  if (kPair || kSplit)
+  if (kPair)
     cluster_sync();      // the peer's barriers are initialised before anything signals them
   else
     __syncthreads();
@@ -380,19 +362,10 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           continue;
         }
         int kcol = 0;
-        int kit = 0;       // pipeline iteration of this work item (split mode: only [k_lo, k_hi) are this CTA's)
         for (int t_h = 0; t_h < p.taps_h; ++t_h) {
           for (int t_w = 0; t_w < p.taps_w; ++t_w) {
             for (int s = 0; s < 2; ++s) {
               for (int c = 0; c < p.src_chunks[s]; ++c) {
-                if (kSplit) {
-                  const bool mine = kit >= k_lo && kit < k_hi;
-                  ++kit;
-                  if (!mine) {
-                    kcol += kBlockK;
-                    continue;
-                  }
-                }
                 if ((it++ & 1u) == my_par) {
                   mbar_wait(empty_bar(stage), phase ^ 1u);
                   if (arm) mbar_expect_tx(full_bar(stage), tx_bytes);
@@ -438,7 +411,7 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int k_iter = 0; k_iter < k_hi - k_lo; ++k_iter) {
+        for (int k_iter = 0; k_iter < p.k_iters; ++k_iter) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
@@ -510,29 +483,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
 
-    if (kSplit && k_rank != 0) {
-      // ---- split mode, ranks > 0: TMEM partial -> own shared memory, then tell the leader (one work item per cluster)
-      if (tile0 < p.total_tiles) {
-        mbar_wait(tfull_bar(0), 0u);
-        tc_fence_after();
-        const int n_chunks = p.block_n >> 4;
-        for (int j = 0; j < p.mt; ++j) {
-          const uint32_t t_row = tmem_base + j * p.block_n + (static_cast<uint32_t>(q * 32) << 16);
-          const uint32_t dst_row = part_base + static_cast<uint32_t>(j * kBlockM + row) * p.part_stride;
-          for (int c = half; c < n_chunks; c += 2) {
-            uint32_t raw[16];
-            tmem_ld16(t_row + c * 16, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int v = 0; v < 4; ++v)
-              st_shared_v4(dst_row + c * 64 + v * 16, raw[4 * v], raw[4 * v + 1], raw[4 * v + 2], raw[4 * v + 3]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_cluster(part_bar, 0u));   // release.cluster: the stores above are visible
-      }
-    } else
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
       const WorkCoord wc = decode_work(p, tile);
       const int sm_own = kPair ? (wc.sm * 2 + static_cast<int>(cta_rank)) : wc.sm;
@@ -561,7 +511,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
       // data pipe, which the tensor-core operand reads and TMA writes keep ~70 % busy, not on DRAM.)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (kSplit) mbar_wait_cluster(part_bar, 0u);      // every peer's partial tile is parked in its shared memory
       const int n_chunks = p.block_n >> 4;
       for (int j = 0; j < p.mt; ++j) {
         const MTile mtile = decode_mtile(p, sm_own * p.mt + j);
@@ -627,19 +576,6 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
           float f[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) f[jj] = __uint_as_float(raw[jj]);
-          if (kSplit) {
-            // + the peers' partial sums of this row chunk, in rank order, through distributed shared memory
-            const uint32_t src = part_base + static_cast<uint32_t>(j * kBlockM + row) * p.part_stride + c * 64;
-            for (int r = 1; r < p.split; ++r) {
-              const uint32_t ra = mapa_cluster(src, static_cast<uint32_t>(r));
-              const float4 v0 = ld_shared_cluster_f4(ra), v1 = ld_shared_cluster_f4(ra + 16);
-              const float4 v2 = ld_shared_cluster_f4(ra + 32), v3 = ld_shared_cluster_f4(ra + 48);
-              f[0] += v0.x; f[1] += v0.y; f[2] += v0.z; f[3] += v0.w;
-              f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
-              f[8] += v2.x; f[9] += v2.y; f[10] += v2.z; f[11] += v2.w;
-              f[12] += v3.x; f[13] += v3.y; f[14] += v3.z; f[15] += v3.w;
-            }
-          }
           if (kEpi == 1 && col0 >= p.bwd_c0) {
             // d = mask(y) ? g (+ g2) : slope * g  with mask = (y*scale + shift > 0); sums of d and d*y
             const uint32_t* yw = reinterpret_cast<const uint32_t*>(yq[ci]);
@@ -756,8 +692,8 @@ conv_fprop_kernel(const __grid_constant__ FpropParams p) {
   }
 
   tc_fence_before();
-  if (kPair || kSplit)
-    cluster_sync();      // no CTA frees its TMEM / exits while a peer's MMAs, remote arrivals or DSMEM reads may still touch it
+  if (kPair)
+    cluster_sync();      // neither CTA frees its TMEM / exits while the peer's MMAs or remote arrivals may still touch it
   else
     __syncthreads();
   if (warp == 1) {
@@ -853,8 +789,6 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   const int sms = sm_count();
   const int force_bn = debug_get("fprop_block_n", 0);
   int model_mt = 0;
-  int split = 1;
-  const int k_iters_all = a->taps_h * a->taps_w * ((a->src_c[0] + a->src_c[1]) / 64);
   if (force_bn > 0) {
     block_n = force_bn;
     n_tiles = (n_pad + block_n - 1) / block_n;
@@ -863,12 +797,6 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     // pick the N tile and the M tiles per item by a per-iteration cost model fitted to tools/sweep_deep.py:
     // cycles per pipeline iteration ~ max(130 + 280 per A tile + 80 per 64 B rows, MMA time 2*mt*bn + 100), times
     // the number of waves.  (The old rule halved block_n until every SM had an item: up to 2x slower.)
-    // Split-K across a cluster of s CTAs (FpropParams::split) divides the iterations of a work item by s at the price
-    // of the reduction through distributed shared memory (~1500 cycles + ~600 per peer); it needs one work item per
-    // cluster (items * s CTAs resident at once: clusters of 4 / 8 fill at most 16 of a GPC's SMs), a partial tile of at
-    // most 64 KiB (mt * block_n <= 128) and an epilogue without accumulate.  fprop_split: 0 = never, s >= 2 = force s.
-    const int split_knob = debug_get("fprop_split", 0);        // -1: by the cost model below
-    const bool split_ok = split_knob != 0 && !a->accumulate && n_pad % 16 == 0;
     const int wide = block_n;
     long long best = -1;
     for (int bn_c : {wide, 128, 64}) {
@@ -877,23 +805,13 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
         if (mt_c == 2 && m_tiles_pp < 2) continue;
         const long long items =
             static_cast<long long>((m_tiles_pp + mt_c - 1) / mt_c) * a->n_phase * ((n_pad + bn_c - 1) / bn_c);
+        const long long waves = (items + sms - 1) / sms;
         const long long it_cost = std::max(130 + 280 * mt_c + 80 * bn_c / 64, 2 * mt_c * bn_c + 100);
-        for (int s_c : {1, 2, 4, 8}) {
-          if (s_c > 1) {
-            if (!split_ok || mt_c * bn_c > 128 || bn_c % 16 != 0 || k_iters_all / s_c < 4) continue;
-            if (items * s_c > (s_c == 2 ? sms : 128)) continue;
-            if (split_knob >= 2 && s_c != split_knob) continue;
-          }
-          const long long waves = (items * s_c + sms - 1) / sms;
-          const long long iters = (k_iters_all + s_c - 1) / s_c;
-          long long cost = waves * iters * it_cost + (s_c > 1 ? 1500 + 600 * (s_c - 1) : 0);
-          if (s_c == 1 && split_knob >= 2) cost += (1ll << 40);     // forced split: unsplit only as the fallback
-          if (best < 0 || cost < best) {
-            best = cost;
-            block_n = bn_c;
-            model_mt = mt_c;
-            split = s_c;
-          }
+        const long long cost = waves * it_cost;
+        if (best < 0 || cost < best) {
+          best = cost;
+          block_n = bn_c;
+          model_mt = mt_c;
         }
       }
     }
@@ -916,16 +834,13 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
   // so pairs are used only for single-phase launches with a 256-wide N tile, >= 64 K iterations and enough work items
   // for every cluster.  fprop_pair = 2 forces pairs wherever they are legal (tests, A/B runs), 0 disables them.
   const int pair_knob = debug_get("fprop_pair", 1);
-  bool pair = pair_knob != 0 && split == 1 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32 && !a->accumulate;
+  bool pair = pair_knob != 0 && sms % 2 == 0 && block_n % 16 == 0 && block_n >= 32 && !a->accumulate;
   if (pair && pair_knob != 2 && !(block_n == 256 && a->n_phase == 1 && k_iters_full >= 64)) pair = false;
   if (pair) {
     const long long pair_items = static_cast<long long>((m_tiles_pp + 2 * mt - 1) / (2 * mt)) * a->n_phase * n_tiles;
     if (pair_items < sms / 2) pair = false;
   }
   p.pair = pair ? 1 : 0;
-  if (force_mt > 0 && split > 1 && mt * block_n > 128) split = 1;
-  p.split = split;
-  p.part_stride = block_n * 4 + 16;
   p.mt = mt;
   p.m_tiles_pp = m_tiles_pp;
   p.sm_tiles = pair ? (m_tiles_pp + 2 * mt - 1) / (2 * mt) : (m_tiles_pp + mt - 1) / mt;
@@ -1014,14 +929,12 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
                 "gap_conv_gemm: accumulate excludes the backward-fused epilogue, out2 and stats");
 
   const int stage_bytes = mt * p.a_tile_bytes + p.b_per_stage * (pair ? block_n / 2 : block_n) * 128;
-  const int part_bytes = split > 1 ? mt * kBlockM * p.part_stride : 0;
-  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes - kColStageBytes - part_bytes) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - kBarrierBytes - kStatsBytes - kParamBytes - kColStageBytes) / stage_bytes;
   stages = std::min(stages, kMaxStages);
   const int force_st = debug_get("fprop_stages", 0);
   if (force_st > 0) stages = std::min(force_st, stages);
   p.num_stages = stages;
-  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes + kParamBytes +
-                            kColStageBytes + part_bytes;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + kStatsBytes + kParamBytes + kColStageBytes;
 
   // ---- tensor maps
   const uint32_t bx_w = static_cast<uint32_t>(BW * a->in_stride);
@@ -1057,18 +970,7 @@ extern "C" int gap_conv_gemm(const gap_conv_gemm_args* a, void* stream_v) {
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    GAP_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
-  }
-  if (split > 1) {
-    const dim3 grid_s(static_cast<unsigned>(p.total_tiles * split));      // one work item per cluster
-    if (bwd)
-      GAP_CUDA(launch_cluster(conv_fprop_kernel<1, false, true>, split, grid_s, dim3(kFpropThreads), smem_bytes, stream, p));
-    else
-      GAP_CUDA(launch_cluster(conv_fprop_kernel<0, false, true>, split, grid_s, dim3(kFpropThreads), smem_bytes, stream, p));
-    GAP_CUDA(cudaGetLastError());
-    return 0;
   }
   // Persistent grid: with W = ceil(items / slots) passes over the work list, ceil(items / W) CTAs finish at the same
   // time as `slots` would (the 3.46-wave launches of the 512-tile layers: 128 CTAs x 4 items instead of 148 CTAs of which

@@ -192,36 +192,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Split-K across a cluster (conv_fprop.cu): acquire at cluster scope, so that what the peer CTAs stored to their shared
-// memory before their (release.cluster) arrival is visible to this CTA's ld.shared::cluster reads.
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-#ifndef GAP_NO_HANG_GUARD
-    if (++spins > (1u << 26)) __trap();
-#endif
-  }
-}
-// 16 bytes from the shared memory of another CTA of the cluster (`cluster_addr` from mapa_cluster)
-__device__ __forceinline__ float4 ld_shared_cluster_f4(uint32_t cluster_addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(cluster_addr)
-               : "memory");
-  return v;
-}
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA with the given cluster rank
 __device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
   uint32_t r;

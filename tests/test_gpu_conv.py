@@ -358,62 +358,3 @@ def _pair_bwd_epilogue(g):
     denom = (od ** 2).sum((0, 1, 2)).sqrt().max()
     assert float((stats[:cin].cpu() - od.sum((0, 1, 2))).abs().max() / denom) < 1e-5
     assert float((stats[cin:].cpu() - (od * y.double()).sum((0, 1, 2))).abs().max() / denom) < 1e-5
-
-
-@pytest.mark.parametrize("split", [2, 4, 8])
-def test_cluster_split_k_on_the_bottleneck_geometries(split):
-    """fprop_split = s: the K loop of an under-filled launch is divided over a cluster of s CTAs, the partial tiles are
-    reduced through distributed shared memory by the leader, which runs the usual fused epilogue — stride-2 forward with
-    bias + BatchNorm statistics (2x2 outputs), the four-phase transposed geometry (1x1 -> 2x2) and the backward-fused
-    epilogue, against fp32 CPU convolutions."""
-    from gan_aug_pfa_b200 import _lib
-    g = torch.Generator().manual_seed(300 + split)
-    _lib.debug_set("fprop_split", split)
-    try:
-        # Conv2d 512 -> 512, k4 s2 p1, 4x4 -> 2x2, batch 64 (M = 256)
-        n, cin, cout, h = 64, 512, 512, 4
-        x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
-        w = (torch.randn(cout, cin, 4, 4, generator=g) / 90).to(torch.bfloat16)
-        b = torch.randn(cout, generator=g)
-        out = torch.full((n, h // 2, h // 2, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
-        stats = torch.zeros(2 * cout, device=DEV, dtype=torch.float64)
-        ops.conv_gemm([nhwc(x).to(DEV)], pack_conv(w).to(DEV), ops.geom_conv_fwd(4, 2, 1), out, cout, (h // 2, h // 2),
-                      bias=b.to(DEV), stats=stats, act=ops.ACT_LRELU)
-        ref = nhwc(F.conv2d(x.float(), w.float(), b, 2, 1))
-        assert rel(out.cpu().float(), F.leaky_relu(ref, 0.2)) < FWD_TOL
-        s2 = (ref.double() ** 2).sum((0, 1, 2))
-        assert float((stats[:cout].cpu() - ref.double().sum((0, 1, 2))).abs().max() / s2.sqrt().max()) < 5e-3
-        assert rel(stats[cout:].cpu(), s2) < 5e-3
-        # ConvTranspose2d 512 -> 512 forward, 1x1 -> 2x2, batch 48 (one half-empty M tile per phase, K = 32 iterations)
-        n, cin, cout, h = 48, 512, 512, 1
-        x = torch.randn(n, cin, h, h, generator=g).to(torch.bfloat16)
-        w = (torch.randn(cin, cout, 4, 4, generator=g) / 45).to(torch.bfloat16)
-        out = torch.full((n, 2 * h, 2 * h, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
-        ops.conv_gemm([nhwc(x).to(DEV)], pack_phase(w.permute(1, 0, 2, 3)).to(DEV), ops.geom_phase_k4s2p1(), out, cout, (h, h))
-        assert rel(out.cpu().float(), nhwc(F.conv_transpose2d(x.float(), w.float(), None, 2, 1))) < FWD_TOL
-        assert not torch.isnan(out.float()).any()
-        # Conv2d(512 -> 512, k4 s2 p1) dgrad onto a 4x4 input with the activation / BatchNorm backward fused in
-        n, cin, cout, h, slope = 32, 512, 512, 4, 0.2
-        dy = torch.randn(n, cout, h // 2, h // 2, generator=g).to(torch.bfloat16)
-        w = torch.randn(cout, cin, 4, 4, generator=g) / 64.0
-        xz = torch.zeros(n, cin, h, h, requires_grad=True)
-        (gref,) = torch.autograd.grad(F.conv2d(xz, w.to(torch.bfloat16).float(), None, 2, 1), xz, dy.float())
-        gref = nhwc(gref)
-        y = torch.randn(n, h, h, cin, generator=g).to(torch.bfloat16)
-        scale, shift = torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.3
-        yh = y.float() * scale + shift
-        dref = torch.where(yh > 0, gref, slope * gref)
-        out = torch.full((n, h, h, cin), float("nan"), device=DEV, dtype=torch.bfloat16)
-        stats = torch.zeros(2 * cin, device=DEV, dtype=torch.float64)
-        ops.conv_gemm([nhwc(dy).to(DEV)], pack_phase(w.to(torch.bfloat16).permute(1, 0, 2, 3)).to(DEV),
-                      ops.geom_phase_k4s2p1(), out, cin, (h // 2, h // 2), stats=stats,
-                      bwd=dict(y=y.to(DEV), slope=slope, scale=scale.to(DEV), shift=shift.to(DEV)))
-        o = out.cpu().float()
-        safe = yh.abs() > 1e-3
-        assert float(((o - dref) * safe).norm() / dref.norm()) < FWD_TOL
-        od = o.double()
-        denom = (od ** 2).sum((0, 1, 2)).sqrt().max()
-        assert float((stats[:cin].cpu() - od.sum((0, 1, 2))).abs().max() / denom) < 1e-5
-        assert float((stats[cin:].cpu() - (od * y.double()).sum((0, 1, 2))).abs().max() / denom) < 1e-5
-    finally:
-        _lib.debug_set("fprop_split", 0)

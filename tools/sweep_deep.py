@@ -1,5 +1,4 @@
-"""block_n x mt sweep on the deep (8x8 .. 2x2) layers, with BatchNorm statistics on (run under gpurun).
-usage: sweep_deep.py [split]   (split: only the default launch vs cluster split-K, fprop_split = -1)"""
+"""block_n x mt sweep on the deep (8x8 .. 2x2) layers, with BatchNorm statistics on (run under gpurun)."""
 import sys
 from pathlib import Path
 import torch
@@ -24,7 +23,6 @@ def timeit(fn, iters=20):
 
 
 N = 64
-SPLIT_ONLY = len(sys.argv) > 1 and sys.argv[1] == "split"      # only default vs cluster split-K
 cases = []
 for cin, cout, g in ((512, 512, 8), (512, 1024, 8), (512, 512, 4), (512, 1024, 4), (512, 512, 2), (512, 512, 1)):
     src = torch.randn(N, 2 * g, 2 * g, cin, **bf)
@@ -48,12 +46,6 @@ for name, fl, fn in cases:
     _lib.debug_set("fprop_mt", 0)
     _lib.debug_set("fprop_block_n", 0)
     line.append(f"default {timeit(fn):6.1f}us")
-    _lib.debug_set("fprop_split", -1)          # cluster split-K where the cost model wants it
-    line.append(f"split-K {timeit(fn):6.1f}us")
-    _lib.debug_set("fprop_split", 0)
-    if SPLIT_ONLY:
-        print(" | ".join(line), flush=True)
-        continue
     for bn in (64, 128, 256):
         for mt in (1, 2):
             _lib.debug_set("fprop_mt", mt)
