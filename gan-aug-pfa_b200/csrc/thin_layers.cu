@@ -131,27 +131,47 @@ __global__ void __launch_bounds__(256, 4) cout1_z_kernel(const bf16* __restrict_
 }
 
 // stage 2: logits[n][oy][ox] = bias + sum_{kh,kw} z[n][oy+kh-pad][ox+kw-pad][kh*4+kw]
-__global__ void cout1_gather_kernel(const float* __restrict__ z, const float* __restrict__ bias, int n, int ih, int iw,
-                                    int oh, int ow, int pad, float* __restrict__ logits) {
+// Four adjacent lanes per output, one kernel row each (its four loads are issued together, then two shuffles): the
+// one-thread-per-output loop with 16 conditional loads was latency-bound (6.9 us for 57600 outputs, ncu).
+__global__ void __launch_bounds__(256) cout1_gather_kernel(const float* __restrict__ z, const float* __restrict__ bias, int n,
+                                                           int ih, int iw, int oh, int ow, int pad,
+                                                           float* __restrict__ logits) {
   const long long total = static_cast<long long>(n) * oh * ow;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ox = static_cast<int>(i % ow);
-    const int oy = static_cast<int>((i / ow) % oh);
-    const long long img = i / (static_cast<long long>(ow) * oh);
-    float s = bias ? __ldg(bias) : 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
+  const long long groups = (total + 63) / 64;      // 64 outputs per block pass; every lane of a warp stays in the loop
+  for (long long gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+    const long long i = gi * 64 + (threadIdx.x >> 2);
+    const int kh = threadIdx.x & 3;
+    float s = 0.f;
+    if (i < total) {
+      long long img;
+      int ox, oy;
+      if (total <= 0x7fffffffLL) {      // 32-bit divisions (the 64-bit ones are ~100 instructions each)
+        const uint32_t i32 = static_cast<uint32_t>(i), q = i32 / static_cast<uint32_t>(ow);
+        const uint32_t im = q / static_cast<uint32_t>(oh);
+        ox = static_cast<int>(i32 - q * static_cast<uint32_t>(ow));
+        oy = static_cast<int>(q - im * static_cast<uint32_t>(oh));
+        img = im;
+      } else {
+        const long long q = i / ow;
+        ox = static_cast<int>(i - q * ow);
+        img = q / oh;
+        oy = static_cast<int>(q - img * oh);
+      }
       const int iy = oy + kh - pad;
-      if (iy < 0 || iy >= ih) continue;
+      if (iy >= 0 && iy < ih) {
+        const float* zr = z + ((img * ih + iy) * iw) * 16 + kh * 4;
+        float v[4];
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int ix = ox + kw - pad;
-        if (ix < 0 || ix >= iw) continue;
-        s += __ldg(z + ((img * ih + iy) * iw + ix) * 16 + kh * 4 + kw);
+        for (int kw = 0; kw < 4; ++kw) {
+          const int ix = ox + kw - pad;
+          v[kw] = (ix >= 0 && ix < iw) ? __ldg(zr + static_cast<long long>(ix) * 16 + kw) : 0.f;
+        }
+        s = (v[0] + v[1]) + (v[2] + v[3]);
       }
     }
-    logits[i] = s;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (kh == 0 && i < total) logits[i] = s + (bias ? __ldg(bias) : 0.f);
   }
 }
 
@@ -168,15 +188,61 @@ __device__ __forceinline__ float gather_dlogit(const float* __restrict__ dlog, l
   return __ldg(dlog + (img * oh + oy) * ow + ox);
 }
 
+// Streaming unit of the Cout = 1 kernels: [16 pixels x 64 channels] bf16 = 2 KiB, one full 128-byte line per pixel,
+// copied by ONE warp with cp.async into its private ring; the 16-byte granules of a row are XOR-swizzled by (row & 7)
+// so that ldmatrix (plain and .trans) and per-lane 128-bit reads of the unit are bank-conflict-free.
+constexpr int kC1Ring = 8;     // ring depth of the forward / wgrad kernels (14 KiB in flight per warp)
+constexpr int kC1YRing = 4;    // ring depth of the y stream of the backward-fused dgrad (two CTAs per SM)
+constexpr int kC1Unit = 2048;
+constexpr int kC1Round = 32;   // wgrad: slabs whose gathered dlogits table is built at once (24 KiB)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// Per-lane invariants of the unit copy (lane -> rows (lane >> 3) + 4 i, granule lane & 7): the first version
+// recomputed the 64-bit source addresses and the swizzle per row and unit, ~110 instructions per unit next to the
+// ~160 of the MMA loop it feeds (ncu source page of cout1_z2_kernel).
+struct C1Lane {
+  long long src_off;    // (lane >> 3) * ld + (lane & 7) * 8   (elements)
+  long long row_step;   // 4 * ld
+  uint32_t dst_off[4];  // swizzled byte offsets of the lane's four granules inside a unit
+  int r0;               // lane >> 3
+};
+__device__ __forceinline__ C1Lane c1_lane(long long ld, uint32_t lane) {
+  C1Lane L;
+  const uint32_t gran = lane & 7;
+  L.r0 = static_cast<int>(lane >> 3);
+  L.src_off = L.r0 * ld + gran * 8;
+  L.row_step = 4 * ld;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t r = (lane >> 3) + 4 * i;
+    L.dst_off[i] = r * 128 + ((gran ^ (r & 7)) << 4);
+  }
+  return L;
+}
+// one unit: pixels pix0 .. pix0+15 (rows at or beyond pix_end are zero-filled: src-size 0, nothing is read),
+// 64 channels starting at x_ch = x + ch0
+__device__ __forceinline__ void c1_issue_unit(uint32_t dst, const bf16* __restrict__ x_ch, long long ld, const C1Lane& L,
+                                              long long pix0, long long pix_end) {
+  const bf16* src = x_ch + pix0 * ld + L.src_off;
+  const long long lim = pix_end - pix0 - L.r0;      // row i of this lane is real iff 4 i < lim
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cp_async16(dst + L.dst_off[i], src + i * L.row_step, 4 * i < lim ? 16 : 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Cout = 1 dgrad: gx[pix][c] = sum_tap u[pix][tap] * w[tap][c]   (one k16 MMA step per output tile)
 // CTA = 128 input pixels; warp = one 64-channel range, its 8 B fragments held in registers.
-// dynamic smem: wT[c][24] | us[128][24] | out_s[8][16][72]   (bf16)
+// dynamic smem: wT[c][24] | us[128][24] | out_s[8][16][72]   (bf16) | BWD: yring[8 warps][kC1YRing][2 KiB]
 // ------------------------------------------------------------------------------------------------
 // BWD: the copy-out also applies the activation backward of the layer below (d = (y*scale+shift > 0) ? g : slope*g,
 // the LeakyReLU after BatchNorm, models.py:239-240) and accumulates that layer's BatchNorm-backward sums
 // [sum d | sum d*y] (of the stored bf16 d) -- the same contract as the tcgen05 dgrad epilogue, so the separate
-// reduce pass over y and g disappears.  Needs c <= 512 (one 64-channel range per warp).
+// reduce pass over y and g disappears.  Needs c <= 512 (one 64-channel range per warp).  The y slabs stream through a
+// per-warp cp.async ring (issued kC1YRing - 1 slabs ahead, the first ones before the weight staging): loading them
+// with plain global loads right before their use left the kernel bound by that latency (54 us vs 21 us plain).
 struct Cout1Bwd {
   const bf16* y;
   long long ld_y;
@@ -196,10 +262,34 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
   bf16* out_s = us + 128 * 24;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  for (int idx = tid; idx < c * 16; idx += 256) {
-    const int tap = idx / c, cc = idx - tap * c;
-    wT[cc * 24 + tap] = w[idx];
+  // BWD: producer / consumer state of this warp's y stream (units in (tile, 16-pixel slab) order)
+  const uint8_t* yring = nullptr;
+  uint32_t yring_a = 0;
+  const C1Lane ylane = c1_lane(BWD ? b.ld_y : 0, static_cast<uint32_t>(lane));
+  long long p_tile = blockIdx.x;
+  int p_mt = 0, p_unit = 0, c_unit = 0;
+  auto y_issue = [&]() {
+    if (p_tile * 128 < npix) {
+      c1_issue_unit(yring_a + (p_unit & (kC1YRing - 1)) * kC1Unit, b.y + warp * 64, b.ld_y, ylane, p_tile * 128 + p_mt * 16,
+                    npix);
+      ++p_unit;
+      if (++p_mt == 8) {
+        p_mt = 0;
+        p_tile += gridDim.x;
+      }
+    }
+    cp_async_commit();
+  };
+  if (BWD && warp * 64 < c) {
+    const uint32_t raw = smem_u32(out_s + 8 * 16 * 72);
+    const uint32_t al = (raw + 127u) & ~127u;
+    yring_a = al + warp * (kC1YRing * kC1Unit);
+    yring = reinterpret_cast<const uint8_t*>(out_s + 8 * 16 * 72) + (al - raw) + warp * (kC1YRing * kC1Unit);
+#pragma unroll 1
+    for (int j = 0; j < kC1YRing - 1; ++j) y_issue();
   }
+  for (int tap = 0; tap < 16; ++tap)
+    for (int cc = tid; cc < c; cc += 256) wT[cc * 24 + tap] = w[tap * c + cc];
   const uint32_t us_a = smem_u32(us);
   bf16* my_out = out_s + warp * 16 * 72;
   // BWD: this lane always copies out the same 8 channels (warp's 64-channel range, segment lane & 7)
@@ -215,10 +305,40 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
   }
   for (long long tile = blockIdx.x; tile * 128 < npix; tile += gridDim.x) {
     __syncthreads();  // wT ready (first pass) / previous tile's us consumed
+    {
+      // one pixel and eight taps (two kernel rows) per thread: ONE (n, y, x) decomposition instead of eight 64-bit ones
+      // (the staging, not the stores, bounded this kernel), one 128-bit shared-memory store
+      const int px = tid & 127, kh0 = (tid >> 7) * 2;
+      const long long pix = tile * 128 + px;
+      uint32_t pk[4] = {0u, 0u, 0u, 0u};
+      if (pix < npix) {
+        int xx, yy;
+        long long img;
+        if (npix <= 0x7fffffffLL) {
+          const uint32_t p32 = static_cast<uint32_t>(pix), q = p32 / static_cast<uint32_t>(iw);
+          xx = static_cast<int>(p32 - q * static_cast<uint32_t>(iw));
+          const uint32_t im = q / static_cast<uint32_t>(ih);
+          yy = static_cast<int>(q - im * static_cast<uint32_t>(ih));
+          img = im;
+        } else {
+          xx = static_cast<int>(pix % iw);
+          yy = static_cast<int>((pix / iw) % ih);
+          img = pix / (static_cast<long long>(iw) * ih);
+        }
+        const float* dl = dlog + img * oh * ow;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int idx = tid + i * 256, px = idx >> 4, tap = idx & 15;
-      us[px * 24 + tap] = __float2bfloat16(gather_dlogit(dlog, tile * 128 + px, npix, tap, ih, iw, oh, ow, pad));
+        for (int j2 = 0; j2 < 4; ++j2) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * j2 + e;
+            const int oy = yy - (kh0 + (j >> 2)) + pad, ox = xx - (j & 3) + pad;
+            v[e] = (oy >= 0 && oy < oh && ox >= 0 && ox < ow) ? __ldg(dl + oy * ow + ox) : 0.f;
+          }
+          pk[j2] = pack_bf16x2(v[0], v[1]);
+        }
+      }
+      *reinterpret_cast<uint4*>(us + px * 24 + kh0 * 4) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     __syncthreads();
     for (int nr = warp; nr < (c >> 6); nr += 8) {
@@ -231,17 +351,13 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
         bfr[nt][1] = *reinterpret_cast<const uint32_t*>(row + 2 * t + 8);
       }
       for (int mt = 0; mt < 8; ++mt) {
-        // BWD: request this 16-pixel slab's y values before the MMAs (they are independent of them): the copy-out
-        // below was latency-bound on these loads
-        uint4 yq[4];
+        const uint8_t* ystage = nullptr;
         if (BWD) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int idx = lane + i * 32, r = idx >> 3, seg = idx & 7;
-            const long long pix = tile * 128 + mt * 16 + r;
-            yq[i] = pix < npix ? __ldg(reinterpret_cast<const uint4*>(b.y + pix * b.ld_y + n0 + seg * 8))
-                               : make_uint4(0, 0, 0, 0);
-          }
+          cp_async_wait<kC1YRing - 2>();
+          __syncwarp();          // this slab's y rows have landed for every lane; the previous slab's reads are done
+          y_issue();             // refills the stage read one iteration ago
+          ystage = yring + (c_unit & (kC1YRing - 1)) * kC1Unit;
+          ++c_unit;
         }
         uint32_t a[4];
         lda_16x16(a, us_a + mt * 16 * 48, 48, lane);
@@ -260,7 +376,7 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
           if (pix < npix) {
             uint4 v = *reinterpret_cast<const uint4*>(my_out + r * 72 + seg * 8);
             if (BWD) {
-              const uint4 yv = yq[i];
+              const uint4 yv = *reinterpret_cast<const uint4*>(ystage + r * 128 + ((seg ^ (r & 7)) << 4));
               const uint32_t gw[4] = {v.x, v.y, v.z, v.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
               uint32_t pk[4];
 #pragma unroll
@@ -293,6 +409,7 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
     }
   }
   if (BWD) {
+    cp_async_wait<0>();
     // lanes l, l+8, l+16, l+24 hold the same channels
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -409,6 +526,258 @@ __global__ void __launch_bounds__(256, 4) cout1_wgrad_kernel(const float* __rest
     // t ^ 1 swap halves so that the even lane owns 4 consecutive columns of tap row g, the odd lane those of row g + 8.
     const bool odd = t & 1;
     const bool vec = (reinterpret_cast<uintptr_t>(dw) & 15) == 0;      // c % 64 == 0 keeps every row 16-byte aligned
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float s0 = odd ? acc[nt][0] : acc[nt][2], s1 = odd ? acc[nt][1] : acc[nt][3];
+      const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const int col = n0 + nt * 8 + 4 * (t >> 1);
+      float* dst = dw + static_cast<long long>(odd ? g + 8 : g) * c + col;
+      const float v0 = odd ? r0 : acc[nt][0], v1 = odd ? r1 : acc[nt][1];
+      const float v2 = odd ? acc[nt][2] : r0, v3 = odd ? acc[nt][3] : r1;
+      if (vec) {
+        red_add_v4_f32(dst, v0, v1, v2, v3);
+      } else {
+        atomicAdd(dst, v0);
+        atomicAdd(dst + 1, v1);
+        atomicAdd(dst + 2, v2);
+        atomicAdd(dst + 3, v3);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming versions of the Cout = 1 forward and weight gradient (c <= 512, 0 <= slope <= 1, < 2^31 pixels; the
+// kernels above stay as the general path).  The kernels above hold ONE 16 KiB chunk per CTA in flight between two
+// __syncthreads (1.4-1.9 TB/s on the 63 MB head input).  Here every warp streams its own [16 pixels x 64 channels]
+// units (2 KiB: one full 128-byte line per pixel) through a private ring of eight cp.async stages, so a CTA of
+// eight warps keeps 112 KiB in flight without any CTA-wide barrier in the load path; the 16-byte granules of a
+// row are XOR-swizzled by (row & 7), which makes both ldmatrix forms below conflict-free.  BatchNorm + LeakyReLU of
+// the layer below (PRE) are applied to the MMA FRAGMENTS (a lane always sees the same channels, so its scale /
+// shift sit in registers); LeakyReLU is max(v, slope*v).
+// ------------------------------------------------------------------------------------------------
+// two packed bf16 values -> LeakyReLU(v*scale + shift) with one (scale, shift) pair per half
+__device__ __forceinline__ uint32_t bn_lrelu2(uint32_t v, float sc_lo, float sh_lo, float sc_hi, float sh_hi, float slope) {
+  const float a = fmaf(bf16_lo(v), sc_lo, sh_lo), b = fmaf(bf16_hi(v), sc_hi, sh_hi);
+  return pack_bf16x2(fmaxf(a, slope * a), fmaxf(b, slope * b));
+}
+
+// Forward stage 1 (z[pix][tap], as cout1_z_kernel).  CTA tile = 32 pixels: warp = (16-pixel slab, quarter of the
+// channels); its B fragments (the weights of its <= 2 chunks) and PRE parameters stay in registers for the whole
+// kernel.  The four K quarters of a slab are summed through shared memory (double-buffered: one barrier per tile).
+// dynamic smem: ring[8 warps][kC1Ring][2 KiB] | red[2][8][256] fp32
+template <bool PRE>
+__global__ void __launch_bounds__(256, 1) cout1_z2_kernel(const bf16* __restrict__ x, long long ld_x, int npix, int c,
+                                                          const bf16* __restrict__ w, float* __restrict__ z,
+                                                          const Cout1Pre pre) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t sbase = (smem_u32(dsm) + 127u) & ~127u;      // 128-byte rows: the swizzle assumes aligned units
+  const uint32_t ring = sbase + warp * (kC1Ring * kC1Unit);
+  float* red = reinterpret_cast<float*>(dsm + (sbase - smem_u32(dsm)) + 8 * kC1Ring * kC1Unit);
+  const int sj = warp >> 2, kq = warp & 3;
+  const int nch = c >> 6;
+  const int cpw = (nch + 3) >> 2;                                  // chunks per warp (<= 2)
+  const int ch_first = kq * cpw;
+  const int my_chunks = max(0, min(cpw, nch - ch_first));
+  const int ntiles = (npix + 31) >> 5;
+  const int my_tiles = static_cast<int>(blockIdx.x) < ntiles ? (ntiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  const int n_units = my_tiles * my_chunks;
+
+  // producer state: unit -> (tile, chunk)
+  const C1Lane xlane = c1_lane(ld_x, lane);
+  int p_unit = 0, p_ti = 0, p_cc = 0;
+  auto issue_next = [&]() {
+    if (p_unit < n_units) {
+      const long long pix0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(p_ti) * gridDim.x) * 32 + sj * 16;
+      c1_issue_unit(ring + (p_unit & (kC1Ring - 1)) * kC1Unit, x + (ch_first + p_cc) * 64, ld_x, xlane, pix0, npix);
+      ++p_unit;
+      if (++p_cc == my_chunks) {
+        p_cc = 0;
+        ++p_ti;
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int j = 0; j < kC1Ring - 1; ++j) issue_next();
+
+  uint32_t bq[2][4][4];      // [chunk][k step]{n tile 0: b0 b1 | n tile 1: b0 b1}
+  float sc[2][4][4], sh[2][4][4];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const bool have = cc < my_chunks;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int cb = (ch_first + cc) * 64 + ks * 16 + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const bf16* wr = w + static_cast<long long>(nt * 8 + g) * c + cb;
+        bq[cc][ks][2 * nt] = have ? __ldg(reinterpret_cast<const uint32_t*>(wr)) : 0u;
+        bq[cc][ks][2 * nt + 1] = have ? __ldg(reinterpret_cast<const uint32_t*>(wr + 8)) : 0u;
+      }
+      if (PRE) {
+        const int off[4] = {0, 1, 8, 9};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc[cc][ks][j] = have ? __ldg(pre.scale + cb + off[j]) : 0.f;
+          sh[cc][ks][j] = have ? __ldg(pre.shift + cb + off[j]) : 0.f;
+        }
+      }
+    }
+  }
+
+  int stage = 0;
+  for (int ti = 0; ti < my_tiles; ++ti) {
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      if (cc < my_chunks) {
+        cp_async_wait<kC1Ring - 2>();
+        __syncwarp();            // every lane's copies of this unit have landed; the previous unit's reads are done
+        issue_next();            // refills the stage consumed one iteration ago
+        const uint32_t ub = ring + stage * kC1Unit;
+        stage = (stage + 1) & (kC1Ring - 1);
+        const uint32_t r = lane & 15;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t a[4];
+          ldmatrix_x4(a, ub + r * 128 + (((2 * ks + (lane >> 4)) ^ (r & 7)) << 4));
+          if (PRE) {
+            a[0] = bn_lrelu2(a[0], sc[cc][ks][0], sh[cc][ks][0], sc[cc][ks][1], sh[cc][ks][1], pre.slope);
+            a[1] = bn_lrelu2(a[1], sc[cc][ks][0], sh[cc][ks][0], sc[cc][ks][1], sh[cc][ks][1], pre.slope);
+            a[2] = bn_lrelu2(a[2], sc[cc][ks][2], sh[cc][ks][2], sc[cc][ks][3], sh[cc][ks][3], pre.slope);
+            a[3] = bn_lrelu2(a[3], sc[cc][ks][2], sh[cc][ks][2], sc[cc][ks][3], sh[cc][ks][3], pre.slope);
+          }
+          mma_bf16_16816(acc[0], a, bq[cc][ks][0], bq[cc][ks][1]);
+          mma_bf16_16816(acc[1], a, bq[cc][ks][2], bq[cc][ks][3]);
+        }
+      }
+    }
+    float* rb = red + ((ti & 1) * 8 + warp) * 256;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      *reinterpret_cast<float2*>(rb + g * 16 + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(rb + (g + 8) * 16 + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+    __syncthreads();
+    // thread -> two consecutive taps of one pixel: sum of the four K quarters of its slab
+    const int o = tid * 2, oj = o >> 8, idx = o & 255;
+    const float* rs = red + ((ti & 1) * 8 + oj * 4) * 256 + idx;
+    float2 s = *reinterpret_cast<const float2*>(rs);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float2 v = *reinterpret_cast<const float2*>(rs + q * 256);
+      s.x += v.x;
+      s.y += v.y;
+    }
+    const long long pix = (static_cast<long long>(blockIdx.x) + static_cast<long long>(ti) * gridDim.x) * 32 + oj * 16 + (idx >> 4);
+    if (pix < npix) *reinterpret_cast<float2*>(z + pix * 16 + (idx & 15)) = s;
+  }
+  cp_async_wait<0>();
+}
+
+// Weight gradient (as cout1_wgrad_kernel): CTA = a contiguous pixel range, warp = one 64-channel range with its
+// 16 x 64 accumulator in registers over the whole range; the gathered output gradients u[tap][pixel] of up to
+// kC1Round slabs are tabulated in shared memory by the whole CTA (one (n, y, x) decomposition per pixel, 32-bit)
+// while the first units are already in flight.  One CTA per SM: 148 partial flushes instead of 592.
+// dynamic smem: ring[8 warps][kC1Ring][2 KiB] | U[kC1Round][16 taps][24] bf16
+template <bool PRE>
+__global__ void __launch_bounds__(256, 1) cout1_wgrad2_kernel(const float* __restrict__ dlog, int ih, int iw, int oh, int ow,
+                                                              int pad, int npix, int chunk, const bf16* __restrict__ x,
+                                                              long long ld_x, int c, float* __restrict__ dw,
+                                                              const Cout1Pre pre) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t sbase = (smem_u32(dsm) + 127u) & ~127u;
+  const uint32_t ring = sbase + warp * (kC1Ring * kC1Unit);
+  bf16* U = reinterpret_cast<bf16*>(dsm + (sbase - smem_u32(dsm)) + 8 * kC1Ring * kC1Unit);
+  const uint32_t U_a = smem_u32(U);
+  const int p0 = static_cast<int>(blockIdx.x) * chunk, p1 = min(npix, p0 + chunk);
+  const int n_slabs = (p1 - p0 + 15) >> 4;
+  const int n0 = warp * 64;
+  const bool active = n0 < c;
+  const C1Lane xlane = c1_lane(ld_x, lane);
+  int p_slab = 0;
+  auto issue_next = [&]() {
+    if (p_slab < n_slabs) {
+      c1_issue_unit(ring + (p_slab & (kC1Ring - 1)) * kC1Unit, x + n0, ld_x, xlane, p0 + 16 * p_slab, p1);
+      ++p_slab;
+    }
+    cp_async_commit();
+  };
+  if (active) {
+#pragma unroll 1
+    for (int j = 0; j < kC1Ring - 1; ++j) issue_next();
+  }
+  float sc[8], sh[8];
+  if (PRE) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sc[nt] = active ? __ldg(pre.scale + n0 + nt * 8 + g) : 0.f;
+      sh[nt] = active ? __ldg(pre.shift + n0 + nt * 8 + g) : 0.f;
+    }
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+
+  for (int r0 = 0; r0 < n_slabs; r0 += kC1Round) {
+    const int rs = min(kC1Round, n_slabs - r0);
+    if (r0) __syncthreads();        // the previous round's table has been consumed
+    for (int i = tid; i < rs * 16; i += 256) {
+      const int pix = p0 + r0 * 16 + i;
+      bf16* ur = U + (i >> 4) * (16 * 24) + (i & 15);
+      if (pix < p1) {
+        const int xx = pix % iw, q = pix / iw, yy = q % ih, img = q / ih;
+        const float* dl = dlog + static_cast<long long>(img) * oh * ow;
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) {
+          const int oy = yy - (tap >> 2) + pad, ox = xx - (tap & 3) + pad;
+          const bool in = oy >= 0 && oy < oh && ox >= 0 && ox < ow;
+          ur[tap * 24] = __float2bfloat16(in ? __ldg(dl + oy * ow + ox) : 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) ur[tap * 24] = __float2bfloat16(0.f);
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int s = 0; s < rs; ++s) {
+        cp_async_wait<kC1Ring - 2>();
+        __syncwarp();
+        issue_next();
+        const uint32_t ub = ring + ((r0 + s) & (kC1Ring - 1)) * kC1Unit;
+        uint32_t a[4];
+        lda_16x16(a, U_a + s * (16 * 48), 48, lane);
+        const uint32_t r = lane & 15;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, ub + r * 128 + (((2 * np + (lane >> 4)) ^ (r & 7)) << 4));
+          if (PRE) {
+            b[0] = bn_lrelu2(b[0], sc[2 * np], sh[2 * np], sc[2 * np], sh[2 * np], pre.slope);
+            b[1] = bn_lrelu2(b[1], sc[2 * np], sh[2 * np], sc[2 * np], sh[2 * np], pre.slope);
+            b[2] = bn_lrelu2(b[2], sc[2 * np + 1], sh[2 * np + 1], sc[2 * np + 1], sh[2 * np + 1], pre.slope);
+            b[3] = bn_lrelu2(b[3], sc[2 * np + 1], sh[2 * np + 1], sc[2 * np + 1], sh[2 * np + 1], pre.slope);
+          }
+          mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
+          mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (active && p1 > p0) {       // same flush as cout1_wgrad_kernel: one 128-bit reduction per lane and 8-column block
+    const bool odd = t & 1;
+    const bool vec = (reinterpret_cast<uintptr_t>(dw) & 15) == 0;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float s0 = odd ? acc[nt][0] : acc[nt][2], s1 = odd ? acc[nt][1] : acc[nt][3];
@@ -924,10 +1293,6 @@ struct ThinWgradParams {
   int tiles_x, tiles_y;
   long long total_tiles;
 };
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
 
 template <int CT>
 __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const __grid_constant__ ThinWgradParams p) {
@@ -1649,6 +2014,15 @@ __global__ void sum_f32_kernel(const float* __restrict__ x, long long count, flo
 
 using namespace gap;
 
+// The streaming Cout = 1 kernels (cout1_z2 / cout1_wgrad2) cover c <= 512, 32-bit pixel indices and slopes for which
+// LeakyReLU(v) = max(v, slope*v); `cout1_stream=0` (bring-up knob) forces the general kernels.
+static bool cout1_streaming_ok(long long npix, int c, const float* in_scale, float in_slope) {
+  if (debug_get("cout1_stream", 1) == 0) return false;
+  if (c > 512 || npix > 0x7fffffe0LL) return false;
+  if (in_scale && !(in_slope >= 0.f && in_slope <= 1.f)) return false;
+  return true;
+}
+
 extern "C" {
 
 int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c, const void* w, const float* bias,
@@ -1669,15 +2043,33 @@ int gap_cout1_conv_fwd(const void* x, int64_t ld_x, int n, int ih, int iw, int c
   const long long npix = static_cast<long long>(n) * ih * iw;
   const int tiles = static_cast<int>((npix + 127) / 128);
   const Cout1Pre pre{in_scale, in_shift, in_slope};
-  if (in_scale)
+  if (cout1_streaming_ok(npix, c, in_scale, in_slope)) {
+    // streaming kernel: one CTA per SM over 32-pixel tiles
+    constexpr int smem = 128 + 8 * kC1Ring * kC1Unit + 2 * 8 * 256 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GAP_CUDA(cudaFuncSetAttribute(cout1_z2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      GAP_CUDA(cudaFuncSetAttribute(cout1_z2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    const int tiles32 = static_cast<int>((npix + 31) / 32);
+    const int grid = std::min(tiles32, sm_count());
+    if (in_scale)
+      cout1_z2_kernel<true><<<grid, 256, smem, st>>>(static_cast<const bf16*>(x), ld_x, static_cast<int>(npix), c,
+                                                      static_cast<const bf16*>(w), z_ws, pre);
+    else
+      cout1_z2_kernel<false><<<grid, 256, smem, st>>>(static_cast<const bf16*>(x), ld_x, static_cast<int>(npix), c,
+                                                       static_cast<const bf16*>(w), z_ws, pre);
+  } else if (in_scale) {
     cout1_z_kernel<true><<<std::min(tiles, 8 * sm_count()), 256, 0, st>>>(static_cast<const bf16*>(x), ld_x, npix, c,
                                                                            static_cast<const bf16*>(w), z_ws, pre);
-  else
+  } else {
     cout1_z_kernel<false><<<std::min(tiles, 8 * sm_count()), 256, 0, st>>>(static_cast<const bf16*>(x), ld_x, npix, c,
                                                                             static_cast<const bf16*>(w), z_ws, pre);
+  }
   GAP_CUDA(cudaGetLastError());
   const long long total = static_cast<long long>(n) * oh * ow;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * sm_count()));
+  const int blocks = static_cast<int>(std::min<long long>((total + 63) / 64, 8LL * sm_count()));
   cout1_gather_kernel<<<blocks, 256, 0, st>>>(z_ws, bias, n, ih, iw, oh, ow, pad, logits);
   GAP_CUDA(cudaGetLastError());
   return 0;
@@ -1695,7 +2087,8 @@ static int cout1_dgrad_launch(const char* who, const float* dlogits, int n, int 
     return GAP_ERR_UNSUPPORTED;
   }
   const long long npix = static_cast<long long>(n) * ih * iw;
-  const size_t smem = (static_cast<size_t>(c) * 24 + 128 * 24 + 8 * 16 * 72) * sizeof(bf16);
+  const size_t smem = (static_cast<size_t>(c) * 24 + 128 * 24 + 8 * 16 * 72) * sizeof(bf16) +
+                      (bwd ? 128 + 8 * kC1YRing * kC1Unit : 0);
   if (smem > 200 * 1024) {
     set_error("%s: %d channels do not fit shared memory", who, c);
     return GAP_ERR_UNSUPPORTED;
@@ -1747,6 +2140,29 @@ int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void
     return GAP_ERR_UNSUPPORTED;
   }
   const long long npix = static_cast<long long>(n) * ih * iw;
+  if (cout1_streaming_ok(npix, c, in_scale, in_slope)) {
+    // streaming kernel: one CTA per SM, each a contiguous range of 16-pixel slabs
+    constexpr int smem2 = 128 + 8 * kC1Ring * kC1Unit + kC1Round * 16 * 24 * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GAP_CUDA(cudaFuncSetAttribute(cout1_wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      GAP_CUDA(cudaFuncSetAttribute(cout1_wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr_set = true;
+    }
+    const long long slabs = (npix + 15) / 16;
+    const int per_cta = static_cast<int>((slabs + sm_count() - 1) / sm_count());
+    const int chunk2 = per_cta * 16;
+    const int grid2 = static_cast<int>((npix + chunk2 - 1) / chunk2);
+    const Cout1Pre pre2{in_scale, in_shift, in_slope};
+    if (in_scale)
+      cout1_wgrad2_kernel<true><<<grid2, 256, smem2, st>>>(dlogits, ih, iw, oh, ow, pad, static_cast<int>(npix), chunk2,
+                                                            static_cast<const bf16*>(x), ld_x, c, dw, pre2);
+    else
+      cout1_wgrad2_kernel<false><<<grid2, 256, smem2, st>>>(dlogits, ih, iw, oh, ow, pad, static_cast<int>(npix), chunk2,
+                                                             static_cast<const bf16*>(x), ld_x, c, dw, pre2);
+    GAP_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (static_cast<size_t>(16) * (c + 8) + 16 * 24) * sizeof(bf16) + (in_scale ? 2 * c * sizeof(float) : 0);
   const int want = debug_get("cout1_wg_mult", 4) * sm_count();
   long long chunk = (npix + want - 1) / want;
