@@ -333,7 +333,69 @@ __device__ __forceinline__ void loadf8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-template <bool APPLY>
+// bn_act for the activations of the training path (identity / LeakyReLU(0.2) / ReLU), in bn_bwd_kernel's thread layout:
+// threadIdx.x walks 8-channel groups, whose scale / shift stay in registers, threadIdx.y walks pixels, U pixels in
+// flight per thread.  The general kernel above pays a 64-bit division, four parameter loads and a per-element
+// activation switch (Tanh / Sigmoid included) per 16-byte vector: ~3500 SASS instructions, instruction-bound at
+// 3.2-4.3 TB/s on the 33-134 MB tensors of the step.
+__device__ __forceinline__ void act8_slope(const float (&v)[8], int act, uint32_t (&pk)[4]) {
+  if (act == GAP_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f));
+  } else if (act == GAP_ACT_LRELU) {      // v > 0 ? v : 0.2 v  ==  max(v, 0.2 v)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(fmaxf(v[2 * j], 0.2f * v[2 * j]), fmaxf(v[2 * j + 1], 0.2f * v[2 * j + 1]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(256, 3) bn_act_slope_kernel(const __nv_bfloat16* __restrict__ y, long long ld_y,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           long long pixels, int c, __nv_bfloat16* __restrict__ o1,
+                                                           long long ld1, int act1, __nv_bfloat16* __restrict__ o2,
+                                                           long long ld2, int act2) {
+  pdl_trigger();
+  pdl_wait();
+  const int cv = c >> 3;
+  const long long pstride = (long long)gridDim.x * blockDim.y;
+  for (int cg = threadIdx.x; cg < cv; cg += blockDim.x) {
+    const int c8 = cg << 3;
+    float sc[8], sh[8];
+    loadf8(scale + c8, sc);
+    loadf8(shift + c8, sh);
+    for (long long pix0 = blockIdx.x * (long long)blockDim.y + threadIdx.y; pix0 < pixels; pix0 += U * pstride) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * pstride;
+        if (pix < pixels) raw[u] = __ldg(reinterpret_cast<const uint4*>(y + pix * ld_y + c8));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pix = pix0 + u * pstride;
+        if (pix >= pixels) break;
+        float v[8];
+        unpack_u4(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        uint32_t pk[4];
+        act8_slope(v, act1, pk);
+        *reinterpret_cast<uint4*>(o1 + pix * ld1 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (o2) {
+          act8_slope(v, act2, pk);
+          *reinterpret_cast<uint4*>(o2 + pix * ld2 + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+}
+
+// G2: a second gradient source exists (its registers disappear otherwise); U: pixels in flight per thread (six instead
+// of four measured no gain: 65.6 -> 68.3, 37.6 -> 36.4, 19.2 -> 19.2, 35.5 -> 34.8 us, tools/bench_bn_act.py).
+template <bool APPLY, bool G2, int U>
 __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -366,17 +428,17 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
       }
     }
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    constexpr int U = 4;   // pixels in flight per thread: loads of all U issued before any use
+    // pixels in flight per thread: loads of all U issued before any use
     const long long pstride = (long long)gridDim.x * blockDim.y;
     for (long long pix0 = blockIdx.x * (long long)blockDim.y + threadIdx.y; pix0 < a.pixels; pix0 += U * pstride) {
-      uint4 yr[U], g1r[U], g2r[U];
+      uint4 yr[U], g1r[U], g2r[G2 ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long pix = pix0 + u * pstride;
         if (pix < a.pixels) {
           yr[u] = __ldg(reinterpret_cast<const uint4*>(a.y + pix * a.ld_y + c8));
           g1r[u] = __ldg(reinterpret_cast<const uint4*>(a.g1 + pix * a.ld_g1 + c8));
-          if (a.g2) g2r[u] = __ldg(reinterpret_cast<const uint4*>(a.g2 + pix * a.ld_g2 + c8));
+          if (G2) g2r[u] = __ldg(reinterpret_cast<const uint4*>(a.g2 + pix * a.ld_g2 + c8));
         }
       }
 #pragma unroll
@@ -386,12 +448,12 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdArgs a) {
         float y[8], g1[8], g2[8];
         unpack_u4(yr[u], y);
         unpack_u4(g1r[u], g1);
-        if (a.g2) unpack_u4(g2r[u], g2);
+        if (G2) unpack_u4(g2r[G2 ? u : 0], g2);
         float d[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float yh = fmaf(y[j], sc[j], sh[j]);
-          const float gp = a.g2 ? g1[j] + g2[j] : g1[j];
+          const float gp = G2 ? g1[j] + g2[j] : g1[j];
           d[j] = yh > 0.f ? gp : a.slope * g1[j];
         }
         if (APPLY) {
@@ -834,6 +896,22 @@ int gap_bn_act(const void* y, int64_t ld_y, const float* scale, const float* shi
     set_error("gap_bn_act: pixel strides must be multiples of 8");
     return GAP_ERR_ALIGNMENT;
   }
+  auto slope_type = [](int a) { return a == GAP_ACT_NONE || a == GAP_ACT_LRELU || a == GAP_ACT_RELU; };
+  if (slope_type(act1) && (!out2 || slope_type(act2)) && debug_get("bn_act_fast", 1) != 0) {
+    const int cv = c / 8;
+    const int bx = cv < 128 ? cv : 128;
+    const int by = 256 / bx < 1 ? 1 : 256 / bx;
+    const long long slabs = (pixels + by - 1) / by;
+    // three resident blocks per SM (78 registers): measured 45.8 / 25.9 / 13.0 us on the 128 / 64 / 32-pixel-wide
+    // batch-64 tensors against 55.7 / 31.0 / 17.6 us of the general kernel (tools/bench_bn_act.py)
+    GAP_CUDA(launch_pdl(bn_act_slope_kernel<4>, dim3(grid_even(slabs, 4, 148 * debug_get("bn_act_bps", 3))), dim3(bx, by), 0,
+                        static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(y), static_cast<long long>(ld_y),
+                        scale, shift, static_cast<long long>(pixels), c, static_cast<__nv_bfloat16*>(out1),
+                        static_cast<long long>(ld1), act1, static_cast<__nv_bfloat16*>(out2), static_cast<long long>(ld2),
+                        act2));
+    GAP_LAUNCH_CHECK();
+    return 0;
+  }
   // 4 vectors per thread and sweep (U in the kernel)
   GAP_CUDA(launch_pdl(bn_act_kernel, dim3(grid_even(pixels * (c / 8), 256 * 4, 148 * debug_get("bn_act_bps", 4))), dim3(256), 0, static_cast<cudaStream_t>(stream),
                       static_cast<const __nv_bfloat16*>(y), static_cast<long long>(ld_y), scale, shift,
@@ -850,19 +928,27 @@ static int bn_bwd_launch(bool apply, const BnBwdArgs& a, cudaStream_t st) {
   if (by < 1) by = 1;
   dim3 block(bx, by);
   const long long slabs = (a.pixels + by - 1) / by;
+  const bool g2 = a.g2 != nullptr;
   const int grid = grid_even(slabs, 4, 148 * debug_get("bn_bwd_bps", 2));   // 4 pixel slabs per block and sweep (U in the kernel); resident blocks only
   if (apply) {
-    GAP_CUDA(launch_pdl(bn_bwd_kernel<true>, dim3(grid), block, 0, st, a));
+    if (g2)
+      GAP_CUDA(launch_pdl(bn_bwd_kernel<true, true, 4>, dim3(grid), block, 0, st, a));
+    else
+      GAP_CUDA(launch_pdl(bn_bwd_kernel<true, false, 4>, dim3(grid), block, 0, st, a));
   } else {
     const size_t smem = static_cast<size_t>(by) * a.c * 2 * sizeof(float);
     if (smem > 48 * 1024) {
       static bool set = false;
       if (!set) {
-        GAP_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        GAP_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        GAP_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         set = true;
       }
     }
-    GAP_CUDA(launch_pdl(bn_bwd_kernel<false>, dim3(grid), block, smem, st, a));
+    if (g2)
+      GAP_CUDA(launch_pdl(bn_bwd_kernel<false, true, 4>, dim3(grid), block, smem, st, a));
+    else
+      GAP_CUDA(launch_pdl(bn_bwd_kernel<false, false, 4>, dim3(grid), block, smem, st, a));
   }
   GAP_CUDA(cudaGetLastError());
   return 0;
