@@ -161,6 +161,62 @@ def test_bce_and_l1_kernels():
     assert rel(dpre[..., :3].cpu().float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize("n,h,w,c", [(3, 7, 5, 64), (2, 9, 11, 128), (1, 5, 3, 512), (2, 4, 4, 1024)])
+def test_bn_act_slope_kernel_equals_the_general_one(n, h, w, c):
+    """gap_bn_act: the kernel for identity / LeakyReLU / ReLU (channel group per thread, `bn_act_fast` knob) against the
+    general kernel: bit-identical outputs, one and two outputs, outputs that are channel slots of a wider tensor, ragged
+    pixel counts."""
+    from gan_aug_pfa_b200 import _lib
+    g = torch.Generator().manual_seed(17 + c)
+    y = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).to(DEV)
+    sc = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    sh = torch.randn(c, generator=g).to(DEV)
+    try:
+        for act1, act2 in ((ops.ACT_LRELU, None), (ops.ACT_RELU, ops.ACT_LRELU), (ops.ACT_NONE, ops.ACT_RELU)):
+            got = []
+            for knob in (0, 1):
+                _lib.debug_set("bn_act_fast", knob)
+                o1 = torch.full((n, h, w, c), float("nan"), device=DEV, dtype=torch.bfloat16)
+                wide = torch.full((n, h, w, 2 * c), float("nan"), device=DEV, dtype=torch.bfloat16)
+                if act2 is None:
+                    ops.bn_act(y, sc, sh, wide[..., c:], act1)
+                else:
+                    ops.bn_act(y, sc, sh, o1, act1, wide[..., :c], act2)
+                got.append((o1.cpu(), wide.cpu()))
+            for a, b in zip(got[0], got[1]):
+                assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    finally:
+        _lib.debug_set("bn_act_fast", 1)
+
+
+def test_gen_out_bwd_four_pixel_kernel_equals_the_scalar_one():
+    """gap_gen_out_bwd / _u8: the four-pixels-per-thread kernel (3 channels in 4-slot tensors) against the per-pixel
+    kernel it replaces on that layout (`gen_out_c3` knob): identical bf16 gradients, the same L1 sum."""
+    from gan_aug_pfa_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    n, h, w = 3, 20, 36
+    fake = torch.tanh(torch.randn(n, h, w, 4, generator=g)).to(DEV)
+    dfd = (torch.randn(n, h, w, 4, generator=g) * 1e-3).to(DEV)
+    real_f = (torch.rand(n, 3, h, w, generator=g) * 2 - 1).to(DEV)
+    real_u8 = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8).to(DEV)
+    lam = 100.0 / (n * 3 * h * w)
+    try:
+        for real in (real_f, real_u8):
+            for d in (dfd, None):
+                out = []
+                for knob in (0, 1):
+                    _lib.debug_set("gen_out_c3", knob)
+                    acc = torch.zeros(1, device=DEV, dtype=torch.float64)
+                    dpre = torch.zeros(n, h, w, 4, device=DEV, dtype=torch.bfloat16)
+                    ops.gen_out_bwd(fake, real, d, lam, dpre, acc)
+                    out.append((dpre.cpu(), float(acc)))
+                assert torch.equal(out[0][0], out[1][0])
+                assert float(out[1][0][..., 3].abs().max()) == 0.0
+                assert abs(out[0][1] - out[1][1]) <= 1e-6 * abs(out[0][1])
+    finally:
+        _lib.debug_set("gen_out_c3", 1)
+
+
 def test_adam_kernel_matches_oracle():
     g = torch.Generator().manual_seed(1)
     n = 1027                                            # exercises the vector body and the scalar tail
