@@ -222,14 +222,18 @@ __device__ __forceinline__ C1Lane c1_lane(long long ld, uint32_t lane) {
   }
   return L;
 }
-// one unit: pixels pix0 .. pix0+15 (rows at or beyond pix_end are zero-filled: src-size 0, nothing is read),
+// one unit: pixels pix0 .. pix0+15 (rows at or beyond pix_end are zero-filled: src-size 0, nothing is read, and the
+// address handed to the copy is the tensor's base so that it is a mapped one whatever follows the tensor),
 // 64 channels starting at x_ch = x + ch0
 __device__ __forceinline__ void c1_issue_unit(uint32_t dst, const bf16* __restrict__ x_ch, long long ld, const C1Lane& L,
                                               long long pix0, long long pix_end) {
   const bf16* src = x_ch + pix0 * ld + L.src_off;
   const long long lim = pix_end - pix0 - L.r0;      // row i of this lane is real iff 4 i < lim
 #pragma unroll
-  for (int i = 0; i < 4; ++i) cp_async16(dst + L.dst_off[i], src + i * L.row_step, 4 * i < lim ? 16 : 0);
+  for (int i = 0; i < 4; ++i) {
+    const bool ok = 4 * i < lim;
+    cp_async16(dst + L.dst_off[i], ok ? src + i * L.row_step : x_ch, ok ? 16 : 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,8 +292,34 @@ __global__ void __launch_bounds__(256, 2) cout1_dgrad_kernel(const float* __rest
 #pragma unroll 1
     for (int j = 0; j < kC1YRing - 1; ++j) y_issue();
   }
-  for (int tap = 0; tap < 16; ++tap)
-    for (int cc = tid; cc < c; cc += 256) wT[cc * 24 + tap] = w[tap * c + cc];
+  {
+    // wT[channel][tap] <- w[tap][channel]: 128-bit loads, four per thread issued together, lanes walk the taps so that
+    // the 2-byte transposing stores of a half-warp fall into 32 contiguous bytes.  (As one 2-byte load + store per
+    // element -- 32 dependent global round trips per thread -- this staging held 33 % / 48 % of the stall samples of
+    // the fused / plain kernel: every CTA pays it for only ~1.6 tiles.)
+    const int cv = c >> 3, nvec = 16 * cv;
+    for (int base = 0; base < nvec; base += 1024) {
+      uint4 q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = base + tid + i * 256, tap = k & 15, seg = k >> 4;
+        q[i] = k < nvec ? ldg128(w + static_cast<long long>(tap) * c + seg * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = base + tid + i * 256, tap = k & 15, seg = k >> 4;
+        if (k < nvec) {
+          const uint32_t wd[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+          unsigned short* d = reinterpret_cast<unsigned short*>(wT) + seg * 8 * 24 + tap;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            d[(2 * j) * 24] = static_cast<unsigned short>(wd[j] & 0xffffu);
+            d[(2 * j + 1) * 24] = static_cast<unsigned short>(wd[j] >> 16);
+          }
+        }
+      }
+    }
+  }
   const uint32_t us_a = smem_u32(us);
   bf16* my_out = out_s + warp * 16 * 72;
   // BWD: this lane always copies out the same 8 channels (warp's 64-channel range, segment lane & 7)
@@ -2082,8 +2112,9 @@ static int cout1_dgrad_launch(const char* who, const float* dlogits, int n, int 
     set_error("%s: bad arguments", who);
     return GAP_ERR_BAD_ARG;
   }
-  if (ksize != 4 || c % 64 != 0 || c <= 0 || ld_gx % 8 != 0 || (reinterpret_cast<uintptr_t>(gx) & 15)) {
-    set_error("%s: needs ksize 4, channels %% 64 == 0 and 16-byte aligned rows", who);
+  if (ksize != 4 || c % 64 != 0 || c <= 0 || ld_gx % 8 != 0 || (reinterpret_cast<uintptr_t>(gx) & 15) ||
+      (reinterpret_cast<uintptr_t>(w) & 15)) {
+    set_error("%s: needs ksize 4, channels %% 64 == 0 and 16-byte aligned rows / weights", who);
     return GAP_ERR_UNSUPPORTED;
   }
   const long long npix = static_cast<long long>(n) * ih * iw;
