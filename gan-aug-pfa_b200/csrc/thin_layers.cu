@@ -2181,7 +2181,8 @@ int gap_cout1_conv_wgrad(const float* dlogits, int n, int oh, int ow, const void
       attr_set = true;
     }
     const long long slabs = (npix + 15) / 16;
-    const int per_cta = static_cast<int>((slabs + sm_count() - 1) / sm_count());
+    // at most kC1Round slabs per CTA (one table round; larger inputs simply take more CTAs than SMs)
+    const int per_cta = static_cast<int>(std::min<long long>((slabs + sm_count() - 1) / sm_count(), kC1Round));
     const int chunk2 = per_cta * 16;
     const int grid2 = static_cast<int>((npix + chunk2 - 1) / chunk2);
     const Cout1Pre pre2{in_scale, in_shift, in_slope};
