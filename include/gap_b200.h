@@ -192,8 +192,10 @@ int gap_sum_f32(const float* x, int64_t count, float* out, void* stream);
  *   fwd:   z_ws[pix][16] = x[pix][:] . w[tap][:]  then  logits[n][oy][ox] = bias + sum_taps z[...]
  *   dgrad: gx[pix][c]  = sum_taps dlogits[n][y-kh+pad][x-kw+pad] * w[tap][c]            (bf16 out)
  *   wgrad: dw[tap][c] += sum_pix  dlogits[n][y-kh+pad][x-kw+pad] * x[pix][c]            (fp32)
- * x / gx: NHWC bf16 (pixel stride ld, multiple of 8); w: bf16 [16][c] ([kh][kw][c], the packed
- * forward operand); logits / dlogits: fp32 [n][oh][ow]; z_ws: fp32 workspace [n*ih*iw*16].
+ * x / gx: NHWC bf16 (pixel stride ld, multiple of 8; 16-byte aligned); w: bf16 [16][c] ([kh][kw][c], the packed
+ * forward operand; 16-byte aligned); logits / dlogits: fp32 [n][oh][ow]; z_ws: fp32 workspace [n*ih*iw*16].
+ * c % 64 == 0.  Up to c = 512 (and 2^31 pixels, 0 <= in_slope <= 1) forward and wgrad run as streaming kernels (per-warp
+ * cp.async rings, one CTA per SM); other shapes take the general kernels -- same results, same contract.
  * in_scale / in_shift (fp32 [c], both or neither; c <= 512) + in_slope: x is then the RAW conv output of the layer below
  * and the kernels form LeakyReLU_slope(x*in_scale + in_shift) while staging it -- the BatchNorm apply + activation of
  * models.py:239-240 fused into its consumer, so the activated tensor never makes an HBM round trip.
