@@ -58,6 +58,8 @@ def rows_of(rep):
 
 def main():
     out_path, reps = sys.argv[1], sys.argv[2:]
+    if out_path.endswith(".ncu-rep") or not reps:      # a report given as the output path would be overwritten
+        sys.exit(__doc__)
     cols = [s for _, s in WANT]
     with open(out_path, "w") as f:
         f.write("# ncu --set full summaries (B200, --clock-control none; per-launch, cold-cache, serialised)\n\n")
